@@ -1,0 +1,169 @@
+// Internal declarations shared by the libbgp translation units.
+// Host control flow is C++; every FLOP on the hot path runs in the sm_100a kernels
+// declared at the bottom.  There is no CPU fallback: if CUDA is unavailable every entry
+// point returns BGP_ERR_CUDA.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bgp.h"
+
+namespace bgp {
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local std::string g_last_error;
+
+struct Status {
+  int code;
+  Status(int c = BGP_OK) : code(c) {}
+  bool ok() const { return code == BGP_OK; }
+};
+
+#define BGP_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::bgp::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,  \
+                       cudaGetErrorString(_e));                                                 \
+      return BGP_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define BGP_TRY(expr)              \
+  do {                             \
+    int _s = (expr);               \
+    if (_s != BGP_OK) return _s;   \
+  } while (0)
+
+extern int64_t g_launch_count;
+inline void count_launch(int64_t k = 1) { g_launch_count += k; }
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- device model ---------------------------------------------------------------------------
+struct RandomBlock {
+  int d = 0;
+  int off = 0;              // first W index of U_j
+  bool diag = true;
+  double* P_dev = nullptr;  // d (diag) or d*d column-major
+  double logPdet = 0, u = 1, alpha = 0.5;
+};
+
+// scalars produced on the device and read by the host once per Newton iteration
+struct EvalScalars {
+  double f;        // objective f(W, theta)
+  double ll;       // log-likelihood part
+  double gmax;     // max |g|
+  double quad;     // (W-mu0)^T Q (W-mu0)
+  double smax;     // max |step| of the last solve
+  double logdet;   // log det H of the last factorisation
+  int chol_info;   // 0 ok, j+1: non-positive pivot at column j
+  int nonfinite;   // 1 if eta / ll produced a non-finite value
+  double sumsq;    // Gaussian: sum (y-eta)^2
+  double pad;
+};
+
+struct Comm;   // NCCL communicator wrapper (comm.cpp)
+
+}  // namespace bgp
+
+struct bgp_model {
+  // ---- description -------------------------------------------------------------------------
+  int64_t n = 0;        // local rows
+  int family = 0;
+  int device = 0;
+  bool finalized = false;
+  int p = 0, S = 0, J = 0;
+  int lda = 0;          // row pitch of A in doubles (multiple of 16)
+  std::vector<bgp::RandomBlock> rnd;
+  std::vector<int> bnd_dim, fix_dim;
+  std::vector<double> bnd_prec, bnd_mean, fix_prec, fix_mean;
+  std::vector<double> theta_u, theta_alpha;   // length S (noise last)
+  double noise_u = 1.0, noise_alpha = 0.5;
+  // staging of host blocks before finalize (column-major device copies)
+  struct Staged { int ncol; double* dev; };
+  std::vector<Staged> st_rnd, st_bnd, st_fix;
+  // ---- device state --------------------------------------------------------------------------
+  cudaStream_t stream = nullptr;
+  double* A = nullptr;          // n x lda row-major (observation-major)
+  double* y = nullptr;
+  double* size = nullptr;
+  double* eta = nullptr;
+  double* wobs = nullptr;       // -d2 ll / d eta2, padded to a multiple of 64 with zeros
+  double* c3 = nullptr;         // d w / d eta (only filled on request)
+  double* qfix = nullptr;       // theta-independent diagonal of Q (p)
+  double* mu0 = nullptr;        // prior mean (p)
+  double* W = nullptr;          // current iterate (lda)
+  double* Wtrial = nullptr;     // trial point (lda)
+  double* Wmode = nullptr;      // warm start / last mode (lda)
+  double* g = nullptr;          // gradient (lda)
+  double* step = nullptr;       // Newton step (lda)
+  double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)
+  double* L = nullptr;          // Cholesky factor (lower, column-major p x ldh)
+  int ldh = 0;
+  double* theta_dev = nullptr;  // S (+ exp(theta))
+  double* part_g = nullptr;     // [lik_blocks][lda]
+  double* part_s = nullptr;     // [lik_blocks][4]  (ll, sumsq, nonfinite, -)
+  int lik_blocks = 0;
+  double* part_H = nullptr;     // split-K partial tiles
+  size_t part_H_bytes = 0;
+  bgp::EvalScalars* sc_dev = nullptr;
+  bgp::EvalScalars* sc_host = nullptr;   // pinned
+  double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
+  void* syrk_plan = nullptr;    // opaque (syrk.cu)
+  // ---- solver controls ---------------------------------------------------------------------
+  double grad_tol = 1e-8, step_tol = 1e-8;
+  int maxit = 100;
+  // ---- sharding ------------------------------------------------------------------------------
+  int rank = 0, world = 1;
+  int64_t n_total = 0;
+  bgp::Comm* comm = nullptr;
+  double* red_buf = nullptr;    // packed [H | g | scalars] for the allreduce
+  // ---- timing ----------------------------------------------------------------------------------
+  cudaEvent_t ev[8] = {nullptr};
+  double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0;
+  int64_t n_lik = 0, n_hess = 0, n_chol = 0;
+  bool timing = false;
+};
+
+namespace bgp {
+
+// ---- kernels (each in its own .cu) ------------------------------------------------------------
+// lik.cu: eta = A W ; per-observation likelihood ; partial g = A^T r ; block partials
+int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau);
+int lik_max_lda();
+// finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
+int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
+double theta_constant(const bgp_model* m, const double* theta);
+// syrk.cu: H = A^T diag(w) A (+ allreduce when sharded) + Q(theta)
+int syrk_plan_create(bgp_model* m);
+void syrk_plan_destroy(bgp_model* m);
+int launch_hessian(bgp_model* m, const double* theta);
+// chol.cu: L = chol(H), logdet, optionally step = -H^-1 g and max|step|
+int launch_chol_solve(bgp_model* m, bool solve);
+// basis.cu
+int launch_iwp_block(bgp_model* m, const double* x_dev, int64_t n, double x0, const double* kneg, int nneg,
+                     const double* kpos, int npos, int order, double* dstB, int ldB, double* dstX, int ldX,
+                     bool col_major, cudaStream_t st);
+// newton.cu
+int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
+int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
+// grad.cu: d/dtheta of the Laplace objective at the mode left on the device by laplace_inner
+int laplace_gradient(bgp_model* m, const double* theta, double* grad_host);
+
+// comm.cpp
+int comm_unique_id(void* id128);
+int comm_create(bgp_model* m, const void* id128);
+void comm_destroy(bgp_model* m);
+int comm_allreduce_sum(bgp_model* m, double* buf, size_t count);
+
+}  // namespace bgp

@@ -1,0 +1,300 @@
+// chol.cu — dense p x p Cholesky, log-determinant and Newton solve for one Laplace problem.
+//
+// Replaces the CHOLMOD factorisation / solve TMB's inner `newton()` performs on the random-effect
+// Hessian and the 1/2 logdet H term of the Laplace approximation (TMB::MakeADFun(random = "W"),
+// call site /root/reference/R/02_model_fit.R:276-284).
+//
+// One CTA (512 threads) owns one problem; H stays in global memory (L2-resident: <= 8 MB).
+// Right-looking blocked algorithm, panel width NB:
+//   1. the NB x NB diagonal block is factored in shared memory;
+//   2. the panel below it is solved one row per thread and kept in shared memory;
+//   3. the trailing update C -= P P^T runs on the FP64 tensor pipe (mma.sync m8n8k4 / DMMA),
+//      32x32 tiles per warp, fragments read conflict-free from the padded panel.
+// The same kernel then does the blocked forward/backward substitution for step = -H^-1 g.
+#include <algorithm>
+
+#include "bgp_internal.h"
+
+namespace bgp {
+
+struct CholArgs {
+  double* L;         // p x ldh column-major; on entry a copy of H (lower triangle is used)
+  int p, ldh;
+  const double* g;   // gradient (p)
+  double* step;      // out: -H^-1 g (p)
+  EvalScalars* sc;
+  int solve;
+};
+
+__device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int CH_THREADS = 512;   // 128 registers / thread for the 32x32 DMMA accumulators
+constexpr int CH_MAXP = 2048;
+
+template <int NB>
+__global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
+  extern __shared__ double sm[];
+  constexpr int DP = NB + 1;        // pitch of the diagonal block
+  constexpr int PP = NB + 4;        // pitch of the panel (conflict-free DMMA fragment loads)
+  double* sD = sm;                  // NB x DP
+  double* sS = sD + 32 * 33;        // 32 x 33 scratch for the substitution phase
+  double* sv = sS + 32 * 33;        // CH_MAXP solution vector
+  double* sP = sv + CH_MAXP;        // panel rows x PP
+  __shared__ int s_info;
+  __shared__ double s_red[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = a.p, ldh = a.ldh;
+  double* L = a.L;
+  if (tid == 0) s_info = 0;
+  __syncthreads();
+
+  for (int k0 = 0; k0 < p; k0 += NB) {
+    const int nb = (p - k0) < NB ? (p - k0) : NB;
+    const int m = p - k0 - nb;
+    // ---- 1. diagonal block -> shared, factor -----------------------------------------------
+    for (int t = tid; t < NB * NB; t += CH_THREADS) {
+      const int i = t % NB, c = t / NB;
+      if (i < nb && c < nb && i >= c) sD[i * DP + c] = L[(size_t)(k0 + c) * ldh + k0 + i];
+    }
+    for (int j = 0; j < nb; ++j) {
+      __syncthreads();
+      const double d = sD[j * DP + j];
+      if (!(d > 0.0) || !isfinite(d)) {          // uniform across the CTA
+        if (tid == 0) s_info = k0 + j + 1;
+        break;
+      }
+      const double sq = sqrt(d);
+      __syncthreads();
+      for (int t = tid; t < NB; t += CH_THREADS) {
+        if (t == j) sD[j * DP + j] = sq;
+        else if (t > j && t < nb) sD[t * DP + j] /= sq;
+      }
+      __syncthreads();
+      for (int t = tid; t < NB * NB; t += CH_THREADS) {
+        const int i = t % NB, c = t / NB;
+        if (c > j && i >= c && i < nb) sD[i * DP + c] -= sD[i * DP + j] * sD[c * DP + j];
+      }
+    }
+    __syncthreads();
+    if (s_info != 0) break;
+    for (int t = tid; t < NB * NB; t += CH_THREADS) {
+      const int i = t % NB, c = t / NB;
+      if (i < nb && c < nb && i >= c) L[(size_t)(k0 + c) * ldh + k0 + i] = sD[i * DP + c];
+    }
+    if (m <= 0) break;
+    // ---- 2. panel solve: row r of L[k0+nb.., k0..k0+NB) <- row * L_kk^-T -----------------------
+    const int mpad = (m + 31) & ~31;
+    for (int t = tid; t < mpad; t += CH_THREADS) {
+      double x[NB];
+      if (t < m) {
+        const int r = k0 + nb + t;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x[c] = L[(size_t)(k0 + c) * ldh + r];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          x[c] /= sD[c * DP + c];
+#pragma unroll
+          for (int q = c + 1; q < NB; ++q) x[q] = fma(-x[c], sD[q * DP + c], x[q]);
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) L[(size_t)(k0 + c) * ldh + r] = x[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) sP[(size_t)t * PP + c] = x[c];
+    }
+    __syncthreads();
+    // ---- 3. trailing update on the FP64 tensor pipe ------------------------------------------
+    const int ntd = mpad / 32;
+    const int ntile = ntd * (ntd + 1) / 2;
+    const int fj = lane >> 2, fk = lane & 3;
+    for (int idx = warp; idx < ntile; idx += CH_THREADS / 32) {
+      // idx -> (ti >= tj)
+      int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+      while (ti * (ti + 1) / 2 > idx) --ti;
+      const int tj = idx - ti * (ti + 1) / 2;
+      double acc[4][4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      const double* pa = sP + (size_t)(ti * 32 + fj) * PP + fk;
+      const double* pb = sP + (size_t)(tj * 32 + fj) * PP + fk;
+#pragma unroll
+      for (int kk = 0; kk < NB / 4; ++kk) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          af[i] = pa[(size_t)(i * 8) * PP + kk * 4];
+          bf[i] = pb[(size_t)(i * 8) * PP + kk * 4];
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884c(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
+      const int base = k0 + nb;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int row = ti * 32 + mi * 8 + fj;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = tj * 32 + ni * 8 + 2 * fk + e;
+            if (row < m && col <= row) L[(size_t)(base + col) * ldh + base + row] -= acc[mi][ni][e];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_info != 0) {
+    if (tid == 0) {
+      a.sc->chol_info = s_info;
+      a.sc->logdet = NAN;
+      a.sc->smax = NAN;
+    }
+    return;
+  }
+  // ---- log det H = 2 sum log L_jj (fixed-order tree) ------------------------------------------
+  {
+    double s = 0.0;
+    for (int j = tid; j < p; j += CH_THREADS) s += log(L[(size_t)j * ldh + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < CH_THREADS / 32; ++w) t += s_red[w];
+      a.sc->logdet = 2.0 * t;
+      a.sc->chol_info = 0;
+    }
+    __syncthreads();
+  }
+  if (!a.solve) return;
+  // ---- forward substitution L y = -g, blocks of 32 -----------------------------------------------
+  for (int i = tid; i < p; i += CH_THREADS) sv[i] = -a.g[i];
+  __syncthreads();
+  for (int b0 = 0; b0 < p; b0 += 32) {
+    const int bn = (p - b0) < 32 ? (p - b0) : 32;
+    for (int t = tid; t < 1024; t += CH_THREADS) {
+      const int i = t & 31, c = t >> 5;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double yv = lane < bn ? sv[b0 + lane] : 0.0;
+      for (int j = 0; j < bn; ++j) {
+        double yj = __shfl_sync(0xffffffffu, yv, j) / sS[j * 33 + j];
+        if (lane == j) yv = yj;
+        else if (lane > j) yv = fma(-yj, sS[lane * 33 + j], yv);
+      }
+      if (lane < bn) sv[b0 + lane] = yv;
+    }
+    __syncthreads();
+    for (int i = b0 + bn + tid; i < p; i += CH_THREADS) {
+      double s = sv[i];
+#pragma unroll 8
+      for (int c = 0; c < bn; ++c) s = fma(-L[(size_t)(b0 + c) * ldh + i], sv[b0 + c], s);
+      sv[i] = s;
+    }
+    __syncthreads();
+  }
+  // ---- backward substitution L^T x = y ---------------------------------------------------------------
+  const int nblk = (p + 31) / 32;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int b0 = bi * 32;
+    const int bn = (p - b0) < 32 ? (p - b0) : 32;
+    // y_block[c] -= sum_{i >= b0+bn} L[i][b0+c] x[i]   (warp c owns column c)
+    for (int c = warp; c < bn; c += CH_THREADS / 32) {
+      const double* col = L + (size_t)(b0 + c) * ldh;
+      double s = 0.0;
+      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(col[i], sv[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_red[c] = s;
+    }
+    for (int t = tid; t < 1024; t += CH_THREADS) {
+      const int i = t & 31, c = t >> 5;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xv = lane < bn ? sv[b0 + lane] - s_red[lane] : 0.0;
+      for (int j = bn - 1; j >= 0; --j) {
+        double xj = __shfl_sync(0xffffffffu, xv, j) / sS[j * 33 + j];
+        if (lane == j) xv = xj;
+        else if (lane < j) xv = fma(-xj, sS[j * 33 + lane], xv);
+      }
+      if (lane < bn) sv[b0 + lane] = xv;
+    }
+    __syncthreads();
+  }
+  double mx = 0.0;
+  for (int i = tid; i < p; i += CH_THREADS) {
+    const double x = sv[i];
+    a.step[i] = x;
+    mx = fmax(mx, isfinite(x) ? fabs(x) : INFINITY);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < CH_THREADS / 32; ++w) t = fmax(t, s_red[w]);
+    a.sc->smax = t;
+  }
+}
+
+template <int NB>
+static int launch_chol_t(bgp_model* m, const CholArgs& a) {
+  const int mpad = round_up(std::max(0, a.p - NB), 32);
+  const size_t smem = (size_t)(2 * 32 * 33 + CH_MAXP + (size_t)mpad * (NB + 4)) * sizeof(double);
+  if (smem > 227 * 1024) {
+    set_error("Cholesky panel does not fit shared memory (p = %d)", a.p);
+    return BGP_ERR_ARG;
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    BGP_CUDA(cudaFuncSetAttribute(chol_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  chol_kernel<NB><<<1, CH_THREADS, smem, m->stream>>>(a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
+// L <- chol(H) (H is left untouched), logdet, optionally step = -H^-1 g
+int launch_chol_solve(bgp_model* m, bool solve) {
+  BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  CholArgs a;
+  a.L = m->L;
+  a.p = m->p;
+  a.ldh = m->ldh;
+  a.g = m->g;
+  a.step = m->step;
+  a.sc = m->sc_dev;
+  a.solve = solve ? 1 : 0;
+  if (m->p > CH_MAXP) {
+    set_error("p = %d exceeds the Cholesky kernel limit %d", m->p, CH_MAXP);
+    return BGP_ERR_ARG;
+  }
+  if (m->p <= 512) return launch_chol_t<32>(m, a);
+  if (m->p <= 1200) return launch_chol_t<16>(m, a);
+  return launch_chol_t<8>(m, a);
+}
+
+}  // namespace bgp

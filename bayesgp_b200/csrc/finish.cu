@@ -1,0 +1,149 @@
+// finish.cu — fixed-order reduction of the likelihood partials and the Gaussian-prior terms.
+//
+// Completes f(W,theta) = -(ll + lpW + lpT) and g = -A^T r + Q(theta)(W - mu0):
+//   lpW, Q(theta) = blockdiag(e^{theta_j} P_j, betaprec, beta_fixed_prec)   src/BayesGP.cpp:219-238
+//   lpT (theta only; computed on the host and passed in `theta_const`)      src/BayesGP.cpp:241-246
+// Two tiny kernels so that, when observations are sharded across GPUs, the packed buffer
+// [g_lik (lda) | ll | sumsq | nonfinite | -] can be all-reduced between them.
+#include "bgp_internal.h"
+
+namespace bgp {
+
+constexpr int MAX_RND = 16;
+
+struct RndDev {
+  int off, d, diag;
+  const double* P;
+  double etheta;
+};
+
+struct PriorArgs {
+  const double* red;     // [lda + 4]
+  int lda, p;
+  const double* W;
+  const double* mu0;
+  const double* qfix;
+  double* g;
+  EvalScalars* sc;
+  double theta_const;    // lpT + 1/2 sum(d_j theta_j + logPdet_j) + likelihood constants
+  double tau;
+  int family;
+  int nrnd;
+  RndDev rnd[MAX_RND];
+};
+
+__global__ void __launch_bounds__(1024) finish_reduce_kernel(const double* __restrict__ part_g,
+                                                             const double* __restrict__ part_s, int nblocks, int lda,
+                                                             double* __restrict__ red) {
+  for (int c = threadIdx.x; c < lda; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part_g[(size_t)b * lda + c];
+    red[c] = s;
+  }
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part_s[(size_t)b * 4 + threadIdx.x];
+    red[lda + threadIdx.x] = s;
+  }
+  if (threadIdx.x == 3) red[lda + 3] = 0.0;
+}
+
+__global__ void __launch_bounds__(1024) finish_prior_kernel(const PriorArgs a) {
+  __shared__ double s_quad[1024];
+  __shared__ double s_gmax[1024];
+  double quad = 0.0, gmax = 0.0;
+  for (int c = threadIdx.x; c < a.lda; c += blockDim.x) {
+    double gv = 0.0;
+    if (c < a.p) {
+      const double dW = a.W[c] - a.mu0[c];
+      double q = a.qfix[c] * dW;
+      for (int b = 0; b < a.nrnd; ++b) {
+        const RndDev& rb = a.rnd[b];
+        if (c >= rb.off && c < rb.off + rb.d) {
+          const int i = c - rb.off;
+          if (rb.diag) {
+            q = rb.etheta * rb.P[i] * dW;
+          } else {
+            double s = 0.0;
+            for (int k = 0; k < rb.d; ++k) s = fma(rb.P[(size_t)k * rb.d + i], a.W[rb.off + k], s);
+            q = rb.etheta * s;
+          }
+        }
+      }
+      gv = -a.red[c] + q;
+      quad = fma(dW, q, quad);
+      gmax = fmax(gmax, fabs(gv));
+      if (!isfinite(gv)) gmax = INFINITY;
+    }
+    a.g[c] = gv;
+  }
+  s_quad[threadIdx.x] = quad;
+  s_gmax[threadIdx.x] = gmax;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_quad[threadIdx.x] += s_quad[threadIdx.x + o];
+      s_gmax[threadIdx.x] = fmax(s_gmax[threadIdx.x], s_gmax[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double ll_raw = a.red[a.lda + 0], sumsq = a.red[a.lda + 1], bad = a.red[a.lda + 2];
+    const double ll = a.family == BGP_FAMILY_GAUSSIAN ? -0.5 * a.tau * sumsq : ll_raw;
+    const double f = -(ll + a.theta_const - 0.5 * s_quad[0]);
+    a.sc->f = f;
+    a.sc->ll = ll;
+    a.sc->gmax = s_gmax[0];
+    a.sc->quad = s_quad[0];
+    a.sc->sumsq = sumsq;
+    a.sc->nonfinite = (bad != 0.0 || !isfinite(f)) ? 1 : 0;
+  }
+}
+
+// host side -------------------------------------------------------------------------------------
+double theta_constant(const bgp_model* m, const double* theta) {
+  // lpT  (src/BayesGP.cpp:241-246)
+  double c = 0.0;
+  for (int i = 0; i < m->S; ++i) {
+    const double phi = -std::log(m->theta_alpha[i]) / m->theta_u[i];
+    c += std::log(0.5 * phi) - phi * std::exp(-0.5 * theta[i]) - 0.5 * theta[i];
+  }
+  // 1/2 (d_j theta_j + logPdet_j)  (src/BayesGP.cpp:229-231)
+  for (int j = 0; j < m->J; ++j) c += 0.5 * (m->rnd[j].d * theta[j] + m->rnd[j].logPdet);
+  // likelihood constants: -sum lgamma(y+1) | sum lchoose | -n/2 log(2 pi) + n/2 theta_S
+  c += m->ll_const;
+  if (m->family == BGP_FAMILY_GAUSSIAN) c += 0.5 * (double)m->n_total * theta[m->S - 1];
+  return c;
+}
+
+int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau) {
+  finish_reduce_kernel<<<1, 1024, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
+  count_launch();
+  if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda + 4));
+  PriorArgs a;
+  a.red = m->red_buf;
+  a.lda = m->lda;
+  a.p = m->p;
+  a.W = W_dev;
+  a.mu0 = m->mu0;
+  a.qfix = m->qfix;
+  a.g = m->g;
+  a.sc = m->sc_dev;
+  a.theta_const = theta_constant(m, theta);
+  a.tau = tau;
+  a.family = m->family;
+  a.nrnd = m->J;
+  for (int j = 0; j < m->J; ++j) {
+    a.rnd[j].off = m->rnd[j].off;
+    a.rnd[j].d = m->rnd[j].d;
+    a.rnd[j].diag = m->rnd[j].diag ? 1 : 0;
+    a.rnd[j].P = m->rnd[j].P_dev;
+    a.rnd[j].etheta = std::exp(theta[j]);
+  }
+  finish_prior_kernel<<<1, 1024, 0, m->stream>>>(a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
+}  // namespace bgp

@@ -1,0 +1,452 @@
+// model.cu — device-resident model: replaces the `tmbdat` list handed to TMB::MakeADFun
+// (/root/reference/R/02_model_fit.R:152-183) and the DATA_* unpacking of
+// /root/reference/src/BayesGP.cpp:34-73.
+//
+// HBM layout: the design matrix A = [B_1..B_J | X_1..X_J | Xf_0..Xf_F] is
+// stored ONCE, observation-major (n x lda doubles, lda = round_up(p, 16), zero padded), so that
+//   * the likelihood pass streams whole rows with 16-byte coalesced loads, and
+//   * the Hessian kernel TMA-loads {16 column x 16 row} boxes whose 128-byte lines take the
+//     hardware swizzle.
+// R hands the blocks over column-major; they are transposed into place on the device.
+#include <algorithm>
+
+#include "bgp_internal.h"
+
+namespace bgp {
+
+// src: n x d column-major  ->  dst[i * lda + off + c]
+__global__ void transpose_in_kernel(const double* __restrict__ src, int64_t n, int d, double* __restrict__ dst, int lda,
+                                    int off) {
+  __shared__ double tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    const int64_t i = i0 + threadIdx.x;
+    const int c = c0 + cc;
+    tile[cc][threadIdx.x] = (i < n && c < d) ? src[(size_t)c * n + i] : 0.0;
+  }
+  __syncthreads();
+  for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+    const int64_t i = i0 + ii;
+    const int c = c0 + threadIdx.x;
+    if (i < n && c < d) dst[(size_t)i * lda + off + c] = tile[threadIdx.x][ii];
+  }
+}
+
+static int stage_block(bgp_model* m, std::vector<bgp_model::Staged>& dst, int ncol, const double* host) {
+  bgp_model::Staged s;
+  s.ncol = ncol;
+  s.dev = nullptr;
+  if (ncol > 0) {
+    if (!host) {
+      set_error("NULL matrix for a block with %d columns", ncol);
+      return BGP_ERR_ARG;
+    }
+    const size_t bytes = (size_t)m->n * ncol * sizeof(double);
+    BGP_CUDA(cudaMalloc(&s.dev, bytes));
+    BGP_CUDA(cudaMemcpyAsync(s.dev, host, bytes, cudaMemcpyHostToDevice, m->stream));
+    BGP_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  dst.push_back(s);
+  return BGP_OK;
+}
+
+static double lgamma_sum_poisson(const double* y, int64_t n) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += std::lgamma(y[i] + 1.0);
+  return -s;
+}
+
+static double lchoose_sum(const double* y, const double* size, int64_t n) {
+  // TMB dbinom_robust adds lgamma(size+1) - lgamma(k+1) - lgamma(size-k+1) only when size > 1
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double sz = size ? size[i] : 1.0;
+    if (sz > 1.0) s += std::lgamma(sz + 1.0) - std::lgamma(y[i] + 1.0) - std::lgamma(sz - y[i] + 1.0);
+  }
+  return s;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+extern "C" {
+
+int bgp_model_new(int64_t n, int family, const double* y, const double* size, int device, bgp_model** out) {
+  if (!out || !y || n <= 0) {
+    set_error("bgp_model_new: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  if (family != BGP_FAMILY_GAUSSIAN && family != BGP_FAMILY_POISSON && family != BGP_FAMILY_BINOMIAL &&
+      family != BGP_FAMILY_NONE) {
+    set_error("bgp_model_new: unsupported family code %d (Coxph / case-crossover are out of scope)", family);
+    return BGP_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available: libbgp has no CPU fallback");
+    return BGP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("device %d out of range (%d devices)", device, ndev);
+    return BGP_ERR_ARG;
+  }
+  BGP_CUDA(cudaSetDevice(device));
+  bgp_model* m = new bgp_model();
+  m->n = n;
+  m->n_total = n;
+  m->family = family;
+  m->device = device;
+  int st = [&]() -> int {
+    BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    const size_t nb = (size_t)n * sizeof(double);
+    BGP_CUDA(cudaMalloc(&m->y, nb));
+    BGP_CUDA(cudaMemcpyAsync(m->y, y, nb, cudaMemcpyHostToDevice, m->stream));
+    if (family == BGP_FAMILY_BINOMIAL) {
+      BGP_CUDA(cudaMalloc(&m->size, nb));
+      if (size) {
+        BGP_CUDA(cudaMemcpyAsync(m->size, size, nb, cudaMemcpyHostToDevice, m->stream));
+      } else {
+        std::vector<double> ones((size_t)n, 1.0);   // R/02_model_fit.R:176-183
+        BGP_CUDA(cudaMemcpyAsync(m->size, ones.data(), nb, cudaMemcpyHostToDevice, m->stream));
+        BGP_CUDA(cudaStreamSynchronize(m->stream));
+      }
+    }
+    BGP_CUDA(cudaStreamSynchronize(m->stream));
+    return BGP_OK;
+  }();
+  if (st != BGP_OK) {
+    bgp_model_destroy(m);
+    return st;
+  }
+  if (family == BGP_FAMILY_POISSON) m->ll_const = lgamma_sum_poisson(y, n);
+  else if (family == BGP_FAMILY_BINOMIAL) m->ll_const = lchoose_sum(y, size, n);
+  else if (family == BGP_FAMILY_GAUSSIAN) m->ll_const = -0.5 * (double)n * std::log(2.0 * M_PI);
+  *out = m;
+  return BGP_OK;
+}
+
+#define BGP_CHECK_BUILDING(m)                                       \
+  do {                                                              \
+    if (!(m)) {                                                     \
+      set_error("NULL model handle");                               \
+      return BGP_ERR_ARG;                                           \
+    }                                                               \
+    if ((m)->finalized) {                                           \
+      set_error("model already finalized");                         \
+      return BGP_ERR_STATE;                                         \
+    }                                                               \
+    BGP_CUDA(cudaSetDevice((m)->device));                           \
+  } while (0)
+
+int bgp_model_add_random(bgp_model* m, int d, const double* B, const double* P, int p_is_diag, double logPdet, double u,
+                         double alpha) {
+  BGP_CHECK_BUILDING(m);
+  if (d <= 0 || !B || !P) {
+    set_error("bgp_model_add_random: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  if ((int)m->rnd.size() >= 16) {
+    set_error("at most 16 smoothing terms are supported");
+    return BGP_ERR_ARG;
+  }
+  BGP_TRY(stage_block(m, m->st_rnd, d, B));
+  RandomBlock rb;
+  rb.d = d;
+  rb.diag = p_is_diag != 0;
+  rb.logPdet = logPdet;
+  rb.u = u;
+  rb.alpha = alpha;
+  const size_t pb = (rb.diag ? (size_t)d : (size_t)d * d) * sizeof(double);
+  BGP_CUDA(cudaMalloc(&rb.P_dev, pb));
+  BGP_CUDA(cudaMemcpy(rb.P_dev, P, pb, cudaMemcpyHostToDevice));
+  m->rnd.push_back(rb);
+  return BGP_OK;
+}
+
+int bgp_model_add_boundary(bgp_model* m, int ncol, const double* X, double prec, double mean) {
+  BGP_CHECK_BUILDING(m);
+  if (ncol < 0) {
+    set_error("bgp_model_add_boundary: negative column count");
+    return BGP_ERR_ARG;
+  }
+  BGP_TRY(stage_block(m, m->st_bnd, ncol, X));
+  m->bnd_dim.push_back(ncol);
+  m->bnd_prec.push_back(prec);
+  m->bnd_mean.push_back(mean);
+  return BGP_OK;
+}
+
+int bgp_model_add_fixed(bgp_model* m, int ncol, const double* Xf, double prec, double mean) {
+  BGP_CHECK_BUILDING(m);
+  if (ncol <= 0) {
+    set_error("bgp_model_add_fixed: column count must be positive");
+    return BGP_ERR_ARG;
+  }
+  BGP_TRY(stage_block(m, m->st_fix, ncol, Xf));
+  m->fix_dim.push_back(ncol);
+  m->fix_prec.push_back(prec);
+  m->fix_mean.push_back(mean);
+  return BGP_OK;
+}
+
+int bgp_model_set_noise_prior(bgp_model* m, double u, double alpha) {
+  BGP_CHECK_BUILDING(m);
+  m->noise_u = u;
+  m->noise_alpha = alpha;
+  return BGP_OK;
+}
+
+int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, const double* knots, int nknots, int order,
+                      double u, double alpha, double boundary_prec, double boundary_mean) {
+  BGP_CHECK_BUILDING(m);
+  if (!x || !knots || nknots < 2 || order < 1 || order > 8) {
+    set_error("bgp_model_add_iwp: bad arguments (order must be 1..8)");
+    return BGP_ERR_ARG;
+  }
+  if ((int)m->rnd.size() >= 16) {
+    set_error("at most 16 smoothing terms are supported");
+    return BGP_ERR_ARG;
+  }
+  // knot split of local_poly_helper / compute_weights_precision (R/01_utility.R:325-344,378-401)
+  std::vector<double> kneg, kpos;
+  double kmin = knots[0], kmax = knots[0];
+  for (int i = 1; i < nknots; ++i) {
+    kmin = std::min(kmin, knots[i]);
+    kmax = std::max(kmax, knots[i]);
+  }
+  auto uniq_sorted = [](std::vector<double>& v) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  };
+  if (kmin >= 0) {
+    kpos.assign(knots, knots + nknots);
+  } else {
+    for (int i = 0; i < nknots; ++i) kneg.push_back(knots[i] < 0 ? -knots[i] : 0.0);
+    uniq_sorted(kneg);
+    if (kmax > 0) {
+      for (int i = 0; i < nknots; ++i) kpos.push_back(knots[i] > 0 ? knots[i] : 0.0);
+      uniq_sorted(kpos);
+    }
+  }
+  const int nneg = kneg.empty() ? 0 : (int)kneg.size() - 1;
+  const int npos = kpos.empty() ? 0 : (int)kpos.size() - 1;
+  const int d = nneg + npos;
+  if (d <= 0) {
+    set_error("bgp_model_add_iwp: knots define no basis function");
+    return BGP_ERR_ARG;
+  }
+  std::vector<double> Pdiag;
+  for (int i = 0; i < nneg; ++i) Pdiag.push_back(kneg[i + 1] - kneg[i]);
+  for (int i = 0; i < npos; ++i) Pdiag.push_back(kpos[i + 1] - kpos[i]);
+  double logPdet = 0.0;
+  for (double v : Pdiag) logPdet += std::log(v);
+
+  double *x_dev = nullptr, *kn_dev = nullptr, *kp_dev = nullptr;
+  const size_t nb = (size_t)m->n * sizeof(double);
+  BGP_CUDA(cudaMalloc(&x_dev, nb));
+  BGP_CUDA(cudaMemcpyAsync(x_dev, x, nb, cudaMemcpyHostToDevice, m->stream));
+  if (!kneg.empty()) {
+    BGP_CUDA(cudaMalloc(&kn_dev, kneg.size() * sizeof(double)));
+    BGP_CUDA(cudaMemcpyAsync(kn_dev, kneg.data(), kneg.size() * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  }
+  if (!kpos.empty()) {
+    BGP_CUDA(cudaMalloc(&kp_dev, kpos.size() * sizeof(double)));
+    BGP_CUDA(cudaMemcpyAsync(kp_dev, kpos.data(), kpos.size() * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  }
+  bgp_model::Staged sB, sX;
+  sB.ncol = d;
+  sX.ncol = order - 1;
+  sB.dev = sX.dev = nullptr;
+  BGP_CUDA(cudaMalloc(&sB.dev, (size_t)m->n * d * sizeof(double)));
+  if (sX.ncol > 0) BGP_CUDA(cudaMalloc(&sX.dev, (size_t)m->n * sX.ncol * sizeof(double)));
+  BGP_TRY(launch_iwp_block(m, x_dev, m->n, initial_location, kn_dev, (int)kneg.size(), kp_dev, (int)kpos.size(), order,
+                           sB.dev, (int)m->n, sX.dev, (int)m->n, true, m->stream));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(x_dev);
+  if (kn_dev) cudaFree(kn_dev);
+  if (kp_dev) cudaFree(kp_dev);
+  m->st_rnd.push_back(sB);
+  m->st_bnd.push_back(sX);
+  RandomBlock rb;
+  rb.d = d;
+  rb.diag = true;
+  rb.logPdet = logPdet;
+  rb.u = u;
+  rb.alpha = alpha;
+  BGP_CUDA(cudaMalloc(&rb.P_dev, (size_t)d * sizeof(double)));
+  BGP_CUDA(cudaMemcpy(rb.P_dev, Pdiag.data(), (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+  m->rnd.push_back(rb);
+  m->bnd_dim.push_back(order - 1);
+  m->bnd_prec.push_back(boundary_prec);
+  m->bnd_mean.push_back(boundary_mean);
+  return BGP_OK;
+}
+
+int bgp_nccl_unique_id(void* id128) { return comm_unique_id(id128); }
+
+int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_unique_id) {
+  BGP_CHECK_BUILDING(m);
+  if (world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_unique_id)) {
+    set_error("bgp_model_set_shard: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  m->rank = rank;
+  m->world = world;
+  if (world > 1) BGP_TRY(comm_create(m, nccl_unique_id));
+  return BGP_OK;
+}
+
+int bgp_model_finalize(bgp_model* m) {
+  BGP_CHECK_BUILDING(m);
+  if (m->st_fix.empty() && m->st_bnd.empty() && m->st_rnd.empty()) {
+    set_error("model has no design columns");
+    return BGP_ERR_ARG;
+  }
+  m->J = (int)m->rnd.size();
+  m->S = m->J + (m->family == BGP_FAMILY_GAUSSIAN ? 1 : 0);
+  int p = 0;
+  for (auto& rb : m->rnd) {
+    rb.off = p;
+    p += rb.d;
+  }
+  for (int d : m->bnd_dim) p += d;
+  for (int d : m->fix_dim) p += d;
+  m->p = p;
+  m->lda = round_up(p, 16);
+  m->ldh = round_up(p, 8);
+  if (m->lda > lik_max_lda()) {
+    set_error("latent dimension p = %d exceeds the supported maximum %d", p, lik_max_lda());
+    return BGP_ERR_ARG;
+  }
+  for (int j = 0; j < m->J; ++j) {
+    m->theta_u.push_back(m->rnd[j].u);
+    m->theta_alpha.push_back(m->rnd[j].alpha);
+  }
+  if (m->family == BGP_FAMILY_GAUSSIAN) {
+    m->theta_u.push_back(m->noise_u);
+    m->theta_alpha.push_back(m->noise_alpha);
+  }
+  const int64_t n = m->n;
+  const size_t abytes = (size_t)n * m->lda * sizeof(double);
+  BGP_CUDA(cudaMalloc(&m->A, abytes));
+  BGP_CUDA(cudaMemsetAsync(m->A, 0, abytes, m->stream));
+  int off = 0;
+  auto place = [&](std::vector<bgp_model::Staged>& v) -> int {
+    for (auto& s : v) {
+      if (s.ncol > 0) {
+        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((s.ncol + 31) / 32)), block(32, 8);
+        transpose_in_kernel<<<grid, block, 0, m->stream>>>(s.dev, n, s.ncol, m->A, m->lda, off);
+        count_launch();
+        BGP_CUDA(cudaGetLastError());
+      }
+      off += s.ncol;
+    }
+    return BGP_OK;
+  };
+  BGP_TRY(place(m->st_rnd));
+  BGP_TRY(place(m->st_bnd));
+  BGP_TRY(place(m->st_fix));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix}) {
+    for (auto& s : *v)
+      if (s.dev) cudaFree(s.dev);
+    v->clear();
+  }
+  // prior mean and the theta-independent diagonal of Q (src/BayesGP.cpp:222-238)
+  std::vector<double> mu0((size_t)m->lda, 0.0), qfix((size_t)m->lda, 0.0);
+  int o = 0;
+  for (auto& rb : m->rnd) o += rb.d;
+  for (size_t b = 0; b < m->bnd_dim.size(); ++b)
+    for (int c = 0; c < m->bnd_dim[b]; ++c, ++o) {
+      mu0[o] = m->bnd_mean[b];
+      qfix[o] = m->bnd_prec[b];
+    }
+  for (size_t b = 0; b < m->fix_dim.size(); ++b)
+    for (int c = 0; c < m->fix_dim[b]; ++c, ++o) {
+      mu0[o] = m->fix_mean[b];
+      qfix[o] = m->fix_prec[b];
+    }
+  const size_t vb = (size_t)m->lda * sizeof(double);
+  auto dalloc = [&](double** ptr, size_t bytes) -> int {
+    BGP_CUDA(cudaMalloc(ptr, bytes));
+    BGP_CUDA(cudaMemset(*ptr, 0, bytes));
+    return BGP_OK;
+  };
+  BGP_TRY(dalloc(&m->mu0, vb));
+  BGP_TRY(dalloc(&m->qfix, vb));
+  BGP_CUDA(cudaMemcpy(m->mu0, mu0.data(), vb, cudaMemcpyHostToDevice));
+  BGP_CUDA(cudaMemcpy(m->qfix, qfix.data(), vb, cudaMemcpyHostToDevice));
+  for (double** ptr : {&m->W, &m->Wtrial, &m->Wmode, &m->g, &m->step}) BGP_TRY(dalloc(ptr, vb));
+  const size_t nob = (size_t)(round_up64(n, 64) + 64) * sizeof(double);
+  BGP_TRY(dalloc(&m->eta, nob));
+  BGP_TRY(dalloc(&m->wobs, nob));
+  BGP_TRY(dalloc(&m->c3, nob));
+  const size_t hb = (size_t)m->ldh * m->p * sizeof(double);
+  BGP_TRY(dalloc(&m->H, hb));
+  BGP_TRY(dalloc(&m->L, hb));
+  BGP_TRY(dalloc(&m->theta_dev, 64 * sizeof(double)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const int nj = (m->lda + 63) / 64;
+  const int rows_per_it = nj <= 2 ? 4 : (nj <= 8 ? 2 : 1);
+  int64_t blocks = (int64_t)sms * (nj <= 5 ? 4 : (nj <= 8 ? 3 : 1));
+  const int64_t max_blocks = (n + 8 * rows_per_it - 1) / (8 * rows_per_it);
+  m->lik_blocks = (int)std::max<int64_t>(1, std::min(blocks, max_blocks));
+  BGP_TRY(dalloc(&m->part_g, (size_t)m->lik_blocks * m->lda * sizeof(double)));
+  BGP_TRY(dalloc(&m->part_s, (size_t)m->lik_blocks * 4 * sizeof(double)));
+  BGP_TRY(dalloc(&m->red_buf, ((size_t)m->lda + 8) * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&m->sc_dev, sizeof(EvalScalars)));
+  BGP_CUDA(cudaMemset(m->sc_dev, 0, sizeof(EvalScalars)));
+  BGP_CUDA(cudaMallocHost(&m->sc_host, sizeof(EvalScalars)));
+  for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
+  BGP_TRY(syrk_plan_create(m));
+  if (m->world > 1) {
+    // the likelihood constant and n are global quantities
+    double buf[2] = {m->ll_const, (double)m->n};
+    BGP_CUDA(cudaMemcpy(m->red_buf, buf, sizeof(buf), cudaMemcpyHostToDevice));
+    BGP_TRY(comm_allreduce_sum(m, m->red_buf, 2));
+    BGP_CUDA(cudaStreamSynchronize(m->stream));
+    BGP_CUDA(cudaMemcpy(buf, m->red_buf, sizeof(buf), cudaMemcpyDeviceToHost));
+    m->ll_const = buf[0];
+    m->n_total = (int64_t)std::llround(buf[1]);
+  }
+  m->finalized = true;
+  return BGP_OK;
+}
+
+void bgp_model_destroy(bgp_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  syrk_plan_destroy(m);
+  comm_destroy(m);
+  for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix})
+    for (auto& s : *v)
+      if (s.dev) cudaFree(s.dev);
+  for (auto& rb : m->rnd)
+    if (rb.P_dev) cudaFree(rb.P_dev);
+  for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
+                      m->step, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+    if (ptr) cudaFree(ptr);
+  if (m->sc_dev) cudaFree(m->sc_dev);
+  if (m->sc_host) cudaFreeHost(m->sc_host);
+  for (int i = 0; i < 8; ++i)
+    if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int bgp_model_dims(const bgp_model* m, int64_t* n, int* p, int* S) {
+  if (!m || !m->finalized) {
+    set_error("model not finalized");
+    return BGP_ERR_STATE;
+  }
+  if (n) *n = m->n;
+  if (p) *p = m->p;
+  if (S) *S = m->S;
+  return BGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// newton.cu — the inner Newton / Laplace driver: host control flow around the device kernels.
+//
+// Replaces TMB's `ff$fn(theta)` for MakeADFun(random = "W") (call site
+// /root/reference/R/02_model_fit.R:276-284; algorithm SURVEY.md Appendix A.1): minimise
+// f(., theta) over W by damped Newton from the previous mode (TMB warm start), then
+//   value = f(w_hat, theta) + 1/2 logdet H(w_hat, theta) - p/2 log(2 pi).
+// Convergence mirrors TMB newton(): max|g| < grad.tol or max|step| < step.tol (both 1e-8),
+// maxit 100; a step is accepted when the objective is finite and either it or max|g| decreased.
+// One device->host read of 80 bytes of scalars per Newton iteration is the only synchronisation.
+#include "bgp_internal.h"
+
+namespace bgp {
+
+__global__ void axpy_trial_kernel(const double* __restrict__ W, const double* __restrict__ step, double t, int p, int lda,
+                                  double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < lda) out[i] = i < p ? fma(t, step[i], W[i]) : 0.0;
+}
+
+static inline double tau_of(const bgp_model* m, const double* theta) {
+  return m->family == BGP_FAMILY_GAUSSIAN ? std::exp(theta[m->S - 1]) : 1.0;
+}
+
+static int read_scalars(bgp_model* m, EvalScalars* out) {
+  BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  *out = *m->sc_host;
+  return BGP_OK;
+}
+
+// f, g (device), gmax at W_dev; leaves eta / wobs (/ c3) of that point on the device
+int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3) {
+  const double tau = tau_of(m, theta);
+  BGP_TRY(launch_lik(m, W_dev, want_c3, tau));
+  m->n_lik++;
+  return launch_finish(m, W_dev, theta, tau);
+}
+
+int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_out) {
+  EvalScalars sc;
+  const int threads = 256, blocks = (m->lda + threads - 1) / threads;
+  // start from the previous mode (TMB last.par.best); fall back to W = 0 if that point is non-finite
+  BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  BGP_TRY(eval_fg_async(m, m->W, theta, false));
+  BGP_TRY(read_scalars(m, &sc));
+  if (sc.nonfinite) {
+    BGP_CUDA(cudaMemsetAsync(m->W, 0, (size_t)m->lda * sizeof(double), m->stream));
+    BGP_TRY(eval_fg_async(m, m->W, theta, false));
+    BGP_TRY(read_scalars(m, &sc));
+    if (sc.nonfinite) {
+      set_error("objective is not finite at the starting point");
+      *value = NAN;
+      return BGP_ERR_NONFINITE;
+    }
+  }
+  double f = sc.f, gmax = sc.gmax;
+  int iters = 0;
+  bool converged = false, have_factor = false;
+  double logdet = NAN;
+  for (int it = 0; it < m->maxit; ++it) {
+    if (gmax < m->grad_tol) {
+      converged = true;
+      break;
+    }
+    BGP_TRY(launch_hessian(m, theta));
+    m->n_hess++;
+    BGP_TRY(launch_chol_solve(m, true));
+    m->n_chol++;
+    // speculative full step: evaluate the trial point before reading anything back
+    axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, 1.0, m->p, m->lda, m->Wtrial);
+    count_launch();
+    // the Cholesky scalars must be captured before the trial evaluation overwrites f / gmax:
+    // they live in different fields of EvalScalars, so one read after the trial eval suffices.
+    BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
+    BGP_TRY(read_scalars(m, &sc));
+    if (sc.chol_info != 0) {
+      set_error("Hessian not positive definite (pivot %d) at Newton iteration %d", sc.chol_info, it);
+      *value = NAN;
+      *iters_out = iters;
+      return BGP_ERR_NOT_PD;
+    }
+    if (sc.smax < m->step_tol) {
+      // W is at the precision limit: keep W (H, L, logdet were computed at W)
+      converged = true;
+      have_factor = true;
+      logdet = sc.logdet;
+      // the trial evaluation overwrote eta/wobs/g with those of W + step; they differ from W's by
+      // less than step_tol and are not used again for this theta.
+      break;
+    }
+    double t = 1.0;
+    bool accepted = false;
+    for (int h = 0; h < 40; ++h) {
+      if (!sc.nonfinite && (sc.f <= f || sc.gmax < gmax)) {
+        accepted = true;
+        break;
+      }
+      t *= 0.5;
+      axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, t, m->p, m->lda, m->Wtrial);
+      count_launch();
+      BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
+      BGP_TRY(read_scalars(m, &sc));
+    }
+    if (!accepted) break;
+    std::swap(m->W, m->Wtrial);
+    f = sc.f;
+    gmax = sc.gmax;
+    ++iters;
+  }
+  *iters_out = iters;
+  if (!converged) {
+    set_error("inner Newton did not converge in %d iterations (max|g| = %.3e)", m->maxit, gmax);
+    *value = NAN;
+    return BGP_ERR_NO_CONVERGENCE;
+  }
+  if (!have_factor) {
+    // Hessian and factor at the mode (eta / wobs on the device belong to W)
+    BGP_TRY(launch_hessian(m, theta));
+    m->n_hess++;
+    BGP_TRY(launch_chol_solve(m, false));
+    m->n_chol++;
+    BGP_TRY(read_scalars(m, &sc));
+    if (sc.chol_info != 0) {
+      set_error("Hessian not positive definite at the mode (pivot %d)", sc.chol_info);
+      *value = NAN;
+      return BGP_ERR_NOT_PD;
+    }
+    logdet = sc.logdet;
+  }
+  BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  *value = f + 0.5 * logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
+  return BGP_OK;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+#define BGP_CHECK_READY(m)                    \
+  do {                                        \
+    if (!(m) || !(m)->finalized) {            \
+      set_error("model not finalized");       \
+      return BGP_ERR_STATE;                   \
+    }                                         \
+    BGP_CUDA(cudaSetDevice((m)->device));     \
+  } while (0)
+
+static int copy_H_out(bgp_model* m, double* H) {
+  // device H is p x ldh column-major -> host p x p column-major
+  BGP_CUDA(cudaMemcpy2DAsync(H, (size_t)m->p * sizeof(double), m->H, (size_t)m->ldh * sizeof(double),
+                             (size_t)m->p * sizeof(double), m->p, cudaMemcpyDeviceToHost, m->stream));
+  return BGP_OK;
+}
+
+extern "C" {
+
+int bgp_objective(bgp_model* m, const double* W, const double* theta, double* f, double* grad, double* H) {
+  BGP_CHECK_READY(m);
+  if (!W || !theta) {
+    set_error("bgp_objective: NULL W / theta");
+    return BGP_ERR_ARG;
+  }
+  BGP_CUDA(cudaMemsetAsync(m->Wtrial, 0, (size_t)m->lda * sizeof(double), m->stream));
+  BGP_CUDA(cudaMemcpyAsync(m->Wtrial, W, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
+  EvalScalars sc;
+  BGP_TRY(read_scalars(m, &sc));
+  if (f) *f = sc.nonfinite ? NAN : sc.f;
+  if (grad) BGP_CUDA(cudaMemcpyAsync(grad, m->g, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (H) {
+    BGP_TRY(launch_hessian(m, theta));
+    BGP_TRY(copy_H_out(m, H));
+  }
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  return BGP_OK;
+}
+
+int bgp_model_set_start(bgp_model* m, const double* W) {
+  BGP_CHECK_READY(m);
+  BGP_CUDA(cudaMemsetAsync(m->Wmode, 0, (size_t)m->lda * sizeof(double), m->stream));
+  if (W) BGP_CUDA(cudaMemcpyAsync(m->Wmode, W, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  return BGP_OK;
+}
+
+int bgp_model_set_newton(bgp_model* m, double grad_tol, double step_tol, int maxit) {
+  if (!m) return BGP_ERR_ARG;
+  if (grad_tol > 0) m->grad_tol = grad_tol;
+  if (step_tol > 0) m->step_tol = step_tol;
+  if (maxit > 0) m->maxit = maxit;
+  return BGP_OK;
+}
+
+int bgp_laplace_eval(bgp_model* m, const double* theta, double* value, double* grad, double* w_mode, double* H,
+                     int* newton_iters) {
+  BGP_CHECK_READY(m);
+  if (!theta || !value) {
+    set_error("bgp_laplace_eval: NULL theta / value");
+    return BGP_ERR_ARG;
+  }
+  int iters = 0;
+  cudaEventRecord(m->ev[0], m->stream);
+  int st = laplace_inner(m, theta, value, &iters);
+  if (newton_iters) *newton_iters = iters;
+  if (st != BGP_OK) {
+    // inner failure: NaN value so a vmmin-style caller can backtrack (R_FINITE test)
+    *value = NAN;
+    if (st == BGP_ERR_NOT_PD || st == BGP_ERR_NO_CONVERGENCE || st == BGP_ERR_NONFINITE) {
+      cudaStreamSynchronize(m->stream);
+      return st;
+    }
+    return st;
+  }
+  if (grad) {
+    BGP_TRY(laplace_gradient(m, theta, grad));
+  }
+  if (w_mode)
+    BGP_CUDA(cudaMemcpyAsync(w_mode, m->Wmode, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (H) BGP_TRY(copy_H_out(m, H));
+  cudaEventRecord(m->ev[1], m->stream);
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+  m->t_total = ms;
+  return BGP_OK;
+}
+
+int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* values, double* modes, double* Hs,
+                           int* newton_iters_total) {
+  BGP_CHECK_READY(m);
+  if (K <= 0 || !theta || !values) {
+    set_error("bgp_laplace_eval_batch: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  int total = 0, worst = BGP_OK;
+  cudaEventRecord(m->ev[0], m->stream);
+  for (int j = 0; j < K; ++j) {
+    int iters = 0;
+    double v = NAN;
+    int st = laplace_inner(m, theta + (size_t)j * m->S, &v, &iters);
+    total += iters;
+    values[j] = st == BGP_OK ? v : NAN;
+    if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
+    if (st != BGP_OK) {
+      worst = st;
+      continue;
+    }
+    if (modes)
+      BGP_CUDA(cudaMemcpyAsync(modes + (size_t)j * m->p, m->Wmode, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost,
+                               m->stream));
+    if (Hs) BGP_TRY(copy_H_out(m, Hs + (size_t)j * m->p * m->p));
+  }
+  cudaEventRecord(m->ev[1], m->stream);
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+  m->t_total = ms;
+  if (newton_iters_total) *newton_iters_total = total;
+  return worst;
+}
+
+int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,
+                          int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches) {
+  if (!m) return BGP_ERR_ARG;
+  if (total_ms) *total_ms = m->t_total;
+  if (lik_ms) *lik_ms = m->t_lik;
+  if (hess_ms) *hess_ms = m->t_hess;
+  if (chol_ms) *chol_ms = m->t_chol;
+  if (lik_launches) *lik_launches = m->n_lik;
+  if (hess_launches) *hess_launches = m->n_hess;
+  if (chol_launches) *chol_launches = m->n_chol;
+  return BGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""``ff`` — the TMB-style Laplace objective, backed by libbgp on a B200.
+
+Host-side mirror of what ``TMB::MakeADFun(data = tmbdat, parameters = tmbparams,
+random = "W", DLL = "BayesGP")`` returns at ``/root/reference/R/02_model_fit.R:276-283``:
+the same names (``par``, ``fn``, ``gr``, ``he``, ``env.last_par``, ``env.spHess``), the
+same argument meaning and the same failure behaviour (NaN value on inner-Newton failure).
+All arithmetic runs in the CUDA library; this file only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BgpError, check, dptr, fmat, fvec
+
+FAMILY_CODES = {"Gaussian": 0, "Poisson": 1, "Binomial": 2, "none": -2}   # R/02_model_fit.R:9-28
+
+
+class TMBData:
+    """The ``tmbdat`` list of R/02_model_fit.R:152-183 (dense column-major blocks)."""
+
+    def __init__(self, y, family, B, P, logPdet, u, alpha, X, betaprec, betamean, Xf, beta_fixed_prec,
+                 beta_fixed_mean, size=None):
+        self.y = fvec(y)
+        self.family = FAMILY_CODES[family] if isinstance(family, str) else int(family)
+        self.B = [fmat(b) for b in B]
+        self.P = [np.asarray(p, dtype=np.float64) for p in P]       # 1-D => diagonal
+        self.logPdet = [float(v) for v in logPdet]
+        self.u = [float(v) for v in u]
+        self.alpha = [float(v) for v in alpha]
+        self.X = [fmat(np.asarray(x, dtype=np.float64).reshape(len(self.y), -1)) for x in X]
+        self.betaprec = [float(v) for v in betaprec]
+        self.betamean = [float(v) for v in betamean]
+        self.Xf = [fmat(np.asarray(x, dtype=np.float64).reshape(len(self.y), -1)) for x in Xf]
+        self.beta_fixed_prec = [float(v) for v in beta_fixed_prec]
+        self.beta_fixed_mean = [float(v) for v in beta_fixed_mean]
+        self.size = None if size is None else fvec(size)
+
+
+class _Env:
+    """``ff$env``: last.par (mode of the most recent evaluation) and spHess."""
+
+    def __init__(self, owner):
+        self._o = owner
+        self.last_par = None
+        self.last_theta = None
+        self.last_H = None
+
+    def spHess(self, par=None, random=True):
+        return self.last_H
+
+
+class LaplaceObjective:
+    """ff <- MakeADFun(..., random = "W").  ``fn``/``gr`` take theta (length S)."""
+
+    def __init__(self, data: Optional[TMBData] = None, device: int = 0, *, handle=None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = device
+        if handle is not None:
+            self._h = handle
+        else:
+            d = data
+            self._keep = d
+            check(self._lib.bgp_model_new(len(d.y), d.family, dptr(d.y), dptr(d.size), device, C.byref(self._h)))
+            try:
+                nu = len(d.B)
+                for j in range(nu):
+                    P = d.P[j]
+                    diag = P.ndim == 1
+                    Pm = fvec(P) if diag else fmat(P)
+                    check(self._lib.bgp_model_add_random(self._h, d.B[j].shape[1], dptr(d.B[j]), dptr(Pm), int(diag),
+                                                         d.logPdet[j], d.u[j], d.alpha[j]))
+                for j in range(len(d.X)):
+                    ncol = d.X[j].shape[1]
+                    check(self._lib.bgp_model_add_boundary(self._h, ncol, dptr(d.X[j]) if ncol else None,
+                                                           d.betaprec[j], d.betamean[j]))
+                for j in range(len(d.Xf)):
+                    check(self._lib.bgp_model_add_fixed(self._h, d.Xf[j].shape[1], dptr(d.Xf[j]), d.beta_fixed_prec[j],
+                                                        d.beta_fixed_mean[j]))
+                if d.family == 0:
+                    check(self._lib.bgp_model_set_noise_prior(self._h, d.u[-1], d.alpha[-1]))
+            except Exception:
+                self._lib.bgp_model_destroy(self._h)
+                self._h = C.c_void_p()
+                raise
+        self._finalized = False
+        self.env = _Env(self)
+        self.n_fn = 0
+        self.n_gr = 0
+        self.newton_iters = 0
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def set_shard(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self._lib.bgp_model_set_shard(self._h, rank, world, buf))
+
+    def finalize(self):
+        check(self._lib.bgp_model_finalize(self._h))
+        n, p, S = C.c_int64(), C.c_int(), C.c_int()
+        check(self._lib.bgp_model_dims(self._h, C.byref(n), C.byref(p), C.byref(S)))
+        self.n, self.p, self.S = n.value, p.value, S.value
+        self.par = np.zeros(self.S)                      # tmbparams theta = 0 (R/02_model_fit.R:249-252)
+        self.env.last_par = np.zeros(self.p)
+        self._finalized = True
+        self._keep = None
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.bgp_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- the TMB objective itself (objective_function::operator()) ---------------------------------
+    def objective(self, W, theta, want_grad=True, want_hess=False):
+        W = fvec(W)
+        theta = fvec(np.atleast_1d(theta))
+        f = C.c_double()
+        g = np.empty(self.p) if want_grad else None
+        H = np.empty((self.p, self.p), order="F") if want_hess else None
+        check(self._lib.bgp_objective(self._h, dptr(W), dptr(theta), C.byref(f), dptr(g), dptr(H)))
+        return f.value, g, H
+
+    # -- ff$fn / ff$gr ------------------------------------------------------------------------------
+    def _eval(self, theta, want_grad=False, want_mode=True, want_hess=False):
+        theta = fvec(np.atleast_1d(theta))
+        val = C.c_double()
+        iters = C.c_int()
+        g = np.empty(self.S) if want_grad else None
+        w = np.empty(self.p) if want_mode else None
+        H = np.empty((self.p, self.p), order="F") if want_hess else None
+        code = self._lib.bgp_laplace_eval(self._h, dptr(theta), C.byref(val), dptr(g), dptr(w), dptr(H),
+                                          C.byref(iters))
+        self.newton_iters += iters.value
+        if code in (3, 4, 5):        # NOT_PD / NONFINITE / NO_CONVERGENCE: TMB returns NaN (+ warning)
+            return float("nan"), (np.full(self.S, np.nan) if want_grad else None), None, None
+        check(code)
+        if want_mode:
+            self.env.last_par = w
+            self.env.last_theta = theta.copy()
+        if want_hess:
+            self.env.last_H = H
+        return val.value, g, w, H
+
+    def fn(self, theta, want_hess=False):
+        self.n_fn += 1
+        return self._eval(theta, want_hess=want_hess)[0]
+
+    def gr(self, theta):
+        self.n_gr += 1
+        return self._eval(theta, want_grad=True)[1]
+
+    def fn_batch(self, thetas, want_modes=True, want_hess=False):
+        """K Laplace evaluations through one C call; thetas is K x S."""
+        thetas = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(-1, self.S))
+        K = thetas.shape[0]
+        vals = np.empty(K)
+        modes = np.empty((K, self.p)) if want_modes else None
+        Hs = np.empty((K, self.p, self.p)) if want_hess else None
+        iters = C.c_int()
+        code = self._lib.bgp_laplace_eval_batch(self._h, K, dptr(thetas), dptr(vals), dptr(modes), dptr(Hs),
+                                                C.byref(iters))
+        self.newton_iters += iters.value
+        self.n_fn += K
+        if code not in (0, 3, 4, 5):
+            check(code)
+        return vals, modes, Hs, iters.value
+
+    def set_start(self, W=None):
+        check(self._lib.bgp_model_set_start(self._h, dptr(fvec(W)) if W is not None else None))
+
+    def set_newton(self, grad_tol=1e-8, step_tol=1e-8, maxit=100):
+        check(self._lib.bgp_model_set_newton(self._h, grad_tol, step_tol, maxit))
+
+    def last_timing(self):
+        t = [C.c_double() for _ in range(4)]
+        k = [C.c_int64() for _ in range(3)]
+        check(self._lib.bgp_model_last_timing(self._h, *[C.byref(v) for v in t], *[C.byref(v) for v in k]))
+        return {"total_ms": t[0].value, "lik_launches": k[0].value, "hess_launches": k[1].value,
+                "chol_launches": k[2].value}
+
+
+def make_objective(data: TMBData, device: int = 0) -> LaplaceObjective:
+    return LaplaceObjective(data, device).finalize()

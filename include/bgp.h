@@ -1,0 +1,167 @@
+/*
+ * bgp.h — C ABI of libbgp, the B200-native replacement for BayesGP's inner
+ * inference hot path (everything below `get_result_by_method`,
+ * /root/reference/R/02_model_fit.R:275-285, plus the sample -> function
+ * evaluation of /root/reference/R/03_post_fit.R:200-296).
+ *
+ * Conventions
+ *   - every matrix crossing this boundary is FP64, COLUMN-MAJOR (R's layout);
+ *   - all pointers are HOST pointers unless the name ends in `_dev`;
+ *   - the caller owns every buffer; the library copies inputs to the device;
+ *   - every entry point returns an int status (BGP_OK == 0); the message of the
+ *     last failure on this thread is available from bgp_last_error();
+ *   - no exceptions / longjmp cross the boundary; all calls are blocking;
+ *   - one host thread drives one model (same as R's single thread).
+ *
+ * Each group cites the reference interface it replaces.
+ */
+#ifndef BGP_H
+#define BGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bgp_model bgp_model;   /* replaces the TMB ADFun external pointer (`ff`) */
+typedef struct bgp_fit bgp_fit;       /* replaces the `marginallaplace`/`aghq` list (`mod`) */
+
+enum {
+  BGP_OK = 0,
+  BGP_ERR_ARG = 1,           /* bad argument / wrong call order                         */
+  BGP_ERR_CUDA = 2,          /* CUDA runtime / driver failure                           */
+  BGP_ERR_NOT_PD = 3,        /* Hessian not positive definite (Cholesky pivot <= 0)     */
+  BGP_ERR_NONFINITE = 4,     /* objective non-finite at the starting point              */
+  BGP_ERR_NO_CONVERGENCE = 5,/* inner Newton hit maxit (value returned as NaN)          */
+  BGP_ERR_NCCL = 6,          /* NCCL failure / NCCL not loadable                        */
+  BGP_ERR_STATE = 7          /* handle not finalized / already finalized                */
+};
+
+/* family codes: /root/reference/R/02_model_fit.R:8-28, src/BayesGP.cpp:155-214 */
+enum { BGP_FAMILY_GAUSSIAN = 0, BGP_FAMILY_POISSON = 1, BGP_FAMILY_BINOMIAL = 2, BGP_FAMILY_NONE = -2 };
+
+const char* bgp_last_error(void);
+int bgp_version(void);
+/* number of CUDA kernels this library has launched in this process (bench `gpu_launches`) */
+int64_t bgp_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Model construction — replaces the `tmbdat` list + TMB::MakeADFun(data, parameters,
+ * random = "W", DLL = "BayesGP")  (/root/reference/R/02_model_fit.R:152-183, :276-282;
+ * DATA_* macros of /root/reference/src/BayesGP.cpp:34-52).
+ * Call order: bgp_model_new -> add_random* -> add_boundary* -> add_fixed* -> finalize.
+ * W layout = [U_1..U_J | beta_1..beta_J | beta_fixed_0..]  (src/BayesGP.cpp:76-127).
+ * ---------------------------------------------------------------------------------------- */
+int bgp_model_new(int64_t n, int family, const double* y, const double* size /* NULL => 1s */, int device,
+                  bgp_model** out);
+/* one smoothing term: B (n x d), P (d x d dense, or length-d diagonal when p_is_diag), logPdet,
+ * PC-prior (u, alpha): tmbdat$B/P/logPdet/u/alpha  (R/02_model_fit.R:64-68) */
+int bgp_model_add_random(bgp_model* m, int d, const double* B, const double* P, int p_is_diag, double logPdet,
+                         double u, double alpha);
+/* boundary block of a term: X (n x ncol), beta ~ N(mean, 1/prec): tmbdat$X/betaprec/betamean (:53-62) */
+int bgp_model_add_boundary(bgp_model* m, int ncol, const double* X, double prec, double mean);
+/* fixed effect block (first call = intercept): tmbdat$Xf/beta_fixed_prec/beta_fixed_mean (:137-149) */
+int bgp_model_add_fixed(bgp_model* m, int ncol, const double* Xf, double prec, double mean);
+/* PC prior of the Gaussian noise theta (appended last, R/02_model_fit.R:120-121) */
+int bgp_model_set_noise_prior(bgp_model* m, double u, double alpha);
+/* GPU-side constructor of an IWP term from the covariate alone: builds B = local_poly_helper(knots,
+ * x - x0, order), X = global_poly(x - x0)[,-1], P = diag(diff(knots)) on the device
+ * (/root/reference/R/01_utility.R:278-300,325-401; R/02_model_fit.R:460-462). Adds the random AND the
+ * boundary block of the term (boundary blocks of generated terms keep the order of the calls). */
+int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, const double* knots, int nknots,
+                      int order, double u, double alpha, double boundary_prec, double boundary_mean);
+/* observation sharding: this process holds rows [row0, row0 + n) of a global problem of n_total rows and
+ * joins an NCCL communicator of `world` ranks (nccl_unique_id: the 128-byte ncclUniqueId produced by
+ * bgp_nccl_unique_id on rank 0 and broadcast by the launcher). Must precede finalize. */
+int bgp_nccl_unique_id(void* id128);
+int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_unique_id);
+int bgp_model_finalize(bgp_model* m);
+void bgp_model_destroy(bgp_model* m);
+
+int bgp_model_dims(const bgp_model* m, int64_t* n, int* p, int* S);
+
+/* ------------------------------------------------------------------------------------------
+ * The TMB objective and its W-derivatives at a given (W, theta) — replaces
+ * objective_function<Type>::operator() (src/BayesGP.cpp:30-253) and the AD sweeps TMB runs
+ * on it. Any output pointer may be NULL. H is p x p column-major (full symmetric).
+ * ---------------------------------------------------------------------------------------- */
+int bgp_objective(bgp_model* m, const double* W, const double* theta, double* f, double* grad /* p */,
+                  double* H /* p*p */);
+
+/* ------------------------------------------------------------------------------------------
+ * TMB-style Laplace objective — replaces ff$fn / ff$gr / ff$env$last.par / ff$env$spHess
+ * (call site R/02_model_fit.R:276-284; consumed inside aghq::marginal_laplace_tmb).
+ *   value  = f(w_hat,theta) + 1/2 logdet H(w_hat,theta) - p/2 log(2 pi)   (NaN on inner failure)
+ *   grad   = d value / d theta  (S)            — NULL to skip (costs a leverage pass)
+ *   w_mode = w_hat (p)                          — ff$env$last.par[random]
+ *   H      = H(w_hat, theta) (p x p)            — ff$env$spHess(last.par, random = TRUE)
+ * The inner Newton warm-starts from the previous call's mode (TMB last.par.best behaviour).
+ * ---------------------------------------------------------------------------------------- */
+int bgp_laplace_eval(bgp_model* m, const double* theta, double* value, double* grad, double* w_mode, double* H,
+                     int* newton_iters);
+/* K evaluations in one call (theta is S x K column-major: node j = theta + j*S); outputs may be NULL:
+ * values[K], modes p x K, Hs p x p x K. */
+int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* values, double* modes, double* Hs,
+                           int* newton_iters_total);
+/* reset / set the warm start (tmbparams W = 0, R/02_model_fit.R:249-252) */
+int bgp_model_set_start(bgp_model* m, const double* W /* NULL => zeros */);
+/* inner solver controls (TMB newton(): tol = grad.tol = step.tol = 1e-8, maxit = 100) */
+int bgp_model_set_newton(bgp_model* m, double grad_tol, double step_tol, int maxit);
+
+/* ------------------------------------------------------------------------------------------
+ * aghq::marginal_laplace_tmb(ff, k, startingvalue)  (R/02_model_fit.R:284): BFGS (vmmin) from
+ * theta0, Richardson Hessian of ff$gr (ff$he, :283), Gauss-Hermite product grid, normalisation,
+ * marginals ("reuse"), per-node modes and Hessians.
+ * ---------------------------------------------------------------------------------------- */
+int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
+/* same, but with the optimisation results supplied (aghq's `optresults` argument) */
+int bgp_aghq_fit_at(bgp_model* m, int k, const double* mode, const double* hessian /* S x S */, bgp_fit** out);
+void bgp_fit_destroy(bgp_fit* f);
+int bgp_fit_dims(const bgp_fit* f, int* S, int* K, int* p, int* k);
+/* getters mirror mod$optresults / mod$normalized_posterior / mod$modesandhessians / mod$marginals */
+int bgp_fit_get_opt(const bgp_fit* f, double* mode /* S */, double* hessian /* S*S */, int* convergence,
+                    int* fn_count, int* gr_count);
+int bgp_fit_get_grid(const bgp_fit* f, double* nodes /* K x S col-major */, double* weights /* K */,
+                     double* logpost /* K */, double* logpost_normalized /* K */, double* lognormconst);
+int bgp_fit_get_modes(const bgp_fit* f, double* modes /* p x K */, double* Hs /* p x p x K, may be NULL */);
+int bgp_fit_get_marginal(const bgp_fit* f, int j, double* theta /* k */, double* logmargpost /* k */,
+                         double* w /* k */);
+
+/* ------------------------------------------------------------------------------------------
+ * aghq::sample_marginal(mod, M)  (R/02_model_fit.R:687-689) with the random inputs explicit:
+ * samps[, m] = mode_{node_idx[m]} + chol(H_{node_idx[m]})^{-1} Z[, m];  Z is p x M standard
+ * normal, node_idx 0-based. Output p x M (rows = W entries, columns = samples, as samps$samps).
+ * ---------------------------------------------------------------------------------------- */
+int bgp_sample(bgp_fit* f, int64_t M, const double* Z, const int32_t* node_idx, double* samps);
+/* library-side draw of (node_idx, Z) with a counter-based generator, then bgp_sample; the
+ * samples stay resident on the device for bgp_predict_* (pass samps = NULL to skip the copy) */
+int bgp_sample_draw(bgp_fit* f, int64_t M, uint64_t seed, double* samps, int32_t* node_idx);
+
+/* ------------------------------------------------------------------------------------------
+ * Sample -> function evaluation and summary — replaces compute_post_fun_IWP
+ * (R/03_post_fit.R:200-241), compute_post_fun_sGP (:261-276) and
+ * extract_mean_interval_given_samps (:287-296; stats::quantile type 7).
+ *   coef    (k-1) x M   spline coefficient samples      (samps$samps[random idx, ])
+ *   global  (order-1) x M boundary coefficient samples  (may be NULL => zeros)
+ *   icpt    M           intercept samples               (may be NULL => zeros)
+ *   x       G           refined_x (already shifted by initial_location and sorted by the caller)
+ * Outputs (any may be NULL): mean/plower/pupper [G]; samples G x M column-major.
+ * ---------------------------------------------------------------------------------------- */
+int bgp_predict_iwp(const double* coef, const double* global, const double* icpt, int64_t M, const double* knots,
+                    int nknots, int order, int degree, const double* x, int64_t G, double level, int device,
+                    double* mean, double* plower, double* pupper, double* samples);
+int bgp_predict_sgp(const double* coef, const double* global, const double* icpt, int64_t M, double a, int k, int m,
+                    const double* region /* 2 */, int boundary, const double* x, int64_t G, double level, int device,
+                    double* mean, double* plower, double* pupper, double* samples);
+/* basis evaluators on the device (R/01_utility.R:378-401, :413-419, :198-208): out is G x ncol col-major */
+int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, int64_t G, int device, double* out);
+
+/* timing of the last call, measured with CUDA events on the model's stream (milliseconds) */
+int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,
+                          int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGP_H */

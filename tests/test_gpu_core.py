@@ -1,0 +1,71 @@
+"""GPU parity: objective / gradient / Hessian / Laplace value / mode, CUDA (through the C ABI)
+versus the CPU oracle on identical seeded inputs.  Tolerances follow BASELINE.json north_star:
+log marginal pieces 1e-8 relative, modes 1e-6 relative."""
+import numpy as np
+import pytest
+
+from helpers import (covid_model, relerr, synth_binomial_sgp, synth_gaussian, synth_poisson, tmbdata_from_oracle)
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "covid_poisson": (covid_model, [np.array([0.0]), np.array([-3.2]), np.array([-2.5])]),
+    "synth_poisson": (synth_poisson, [np.array([0.0]), np.array([4.0]), np.array([7.5])]),
+    "binomial_sgp": (synth_binomial_sgp, [np.array([0.0, 0.0]), np.array([3.0, -1.0])]),
+    "gaussian": (synth_gaussian, [np.array([0.0, 0.0]), np.array([5.0, 1.2])]),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    from bayesgp_b200 import make_objective
+    from oracle.laplace import LaplaceObjective as OracleFF
+    build, thetas = CASES[request.param]
+    model = build()[0]
+    ff = make_objective(tmbdata_from_oracle(model))
+    yield request.param, model, OracleFF(model), ff, thetas
+    ff.close()
+
+
+def test_objective_gradient_hessian(case):
+    name, model, off, ff, thetas = case
+    rng = np.random.default_rng(1)
+    for theta in thetas:
+        for W in (np.zeros(model.p), 0.05 * rng.standard_normal(model.p)):
+            o = model.objective(W, theta, "fgH")
+            f, g, H = ff.objective(W, theta, want_grad=True, want_hess=True)
+            assert abs(f - o["f"]) <= 1e-11 * abs(o["f"]), (name, theta, f, o["f"])
+            assert relerr(g, o["g"]) < 1e-11, (name, theta, relerr(g, o["g"]))
+            assert relerr(H, o["H"]) < 1e-11, (name, theta, relerr(H, o["H"]))
+            assert np.array_equal(H, H.T)
+
+
+def test_laplace_value_and_mode(case):
+    name, model, off, ff, thetas = case
+    for theta in thetas:
+        want = off.fn(theta)
+        got, _, w, H = ff._eval(theta, want_hess=True)
+        assert np.isfinite(got)
+        assert abs(got - want) <= 1e-8 * abs(want), (name, theta, got, want)       # north_star: 1e-8 relative
+        assert relerr(w, off.last_par) < 1e-6, (name, theta, relerr(w, off.last_par))
+        assert relerr(H, off.sp_hess()) < 1e-6
+
+
+def test_warm_start_is_result_invariant(case):
+    name, model, off, ff, thetas = case
+    theta = thetas[-1]
+    ff.set_start(None)
+    cold = ff.fn(theta)
+    warm = ff.fn(theta)
+    assert abs(cold - warm) <= 1e-9 * abs(cold)
+
+
+def test_batch_matches_single(case):
+    name, model, off, ff, thetas = case
+    ff.set_start(None)
+    vals, modes, Hs, iters = ff.fn_batch(np.stack(thetas), want_modes=True, want_hess=True)
+    for j, theta in enumerate(thetas):
+        want = off.fn(theta)
+        assert abs(vals[j] - want) <= 1e-8 * abs(want)
+        assert relerr(modes[j], off.last_par) < 1e-6
+        assert relerr(Hs[j], off.sp_hess()) < 1e-6
