@@ -55,6 +55,7 @@ struct RandomBlock {
   int off = 0;              // first W index of U_j
   bool diag = true;
   double* P_dev = nullptr;  // d (diag) or d*d column-major
+  std::vector<double> P_host;
   double logPdet = 0, u = 1, alpha = 0.5;
 };
 
@@ -109,6 +110,10 @@ struct bgp_model {
   double* step = nullptr;       // Newton step (lda)
   double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)
   double* L = nullptr;          // Cholesky factor (lower, column-major p x ldh)
+  double* Linv = nullptr;       // L^-1, row-major p x ldl (lower; allocated on first gradient call)
+  int ldl = 0;
+  double* zobs = nullptr;       // c3 * leverage per observation
+  void* grad_plan = nullptr;    // opaque (grad.cu)
   int ldh = 0;
   double* theta_dev = nullptr;  // S (+ exp(theta))
   double* part_g = nullptr;     // [lik_blocks][lda]
@@ -132,14 +137,23 @@ struct bgp_model {
   cudaEvent_t ev[8] = {nullptr};
   double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0;
   int64_t n_lik = 0, n_hess = 0, n_chol = 0;
-  bool timing = false;
+  // per-phase device timing: marks are (event, phase starting here); harvested after each sync
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> marks;
 };
+
+namespace bgp {
+enum { PH_OTHER = 0, PH_LIK = 1, PH_HESS = 2, PH_CHOL = 3 };
+void phase_mark(bgp_model* m, int phase);
+void phase_harvest(bgp_model* m);   // call only right after a stream synchronize
+}  // namespace bgp
 
 namespace bgp {
 
 // ---- kernels (each in its own .cu) ------------------------------------------------------------
 // lik.cu: eta = A W ; per-observation likelihood ; partial g = A^T r ; block partials
-int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau);
+// rvec != NULL: only part_g = A^T rvec is produced (W_dev ignored)
+int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, const double* rvec = nullptr);
 int lik_max_lda();
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
@@ -159,6 +173,7 @@ int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool w
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
 // grad.cu: d/dtheta of the Laplace objective at the mode left on the device by laplace_inner
 int laplace_gradient(bgp_model* m, const double* theta, double* grad_host);
+void grad_plan_destroy(bgp_model* m);
 
 // comm.cpp
 int comm_unique_id(void* id128);

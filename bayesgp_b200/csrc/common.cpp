@@ -17,6 +17,30 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
+void phase_mark(bgp_model* m, int phase) {
+  if (m->marks.size() >= m->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    m->ev_pool.push_back(e);
+  }
+  cudaEventRecord(m->ev_pool[m->marks.size()], m->stream);
+  m->marks.push_back(phase);
+}
+
+void phase_harvest(bgp_model* m) {
+  for (size_t i = 0; i + 1 < m->marks.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev_pool[i], m->ev_pool[i + 1]) != cudaSuccess) continue;
+    switch (m->marks[i]) {
+      case PH_LIK: m->t_lik += ms; break;
+      case PH_HESS: m->t_hess += ms; break;
+      case PH_CHOL: m->t_chol += ms; break;
+      default: break;
+    }
+  }
+  m->marks.clear();
+}
+
 }  // namespace bgp
 
 extern "C" {

@@ -30,6 +30,7 @@ struct LikArgs {
   double* c3;
   double* part_g;   // [gridDim.x][lda]
   double* part_s;   // [gridDim.x][4] : ll, sumsq, nonfinite, unused
+  const double* rvec;   // if set: skip the likelihood and accumulate A^T rvec only (leverage term)
 };
 
 constexpr int LIK_THREADS = 256;
@@ -107,22 +108,27 @@ __global__ void __launch_bounds__(LIK_THREADS) lik_kernel(const LikArgs a) {
     for (int r = 0; r < R; ++r) {
       const int64_t row = base + r;
       if (row < a.n) {
-        double s = 0.0;
+        double rr;
+        if (a.rvec) {
+          rr = __ldg(a.rvec + row);
+        } else {
+          double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          s = fma(av[r][j].x, wv[j].x, s);
-          s = fma(av[r][j].y, wv[j].y, s);
-        }
-        s = warp_sum(s);
-        const double yv = __ldg(a.y + row);
-        const double sz = a.size ? __ldg(a.size + row) : 1.0;
-        double rr, ww, cc;
-        obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
-        if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
-        if (lane == 0) {
-          a.eta[row] = s;
-          a.wobs[row] = ww;
-          if (a.c3) a.c3[row] = cc;
+          for (int j = 0; j < NJ; ++j) {
+            s = fma(av[r][j].x, wv[j].x, s);
+            s = fma(av[r][j].y, wv[j].y, s);
+          }
+          s = warp_sum(s);
+          const double yv = __ldg(a.y + row);
+          const double sz = a.size ? __ldg(a.size + row) : 1.0;
+          double ww, cc;
+          obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
+          if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
+          if (lane == 0) {
+            a.eta[row] = s;
+            a.wobs[row] = ww;
+            if (a.c3) a.c3[row] = cc;
+          }
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -176,8 +182,9 @@ static int launch_lik_t(bgp_model* m, const LikArgs& a) {
 
 int lik_max_lda() { return 1024; }
 
-int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau) {
+int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, const double* rvec) {
   LikArgs a;
+  a.rvec = rvec;
   a.A = m->A;
   a.lda = m->lda;
   a.n = m->n;

@@ -161,6 +161,7 @@ int bgp_model_add_random(bgp_model* m, int d, const double* B, const double* P, 
   const size_t pb = (rb.diag ? (size_t)d : (size_t)d * d) * sizeof(double);
   BGP_CUDA(cudaMalloc(&rb.P_dev, pb));
   BGP_CUDA(cudaMemcpy(rb.P_dev, P, pb, cudaMemcpyHostToDevice));
+  rb.P_host.assign(P, P + pb / sizeof(double));
   m->rnd.push_back(rb);
   return BGP_OK;
 }
@@ -277,6 +278,7 @@ int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, co
   rb.alpha = alpha;
   BGP_CUDA(cudaMalloc(&rb.P_dev, (size_t)d * sizeof(double)));
   BGP_CUDA(cudaMemcpy(rb.P_dev, Pdiag.data(), (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+  rb.P_host = Pdiag;
   m->rnd.push_back(rb);
   m->bnd_dim.push_back(order - 1);
   m->bnd_prec.push_back(boundary_prec);
@@ -421,6 +423,7 @@ void bgp_model_destroy(bgp_model* m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   syrk_plan_destroy(m);
+  grad_plan_destroy(m);
   comm_destroy(m);
   for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix})
     for (auto& s : *v)
@@ -434,6 +437,7 @@ void bgp_model_destroy(bgp_model* m) {
   if (m->sc_host) cudaFreeHost(m->sc_host);
   for (int i = 0; i < 8; ++i)
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }

@@ -23,7 +23,9 @@ static inline double tau_of(const bgp_model* m, const double* theta) {
 
 static int read_scalars(bgp_model* m, EvalScalars* out) {
   BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
+  phase_mark(m, PH_OTHER);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
+  phase_harvest(m);
   *out = *m->sc_host;
   return BGP_OK;
 }
@@ -31,9 +33,12 @@ static int read_scalars(bgp_model* m, EvalScalars* out) {
 // f, g (device), gmax at W_dev; leaves eta / wobs (/ c3) of that point on the device
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3) {
   const double tau = tau_of(m, theta);
+  phase_mark(m, PH_LIK);
   BGP_TRY(launch_lik(m, W_dev, want_c3, tau));
   m->n_lik++;
-  return launch_finish(m, W_dev, theta, tau);
+  BGP_TRY(launch_finish(m, W_dev, theta, tau));
+  phase_mark(m, PH_OTHER);
+  return BGP_OK;
 }
 
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_out) {
@@ -62,10 +67,13 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       converged = true;
       break;
     }
+    phase_mark(m, PH_HESS);
     BGP_TRY(launch_hessian(m, theta));
     m->n_hess++;
+    phase_mark(m, PH_CHOL);
     BGP_TRY(launch_chol_solve(m, true));
     m->n_chol++;
+    phase_mark(m, PH_OTHER);
     // speculative full step: evaluate the trial point before reading anything back
     axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, 1.0, m->p, m->lda, m->Wtrial);
     count_launch();
@@ -115,8 +123,10 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   if (!have_factor) {
     // Hessian and factor at the mode (eta / wobs on the device belong to W)
+    phase_mark(m, PH_HESS);
     BGP_TRY(launch_hessian(m, theta));
     m->n_hess++;
+    phase_mark(m, PH_CHOL);
     BGP_TRY(launch_chol_solve(m, false));
     m->n_chol++;
     BGP_TRY(read_scalars(m, &sc));

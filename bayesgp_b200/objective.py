@@ -56,42 +56,68 @@ class _Env:
 class LaplaceObjective:
     """ff <- MakeADFun(..., random = "W").  ``fn``/``gr`` take theta (length S)."""
 
-    def __init__(self, data: Optional[TMBData] = None, device: int = 0, *, handle=None):
+    def __init__(self, data: Optional[TMBData] = None, device: int = 0, *, y=None, family=None, size=None):
+        """Either pass a complete ``TMBData`` (dense blocks, as R builds them) or ``y``/``family``
+        and then add blocks with ``add_random`` / ``add_boundary`` / ``add_fixed`` / ``add_iwp``
+        (same order as the W layout of src/BayesGP.cpp:76-127) before ``finalize()``."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.device = device
-        if handle is not None:
-            self._h = handle
-        else:
-            d = data
-            self._keep = d
-            check(self._lib.bgp_model_new(len(d.y), d.family, dptr(d.y), dptr(d.size), device, C.byref(self._h)))
-            try:
-                nu = len(d.B)
-                for j in range(nu):
-                    P = d.P[j]
-                    diag = P.ndim == 1
-                    Pm = fvec(P) if diag else fmat(P)
-                    check(self._lib.bgp_model_add_random(self._h, d.B[j].shape[1], dptr(d.B[j]), dptr(Pm), int(diag),
-                                                         d.logPdet[j], d.u[j], d.alpha[j]))
-                for j in range(len(d.X)):
-                    ncol = d.X[j].shape[1]
-                    check(self._lib.bgp_model_add_boundary(self._h, ncol, dptr(d.X[j]) if ncol else None,
-                                                           d.betaprec[j], d.betamean[j]))
-                for j in range(len(d.Xf)):
-                    check(self._lib.bgp_model_add_fixed(self._h, d.Xf[j].shape[1], dptr(d.Xf[j]), d.beta_fixed_prec[j],
-                                                        d.beta_fixed_mean[j]))
-                if d.family == 0:
-                    check(self._lib.bgp_model_set_noise_prior(self._h, d.u[-1], d.alpha[-1]))
-            except Exception:
-                self._lib.bgp_model_destroy(self._h)
-                self._h = C.c_void_p()
-                raise
         self._finalized = False
         self.env = _Env(self)
         self.n_fn = 0
         self.n_gr = 0
         self.newton_iters = 0
+        if data is not None:
+            y, family, size = data.y, data.family, data.size
+        fam = FAMILY_CODES[family] if isinstance(family, str) else int(family)
+        self.family = fam
+        yv = fvec(y)
+        sv = None if size is None else fvec(size)
+        check(self._lib.bgp_model_new(len(yv), fam, dptr(yv), dptr(sv), device, C.byref(self._h)))
+        if data is not None:
+            d = data
+            try:
+                for j in range(len(d.B)):
+                    self.add_random(d.B[j], d.P[j], d.logPdet[j], d.u[j], d.alpha[j])
+                for j in range(len(d.X)):
+                    self.add_boundary(d.X[j], d.betaprec[j], d.betamean[j])
+                for j in range(len(d.Xf)):
+                    self.add_fixed(d.Xf[j], d.beta_fixed_prec[j], d.beta_fixed_mean[j])
+                if fam == 0:
+                    self.set_noise_prior(d.u[-1], d.alpha[-1])
+            except Exception:
+                self.close()
+                raise
+
+    # -- builder (tmbdat lists, R/02_model_fit.R:50-71,123-150) -------------------------------------
+    def add_random(self, B, P, logPdet, u=1.0, alpha=0.5):
+        B = fmat(B)
+        P = np.asarray(P, dtype=np.float64)
+        diag = P.ndim == 1
+        Pm = fvec(P) if diag else fmat(P)
+        check(self._lib.bgp_model_add_random(self._h, B.shape[1], dptr(B), dptr(Pm), int(diag), float(logPdet),
+                                             float(u), float(alpha)))
+
+    def add_boundary(self, X, prec=0.01, mean=0.0):
+        X = fmat(X)
+        ncol = X.shape[1] if X.ndim == 2 else 0
+        check(self._lib.bgp_model_add_boundary(self._h, ncol, dptr(X) if ncol else None, float(prec), float(mean)))
+
+    def add_fixed(self, Xf, prec=0.01, mean=0.0):
+        Xf = fmat(np.asarray(Xf, dtype=np.float64).reshape(-1, 1) if np.ndim(Xf) == 1 else Xf)
+        check(self._lib.bgp_model_add_fixed(self._h, Xf.shape[1], dptr(Xf), float(prec), float(mean)))
+
+    def add_iwp(self, x, initial_location, knots, order, u=1.0, alpha=0.5, boundary_prec=0.01, boundary_mean=0.0):
+        """Device-side construction of an IWP term from the covariate (no n x k host matrix)."""
+        x = fvec(x)
+        knots = fvec(knots)
+        check(self._lib.bgp_model_add_iwp(self._h, dptr(x), float(initial_location), dptr(knots), len(knots),
+                                          int(order), float(u), float(alpha), float(boundary_prec),
+                                          float(boundary_mean)))
+
+    def set_noise_prior(self, u=1.0, alpha=0.5):
+        check(self._lib.bgp_model_set_noise_prior(self._h, float(u), float(alpha)))
 
     # -- lifecycle ------------------------------------------------------------------------------
     def set_shard(self, rank: int, world: int, unique_id: bytes):
@@ -106,7 +132,6 @@ class LaplaceObjective:
         self.par = np.zeros(self.S)                      # tmbparams theta = 0 (R/02_model_fit.R:249-252)
         self.env.last_par = np.zeros(self.p)
         self._finalized = True
-        self._keep = None
         return self
 
     def close(self):
@@ -191,8 +216,8 @@ class LaplaceObjective:
         t = [C.c_double() for _ in range(4)]
         k = [C.c_int64() for _ in range(3)]
         check(self._lib.bgp_model_last_timing(self._h, *[C.byref(v) for v in t], *[C.byref(v) for v in k]))
-        return {"total_ms": t[0].value, "lik_launches": k[0].value, "hess_launches": k[1].value,
-                "chol_launches": k[2].value}
+        return {"total_ms": t[0].value, "lik_ms": t[1].value, "hess_ms": t[2].value, "chol_ms": t[3].value,
+                "lik_launches": k[0].value, "hess_launches": k[1].value, "chol_launches": k[2].value}
 
 
 def make_objective(data: TMBData, device: int = 0) -> LaplaceObjective:

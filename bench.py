@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — AGHQ-node Laplace evals/sec at n = 1M, p = 302 (BASELINE.json metric, config C3).
+
+A *step* is one pass of the hot path over one batch: the 15 quadrature nodes of the 1-D AGHQ
+grid are evaluated in node order, each evaluation = inner Newton (warm-started from the previous
+node's mode, as TMB does) to max|g| < 1e-8 + Cholesky log-det, exactly what
+aghq::normalize_logpost does through ff$fn (/root/reference/R/02_model_fit.R:276-284).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n ROWS]
+
+N > 1 is launched by torchrun (one process per GPU); every rank holds a replica of the data and
+evaluates its own 15 nodes (node-sharded, no data-path collective) => weak scaling.
+`value` is timed on the device with CUDA events on the library's stream (inputs resident in HBM);
+`e2e` is the wall clock of the same step through the C ABI with host buffers (theta / warm start
+in, values + modes + Hessians out).  The roofline is for the dominant kernel (the DMMA Hessian).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_NODES = 15
+P_KNOTS = 300
+ORDER = 3
+
+
+def _rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def fp64_peak_tflops(device):
+    """cuBLAS DGEMM 8192^3 on this GPU, burst (best of 5).  MEASURED_PEAKS.json carries no FP64 figure,
+    so the denominator of the Hessian roofline is measured here, the same way the driver measured bf16."""
+    import torch
+    torch.cuda.set_device(device)
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def build_b200(x, y, device):
+    from bayesgp_b200.objective import LaplaceObjective
+    from bayesgp_b200.workloads import iwp_knots
+    x0, knots = iwp_knots(x, P_KNOTS)
+    ff = LaplaceObjective(y=y, family="Poisson", device=device)
+    ff.add_iwp(x, x0, knots, ORDER)                 # device-side B / X / P from the covariate
+    ff.add_fixed(np.ones(len(y)))                   # intercept (R/02_model_fit.R:572-578)
+    ff.finalize()
+    return ff
+
+
+def node_grid(ff):
+    """Untimed setup: centre / scale of the 1-D grid, then theta_j = mode + sd * z_j (A.4)."""
+    from bayesgp_b200.workloads import gh_nodes, locate_mode_1d
+    mode, sd = locate_mode_1d(ff.fn, 2.0, 12.0)
+    thetas = (mode + sd * gh_nodes(K_NODES))[:, None]
+    ff.fn(np.array([mode]))
+    return mode, sd, thetas, ff.env.last_par.copy()
+
+
+def run_b200(args):
+    rank, world, local = _rank_world()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from bayesgp_b200 import _lib
+    from bayesgp_b200.workloads import c3_data
+    lib = _lib.load()
+    x, y = c3_data(args.n)
+    t0 = time.time()
+    ff = build_b200(x, y, local)
+    t_build = time.time() - t0
+    mode, sd, thetas, w_mode = node_grid(ff)
+    p, n = ff.p, ff.n
+
+    def step():
+        ff.set_start(w_mode)                                          # H2D: p doubles
+        t0 = time.perf_counter()
+        vals, modes, Hs, iters = ff.fn_batch(thetas, want_modes=True, want_hess=True)   # D2H: values, modes, Hessians
+        wall = time.perf_counter() - t0
+        return vals, iters, wall, ff.last_timing()["total_ms"]
+
+    for _ in range(max(3, args.warmup)):
+        vals, iters, _, _ = step()
+    tm0 = ff.last_timing()
+    launches0 = lib.bgp_kernel_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    dev_ms, wall_s, iters_tot = 0.0, 0.0, 0
+    t_region = time.perf_counter()
+    for _ in range(args.steps):
+        vals, iters, wall, ms = step()
+        dev_ms += ms
+        wall_s += wall
+        iters_tot += iters
+    if dist:
+        import torch
+        t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
+        dev_ms, wall_s = float(t[0]), float(t[1])
+        dist.barrier()
+    region_s = time.perf_counter() - t_region
+    clocks = sampler.stop() if sampler else None
+    tm1 = ff.last_timing()
+    launches = lib.bgp_kernel_launch_count() - launches0
+    if rank != 0:
+        ff.close()
+        if dist:
+            dist.destroy_process_group()
+        return
+    evals = K_NODES * args.steps * world
+    value = evals / (dev_ms * 1e-3)
+    e2e = evals / wall_s
+    n_hess = tm1["hess_launches"] - tm0["hess_launches"]
+    n_lik = tm1["lik_launches"] - tm0["lik_launches"]
+    hess_ms = (tm1["hess_ms"] - tm0["hess_ms"]) / max(1, n_hess)
+    lik_ms = (tm1["lik_ms"] - tm0["lik_ms"]) / max(1, n_lik)
+    chol_ms = (tm1["chol_ms"] - tm0["chol_ms"]) / max(1, tm1["chol_launches"] - tm0["chol_launches"])
+    peaks, peak_src = measured_peaks()
+    try:
+        fp64_peak = fp64_peak_tflops(local)
+    except Exception as e:     # torch missing / OOM: keep the bench alive, say so
+        fp64_peak = None
+        peak_src += "; fp64 DGEMM peak unavailable (%s)" % type(e).__name__
+    flops = float(n) * p * (p + 1)
+    achieved = flops / (hess_ms * 1e-3) / 1e12
+    lda = (p + 15) // 16 * 16
+    lik_bytes = 8.0 * n * (lda + 3)
+    line = {
+        "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300",
+        "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d), 1-D AGHQ 15 nodes per step "
+                               "per GPU, warm-started inner Newton to max|g|<1e-8 + log-det" % (n, p),
+                   "nodes_per_step": K_NODES, "newton_iters_per_eval": iters_tot / (K_NODES * args.steps),
+                   "theta_mode": mode, "theta_sd": sd, "l2_flush": "inputs (2.4 GB design matrix) exceed the 126 MB L2",
+                   "parallelism": "node-sharded replicas x%d" % world, "model_build_s": t_build},
+        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + K_NODES),
+                "d2h_bytes_per_step": 8 * K_NODES * (1 + p + p * p)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": achieved,
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if fp64_peak else None,
+                     "traffic": None, "ms_per_launch": hess_ms, "algorithmic_flops_per_launch": flops,
+                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
+        "roofline_lik": {"bound": "hbm", "kernel": "lik_kernel (eta, ll, r, w, A^T r)", "achieved": lik_bytes / (lik_ms * 1e-3) / 1e9,
+                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": lik_bytes / (lik_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "ms_per_launch": lik_ms,
+                         "peak_source": peak_src},
+        "chol_ms_per_launch": chol_ms,
+        "clocks": clocks,
+        "wall_s_timed_region": region_s,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(x, y, thetas, w_mode, budget_s=args.cpu_budget)
+    print(json.dumps(line), flush=True)
+    ff.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def oracle_model(x, y):
+    """The reference's CPU path restated (oracle/): dense design built on the host as R does."""
+    from oracle.fit import Term, build_model
+    from oracle.laplace import LaplaceObjective as OracleFF
+    model = build_model(y, [Term("IWP", "x", x, order=ORDER, k=P_KNOTS)], {}, family="Poisson")[0]
+    return model, OracleFF(model)
+
+
+def cpu_baseline(x, y, thetas, w_mode, budget_s=20.0):
+    """Oracle port timed on the host cores on a bounded sample: the first nodes of the same grid at
+    the same n, p (numpy / OpenBLAS, all threads), until >= 3 evaluations and >= budget seconds."""
+    t0 = time.time()
+    model, off = oracle_model(x, y)
+    t_build = time.time() - t0
+    off.last_par = w_mode.copy()
+    done, t0 = 0, time.time()
+    for th in thetas:
+        off.fn(th)
+        done += 1
+        if done >= 3 and time.time() - t0 >= budget_s:
+            break
+        if time.time() - t0 >= 3 * budget_s:
+            break
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "first %d of %d nodes, same n=%d p=%d, warm start from the mode; numpy/OpenBLAS FP64 "
+                      "(oracle/laplace.py), design build %.1f s untimed" % (done, len(thetas), model.n, model.p, t_build),
+            "newton_iters_per_eval": off.newton_iters / max(1, done)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; R/TMB/aghq are not installable here)
+    on the host cores, same config / metric; each step is a bounded sample of the workload."""
+    rank, world, _ = _rank_world()
+    if rank != 0:
+        return
+    from bayesgp_b200.workloads import c3_data, gh_nodes
+    x, y = c3_data(args.n)
+    model, off = oracle_model(x, y)
+    # centre the grid the same way (coarse, untimed)
+    from bayesgp_b200.workloads import locate_mode_1d
+    mode, sd = locate_mode_1d(off.fn, 2.0, 12.0, iters=6)
+    thetas = (mode + sd * gh_nodes(K_NODES))[:, None]
+    off.fn(np.array([mode]))
+    w_mode = off.last_par.copy()
+    nodes_per_step = args.ref_nodes
+    for _ in range(args.warmup):
+        off.last_par = w_mode.copy()
+        off.fn(thetas[0])
+    t0 = time.time()
+    it0 = off.newton_iters
+    for s in range(args.steps):
+        off.last_par = w_mode.copy()
+        for j in range(nodes_per_step):
+            off.fn(thetas[(s * nodes_per_step + j) % K_NODES])
+    dt = time.time() - t0
+    evals = args.steps * nodes_per_step
+    v = evals / dt
+    line = {
+        "impl": "reference", "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300", "value": v, "unit": "evals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d), 1-D AGHQ 15-node grid; "
+                               "each step = %d node evaluations (bounded sample)" % (model.n, model.p, nodes_per_step),
+                   "newton_iters_per_eval": (off.newton_iters - it0) / evals},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d node evaluations per step at full n, numpy/OpenBLAS FP64" % nodes_per_step},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-nodes", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,13 @@ def get_local_poly(knots, refined_x, p):
     """Vectorised form of ``get_local_poly`` (same branch structure and the
     same summation order inside the tail polynomial)."""
     knots = np.asarray(knots, dtype=np.float64)
-    x = np.asarray(refined_x, dtype=np.float64)[:, None]
+    xa = np.asarray(refined_x, dtype=np.float64)
+    if xa.size > 65536:      # bound the temporaries: same arithmetic, row blocks
+        out = np.empty((xa.size, len(knots) - 1))
+        for s in range(0, xa.size, 65536):
+            out[s:s + 65536] = get_local_poly(knots, xa[s:s + 65536], p)
+        return out
+    x = xa[:, None]
     k0 = knots[None, :-1]
     k1 = knots[None, 1:]
     dif = np.diff(knots)[None, :]
