@@ -8,5 +8,10 @@ interface used by the tests and the benchmark.  There is no CPU fallback.
 """
 from ._lib import BgpError, load  # noqa: F401
 from .objective import LaplaceObjective, TMBData, make_objective  # noqa: F401
+from .terms import Term  # noqa: F401
+from .api import (AGHQ, FitResult, build_objective, compute_post_fun_IWP, compute_post_fun_sGP,  # noqa: F401
+                  marginal_laplace_tmb, model_fit, predict, sample_fixed_effect, sample_marginal)
 
-__all__ = ["BgpError", "load", "LaplaceObjective", "TMBData", "make_objective"]
+__all__ = ["BgpError", "load", "LaplaceObjective", "TMBData", "make_objective", "Term", "AGHQ", "FitResult",
+           "build_objective", "compute_post_fun_IWP", "compute_post_fun_sGP", "marginal_laplace_tmb", "model_fit",
+           "predict", "sample_fixed_effect", "sample_marginal"]

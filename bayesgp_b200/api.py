@@ -1,0 +1,287 @@
+"""model_fit() / predict() — host-side mirror of BayesGP's user-facing calls on top of libbgp.
+
+Same names, argument meaning and error behaviour as ``/root/reference/R/02_model_fit.R:336-701``
+(``model_fit``), ``/root/reference/R/03_post_fit.R:53-125`` (``predict.FitResult``), ``:159-165``
+(``sample_fixed_effect``), ``:200-296`` (``compute_post_fun_IWP`` / ``compute_post_fun_sGP`` /
+``extract_mean_interval_given_samps``), with the formula DSL replaced by a list of ``Term``s.
+Everything numerical happens behind the C ABI; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dptr, fmat, fvec
+from .objective import FAMILY_CODES, LaplaceObjective
+from .terms import Term, iid_design, prepare_term, sgp_design, sgp_precision
+
+
+class AGHQ:
+    """The ``c("marginallaplace", "aghq")`` object: fields BayesGP reads."""
+
+    def __init__(self, ff: LaplaceObjective, handle):
+        self._lib = _lib.load()
+        self.ff = ff
+        self._h = handle
+        S, K, p, k = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.bgp_fit_dims(self._h, C.byref(S), C.byref(K), C.byref(p), C.byref(k)))
+        self.S, self.K, self.p, self.k = S.value, K.value, p.value, k.value
+        mode, hess = np.empty(self.S), np.empty((self.S, self.S), order="F")
+        conv, nfn, ngr = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.bgp_fit_get_opt(self._h, dptr(mode), dptr(hess), C.byref(conv), C.byref(nfn), C.byref(ngr)))
+        self.optresults = {"mode": mode, "hessian": np.array(hess), "convergence": conv.value, "ff": ff,
+                           "fn_count": nfn.value, "gr_count": ngr.value}
+        nodes = np.empty((self.K, self.S), order="F")
+        w, lp, lpn = np.empty(self.K), np.empty(self.K), np.empty(self.K)
+        lnc = C.c_double()
+        check(self._lib.bgp_fit_get_grid(self._h, dptr(nodes), dptr(w), dptr(lp), dptr(lpn), C.byref(lnc)))
+        self.normalized_posterior = {"nodesandweights": {"theta": np.array(nodes), "weights": w, "logpost": lp,
+                                                         "logpost_normalized": lpn},
+                                     "lognormconst": lnc.value, "grid": {"level": self.k}}
+        self.marginals = []
+        for j in range(self.S):
+            th, lm, ww = np.empty(self.k), np.empty(self.k), np.empty(self.k)
+            check(self._lib.bgp_fit_get_marginal(self._h, j, dptr(th), dptr(lm), dptr(ww)))
+            self.marginals.append({"theta": th, "logmargpost": lm, "w": ww})
+        self._modes = None
+        self._Hs = None
+
+    @property
+    def lognormconst(self):
+        return self.normalized_posterior["lognormconst"]
+
+    @property
+    def modesandhessians(self):
+        if self._modes is None:
+            modes = np.empty((self.K, self.p))
+            Hs = np.empty((self.K, self.p, self.p))
+            check(self._lib.bgp_fit_get_modes(self._h, dptr(modes), dptr(Hs)))
+            self._modes, self._Hs = modes, Hs
+        return {"theta": self.normalized_posterior["nodesandweights"]["theta"], "mode": self._modes, "H": self._Hs}
+
+    def theta_moments(self):
+        nw = self.normalized_posterior["nodesandweights"]
+        lam = nw["weights"] * np.exp(nw["logpost_normalized"])
+        mean = lam @ nw["theta"]
+        return mean, np.sqrt(lam @ (nw["theta"] - mean[None, :]) ** 2)
+
+    def close(self):
+        if self._h:
+            self._lib.bgp_fit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def marginal_laplace_tmb(ff: LaplaceObjective, k: int, startingvalue, optresults=None) -> AGHQ:
+    """aghq::marginal_laplace_tmb(ff, k, startingvalue)  (R/02_model_fit.R:284)."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    if optresults is None:
+        th0 = fvec(startingvalue)
+        check(lib.bgp_aghq_fit(ff._h, int(k), dptr(th0), C.byref(h)))
+    else:
+        mode = fvec(optresults["mode"])
+        hess = fmat(np.atleast_2d(optresults["hessian"]))
+        check(lib.bgp_aghq_fit_at(ff._h, int(k), dptr(mode), dptr(hess), C.byref(h)))
+    return AGHQ(ff, h)
+
+
+def sample_marginal(quad: AGHQ, M: int, Z=None, node_idx=None, seed: int = 0):
+    """aghq::sample_marginal(quad, M)  (R/02_model_fit.R:687-689).  Returns ``{"samps": p x M,
+    "theta": M x S, "node": M}``.  Pass (Z, node_idx) to fix the random inputs."""
+    lib = _lib.load()
+    samps = np.empty((quad.p, M), order="F")
+    if Z is not None:
+        Zf = fmat(Z)
+        idx = np.ascontiguousarray(node_idx, dtype=np.int32)
+        check(lib.bgp_sample(quad._h, M, dptr(Zf), idx.ctypes.data_as(_lib.c_int32_p), dptr(samps)))
+    else:
+        idx = np.empty(M, dtype=np.int32)
+        check(lib.bgp_sample_draw(quad._h, M, int(seed), dptr(samps), idx.ctypes.data_as(_lib.c_int32_p)))
+    theta = quad.normalized_posterior["nodesandweights"]["theta"][idx]
+    return {"samps": samps, "theta": theta, "node": idx}
+
+
+class FitResult:
+    """class(fit_result) <- "FitResult"  (R/02_model_fit.R:677-700)."""
+
+    def __init__(self, instances, mod, ff, boundary_samp_indexes, random_samp_indexes, fixed_samp_indexes, family,
+                 samps=None):
+        self.instances = instances
+        self.mod = mod
+        self.ff = ff
+        self.boundary_samp_indexes = boundary_samp_indexes
+        self.random_samp_indexes = random_samp_indexes
+        self.fixed_samp_indexes = fixed_samp_indexes
+        self.family = family
+        self.samps = samps
+
+    def close(self):
+        self.mod.close()
+        self.ff.close()
+
+
+def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]] = None, family="Gaussian", size=None,
+                    control_family=None, control_fixed=None, device=0):
+    """get_result_by_method up to MakeADFun (R/02_model_fit.R:1-183,249-282): returns (ff, index maps)."""
+    if family not in FAMILY_CODES:
+        raise ValueError("family %r is outside the B200 hot path (Gaussian / Poisson / Binomial / none)" % family)
+    fixed = fixed or {}
+    control_fixed = dict(control_fixed or {})
+    control_family = control_family or {"u": 1.0, "alpha": 0.5}
+    y = fvec(y)
+    n = len(y)
+    terms = [prepare_term(t) for t in terms]
+    ff = LaplaceObjective(y=y, family=family, size=size, device=device)
+    try:
+        for t in terms:
+            if t.kind == "IWP":
+                # random + boundary block generated on the device (blocks keep the order of the calls)
+                ff.add_iwp(t.x, t.initial_location, t.knots, t.order, t.u, t.alpha, t.boundary_prec, t.boundary_mean)
+            elif t.kind == "sGP":
+                B, X = sgp_design(t)
+                P = sgp_precision(t)
+                ff.add_random(B, P, float(np.linalg.slogdet(P)[1]), t.u, t.alpha)
+                ff.add_boundary(X, t.boundary_prec, t.boundary_mean)
+            else:
+                B, Pd = iid_design(t)
+                ff.add_random(B, Pd, 0.0, t.u, t.alpha)
+        names = ["intercept"] + list(fixed)
+        ff.add_fixed(np.ones(n), control_fixed.get("intercept", {}).get("prec", 0.01),
+                     control_fixed.get("intercept", {}).get("mean", 0.0))
+        for nm, col in fixed.items():
+            cf = control_fixed.get(nm, {})
+            ff.add_fixed(np.asarray(col, dtype=np.float64), cf.get("prec", 0.01), cf.get("mean", 0.0))
+        if FAMILY_CODES[family] == 0:
+            ff.set_noise_prior(control_family.get("u", 1.0), control_family.get("alpha", 0.5))
+        ff.finalize()
+    except Exception:
+        ff.close()
+        raise
+    # index maps (R/02_model_fit.R:627-675), 0-based
+    rand_idx, bnd_idx, fix_idx = {}, {}, {}
+    o = 0
+    for t in terms:
+        rand_idx[t.name] = np.arange(o, o + t.n_basis)
+        o += t.n_basis
+    for t in terms:
+        if t.kind in ("IWP", "sGP"):
+            bnd_idx[t.name] = np.arange(o, o + t.n_boundary)
+            o += t.n_boundary
+    for nm in names:
+        fix_idx[nm] = o
+        o += 1
+    assert o == ff.p, (o, ff.p)
+    return ff, terms, rand_idx, bnd_idx, fix_idx
+
+
+def model_fit(y, terms: List[Term], fixed=None, method="aghq", family="Gaussian", control_family=None,
+              control_fixed=None, aghq_k=4, size=None, M=3000, device=0, Z=None, node_idx=None, seed=0,
+              optresults=None) -> FitResult:
+    """model_fit(formula, data, method = "aghq", family, ..., aghq_k = 4, M = 3000)."""
+    if method != "aghq":
+        raise ValueError("only method = 'aghq' is on the B200 hot path (nlminb / MCMC stay in R)")
+    ff, terms, rand_idx, bnd_idx, fix_idx = build_objective(y, terms, fixed, family, size, control_family,
+                                                            control_fixed, device)
+    if ff.S == 0:
+        ff.close()
+        raise ValueError("For model with no hyper-parameter, the method cannot be aghq or MCMC.")
+    mod = marginal_laplace_tmb(ff, aghq_k, np.zeros(ff.S), optresults)
+    res = FitResult(terms, mod, ff, bnd_idx, rand_idx, fix_idx, family)
+    if M:
+        res.samps = sample_marginal(mod, M, Z, node_idx, seed)
+    return res
+
+
+def sample_fixed_effect(model_fit_result: FitResult, variables):
+    """R/03_post_fit.R:159-165."""
+    samps = model_fit_result.samps["samps"]
+    return samps[[model_fit_result.fixed_samp_indexes[v] for v in variables], :].T
+
+
+def compute_post_fun_IWP(samps, global_samps=None, knots=None, refined_x=None, p=None, degree=0, intercept_samps=None,
+                         level=0.95, only_samples=False, device=0):
+    """R/03_post_fit.R:200-241 fused with extract_mean_interval_given_samps (:287-296)."""
+    lib = _lib.load()
+    samps = fmat(samps)
+    M = samps.shape[1]
+    if p <= degree:
+        print("Error: The degree of derivative to compute is not defined. Should consider higher order smoothing "
+              "model or lower order of the derivative degree.")
+        return None
+    if global_samps is not None and np.asarray(global_samps).reshape(-1, M).shape[0] != p - 1:
+        print("Error: Incorrect dimension of global_samps. Check whether the choice of p is consistent with the "
+              "fitted model.")
+        return None
+    gs = None if global_samps is None or p == 1 else fmat(np.asarray(global_samps).reshape(-1, M))
+    ic = None if intercept_samps is None else fvec(intercept_samps)
+    x = fvec(refined_x)
+    G = len(x)
+    kn = fvec(knots)
+    mean, lo, hi = np.empty(G), np.empty(G), np.empty(G)
+    F = np.empty((G, M), order="F") if only_samples else None
+    check(lib.bgp_predict_iwp(dptr(samps), dptr(gs), dptr(ic), M, dptr(kn), len(kn), int(p), int(degree), dptr(x), G,
+                              float(level), device, dptr(mean), dptr(lo), dptr(hi), dptr(F)))
+    out = {"x": x, "plower": lo, "pupper": hi, "mean": mean}
+    if only_samples:
+        out["samples"] = F
+    return out
+
+
+def compute_post_fun_sGP(samps, global_samps=None, k=None, refined_x=None, a=None, region=None, boundary=True, m=1,
+                         intercept_samps=None, level=0.95, only_samples=False, device=0):
+    """R/03_post_fit.R:261-276 fused with extract_mean_interval_given_samps."""
+    lib = _lib.load()
+    samps = fmat(samps)
+    M = samps.shape[1]
+    gs = None if global_samps is None else fmat(np.asarray(global_samps).reshape(-1, M))
+    ic = None if intercept_samps is None else fvec(intercept_samps)
+    x = fvec(refined_x)
+    G = len(x)
+    reg = fvec(region)
+    mean, lo, hi = np.empty(G), np.empty(G), np.empty(G)
+    F = np.empty((G, M), order="F") if only_samples else None
+    check(lib.bgp_predict_sgp(dptr(samps), dptr(gs), dptr(ic), M, float(a), int(k), int(m), dptr(reg), int(boundary),
+                              dptr(x), G, float(level), device, dptr(mean), dptr(lo), dptr(hi), dptr(F)))
+    out = {"x": x, "plower": lo, "pupper": hi, "mean": mean}
+    if only_samples:
+        out["samples"] = F
+    return out
+
+
+def predict(object: FitResult, newdata=None, variable=None, degree=0, include_intercept=True, only_samples=False,
+            level=0.95):
+    """predict.FitResult(object, newdata, variable, degree, include.intercept, only.samples)."""
+    names = list(object.random_samp_indexes)
+    if names.count(variable) == 0:
+        raise ValueError("The specified variable cannot be found in the fitted model, please check the name.")
+    samps = object.samps["samps"]
+    term = next(t for t in object.instances if t.name == variable)
+    global_samps = samps[object.boundary_samp_indexes[variable], :] if variable in object.boundary_samp_indexes else None
+    coefsamps = samps[object.random_samp_indexes[variable], :]
+    if newdata is None:
+        refined_x = term.observed_x
+    else:
+        refined_x = np.sort(np.asarray(newdata, dtype=np.float64) - term.initial_location)
+    intercept = samps[object.fixed_samp_indexes["intercept"], :] if include_intercept else None
+    dev = object.ff.device
+    if term.kind == "IWP":
+        f = compute_post_fun_IWP(coefsamps, global_samps, term.knots, refined_x, term.order, degree, intercept, level,
+                                 only_samples, dev)
+    elif term.kind == "sGP":
+        f = compute_post_fun_sGP(coefsamps, global_samps, term.k, refined_x, term.a, term.region, term.boundary,
+                                 term.m, intercept, level, only_samples, dev)
+    else:
+        raise ValueError("predict supports IWP and sGP terms")
+    if f is None:
+        return None
+    f["x"] = f["x"] + term.initial_location
+    return f

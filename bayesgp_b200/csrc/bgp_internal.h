@@ -142,6 +142,25 @@ struct bgp_model {
   std::vector<int> marks;
 };
 
+struct bgp_fit {
+  bgp_model* model = nullptr;
+  int S = 0, K = 0, p = 0, k = 0;
+  std::vector<double> mode, hessian;   // S, S*S (column-major)
+  int convergence = 0, fn_count = 0, gr_count = 0;
+  std::vector<double> nodes;           // K x S column-major
+  std::vector<double> weights, logpost, logpost_norm;
+  double lognormconst = 0.0;
+  std::vector<double> modes;           // p x K
+  std::vector<double> Hs;              // p x p x K
+  std::vector<std::vector<double>> marg_theta, marg_lmp, marg_w;
+  // device residents for sampling / prediction (sample.cu)
+  double* samps_dev = nullptr;         // p x M column-major
+  int64_t samps_M = 0;
+  double* Linv_dev = nullptr;          // p x ldl scratch (L^-1 and its transpose)
+  double* LinvT_dev = nullptr;
+  double* mode_dev = nullptr;
+};
+
 namespace bgp {
 enum { PH_OTHER = 0, PH_LIK = 1, PH_HESS = 2, PH_CHOL = 3 };
 void phase_mark(bgp_model* m, int phase);
@@ -174,6 +193,16 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
 // grad.cu: d/dtheta of the Laplace objective at the mode left on the device by laplace_inner
 int laplace_gradient(bgp_model* m, const double* theta, double* grad_host);
 void grad_plan_destroy(bgp_model* m);
+
+// kgemm.cu: C[m][n] = bias[m] + sum_k A[m][k] B[n][k]  (both operands K-major, row pitch multiple of 2 doubles)
+//   out_col_major: out[n' * ldc + m] with n' = col_perm ? col_perm[n] : n ; else out[m * ldc + n]
+int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64_t N, int64_t ldb, int K,
+                 const double* bias, double* out, int64_t ldc, bool out_col_major, const int32_t* col_perm,
+                 cudaStream_t st);
+// grad.cu: L^-1 (row-major, lower) and optionally its transpose (row-major, upper) from m->L
+int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT);
+// sample.cu
+void fit_release_device(bgp_fit* f);
 
 // comm.cpp
 int comm_unique_id(void* id128);

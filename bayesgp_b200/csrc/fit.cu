@@ -1,0 +1,565 @@
+// fit.cu — the outer AGHQ inference: replaces aghq::marginal_laplace_tmb(ff, k, startingvalue)
+// (call site /root/reference/R/02_model_fit.R:284) and the objects BayesGP reads from its result
+// (SURVEY.md section 8b).  Host C++ drives the device Laplace objective:
+//   optimize_theta  -> stats::optim(method = "BFGS") == vmmin()                   (Appendix A.2)
+//   ff$he           -> numDeriv::jacobian(ff$gr, .), Richardson, R/02_model_fit.R:283 (A.3)
+//   normalize_logpost -> mvQuad "GHe" product grid rescaled by chol(H^-1)          (A.4)
+//   marginals ("reuse"), per-node modes and Hessians                               (A.5)
+#include <algorithm>
+#include <functional>
+#include <limits>
+
+#include "bgp_internal.h"
+
+namespace bgp {
+
+void fit_release_device(bgp_fit* f);
+
+// ---- ff$fn / ff$gr with TMB's "same theta => reuse the inner optimum" behaviour ---------------------
+struct FF {
+  bgp_model* m;
+  int n_fn = 0, n_gr = 0;
+  std::vector<double> last_theta;
+  bool have = false;
+  double last_value = NAN;
+
+  int ensure(const double* theta, double* value) {
+    const int S = m->S;
+    if (have && (int)last_theta.size() == S && std::equal(theta, theta + S, last_theta.begin())) {
+      *value = last_value;
+      return BGP_OK;
+    }
+    int iters = 0;
+    int st = laplace_inner(m, theta, value, &iters);
+    if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
+    if (st != BGP_OK) {
+      *value = NAN;          // inner failure => NaN, the optimiser backtracks (R_FINITE test)
+      have = false;
+      return BGP_OK;
+    }
+    last_theta.assign(theta, theta + S);
+    last_value = *value;
+    have = true;
+    return BGP_OK;
+  }
+  int fn(const double* theta, double* value) {
+    ++n_fn;
+    return ensure(theta, value);
+  }
+  int gr(const double* theta, double* g) {
+    ++n_gr;
+    double v;
+    BGP_TRY(ensure(theta, &v));
+    if (!std::isfinite(v)) {
+      for (int i = 0; i < m->S; ++i) g[i] = NAN;
+      return BGP_OK;
+    }
+    return laplace_gradient(m, theta, g);
+  }
+};
+
+// ---- stats::optim(method = "BFGS"): vmmin() of R's optim.c (A.2) ---------------------------------------
+static int vmmin(FF& ff, std::vector<double>& b, double* Fmin_out, int* fail, int maxit = 100) {
+  const double stepredn = 0.2, acctol = 1e-4, reltest = 10.0, abstol = -std::numeric_limits<double>::infinity();
+  const double reltol = std::sqrt(std::numeric_limits<double>::epsilon());
+  const int n = (int)b.size();
+  std::vector<double> g(n), t(n), X(n), c(n), B((size_t)n * n, 0.0);
+  double f;
+  BGP_TRY(ff.fn(b.data(), &f));
+  if (!std::isfinite(f)) {
+    set_error("initial value in 'vmmin' is not finite");
+    return BGP_ERR_NONFINITE;
+  }
+  double Fmin = f;
+  int funcount = 1, gradcount = 1, iter = 1, count = 0;
+  BGP_TRY(ff.gr(b.data(), g.data()));
+  int ilast = gradcount;
+  do {
+    if (ilast == gradcount)
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) B[(size_t)i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int i = 0; i < n; ++i) {
+      X[i] = b[i];
+      c[i] = g[i];
+    }
+    double gradproj = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s -= B[(size_t)i * n + j] * c[j];
+      t[i] = s;
+      gradproj += s * c[i];
+    }
+    if (gradproj < 0.0) {
+      double steplength = 1.0;
+      bool accpoint = false;
+      do {
+        count = 0;
+        for (int i = 0; i < n; ++i) {
+          b[i] = X[i] + steplength * t[i];
+          if (reltest + X[i] == reltest + b[i]) ++count;
+        }
+        if (count < n) {
+          BGP_TRY(ff.fn(b.data(), &f));
+          ++funcount;
+          accpoint = std::isfinite(f) && (f <= Fmin + gradproj * steplength * acctol);
+          if (!accpoint) steplength *= stepredn;
+        }
+      } while (!(count == n || accpoint));
+      const bool enough = (f > abstol) && std::fabs(f - Fmin) > reltol * (std::fabs(Fmin) + reltol);
+      if (!enough) {
+        count = n;
+        Fmin = f;
+      }
+      if (count < n) {
+        Fmin = f;
+        BGP_TRY(ff.gr(b.data(), g.data()));
+        ++gradcount;
+        ++iter;
+        double D1 = 0.0;
+        for (int i = 0; i < n; ++i) {
+          t[i] = steplength * t[i];
+          c[i] = g[i] - c[i];
+          D1 += t[i] * c[i];
+        }
+        if (D1 > 0) {
+          double D2 = 0.0;
+          for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s += B[(size_t)i * n + j] * c[j];
+            X[i] = s;
+            D2 += s * c[i];
+          }
+          D2 = 1.0 + D2 / D1;
+          for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j)
+              B[(size_t)i * n + j] += (D2 * t[i] * t[j] - X[i] * c[j] - t[i] * X[j]) / D1;
+        } else {
+          ilast = gradcount;
+        }
+      } else {
+        if (ilast < gradcount) {
+          count = 0;
+          ilast = gradcount;
+        }
+      }
+    } else {
+      count = 0;
+      if (ilast == gradcount) count = n;
+      else ilast = gradcount;
+    }
+    if (iter >= maxit) break;
+    if (gradcount - ilast > 2 * n) ilast = gradcount;
+  } while (count != n || ilast != gradcount);
+  *Fmin_out = Fmin;
+  *fail = iter < maxit ? 0 : 1;
+  return BGP_OK;
+}
+
+// ---- numDeriv::jacobian(ff$gr, theta), method "Richardson" (A.3) ------------------------------------------
+static int richardson_jacobian(FF& ff, const std::vector<double>& x, std::vector<double>& J /* S x S col-major */) {
+  const int n = (int)x.size(), r = 4;
+  const double d = 1e-4, eps = 1e-4, v = 2.0;
+  const double zero_tol = std::sqrt(std::numeric_limits<double>::epsilon() / 7e-7);
+  std::vector<double> f0(n), h(n), gp(n), gm(n), xx(x);
+  BGP_TRY(ff.gr(x.data(), f0.data()));
+  for (int i = 0; i < n; ++i) h[i] = std::fabs(d * x[i]) + eps * (std::fabs(x[i]) < zero_tol ? 1.0 : 0.0);
+  // a[k][row][col]
+  std::vector<double> a((size_t)r * n * n, 0.0);
+  for (int k = 0; k < r; ++k) {
+    for (int i = 0; i < n; ++i) {
+      xx = x;
+      xx[i] = x[i] + h[i];
+      BGP_TRY(ff.gr(xx.data(), gp.data()));
+      xx[i] = x[i] - h[i];
+      BGP_TRY(ff.gr(xx.data(), gm.data()));
+      for (int row = 0; row < n; ++row) a[((size_t)k * n + row) * n + i] = (gp[row] - gm[row]) / (2.0 * h[i]);
+    }
+    for (int i = 0; i < n; ++i) h[i] /= v;
+  }
+  int rows = r;
+  for (int mm = 1; mm < r; ++mm) {
+    const double f4 = std::pow(4.0, mm);
+    for (int k = 0; k + 1 < rows; ++k)
+      for (int e = 0; e < n * n; ++e)
+        a[(size_t)k * n * n + e] = (a[(size_t)(k + 1) * n * n + e] * f4 - a[(size_t)k * n * n + e]) / (f4 - 1.0);
+    --rows;
+  }
+  J.assign((size_t)n * n, 0.0);
+  for (int row = 0; row < n; ++row)
+    for (int col = 0; col < n; ++col) J[(size_t)col * n + row] = a[(size_t)row * n + col];
+  return BGP_OK;
+}
+
+// ---- Gauss-Hermite ("GHe": probabilists' nodes, weights that integrate g(z) dz) (A.4) ----------------------
+static void gh_rule(int k, std::vector<double>& z, std::vector<double>& w) {
+  // Golub-Welsch on the Jacobi matrix of He_k (off-diagonals sqrt(i)), Jacobi rotations, then Newton polish
+  std::vector<double> A((size_t)k * k, 0.0);
+  for (int i = 0; i + 1 < k; ++i) A[(size_t)i * k + i + 1] = A[(size_t)(i + 1) * k + i] = std::sqrt((double)(i + 1));
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < k; ++i)
+      for (int j = i + 1; j < k; ++j) off += A[(size_t)i * k + j] * A[(size_t)i * k + j];
+    if (off < 1e-30) break;
+    for (int pI = 0; pI < k; ++pI)
+      for (int q = pI + 1; q < k; ++q) {
+        const double apq = A[(size_t)pI * k + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double th = (A[(size_t)q * k + q] - A[(size_t)pI * k + pI]) / (2.0 * apq);
+        const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int r = 0; r < k; ++r) {
+          const double arp = A[(size_t)r * k + pI], arq = A[(size_t)r * k + q];
+          A[(size_t)r * k + pI] = c * arp - s * arq;
+          A[(size_t)r * k + q] = s * arp + c * arq;
+        }
+        for (int r = 0; r < k; ++r) {
+          const double apr = A[(size_t)pI * k + r], aqr = A[(size_t)q * k + r];
+          A[(size_t)pI * k + r] = c * apr - s * aqr;
+          A[(size_t)q * k + r] = s * apr + c * aqr;
+        }
+      }
+  }
+  z.resize(k);
+  for (int i = 0; i < k; ++i) z[i] = A[(size_t)i * k + i];
+  std::sort(z.begin(), z.end());
+  auto he = [&](double x, double& hk, double& hkm1) {   // He_k(x), He_{k-1}(x)
+    double p0 = 1.0, p1 = x;
+    if (k == 0) {
+      hk = 1.0;
+      hkm1 = 0.0;
+      return;
+    }
+    for (int j = 1; j < k; ++j) {
+      const double p2 = x * p1 - j * p0;
+      p0 = p1;
+      p1 = p2;
+    }
+    hk = p1;
+    hkm1 = p0;
+  };
+  for (int i = 0; i < k; ++i)
+    for (int itn = 0; itn < 3; ++itn) {
+      double hk, hkm1;
+      he(z[i], hk, hkm1);
+      z[i] -= hk / (k * hkm1);     // He_k' = k He_{k-1}
+    }
+  for (int i = 0; i < k; ++i) {   // exact symmetry
+    const double a = 0.5 * (z[i] - z[k - 1 - i]);
+    z[i] = a;
+  }
+  for (int i = 0; i < k / 2; ++i) z[k - 1 - i] = -z[i];
+  if (k % 2 == 1) z[k / 2] = 0.0;
+  double kfact = 1.0;
+  for (int j = 2; j <= k; ++j) kfact *= j;
+  w.resize(k);
+  for (int i = 0; i < k; ++i) {
+    double hk, hkm1;
+    he(z[i], hk, hkm1);
+    const double wn = kfact * std::sqrt(2.0 * M_PI) / ((double)k * k * hkm1 * hkm1);   // weight for exp(-z^2/2)
+    w[i] = wn * std::exp(0.5 * z[i] * z[i]);
+  }
+}
+
+static bool chol_lower(std::vector<double>& A, int n) {   // column-major in place, lower
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)k * n + j] * A[(size_t)k * n + j];
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[(size_t)j * n + i];
+      for (int k = 0; k < j; ++k) s -= A[(size_t)k * n + i] * A[(size_t)k * n + j];
+      A[(size_t)j * n + i] = s / d;
+    }
+    for (int i = 0; i < j; ++i) A[(size_t)j * n + i] = 0.0;
+  }
+  return true;
+}
+
+static bool invert_general(const std::vector<double>& Ain, int n, std::vector<double>& inv) {  // Gauss-Jordan, col-major
+  std::vector<double> A(Ain);
+  inv.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(A[(size_t)c * n + r]) > std::fabs(A[(size_t)c * n + piv])) piv = r;
+    if (std::fabs(A[(size_t)c * n + piv]) == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < n; ++j) {
+        std::swap(A[(size_t)j * n + c], A[(size_t)j * n + piv]);
+        std::swap(inv[(size_t)j * n + c], inv[(size_t)j * n + piv]);
+      }
+    const double d = A[(size_t)c * n + c];
+    for (int j = 0; j < n; ++j) {
+      A[(size_t)j * n + c] /= d;
+      inv[(size_t)j * n + c] /= d;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = A[(size_t)c * n + r];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) {
+        A[(size_t)j * n + r] -= f * A[(size_t)j * n + c];
+        inv[(size_t)j * n + r] -= f * inv[(size_t)j * n + c];
+      }
+    }
+  }
+  return true;
+}
+
+static double logsumexp(const std::vector<double>& v) {
+  double mx = -std::numeric_limits<double>::infinity();
+  for (double x : v) mx = std::max(mx, x);
+  if (!std::isfinite(mx)) return mx;
+  double s = 0.0;
+  for (double x : v) s += std::exp(x - mx);
+  return mx + std::log(s);
+}
+
+// mvQuad::rescale(grid, m = mode, C = forceSymmetric(solve(H)), dec.type = 2) for the coordinate order `ord`
+static int rescaled_grid(const std::vector<double>& mode, const std::vector<double>& hess, int S, int k,
+                         const std::vector<int>& ord, std::vector<double>& nodes /* K x S col-major */,
+                         std::vector<double>& weights, double* L00) {
+  std::vector<double> C;
+  if (!invert_general(hess, S, C)) {
+    set_error("theta Hessian is singular");
+    return BGP_ERR_NOT_PD;
+  }
+  for (int i = 0; i < S; ++i)           // forceSymmetric keeps the upper triangle
+    for (int j = i + 1; j < S; ++j) C[(size_t)i * S + j] = C[(size_t)j * S + i];
+  std::vector<double> Cp((size_t)S * S);
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < S; ++j) Cp[(size_t)j * S + i] = C[(size_t)ord[j] * S + ord[i]];
+  if (!chol_lower(Cp, S)) {
+    set_error("inverse theta Hessian is not positive definite (quadrature cannot be centred)");
+    return BGP_ERR_NOT_PD;
+  }
+  std::vector<double> z, w;
+  gh_rule(k, z, w);
+  int K = 1;
+  for (int i = 0; i < S; ++i) K *= k;
+  nodes.assign((size_t)K * S, 0.0);
+  weights.assign(K, 0.0);
+  double detL = 1.0;
+  for (int i = 0; i < S; ++i) detL *= Cp[(size_t)i * S + i];
+  std::vector<int> idx(S);
+  std::vector<double> zz(S);
+  for (int j = 0; j < K; ++j) {
+    int r = j;
+    double wprod = 1.0;
+    for (int d = 0; d < S; ++d) {       // first coordinate fastest (expand.grid)
+      idx[d] = r % k;
+      r /= k;
+      zz[d] = z[idx[d]];
+      wprod *= w[idx[d]];
+    }
+    for (int a = 0; a < S; ++a) {
+      double s = mode[ord[a]];
+      for (int b = 0; b <= a; ++b) s += Cp[(size_t)b * S + a] * zz[b];
+      nodes[(size_t)ord[a] * K + j] = s;
+    }
+    weights[j] = wprod * detL;
+  }
+  *L00 = Cp[0];
+  return BGP_OK;
+}
+
+static int fit_core(bgp_model* m, int k, const double* theta0, const double* mode_in, const double* hess_in,
+                    bgp_fit** out) {
+  const int S = m->S, p = m->p;
+  if (S < 1) {
+    set_error("For model with no hyper-parameter, the method cannot be aghq");   // R/02_model_fit.R:253-255
+    return BGP_ERR_ARG;
+  }
+  if (k < 1 || k > 64) {
+    set_error("aghq_k must be in 1..64");
+    return BGP_ERR_ARG;
+  }
+  bgp_fit* f = new bgp_fit();
+  f->model = m;
+  f->S = S;
+  f->p = p;
+  f->k = k;
+  FF ff{m};
+  auto fail = [&](int code) {
+    delete f;
+    return code;
+  };
+  f->mode.assign(S, 0.0);
+  if (mode_in) {
+    f->mode.assign(mode_in, mode_in + S);
+  } else {
+    for (int i = 0; i < S; ++i) f->mode[i] = theta0 ? theta0[i] : 0.0;
+    double Fmin;
+    int st = vmmin(ff, f->mode, &Fmin, &f->convergence);
+    if (st != BGP_OK) return fail(st);
+  }
+  if (hess_in) {
+    f->hessian.assign(hess_in, hess_in + (size_t)S * S);
+  } else {
+    int st = richardson_jacobian(ff, f->mode, f->hessian);
+    if (st != BGP_OK) return fail(st);
+  }
+  std::vector<int> ord(S);
+  for (int i = 0; i < S; ++i) ord[i] = i;
+  double L00 = 1.0;
+  int st = rescaled_grid(f->mode, f->hessian, S, k, ord, f->nodes, f->weights, &L00);
+  if (st != BGP_OK) return fail(st);
+  const int K = (int)f->weights.size();
+  f->K = K;
+  f->logpost.assign(K, 0.0);
+  f->modes.assign((size_t)p * K, 0.0);
+  f->Hs.assign((size_t)p * p * K, 0.0);
+  std::vector<double> th(S);
+  auto eval_grid = [&](const std::vector<double>& nodes, std::vector<double>& lp, bool keep) -> int {
+    for (int j = 0; j < K; ++j) {
+      for (int a = 0; a < S; ++a) th[a] = nodes[(size_t)a * K + j];
+      double v;
+      BGP_TRY(ff.fn(th.data(), &v));
+      lp[j] = -v;
+      if (keep && std::isfinite(v)) {
+        // mode_j = last.par[random], H_j = spHess(last.par, random = TRUE)   (A.5)
+        BGP_CUDA(cudaMemcpyAsync(&f->modes[(size_t)j * p], m->Wmode, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost,
+                                 m->stream));
+        BGP_CUDA(cudaMemcpy2DAsync(&f->Hs[(size_t)j * p * p], (size_t)p * sizeof(double), m->H,
+                                   (size_t)m->ldh * sizeof(double), (size_t)p * sizeof(double), p,
+                                   cudaMemcpyDeviceToHost, m->stream));
+        BGP_CUDA(cudaStreamSynchronize(m->stream));
+      }
+    }
+    return BGP_OK;
+  };
+  st = eval_grid(f->nodes, f->logpost, true);
+  if (st != BGP_OK) return fail(st);
+  {
+    std::vector<double> t(K);
+    for (int j = 0; j < K; ++j) t[j] = f->logpost[j] + std::log(f->weights[j]);
+    f->lognormconst = logsumexp(t);
+  }
+  f->logpost_norm.resize(K);
+  for (int j = 0; j < K; ++j) f->logpost_norm[j] = f->logpost[j] - f->lognormconst;
+  // marginals, method "reuse" (A.5)
+  std::vector<double> z1, w1;
+  gh_rule(k, z1, w1);
+  f->marg_theta.resize(S);
+  f->marg_lmp.resize(S);
+  f->marg_w.resize(S);
+  for (int j = 0; j < S; ++j) {
+    std::vector<double> nodes_j, weights_j, lpn_j(K);
+    double l00 = L00;
+    if (j == 0) {
+      weights_j = f->weights;
+      lpn_j = f->logpost_norm;
+    } else {
+      std::vector<int> o2;
+      o2.push_back(j);
+      for (int i = 0; i < S; ++i)
+        if (i != j) o2.push_back(i);
+      st = rescaled_grid(f->mode, f->hessian, S, k, o2, nodes_j, weights_j, &l00);
+      if (st != BGP_OK) return fail(st);
+      std::vector<double> lp(K);
+      st = eval_grid(nodes_j, lp, false);
+      if (st != BGP_OK) return fail(st);
+      std::vector<double> t(K);
+      for (int q = 0; q < K; ++q) t[q] = lp[q] + std::log(weights_j[q]);
+      const double lnc = logsumexp(t);
+      for (int q = 0; q < K; ++q) lpn_j[q] = lp[q] - lnc;
+    }
+    f->marg_theta[j].resize(k);
+    f->marg_lmp[j].resize(k);
+    f->marg_w[j].resize(k);
+    for (int q = 0; q < k; ++q) {
+      std::vector<double> t;
+      for (int e = q; e < K; e += k) t.push_back(lpn_j[e] + std::log(weights_j[e]));   // first coordinate == q
+      f->marg_theta[j][q] = f->mode[j] + l00 * z1[q];
+      f->marg_w[j][q] = w1[q] * l00;
+      f->marg_lmp[j][q] = logsumexp(t) - std::log(f->marg_w[j][q]);
+    }
+  }
+  f->fn_count = ff.n_fn;
+  f->gr_count = ff.n_gr;
+  *out = f;
+  return BGP_OK;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+extern "C" {
+
+int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out) {
+  if (!m || !m->finalized || !out) {
+    set_error("bgp_aghq_fit: model not finalized / NULL output");
+    return BGP_ERR_STATE;
+  }
+  BGP_CUDA(cudaSetDevice(m->device));
+  return fit_core(m, k, theta0, nullptr, nullptr, out);
+}
+
+int bgp_aghq_fit_at(bgp_model* m, int k, const double* mode, const double* hessian, bgp_fit** out) {
+  if (!m || !m->finalized || !out || !mode || !hessian) {
+    set_error("bgp_aghq_fit_at: bad arguments");
+    return BGP_ERR_STATE;
+  }
+  BGP_CUDA(cudaSetDevice(m->device));
+  return fit_core(m, k, nullptr, mode, hessian, out);
+}
+
+void bgp_fit_destroy(bgp_fit* f) {
+  if (!f) return;
+  fit_release_device(f);
+  delete f;
+}
+
+int bgp_fit_dims(const bgp_fit* f, int* S, int* K, int* p, int* k) {
+  if (!f) return BGP_ERR_ARG;
+  if (S) *S = f->S;
+  if (K) *K = f->K;
+  if (p) *p = f->p;
+  if (k) *k = f->k;
+  return BGP_OK;
+}
+
+int bgp_fit_get_opt(const bgp_fit* f, double* mode, double* hessian, int* convergence, int* fn_count, int* gr_count) {
+  if (!f) return BGP_ERR_ARG;
+  if (mode) std::copy(f->mode.begin(), f->mode.end(), mode);
+  if (hessian) std::copy(f->hessian.begin(), f->hessian.end(), hessian);
+  if (convergence) *convergence = f->convergence;
+  if (fn_count) *fn_count = f->fn_count;
+  if (gr_count) *gr_count = f->gr_count;
+  return BGP_OK;
+}
+
+int bgp_fit_get_grid(const bgp_fit* f, double* nodes, double* weights, double* logpost, double* logpost_normalized,
+                     double* lognormconst) {
+  if (!f) return BGP_ERR_ARG;
+  if (nodes) std::copy(f->nodes.begin(), f->nodes.end(), nodes);
+  if (weights) std::copy(f->weights.begin(), f->weights.end(), weights);
+  if (logpost) std::copy(f->logpost.begin(), f->logpost.end(), logpost);
+  if (logpost_normalized) std::copy(f->logpost_norm.begin(), f->logpost_norm.end(), logpost_normalized);
+  if (lognormconst) *lognormconst = f->lognormconst;
+  return BGP_OK;
+}
+
+int bgp_fit_get_modes(const bgp_fit* f, double* modes, double* Hs) {
+  if (!f) return BGP_ERR_ARG;
+  if (modes) std::copy(f->modes.begin(), f->modes.end(), modes);
+  if (Hs) std::copy(f->Hs.begin(), f->Hs.end(), Hs);
+  return BGP_OK;
+}
+
+int bgp_fit_get_marginal(const bgp_fit* f, int j, double* theta, double* logmargpost, double* w) {
+  if (!f || j < 0 || j >= f->S) {
+    set_error("bgp_fit_get_marginal: index out of range");
+    return BGP_ERR_ARG;
+  }
+  if (theta) std::copy(f->marg_theta[j].begin(), f->marg_theta[j].end(), theta);
+  if (logmargpost) std::copy(f->marg_lmp[j].begin(), f->marg_lmp[j].end(), logmargpost);
+  if (w) std::copy(f->marg_w[j].begin(), f->marg_w[j].end(), w);
+  return BGP_OK;
+}
+
+}  // extern "C"

@@ -23,7 +23,7 @@ using namespace ptx;
 // ---- 1. triangular inverse ----------------------------------------------------------------------
 // L: p x ldh column-major lower; Linv: p x ldl row-major lower.
 __global__ void __launch_bounds__(32) trtri_diag_kernel(const double* __restrict__ L, int p, int ldh,
-                                                        double* __restrict__ Linv, int ldl) {
+                                                        double* __restrict__ Linv, int ldl, double* __restrict__ LinvT) {
   __shared__ double sD[32][33];
   __shared__ double sX[32][33];
   const int b0 = blockIdx.x * 32, c = threadIdx.x;
@@ -39,11 +39,16 @@ __global__ void __launch_bounds__(32) trtri_diag_kernel(const double* __restrict
   }
   __syncwarp();
   for (int i = 0; i < bn; ++i)
-    if (c < bn) Linv[(size_t)(b0 + i) * ldl + b0 + c] = (c <= i) ? sX[i][c] : 0.0;
+    if (c < bn) {
+      const double v = (c <= i) ? sX[i][c] : 0.0;
+      Linv[(size_t)(b0 + i) * ldl + b0 + c] = v;
+      if (LinvT) LinvT[(size_t)(b0 + c) * ldl + b0 + i] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256) trtri_offdiag_kernel(const double* __restrict__ L, int p, int ldh,
-                                                            double* __restrict__ Linv, int ldl) {
+                                                            double* __restrict__ Linv, int ldl,
+                                                            double* __restrict__ LinvT) {
   __shared__ double sL[32][33];
   __shared__ double sX[32][33];
   __shared__ double sA[32][33];
@@ -91,7 +96,10 @@ __global__ void __launch_bounds__(256) trtri_offdiag_kernel(const double* __rest
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int gj = cb * 32 + oj + e;
-      if (gi < p && gj < p) Linv[(size_t)gi * ldl + gj] = -out[e];
+      if (gi < p && gj < p) {
+        Linv[(size_t)gi * ldl + gj] = -out[e];
+        if (LinvT) LinvT[(size_t)gj * ldl + gi] = -out[e];
+      }
     }
   }
 }
@@ -229,6 +237,18 @@ __global__ void __launch_bounds__(LV_THREADS, 2)
   }
 }
 
+int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT) {
+  const int p = m->p, nb = (p + 31) / 32;
+  trtri_diag_kernel<<<nb, 32, 0, m->stream>>>(m->L, p, m->ldh, Linv, ldl, LinvT);
+  count_launch();
+  if (nb > 1) {
+    trtri_offdiag_kernel<<<nb - 1, 256, 0, m->stream>>>(m->L, p, m->ldh, Linv, ldl, LinvT);
+    count_launch();
+  }
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
 struct GradPlan {
   CUtensorMap tmA, tmL;
   std::vector<double> hLinv, hv, hw;
@@ -285,14 +305,7 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   // exact per-observation quantities at the mode (also fixes sumsq for the Gaussian noise theta)
   BGP_TRY(eval_fg_async(m, m->Wmode, theta, true));
   // 1. L^-1
-  const int nb = (p + 31) / 32;
-  trtri_diag_kernel<<<nb, 32, 0, m->stream>>>(m->L, p, m->ldh, m->Linv, ldl);
-  count_launch();
-  if (nb > 1) {
-    trtri_offdiag_kernel<<<nb - 1, 256, 0, m->stream>>>(m->L, p, m->ldh, m->Linv, ldl);
-    count_launch();
-  }
-  BGP_CUDA(cudaGetLastError());
+  BGP_TRY(launch_trtri(m, m->Linv, ldl, nullptr));
   // 2./3. leverage term v = A^T (c3 * q)
   std::fill(gp->hv.begin(), gp->hv.end(), 0.0);
   if (has_c3) {

@@ -1,0 +1,171 @@
+// kgemm.cu — FP64 tensor-pipe GEMM  C[m][n] = bias[m] + sum_k A[m][k] B[n][k]  (both operands K-major).
+//
+// This is the DGEMM-shaped kernel behind
+//   * posterior sampling     W = mode + chol(H)^-1 Z           (aghq::sample_marginal, call site
+//                                                               /root/reference/R/02_model_fit.R:687-689)
+//   * sample -> function     F = [X | B](x_new) [global; coef]   (compute_post_fun_IWP / _sGP,
+//                                                               /root/reference/R/03_post_fit.R:235, :272)
+// 128 x 64 CTA tile, 8 warps x (32 x 32) DMMA.8x8x4 accumulators, operands staged by TMA as
+// {16 k, rows} boxes with the 128-byte swizzle (3-stage mbarrier ring), conflict-free LDS.64 fragment
+// loads through a row permutation, C staged through shared memory for coalesced stores.
+#include "bgp_internal.h"
+#include "ptx.cuh"
+
+namespace bgp {
+
+using namespace ptx;
+
+constexpr int KG_TM = 128, KG_TN = 64, KG_KB = 16, KG_STAGES = 3, KG_THREADS = 256;
+constexpr int KG_A_BYTES = KG_TM * 128, KG_B_BYTES = KG_TN * 128, KG_STAGE_BYTES = KG_A_BYTES + KG_B_BYTES;
+constexpr int KG_CPITCH = KG_TN + 1;
+constexpr int KG_SMEM_PIPE = KG_STAGES * KG_STAGE_BYTES;                 // 73728
+constexpr int KG_SMEM_C = KG_TM * KG_CPITCH * 8;                         // 66560
+constexpr int KG_SMEM = (KG_SMEM_PIPE > KG_SMEM_C ? KG_SMEM_PIPE : KG_SMEM_C) + 64 + 1024;
+
+struct KgemmArgs {
+  int64_t M, N;
+  int K;
+  const double* bias;
+  double* out;
+  int64_t ldc;
+  int out_col_major;
+  const int32_t* col_perm;
+};
+
+__global__ void __launch_bounds__(KG_THREADS, 2)
+    kgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KgemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int pipe_c = KG_SMEM_PIPE > KG_SMEM_C ? KG_SMEM_PIPE : KG_SMEM_C;
+  const uint32_t bar_base = base + pipe_c;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int fj = lane >> 2, fk = lane & 3;
+  const int64_t m0 = (int64_t)blockIdx.x * KG_TM, n0 = (int64_t)blockIdx.y * KG_TN;
+  const int niter = (a.K + KG_KB - 1) / KG_KB;
+
+  if (tid == 0) {
+    for (int s = 0; s < KG_STAGES; ++s) mbar_init(bar_base + 8 * s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int it) {
+    const int s = it % KG_STAGES;
+    const uint32_t bar = bar_base + 8 * s, sa = base + s * KG_STAGE_BYTES;
+    mbar_expect_tx(bar, KG_STAGE_BYTES);
+    tma_load_2d(sa, &tmA, it * KG_KB, (int)m0, bar);
+    tma_load_2d(sa + KG_A_BYTES, &tmB, it * KG_KB, (int)n0, bar);
+  };
+  if (tid == 0)
+    for (int it = 0; it < KG_STAGES - 1 && it < niter; ++it) issue(it);
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  uint32_t a_off[4], b_off[4];
+  int a_sw[4], b_sw[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int ra = wm * 32 + 16 * (f >> 1) + 2 * fj + (f & 1);
+    const int rb = wn * 32 + 16 * (f >> 1) + 2 * fj + (f & 1);
+    a_off[f] = ra * 128;
+    a_sw[f] = ra & 7;
+    b_off[f] = KG_A_BYTES + rb * 128;
+    b_sw[f] = rb & 7;
+  }
+  for (int it = 0; it < niter; ++it) {
+    __syncthreads();
+    if (tid == 0 && it + KG_STAGES - 1 < niter) issue(it + KG_STAGES - 1);
+    const int s = it % KG_STAGES;
+    mbar_wait(bar_base + 8 * s, (uint32_t)((it / KG_STAGES) & 1));
+    const uint32_t sa = base + s * KG_STAGE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < KG_KB / 4; ++kk) {
+      const int chunk = 2 * kk + (fk >> 1);
+      const uint32_t lo = (fk & 1) * 8;
+      double af[4], bf[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        af[f] = lds64(sa + a_off[f] + ((chunk ^ a_sw[f]) << 4) + lo);
+        bf[f] = lds64(sa + b_off[f] + ((chunk ^ b_sw[f]) << 4) + lo);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+  }
+  // ---- epilogue: accumulators -> shared tile -> coalesced global stores -------------------------------
+  __syncthreads();
+  double* sC = reinterpret_cast<double*>(base_ptr);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = wm * 32 + 16 * (mi >> 1) + 2 * fj + (mi & 1);
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = wn * 32 + 16 * (ni >> 1) + 2 * (2 * fk + e) + (ni & 1);
+        sC[r * KG_CPITCH + c] = acc[mi][ni][e];
+      }
+  }
+  __syncthreads();
+  if (a.out_col_major) {
+    // out[n' * ldc + m]: consecutive threads walk m
+    for (int e = tid; e < KG_TM * KG_TN; e += KG_THREADS) {
+      const int r = e % KG_TM, c = e / KG_TM;
+      const int64_t m = m0 + r, n = n0 + c;
+      if (m < a.M && n < a.N) {
+        const int64_t nn = a.col_perm ? (int64_t)a.col_perm[n] : n;
+        a.out[nn * a.ldc + m] = sC[r * KG_CPITCH + c] + (a.bias ? a.bias[m] : 0.0);
+      }
+    }
+  } else {
+    for (int e = tid; e < KG_TM * KG_TN; e += KG_THREADS) {
+      const int r = e / KG_TN, c = e % KG_TN;
+      const int64_t m = m0 + r, n = n0 + c;
+      if (m < a.M && n < a.N) a.out[m * a.ldc + n] = sC[r * KG_CPITCH + c] + (a.bias ? a.bias[m] : 0.0);
+    }
+  }
+}
+
+int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64_t N, int64_t ldb, int K,
+                 const double* bias, double* out, int64_t ldc, bool out_col_major, const int32_t* col_perm,
+                 cudaStream_t st) {
+  if (M <= 0 || N <= 0) return BGP_OK;
+  if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
+    set_error("kgemm: operands must be 16-byte aligned with an even row pitch");
+    return BGP_ERR_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tensormap_f64(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 16, KG_TM) != 0 ||
+      make_tensormap_f64(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 16, KG_TN) != 0) {
+    set_error("cuTensorMapEncodeTiled failed in kgemm");
+    return BGP_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    BGP_CUDA(cudaFuncSetAttribute(kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KG_SMEM));
+    attr = true;
+  }
+  KgemmArgs a;
+  a.M = M;
+  a.N = N;
+  a.K = K;
+  a.bias = bias;
+  a.out = out;
+  a.ldc = ldc;
+  a.out_col_major = out_col_major ? 1 : 0;
+  a.col_perm = col_perm;
+  dim3 grid((unsigned)((M + KG_TM - 1) / KG_TM), (unsigned)((N + KG_TN - 1) / KG_TN));
+  kgemm_kernel<<<grid, KG_THREADS, KG_SMEM, st>>>(tmA, tmB, a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
+}  // namespace bgp

@@ -1,0 +1,561 @@
+// predict.cu — sample -> function evaluation and its summary.
+//
+// Replaces compute_post_fun_IWP (/root/reference/R/03_post_fit.R:200-241), compute_post_fun_sGP
+// (:261-276), extract_mean_interval_given_samps (:287-296, stats::quantile type 7) and the basis
+// evaluators they call (local_poly_helper / global_poly_helper / Compute_B_sB_helper /
+// global_poly_helper_sGP, /root/reference/R/01_utility.R:198-208,378-440).
+//
+//   F (G x M) = [X_deg(x) | B(x)] [global rows; coef]          fitted_samps_deriv, :235 / :272
+// is never materialised: rows are processed in strips; per strip the design rows are generated on
+// the device, multiplied on the FP64 tensor pipe (kgemm.cu) into an L2-sized scratch strip, and each
+// row is reduced to (mean, two type-7 quantiles) by an exact MSB radix select (one CTA per row).
+#include <algorithm>
+
+#include "basis_dev.cuh"
+#include "bgp_internal.h"
+
+namespace bgp {
+
+// ---- design rows -----------------------------------------------------------------------------------
+struct IwpDesignArgs {
+  const double* x;      // refined_x (already shifted by initial_location)
+  int64_t g0, rows;
+  const double* kneg;
+  int nneg;
+  const double* kpos;
+  int npos;
+  int order, degree;
+  double* D;            // rows x ld, row-major
+  int ld;
+};
+
+__global__ void iwp_design_kernel(const IwpDesignArgs a) {
+  const int64_t r = blockIdx.x;
+  if (r >= a.rows) return;
+  const double x = a.x[a.g0 + r];
+  const int q = a.order - a.degree;            // order of the basis after `degree` derivatives
+  const int nX = q;                            // global polynomial columns kept (R/03_post_fit.R:230-234)
+  const int nB = (a.nneg > 0 ? a.nneg - 1 : 0) + (a.npos > 0 ? a.npos - 1 : 0);
+  const double xn = x < 0.0 ? -x : 0.0, xp = x > 0.0 ? x : 0.0;
+  double* row = a.D + (size_t)r * a.ld;
+  for (int c = threadIdx.x; c < a.ld; c += blockDim.x) {
+    double v = 0.0;
+    if (c < nX) {
+      // column i = c + 1: x^(i-1) * (i + degree - 1)! / (i - 1)!
+      double f = 1.0;
+      for (int t = c + 1; t <= c + a.degree; ++t) f *= (double)t;
+      v = f * ipow(x, c);
+    } else if (c < nX + nB) {
+      int j = c - nX;
+      const int n1 = a.nneg > 0 ? a.nneg - 1 : 0;
+      if (j < n1) {
+        v = iwp_phi(xn, a.kneg[j], a.kneg[j + 1], q);
+      } else {
+        j -= n1;
+        v = iwp_phi(a.nneg > 0 ? xp : x, a.kpos[j], a.kpos[j + 1], q);
+      }
+    }
+    row[c] = v;
+  }
+}
+
+struct SgpDesignArgs {
+  const double* x;      // refined_x
+  int64_t g0, rows;
+  double x0;            // min(refined_x): Compute_B_sB_helper(initial_location = NULL) quirk
+  double a;
+  int k, m, boundary;
+  double lo, hi;
+  double* D;
+  int ld;
+};
+
+__global__ void sgp_design_kernel(const SgpDesignArgs a) {
+  const int64_t r = blockIdx.x;
+  if (r >= a.rows) return;
+  const double x = a.x[a.g0 + r] - a.x0;
+  const int nb = a.boundary ? a.k - 2 : a.k;
+  const int drop = a.boundary ? 2 : 0;
+  double* row = a.D + (size_t)r * a.ld;
+  int first = 0;
+  double v4[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool inside = x >= a.lo && x <= a.hi;
+  if (inside) bspline4(x, a.lo, a.hi, a.k - 2, first, v4);
+  const int nX = 1 + 2 * a.m;
+  for (int c = threadIdx.x; c < a.ld; c += blockDim.x) {
+    double v = 0.0;
+    if (c == 0) {
+      v = 1.0;
+    } else if (c < nX) {
+      const int i = (c - 1) / 2 + 1;
+      v = ((c - 1) & 1) ? sin(i * a.a * x) : cos(i * a.a * x);
+    } else if (c < nX + 3 * nb * a.m) {
+      const int e = c - nX;
+      const int harm = e / (3 * nb) + 1;
+      const int part = (e % (3 * nb)) / nb;          // 0: B cos, 1: B sin, 2: B
+      const int bi = (e % nb) + drop;                  // index in the full k-function basis
+      double bv = 0.0;
+      if (inside && bi >= first && bi < first + 4) bv = v4[bi - first];
+      if (part == 0) v = bv * cos(harm * a.a * x);
+      else if (part == 1) v = bv * sin(harm * a.a * x);
+      else v = bv;
+    }
+    row[c] = v;
+  }
+}
+
+// ---- coefficient matrix C[s][c] (M x ld, K-major) from R-layout sample blocks --------------------------
+struct CoefArgs {
+  const double* icpt;     // M or NULL
+  const double* glob;     // nglob x M column-major or NULL
+  int nglob;
+  const double* coef;     // ncoef x M column-major
+  int ncoef;
+  int skip;               // rows of rbind(icpt, glob) dropped from the top (= degree for IWP, 0 for sGP)
+  int nX;                 // rows of rbind(icpt, glob) kept
+  int64_t M;
+  double* C;
+  int ld;
+};
+
+__global__ void build_coef_kernel(const CoefArgs a) {
+  const int64_t s = blockIdx.x;
+  double* row = a.C + (size_t)s * a.ld;
+  for (int c = threadIdx.x; c < a.ld; c += blockDim.x) {
+    double v = 0.0;
+    if (c < a.nX) {
+      const int r = c + a.skip;          // row of rbind(intercept_samps, global_samps)
+      if (r == 0) v = a.icpt ? a.icpt[s] : 0.0;
+      else v = (a.glob && r - 1 < a.nglob) ? a.glob[(size_t)s * a.nglob + (r - 1)] : 0.0;
+    } else if (c < a.nX + a.ncoef) {
+      v = a.coef[(size_t)s * a.ncoef + (c - a.nX)];
+    }
+    row[c] = v;
+  }
+}
+
+// ---- per-row mean and type-7 quantiles by exact radix select --------------------------------------------
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+constexpr int RS_THREADS = 256;
+
+struct SelectArgs {
+  const double* F;
+  int64_t ldF, M;
+  int64_t g0;
+  int64_t r1, r2;     // 0-based ranks floor(index) - 1 of the two probabilities
+  double h1, h2;      // interpolation weights (0 => no second order statistic needed)
+  double* mean;
+  double* lo;
+  double* hi;
+};
+
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs a) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_below;
+  __shared__ unsigned int s_eq;
+  __shared__ double s_red[RS_THREADS];
+  __shared__ unsigned long long s_min[RS_THREADS];
+  const int tid = threadIdx.x;
+  const double* row = a.F + (size_t)blockIdx.x * a.ldF;
+  const int64_t M = a.M;
+  // mean (fixed-order tree) and, when the row fits, the sortable keys in shared memory
+  double sum = 0.0;
+  for (int64_t i = tid; i < M; i += RS_THREADS) {
+    const double v = row[i];
+    sum += v;
+    if (IN_SMEM) skeys[i] = dkey(v);
+  }
+  s_red[tid] = sum;
+  __syncthreads();
+  for (int o = RS_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) s_red[tid] += s_red[tid + o];
+    __syncthreads();
+  }
+  const double mean = s_red[0] / (double)M;
+  auto key_at = [&](int64_t i) -> unsigned long long { return IN_SMEM ? skeys[i] : dkey(row[i]); };
+
+  double qv[2];
+  for (int which = 0; which < 2; ++which) {
+    const int64_t r = which == 0 ? a.r1 : a.r2;
+    const double h = which == 0 ? a.h1 : a.h2;
+    unsigned long long prefix = 0ull, mask = 0ull;
+    long long below = 0;
+    unsigned int eq = 0;
+    for (int pass = 7; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      hist[tid] = 0;
+      __syncthreads();
+      for (int64_t i = tid; i < M; i += RS_THREADS) {
+        const unsigned long long k = key_at(i);
+        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        long long cum = below;
+        int b = 0;
+        for (; b < 256; ++b) {
+          if (cum + (long long)hist[b] > r) break;
+          cum += hist[b];
+        }
+        if (b > 255) b = 255;
+        s_below = cum;
+        s_prefix = prefix | ((unsigned long long)b << shift);
+        s_eq = hist[b];
+      }
+      __syncthreads();
+      below = s_below;
+      prefix = s_prefix;
+      eq = s_eq;
+      mask |= 0xFFull << shift;
+      __syncthreads();
+    }
+    const double x_lo = dunkey(prefix);
+    double x_hi = x_lo;
+    if (h != 0.0 && below + (long long)eq <= r + 1) {
+      // next order statistic = smallest key strictly above
+      unsigned long long mn = ~0ull;
+      for (int64_t i = tid; i < M; i += RS_THREADS) {
+        const unsigned long long k = key_at(i);
+        if (k > prefix && k < mn) mn = k;
+      }
+      s_min[tid] = mn;
+      __syncthreads();
+      for (int o = RS_THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o && s_min[tid + o] < s_min[tid]) s_min[tid] = s_min[tid + o];
+        __syncthreads();
+      }
+      x_hi = dunkey(s_min[0]);
+      __syncthreads();
+    }
+    // R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]
+    qv[which] = (h != 0.0 && x_hi != x_lo) ? (1.0 - h) * x_lo + h * x_hi : x_lo;
+  }
+  if (tid == 0) {
+    const int64_t g = a.g0 + blockIdx.x;
+    if (a.mean) a.mean[g] = mean;
+    if (a.lo) a.lo[g] = qv[0];
+    if (a.hi) a.hi[g] = qv[1];
+  }
+}
+
+// ---- host orchestration ---------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    BGP_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+    return BGP_OK;
+  }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+struct DesignSpec {
+  bool iwp;
+  // IWP
+  std::vector<double> kneg, kpos;
+  int order = 0, degree = 0;
+  // sGP
+  double a = 0, lo = 0, hi = 0, x0 = 0;
+  int k = 0, m = 0, boundary = 1;
+  int ncols = 0;
+};
+
+static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, int64_t M, const double* x_host,
+                        int64_t G, double level, cudaStream_t st, double* mean, double* plower, double* pupper,
+                        double* samples) {
+  DevBuf xb, knb, kpb, Db, Fb, ob, Sb;
+  BGP_TRY(xb.alloc((size_t)G * sizeof(double)));
+  BGP_CUDA(cudaMemcpyAsync(xb.p, x_host, (size_t)G * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (ds.iwp) {
+    BGP_TRY(knb.alloc(ds.kneg.size() * sizeof(double)));
+    BGP_TRY(kpb.alloc(ds.kpos.size() * sizeof(double)));
+    if (!ds.kneg.empty())
+      BGP_CUDA(cudaMemcpyAsync(knb.p, ds.kneg.data(), ds.kneg.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!ds.kpos.empty())
+      BGP_CUDA(cudaMemcpyAsync(kpb.p, ds.kpos.data(), ds.kpos.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  // strip height: keep the F strip around 96 MB (L2-sized), multiple of 128 rows
+  int64_t strip = (int64_t)(96.0e6 / (8.0 * (double)M));
+  strip = std::max<int64_t>(128, strip / 128 * 128);
+  strip = std::min<int64_t>(strip, round_up64(G, 128));
+  const int64_t ldF = round_up64(M, 2);
+  BGP_TRY(Db.alloc((size_t)strip * ldk * sizeof(double)));
+  BGP_TRY(Fb.alloc((size_t)strip * ldF * sizeof(double)));
+  BGP_TRY(ob.alloc((size_t)3 * G * sizeof(double)));
+  double* o_mean = ob.as<double>();
+  double* o_lo = o_mean + G;
+  double* o_hi = o_lo + G;
+  if (samples) BGP_TRY(Sb.alloc((size_t)G * M * sizeof(double)));
+  const double alpha = 1.0 - level;
+  const double q1 = alpha / 2.0, q2 = level + alpha / 2.0;
+  auto rank_of = [&](double q, int64_t* r, double* h) {
+    const double index = 1.0 + (double)(M - 1) * q;
+    const double lo = std::floor(index);
+    *r = (int64_t)lo - 1;
+    *h = index - lo;
+    if (*r < 0) *r = 0;
+    if (*r > M - 1) *r = M - 1;
+  };
+  SelectArgs sa;
+  rank_of(q1, &sa.r1, &sa.h1);
+  rank_of(q2, &sa.r2, &sa.h2);
+  sa.F = Fb.as<double>();
+  sa.ldF = ldF;
+  sa.M = M;
+  sa.mean = o_mean;
+  sa.lo = o_lo;
+  sa.hi = o_hi;
+  const size_t key_bytes = (size_t)M * sizeof(unsigned long long);
+  const bool in_smem = key_bytes <= 200 * 1024;
+  if (in_smem && key_bytes > 40 * 1024)
+    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_bytes));
+  for (int64_t g0 = 0; g0 < G; g0 += strip) {
+    const int64_t rows = std::min(strip, G - g0);
+    if (ds.iwp) {
+      IwpDesignArgs a;
+      a.x = xb.as<double>();
+      a.g0 = g0;
+      a.rows = rows;
+      a.kneg = knb.as<double>();
+      a.nneg = (int)ds.kneg.size();
+      a.kpos = kpb.as<double>();
+      a.npos = (int)ds.kpos.size();
+      a.order = ds.order;
+      a.degree = ds.degree;
+      a.D = Db.as<double>();
+      a.ld = ldk;
+      iwp_design_kernel<<<(unsigned)rows, 128, 0, st>>>(a);
+    } else {
+      SgpDesignArgs a;
+      a.x = xb.as<double>();
+      a.g0 = g0;
+      a.rows = rows;
+      a.x0 = ds.x0;
+      a.a = ds.a;
+      a.k = ds.k;
+      a.m = ds.m;
+      a.boundary = ds.boundary;
+      a.lo = ds.lo;
+      a.hi = ds.hi;
+      a.D = Db.as<double>();
+      a.ld = ldk;
+      sgp_design_kernel<<<(unsigned)rows, 128, 0, st>>>(a);
+    }
+    count_launch();
+    BGP_CUDA(cudaGetLastError());
+    BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Fb.as<double>(), ldF, false,
+                         nullptr, st));
+    if (samples)   // G x M column-major copy for only.samples = TRUE
+      BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
+                           true, nullptr, st));
+    sa.g0 = g0;
+    if (in_smem) row_select_kernel<true><<<(unsigned)rows, RS_THREADS, key_bytes, st>>>(sa);
+    else row_select_kernel<false><<<(unsigned)rows, RS_THREADS, 0, st>>>(sa);
+    count_launch();
+    BGP_CUDA(cudaGetLastError());
+  }
+  if (mean) BGP_CUDA(cudaMemcpyAsync(mean, o_mean, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (plower) BGP_CUDA(cudaMemcpyAsync(plower, o_lo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (pupper) BGP_CUDA(cudaMemcpyAsync(pupper, o_hi, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (samples)
+    BGP_CUDA(cudaMemcpyAsync(samples, Sb.p, (size_t)G * M * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BGP_CUDA(cudaStreamSynchronize(st));
+  return BGP_OK;
+}
+
+static void split_knots(const double* knots, int nknots, std::vector<double>& kneg, std::vector<double>& kpos) {
+  double kmin = knots[0], kmax = knots[0];
+  for (int i = 1; i < nknots; ++i) {
+    kmin = std::min(kmin, knots[i]);
+    kmax = std::max(kmax, knots[i]);
+  }
+  auto uniq = [](std::vector<double>& v) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  };
+  if (kmin >= 0) {
+    kpos.assign(knots, knots + nknots);
+  } else {
+    for (int i = 0; i < nknots; ++i) kneg.push_back(knots[i] < 0 ? -knots[i] : 0.0);
+    uniq(kneg);
+    if (kmax > 0) {
+      for (int i = 0; i < nknots; ++i) kpos.push_back(knots[i] > 0 ? knots[i] : 0.0);
+      uniq(kpos);
+    }
+  }
+}
+
+// upload R-layout sample blocks and assemble the K-major coefficient matrix
+static int build_coef(const double* coef, int ncoef, const double* glob, int nglob, const double* icpt, int64_t M, int skip,
+                      int nX, int ldk, cudaStream_t st, DevBuf& Cb, bool inputs_on_device) {
+  DevBuf cb, gb, ib;
+  const double *cd = coef, *gd = glob, *id = icpt;
+  if (!inputs_on_device) {
+    BGP_TRY(cb.alloc((size_t)ncoef * M * sizeof(double)));
+    BGP_CUDA(cudaMemcpyAsync(cb.p, coef, (size_t)ncoef * M * sizeof(double), cudaMemcpyHostToDevice, st));
+    cd = cb.as<double>();
+    if (glob && nglob > 0) {
+      BGP_TRY(gb.alloc((size_t)nglob * M * sizeof(double)));
+      BGP_CUDA(cudaMemcpyAsync(gb.p, glob, (size_t)nglob * M * sizeof(double), cudaMemcpyHostToDevice, st));
+      gd = gb.as<double>();
+    } else {
+      gd = nullptr;
+    }
+    if (icpt) {
+      BGP_TRY(ib.alloc((size_t)M * sizeof(double)));
+      BGP_CUDA(cudaMemcpyAsync(ib.p, icpt, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, st));
+      id = ib.as<double>();
+    }
+  }
+  BGP_TRY(Cb.alloc((size_t)M * ldk * sizeof(double)));
+  CoefArgs a;
+  a.icpt = id;
+  a.glob = gd;
+  a.nglob = nglob;
+  a.coef = cd;
+  a.ncoef = ncoef;
+  a.skip = skip;
+  a.nX = nX;
+  a.M = M;
+  a.C = Cb.as<double>();
+  a.ld = ldk;
+  build_coef_kernel<<<(unsigned)M, 128, 0, st>>>(a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  BGP_CUDA(cudaStreamSynchronize(st));   // staging buffers go out of scope
+  return BGP_OK;
+}
+
+}  // namespace bgp
+
+using namespace bgp;
+
+extern "C" {
+
+int bgp_predict_iwp(const double* coef, const double* global, const double* icpt, int64_t M, const double* knots,
+                    int nknots, int order, int degree, const double* x, int64_t G, double level, int device,
+                    double* mean, double* plower, double* pupper, double* samples) {
+  if (!coef || !knots || !x || M <= 0 || G <= 0 || nknots < 2 || order < 1 || order > 8 || degree < 0) {
+    set_error("bgp_predict_iwp: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  if (order <= degree) {   // R/03_post_fit.R:201-203
+    set_error("Error: The degree of derivative to compute is not defined. Should consider higher order smoothing "
+              "model or lower order of the derivative degree.");
+    return BGP_ERR_ARG;
+  }
+  if (!(level > 0.0 && level < 1.0)) {
+    set_error("bgp_predict_iwp: level must be in (0, 1)");
+    return BGP_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_error("no CUDA device %d available: libbgp has no CPU fallback", device);
+    return BGP_ERR_CUDA;
+  }
+  BGP_CUDA(cudaSetDevice(device));
+  DesignSpec ds;
+  ds.iwp = true;
+  ds.order = order;
+  ds.degree = degree;
+  split_knots(knots, nknots, ds.kneg, ds.kpos);
+  const int nB = (ds.kneg.empty() ? 0 : (int)ds.kneg.size() - 1) + (ds.kpos.empty() ? 0 : (int)ds.kpos.size() - 1);
+  const int nX = order - degree;
+  ds.ncols = nX + nB;
+  const int ldk = round_up(ds.ncols, 16);
+  cudaStream_t st;
+  BGP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DevBuf Cb;
+  int rc = build_coef(coef, nB, global, order - 1, icpt, M, degree, nX, ldk, st, Cb, false);
+  if (rc == BGP_OK) rc = predict_core(ds, Cb.as<double>(), ldk, M, x, G, level, st, mean, plower, pupper, samples);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+int bgp_predict_sgp(const double* coef, const double* global, const double* icpt, int64_t M, double a, int k, int m,
+                    const double* region, int boundary, const double* x, int64_t G, double level, int device,
+                    double* mean, double* plower, double* pupper, double* samples) {
+  if (!coef || !region || !x || M <= 0 || G <= 0 || k < 5 || m < 1) {
+    set_error("bgp_predict_sgp: bad arguments (k must be >= 5)");
+    return BGP_ERR_ARG;
+  }
+  if (!(level > 0.0 && level < 1.0)) {
+    set_error("bgp_predict_sgp: level must be in (0, 1)");
+    return BGP_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_error("no CUDA device %d available: libbgp has no CPU fallback", device);
+    return BGP_ERR_CUDA;
+  }
+  BGP_CUDA(cudaSetDevice(device));
+  DesignSpec ds;
+  ds.iwp = false;
+  ds.a = a;
+  ds.k = k;
+  ds.m = m;
+  ds.boundary = boundary ? 1 : 0;
+  ds.lo = std::min(region[0], region[1]);
+  ds.hi = std::max(region[0], region[1]);
+  ds.x0 = x[0];
+  for (int64_t i = 1; i < G; ++i) ds.x0 = std::min(ds.x0, x[i]);   // initial_location = NULL => min(refined_x)
+  const int nb = boundary ? k - 2 : k;
+  const int nX = 1 + 2 * m;
+  ds.ncols = nX + 3 * nb * m;
+  const int ldk = round_up(ds.ncols, 16);
+  cudaStream_t st;
+  BGP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DevBuf Cb;
+  int rc = build_coef(coef, 3 * nb * m, global, 2 * m, icpt, M, 0, nX, ldk, st, Cb, false);
+  if (rc == BGP_OK) rc = predict_core(ds, Cb.as<double>(), ldk, M, x, G, level, st, mean, plower, pupper, samples);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, int64_t G, int device, double* out) {
+  if (!knots || !x || !out || nknots < 2 || order < 1 || order > 8 || G <= 0) {
+    set_error("bgp_basis_iwp: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_error("no CUDA device %d available: libbgp has no CPU fallback", device);
+    return BGP_ERR_CUDA;
+  }
+  BGP_CUDA(cudaSetDevice(device));
+  std::vector<double> kneg, kpos;
+  split_knots(knots, nknots, kneg, kpos);
+  const int nB = (kneg.empty() ? 0 : (int)kneg.size() - 1) + (kpos.empty() ? 0 : (int)kpos.size() - 1);
+  DevBuf xb, knb, kpb, Bb;
+  BGP_TRY(xb.alloc((size_t)G * sizeof(double)));
+  BGP_TRY(knb.alloc(kneg.size() * sizeof(double)));
+  BGP_TRY(kpb.alloc(kpos.size() * sizeof(double)));
+  BGP_TRY(Bb.alloc((size_t)G * nB * sizeof(double)));
+  BGP_CUDA(cudaMemcpy(xb.p, x, (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
+  if (!kneg.empty()) BGP_CUDA(cudaMemcpy(knb.p, kneg.data(), kneg.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (!kpos.empty()) BGP_CUDA(cudaMemcpy(kpb.p, kpos.data(), kpos.size() * sizeof(double), cudaMemcpyHostToDevice));
+  BGP_TRY(launch_iwp_block(nullptr, xb.as<double>(), G, 0.0, kneg.empty() ? nullptr : knb.as<double>(), (int)kneg.size(),
+                           kpos.empty() ? nullptr : kpb.as<double>(), (int)kpos.size(), order, Bb.as<double>(), (int)G,
+                           nullptr, 0, true, 0));
+  BGP_CUDA(cudaDeviceSynchronize());
+  BGP_CUDA(cudaMemcpy(out, Bb.p, (size_t)G * nB * sizeof(double), cudaMemcpyDeviceToHost));
+  return BGP_OK;
+}
+
+}  // extern "C"

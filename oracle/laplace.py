@@ -51,6 +51,8 @@ class LaplaceObjective:
             w = np.zeros(m.p)
             o = m.objective(w, theta, "fgH")
         self.converged = False
+        if not (np.isfinite(o["f"]) and np.all(np.isfinite(o["g"]))):
+            return w, o                              # TMB: NaN value, the outer optimiser backtracks
         for it in range(self.maxit):
             gmax = np.max(np.abs(o["g"]))
             if gmax < self.grad_tol:
@@ -58,7 +60,7 @@ class LaplaceObjective:
                 break
             try:
                 c = cho_factor(o["H"], lower=True)
-            except np.linalg.LinAlgError:
+            except (np.linalg.LinAlgError, ValueError):
                 break
             step = -cho_solve(c, o["g"])
             # TMB newton() also stops on the step size (step.tol = tol): with
@@ -70,7 +72,8 @@ class LaplaceObjective:
             accepted = False
             for _ in range(40):
                 o2 = m.objective(w + t * step, theta, "fgH")
-                if np.isfinite(o2["f"]) and (o2["f"] <= o["f"] or np.max(np.abs(o2["g"])) < gmax):
+                if np.isfinite(o2["f"]) and np.all(np.isfinite(o2["g"])) and (
+                        o2["f"] <= o["f"] or np.max(np.abs(o2["g"])) < gmax):
                     accepted = True
                     break
                 t *= 0.5
