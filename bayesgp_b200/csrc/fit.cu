@@ -132,7 +132,7 @@ static int vmmin(FF& ff, std::vector<double>& b, double* Fmin_out, int* fail, in
           D2 = 1.0 + D2 / D1;
           for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j)
-              B[(size_t)i * n + j] += (D2 * t[i] * t[j] - X[i] * c[j] - t[i] * X[j]) / D1;
+              B[(size_t)i * n + j] += (D2 * t[i] * t[j] - X[i] * t[j] - t[i] * X[j]) / D1;
         } else {
           ilast = gradcount;
         }

@@ -74,7 +74,7 @@ def vmmin(fn, gr, b0, maxit=100, abstol=-np.inf, reltol=np.sqrt(np.finfo(float).
                 if D1 > 0:
                     Xv = Bm @ c
                     D2 = 1.0 + float(Xv @ c) / D1
-                    Bm = Bm + (D2 * np.outer(t, t) - np.outer(Xv, c) - np.outer(t, Xv)) / D1
+                    Bm = Bm + (D2 * np.outer(t, t) - np.outer(Xv, t) - np.outer(t, Xv)) / D1
                 else:
                     ilast = gradcount
             else:
