@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K_NODES = 15
+# centre / scale of the C3 theta grid (seed 20243, n = 1e6), located by the b200 arm's untimed golden-section
+# search (bench.py prints them as config.theta_mode / theta_sd); used by the CPU arm to skip that search.
+C3_THETA_MODE, C3_THETA_SD = -10.5, 0.1
 P_KNOTS = 300
 ORDER = 3
 
@@ -121,7 +124,7 @@ def build_b200(x, y, device):
 def node_grid(ff):
     """Untimed setup: centre / scale of the 1-D grid, then theta_j = mode + sd * z_j (A.4)."""
     from bayesgp_b200.workloads import gh_nodes, locate_mode_1d
-    mode, sd = locate_mode_1d(ff.fn, 2.0, 12.0)
+    mode, sd = locate_mode_1d(ff.fn, -25.0, 10.0, iters=32)
     thetas = (mode + sd * gh_nodes(K_NODES))[:, None]
     ff.fn(np.array([mode]))
     return mode, sd, thetas, ff.env.last_par.copy()
@@ -275,7 +278,7 @@ def run_reference(args):
     model, off = oracle_model(x, y)
     # centre the grid the same way (coarse, untimed)
     from bayesgp_b200.workloads import locate_mode_1d
-    mode, sd = locate_mode_1d(off.fn, 2.0, 12.0, iters=6)
+    mode, sd = C3_THETA_MODE, C3_THETA_SD      # same grid as the b200 arm (constants measured there)
     thetas = (mode + sd * gh_nodes(K_NODES))[:, None]
     off.fn(np.array([mode]))
     w_mode = off.last_par.copy()
