@@ -108,6 +108,10 @@ struct bgp_model {
   double* Wmode = nullptr;      // warm start / last mode (lda)
   double* g = nullptr;          // gradient (lda)
   double* step = nullptr;       // Newton step (lda)
+  double* Tan = nullptr;        // S x lda tangent d w_hat / d theta at the last mode (warm-start predictor)
+  std::vector<double> theta_last;
+  bool tan_valid = false;
+  bool use_predictor = true;
   double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)
   double* L = nullptr;          // Cholesky factor (lower, column-major p x ldh)
   double* Linv = nullptr;       // L^-1, row-major p x ldl (lower; allocated on first gradient call)
@@ -183,6 +187,7 @@ void syrk_plan_destroy(bgp_model* m);
 int launch_hessian(bgp_model* m, const double* theta);
 // chol.cu: L = chol(H), logdet, optionally step = -H^-1 g and max|step|
 int launch_chol_solve(bgp_model* m, bool solve);
+int launch_tangent(bgp_model* m, const double* theta);
 // basis.cu
 int launch_iwp_block(bgp_model* m, const double* x_dev, int64_t n, double x0, const double* kneg, int nneg,
                      const double* kpos, int npos, int order, double* dstB, int ldB, double* dstX, int ldX,

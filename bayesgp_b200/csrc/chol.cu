@@ -26,14 +26,77 @@ struct CholArgs {
   int solve;
 };
 
+constexpr int CH_THREADS = 512;   // 128 registers / thread for the 32x32 DMMA accumulators
+constexpr int CH_MAXP = 2048;
+
 __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
 
-constexpr int CH_THREADS = 512;   // 128 registers / thread for the 32x32 DMMA accumulators
-constexpr int CH_MAXP = 2048;
+
+// x <- (L L^T)^-1 x for the vector held in shared memory (blocked forward / backward substitution,
+// 32-wide diagonal blocks solved by warp 0 from a shared copy, off-diagonal updates by all threads)
+__device__ void tri_solve_inplace(const double* __restrict__ L, int p, int ldh, double* sv, double* sS, double* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- forward substitution, blocks of 32
+  for (int b0 = 0; b0 < p; b0 += 32) {
+    const int bn = (p - b0) < 32 ? (p - b0) : 32;
+    for (int t = tid; t < 1024; t += CH_THREADS) {
+      const int i = t & 31, c = t >> 5;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double yv = lane < bn ? sv[b0 + lane] : 0.0;
+      for (int j = 0; j < bn; ++j) {
+        double yj = __shfl_sync(0xffffffffu, yv, j) / sS[j * 33 + j];
+        if (lane == j) yv = yj;
+        else if (lane > j) yv = fma(-yj, sS[lane * 33 + j], yv);
+      }
+      if (lane < bn) sv[b0 + lane] = yv;
+    }
+    __syncthreads();
+    for (int i = b0 + bn + tid; i < p; i += CH_THREADS) {
+      double s = sv[i];
+#pragma unroll 8
+      for (int c = 0; c < bn; ++c) s = fma(-L[(size_t)(b0 + c) * ldh + i], sv[b0 + c], s);
+      sv[i] = s;
+    }
+    __syncthreads();
+  }
+  // ---- backward substitution L^T x = y ---------------------------------------------------------------
+  const int nblk = (p + 31) / 32;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int b0 = bi * 32;
+    const int bn = (p - b0) < 32 ? (p - b0) : 32;
+    // y_block[c] -= sum_{i >= b0+bn} L[i][b0+c] x[i]   (warp c owns column c)
+    for (int c = warp; c < bn; c += CH_THREADS / 32) {
+      const double* col = L + (size_t)(b0 + c) * ldh;
+      double s = 0.0;
+      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(col[i], sv[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_red[c] = s;
+    }
+    for (int t = tid; t < 1024; t += CH_THREADS) {
+      const int i = t & 31, c = t >> 5;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xv = lane < bn ? sv[b0 + lane] - s_red[lane] : 0.0;
+      for (int j = bn - 1; j >= 0; --j) {
+        double xj = __shfl_sync(0xffffffffu, xv, j) / sS[j * 33 + j];
+        if (lane == j) xv = xj;
+        else if (lane < j) xv = fma(-xj, sS[j * 33 + lane], xv);
+      }
+      if (lane < bn) sv[b0 + lane] = xv;
+    }
+    __syncthreads();
+  }
+}
 
 template <int NB>
 __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
@@ -183,64 +246,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
     __syncthreads();
   }
   if (!a.solve) return;
-  // ---- forward substitution L y = -g, blocks of 32 -----------------------------------------------
   for (int i = tid; i < p; i += CH_THREADS) sv[i] = -a.g[i];
   __syncthreads();
-  for (int b0 = 0; b0 < p; b0 += 32) {
-    const int bn = (p - b0) < 32 ? (p - b0) : 32;
-    for (int t = tid; t < 1024; t += CH_THREADS) {
-      const int i = t & 31, c = t >> 5;
-      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double yv = lane < bn ? sv[b0 + lane] : 0.0;
-      for (int j = 0; j < bn; ++j) {
-        double yj = __shfl_sync(0xffffffffu, yv, j) / sS[j * 33 + j];
-        if (lane == j) yv = yj;
-        else if (lane > j) yv = fma(-yj, sS[lane * 33 + j], yv);
-      }
-      if (lane < bn) sv[b0 + lane] = yv;
-    }
-    __syncthreads();
-    for (int i = b0 + bn + tid; i < p; i += CH_THREADS) {
-      double s = sv[i];
-#pragma unroll 8
-      for (int c = 0; c < bn; ++c) s = fma(-L[(size_t)(b0 + c) * ldh + i], sv[b0 + c], s);
-      sv[i] = s;
-    }
-    __syncthreads();
-  }
-  // ---- backward substitution L^T x = y ---------------------------------------------------------------
-  const int nblk = (p + 31) / 32;
-  for (int bi = nblk - 1; bi >= 0; --bi) {
-    const int b0 = bi * 32;
-    const int bn = (p - b0) < 32 ? (p - b0) : 32;
-    // y_block[c] -= sum_{i >= b0+bn} L[i][b0+c] x[i]   (warp c owns column c)
-    for (int c = warp; c < bn; c += CH_THREADS / 32) {
-      const double* col = L + (size_t)(b0 + c) * ldh;
-      double s = 0.0;
-      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(col[i], sv[i], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) s_red[c] = s;
-    }
-    for (int t = tid; t < 1024; t += CH_THREADS) {
-      const int i = t & 31, c = t >> 5;
-      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double xv = lane < bn ? sv[b0 + lane] - s_red[lane] : 0.0;
-      for (int j = bn - 1; j >= 0; --j) {
-        double xj = __shfl_sync(0xffffffffu, xv, j) / sS[j * 33 + j];
-        if (lane == j) xv = xj;
-        else if (lane < j) xv = fma(-xj, sS[j * 33 + lane], xv);
-      }
-      if (lane < bn) sv[b0 + lane] = xv;
-    }
-    __syncthreads();
-  }
+  tri_solve_inplace(L, p, ldh, sv, sS, s_red);
   double mx = 0.0;
   for (int i = tid; i < p; i += CH_THREADS) {
     const double x = sv[i];
@@ -295,6 +303,94 @@ int launch_chol_solve(bgp_model* m, bool solve) {
   if (m->p <= 512) return launch_chol_t<32>(m, a);
   if (m->p <= 1200) return launch_chol_t<16>(m, a);
   return launch_chol_t<8>(m, a);
+}
+
+// ---- tangent predictor: T_k = d w_hat / d theta_k = -H^-1 c_k, c_k = d2 f / dW dtheta_k -------------------
+// (same closed form as the implicit term of the Laplace gradient).  Used only to
+// warm-start the next inner Newton solve; results do not depend on it.
+struct TanBlock {
+  int off, d, diag;
+  const double* P;
+  double etheta;
+};
+struct TangentArgs {
+  const double* L;
+  int p, ldh, lda;
+  const double* W;      // the mode
+  const double* mu0;
+  const double* qfix;
+  int nrnd, S;
+  TanBlock rnd[16];
+  double* T;            // S x lda
+};
+
+__global__ void __launch_bounds__(CH_THREADS, 1) tangent_kernel(const TangentArgs a) {
+  __shared__ double sS[32 * 33];
+  __shared__ double sv[CH_MAXP];
+  __shared__ double s_red[32];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < a.p; i += CH_THREADS) {
+    double v = 0.0;
+    if (k < a.nrnd) {
+      const TanBlock& rb = a.rnd[k];
+      if (i >= rb.off && i < rb.off + rb.d) {
+        const int r = i - rb.off;
+        if (rb.diag) {
+          v = rb.etheta * rb.P[r] * a.W[i];
+        } else {
+          double s = 0.0;
+          for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
+          v = rb.etheta * s;
+        }
+      }
+    } else {
+      // Gaussian noise theta: c = -A^T r = -Q (w_hat - mu0) at the mode
+      double q = a.qfix[i] * (a.W[i] - a.mu0[i]);
+      for (int b = 0; b < a.nrnd; ++b) {
+        const TanBlock& rb = a.rnd[b];
+        if (i >= rb.off && i < rb.off + rb.d) {
+          const int r = i - rb.off;
+          if (rb.diag) {
+            q = rb.etheta * rb.P[r] * a.W[i];
+          } else {
+            double s = 0.0;
+            for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
+            q = rb.etheta * s;
+          }
+        }
+      }
+      v = -q;
+    }
+    sv[i] = v;
+  }
+  __syncthreads();
+  tri_solve_inplace(a.L, a.p, a.ldh, sv, sS, s_red);
+  for (int i = tid; i < a.lda; i += CH_THREADS) a.T[(size_t)k * a.lda + i] = i < a.p ? -sv[i] : 0.0;
+}
+
+int launch_tangent(bgp_model* m, const double* theta) {
+  TangentArgs a;
+  a.L = m->L;
+  a.p = m->p;
+  a.ldh = m->ldh;
+  a.lda = m->lda;
+  a.W = m->Wmode;
+  a.mu0 = m->mu0;
+  a.qfix = m->qfix;
+  a.nrnd = m->J;
+  a.S = m->S;
+  for (int j = 0; j < m->J; ++j) {
+    a.rnd[j].off = m->rnd[j].off;
+    a.rnd[j].d = m->rnd[j].d;
+    a.rnd[j].diag = m->rnd[j].diag ? 1 : 0;
+    a.rnd[j].P = m->rnd[j].P_dev;
+    a.rnd[j].etheta = std::exp(theta[j]);
+  }
+  a.T = m->Tan;
+  tangent_kernel<<<m->S, CH_THREADS, 0, m->stream>>>(a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
 }
 
 }  // namespace bgp

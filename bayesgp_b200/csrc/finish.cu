@@ -32,20 +32,32 @@ struct PriorArgs {
   RndDev rnd[MAX_RND];
 };
 
-__global__ void __launch_bounds__(1024) finish_reduce_kernel(const double* __restrict__ part_g,
-                                                             const double* __restrict__ part_s, int nblocks, int lda,
-                                                             double* __restrict__ red) {
-  for (int c = threadIdx.x; c < lda; c += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += part_g[(size_t)b * lda + c];
-    red[c] = s;
+// grid = ceil(lda / 32) CTAs of 256 threads: CTA c owns 32 columns, its 8 warps split the partial blocks
+// (block b goes to warp b % 8), partial sums are combined in a fixed order => deterministic.
+__global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __restrict__ part_g,
+                                                            const double* __restrict__ part_s, int nblocks, int lda,
+                                                            double* __restrict__ red) {
+  __shared__ double sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  if (c < lda)
+    for (int b = warp; b < nblocks; b += 8) s += part_g[(size_t)b * lda + c];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < lda) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    red[c] = t;
   }
-  if (threadIdx.x < 3) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += part_s[(size_t)b * 4 + threadIdx.x];
-    red[lda + threadIdx.x] = s;
+  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 67) {
+    const int k = threadIdx.x - 64;
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += part_s[(size_t)b * 4 + k];
+    red[lda + k] = t;
   }
-  if (threadIdx.x == 3) red[lda + 3] = 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 67) red[lda + 3] = 0.0;
 }
 
 __global__ void __launch_bounds__(1024) finish_prior_kernel(const PriorArgs a) {
@@ -117,7 +129,7 @@ double theta_constant(const bgp_model* m, const double* theta) {
 }
 
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau) {
-  finish_reduce_kernel<<<1, 1024, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
+  finish_reduce_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
   count_launch();
   if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda + 4));
   PriorArgs a;

@@ -288,11 +288,21 @@ void grad_plan_destroy(bgp_model* m) {
   m->Linv = m->zobs = nullptr;
 }
 
-__global__ void finish_reduce_only_kernel(const double* __restrict__ part_g, int nblocks, int lda, double* __restrict__ red) {
-  for (int c = threadIdx.x; c < lda; c += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += part_g[(size_t)b * lda + c];
-    red[c] = s;
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ part_g, int nblocks, int lda,
+                                                              double* __restrict__ red) {
+  __shared__ double sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  if (c < lda)
+    for (int b = warp; b < nblocks; b += 8) s += part_g[(size_t)b * lda + c];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < lda) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    red[c] = t;
   }
 }
 
@@ -314,7 +324,7 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
     count_launch();
     BGP_CUDA(cudaGetLastError());
     BGP_TRY(launch_lik(m, m->Wmode, false, 1.0, m->zobs));
-    finish_reduce_only_kernel<<<1, 1024, 0, m->stream>>>(m->part_g, m->lik_blocks, m->lda, m->red_buf);
+    reduce_partials_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->lik_blocks, m->lda, m->red_buf);
     count_launch();
     if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda));
     BGP_CUDA(cudaMemcpyAsync(gp->hv.data(), m->red_buf, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToHost, m->stream));

@@ -10,6 +10,8 @@
 // R hands the blocks over column-major; they are transposed into place on the device.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -98,6 +100,7 @@ int bgp_model_new(int64_t n, int family, const double* y, const double* size, in
   m->n_total = n;
   m->family = family;
   m->device = device;
+  if (const char* e = getenv("BGP_NO_PREDICTOR")) m->use_predictor = !(e[0] == '1');   // diagnostics only
   int st = [&]() -> int {
     BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     const size_t nb = (size_t)n * sizeof(double);
@@ -389,6 +392,7 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->H, hb));
   BGP_TRY(dalloc(&m->L, hb));
   BGP_TRY(dalloc(&m->theta_dev, 64 * sizeof(double)));
+  BGP_TRY(dalloc(&m->Tan, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int nj = (m->lda + 63) / 64;
@@ -431,7 +435,7 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
     if (ptr) cudaFree(ptr);
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);

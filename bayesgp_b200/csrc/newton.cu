@@ -7,6 +7,8 @@
 // Convergence mirrors TMB newton(): max|g| < grad.tol or max|step| < step.tol (both 1e-8),
 // maxit 100; a step is accepted when the objective is finite and either it or max|g| decreased.
 // One device->host read of 80 bytes of scalars per Newton iteration is the only synchronisation.
+#include <algorithm>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -15,6 +17,22 @@ __global__ void axpy_trial_kernel(const double* __restrict__ W, const double* __
                                   double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < lda) out[i] = i < p ? fma(t, step[i], W[i]) : 0.0;
+}
+
+struct PredictArgs {
+  const double* Wmode;
+  const double* Tan;
+  int S, lda;
+  double dtheta[17];
+  double* out;
+};
+// first-order predictor of the next mode: W0 = w_hat(theta_last) + sum_k T_k (theta_k - theta_last_k)
+__global__ void predict_start_kernel(const PredictArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.lda) return;
+  double v = a.Wmode[i];
+  for (int k = 0; k < a.S; ++k) v = fma(a.Tan[(size_t)k * a.lda + i], a.dtheta[k], v);
+  a.out[i] = v;
 }
 
 static inline double tau_of(const bgp_model* m, const double* theta) {
@@ -44,10 +62,36 @@ int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool w
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_out) {
   EvalScalars sc;
   const int threads = 256, blocks = (m->lda + threads - 1) / threads;
-  // start from the previous mode (TMB last.par.best); fall back to W = 0 if that point is non-finite
-  BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  // start from the previous mode (TMB last.par.best), moved along the tangent d w_hat / d theta when the
+  // step in theta is moderate; fall back to the plain warm start, then to W = 0, if that point is non-finite
+  bool predicted = false;
+  if (m->use_predictor && m->tan_valid && (int)m->theta_last.size() == m->S && m->S <= 17) {
+    PredictArgs pa;
+    double dmax = 0.0;
+    for (int k = 0; k < m->S; ++k) {
+      pa.dtheta[k] = theta[k] - m->theta_last[k];
+      dmax = std::max(dmax, std::fabs(pa.dtheta[k]));
+    }
+    if (dmax > 0.0 && dmax <= 2.0) {
+      pa.Wmode = m->Wmode;
+      pa.Tan = m->Tan;
+      pa.S = m->S;
+      pa.lda = m->lda;
+      pa.out = m->W;
+      predict_start_kernel<<<blocks, threads, 0, m->stream>>>(pa);
+      count_launch();
+      predicted = true;
+    }
+  }
+  if (!predicted)
+    BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   BGP_TRY(eval_fg_async(m, m->W, theta, false));
   BGP_TRY(read_scalars(m, &sc));
+  if (sc.nonfinite && predicted) {
+    BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    BGP_TRY(eval_fg_async(m, m->W, theta, false));
+    BGP_TRY(read_scalars(m, &sc));
+  }
   if (sc.nonfinite) {
     BGP_CUDA(cudaMemsetAsync(m->W, 0, (size_t)m->lda * sizeof(double), m->stream));
     BGP_TRY(eval_fg_async(m, m->W, theta, false));
@@ -138,6 +182,11 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     logdet = sc.logdet;
   }
   BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  if (m->use_predictor && m->S <= 17) {
+    BGP_TRY(launch_tangent(m, theta));      // uses the factor of H(w_hat) left in m->L
+    m->theta_last.assign(theta, theta + m->S);
+    m->tan_valid = true;
+  }
   *value = f + 0.5 * logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
   return BGP_OK;
 }
@@ -189,6 +238,7 @@ int bgp_model_set_start(bgp_model* m, const double* W) {
   BGP_CHECK_READY(m);
   BGP_CUDA(cudaMemsetAsync(m->Wmode, 0, (size_t)m->lda * sizeof(double), m->stream));
   if (W) BGP_CUDA(cudaMemcpyAsync(m->Wmode, W, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  m->tan_valid = false;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   return BGP_OK;
 }

@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "bgp_internal.h"
+#include "ptx.cuh"
 
 namespace bgp {
 
@@ -34,7 +35,7 @@ constexpr int SY_BOX_BYTES = 16 * SY_KB * 8;            // 2048
 constexpr int SY_PANEL_BYTES = 4 * SY_BOX_BYTES;        // 8192
 constexpr int SY_STAGE_BYTES = 2 * SY_PANEL_BYTES;      // 16384
 constexpr int SY_W_BYTES = SY_KB * 8;                   // 128
-constexpr int SY_SMEM = SY_STAGES * SY_STAGE_BYTES + SY_STAGES * SY_W_BYTES + 64 + 1024;
+constexpr int SY_SMEM = SY_STAGES * SY_STAGE_BYTES + SY_STAGES * SY_W_BYTES + 16 * SY_STAGES + 16 + 1024;
 
 struct SyrkPlan {
   CUtensorMap tmA;
@@ -43,65 +44,26 @@ struct SyrkPlan {
   int2* tiles_dev = nullptr;
 };
 
-// ---- PTX helpers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double lds64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
+using namespace ptx;
 
 // column permutation inside a 16-column box: fragment row j reads 16-byte chunk ch(j)
 __host__ __device__ __forceinline__ int sy_chunk(int j) { return (j >> 1) + 4 * (j & 1); }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Work is skipped at the granularity of 16 x 16 boxes (the fragment permutation interleaves the two
+// 8-row fragments of a box): a box is computed iff it touches the lower triangle (incl. diagonal)
+// and lies inside the lda x lda matrix.
 __global__ void __launch_bounds__(SY_THREADS, 4)
     syrk_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ wobs, double* __restrict__ part,
-                const int2* __restrict__ tiles, int ntiles, int64_t n, int64_t chunk) {
+                const int2* __restrict__ tiles, int ntiles, int64_t n, int64_t chunk, int lda) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base + SY_STAGES * SY_STAGE_BYTES;
-  const uint32_t bar_base = w_base + SY_STAGES * SY_W_BYTES;
+  const uint32_t full_base = w_base + SY_STAGES * SY_W_BYTES;
+  const uint32_t empty_base = full_base + 8 * SY_STAGES;
 
   const int tile = blockIdx.x % ntiles, split = blockIdx.x / ntiles;
   const int ti = tiles[tile].x, tj = tiles[tile].y;
@@ -112,18 +74,29 @@ __global__ void __launch_bounds__(SY_THREADS, 4)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
-  const bool active = !(diag && wm == 0 && wn == 1);   // strictly-upper quadrant of a diagonal tile
+  // 2 x 2 boxes per warp: bit (bi * 2 + bj)
+  int bmask = 0;
+#pragma unroll
+  for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+    for (int bj = 0; bj < 2; ++bj) {
+      const int r0 = ti * SY_T + (wm * 2 + bi) * 16, c0 = tj * SY_T + (wn * 2 + bj) * 16;
+      if (r0 < lda && c0 < lda && r0 + 15 >= c0) bmask |= 1 << (bi * 2 + bj);
+    }
 
   if (tid == 0) {
-    for (int s = 0; s < SY_STAGES; ++s) mbar_init(bar_base + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < SY_STAGES; ++s) {
+      mbar_init(full_base + 8 * s, 1);
+      mbar_init(empty_base + 8 * s, SY_THREADS / 32);
+    }
+    mbar_fence_init();
   }
   __syncthreads();
 
   const uint32_t stage_tx = (diag ? SY_PANEL_BYTES : 2 * SY_PANEL_BYTES) + SY_W_BYTES;
   auto issue = [&](int it) {
     const int s = it % SY_STAGES;
-    const uint32_t bar = bar_base + 8 * s;
+    const uint32_t bar = full_base + 8 * s;
     const uint32_t sa = base + s * SY_STAGE_BYTES;
     const int row = (int)(k_begin + (int64_t)it * SY_KB);
     mbar_expect_tx(bar, stage_tx);
@@ -136,10 +109,7 @@ __global__ void __launch_bounds__(SY_THREADS, 4)
     }
     bulk_load_1d(w_base + s * SY_W_BYTES, wobs + row, SY_W_BYTES, bar);
   };
-
-  if (tid == 0) {
-    for (int it = 0; it < SY_STAGES - 1 && it < niter; ++it) issue(it);
-  }
+  if (tid == 0 && niter > 0) issue(0);
 
   double acc[4][4][2];
 #pragma unroll
@@ -150,12 +120,17 @@ __global__ void __launch_bounds__(SY_THREADS, 4)
   const int fj = lane >> 2, fk = lane & 3;
   const int ch = sy_chunk(fj);
 
+  // mbarrier ring, no CTA-wide barrier in the loop: the elected producer thread prefetches one stage
+  // ahead into the slot whose readers (all 4 warps, iteration it - 2) released it via empty[slot].
   for (int it = 0; it < niter; ++it) {
-    __syncthreads();   // every warp is done with stage (it-1) % STAGES
-    if (tid == 0 && it + SY_STAGES - 1 < niter) issue(it + SY_STAGES - 1);
+    if (tid == 0 && it + 1 < niter) {
+      const int j = it + 1;
+      if (j >= SY_STAGES) mbar_wait(empty_base + 8 * (j % SY_STAGES), (uint32_t)(((j / SY_STAGES) - 1) & 1));
+      issue(j);
+    }
     const int s = it % SY_STAGES;
-    mbar_wait(bar_base + 8 * s, (uint32_t)((it / SY_STAGES) & 1));
-    if (active) {
+    mbar_wait(full_base + 8 * s, (uint32_t)((it / SY_STAGES) & 1));
+    if (bmask) {
       const uint32_t sa = base + s * SY_STAGE_BYTES;
       const uint32_t pa = sa + (wm * 2) * SY_BOX_BYTES;
       const uint32_t pb = (diag ? sa : sa + SY_PANEL_BYTES) + (wn * 2) * SY_BOX_BYTES;
@@ -170,21 +145,31 @@ __global__ void __launch_bounds__(SY_THREADS, 4)
         const double af[4] = {a0.x * wk, a0.y * wk, a1.x * wk, a1.y * wk};
         const double bf[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int bi = 0; bi < 2; ++bi)
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+          for (int bj = 0; bj < 2; ++bj)
+            if (bmask & (1 << (bi * 2 + bj))) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+                  dmma884(acc[2 * bi + e][2 * bj + f][0], acc[2 * bi + e][2 * bj + f][1], af[2 * bi + e], bf[2 * bj + f]);
+            }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_base + 8 * s);
   }
 
   // ---- epilogue: undo the column permutation, write the 64x64 partial (row-major [M][N]) --------
-  if (active) {
+  if (bmask) {
     double* out = part + ((size_t)split * ntiles + tile) * (SY_T * SY_T);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
       const int M = (wm * 2 + (mi >> 1)) * 16 + 2 * ch + (mi & 1);
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
+        if (!(bmask & (1 << ((mi >> 1) * 2 + (ni >> 1))))) continue;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int jn = 2 * fk + e;
@@ -206,7 +191,6 @@ __global__ void __launch_bounds__(256)
   const int ti = tiles[tile].x, tj = tiles[tile].y;
   const int gr = ti * SY_T + M, gc = tj * SY_T + N;
   if (gr >= p || gc >= p || gc > gr) return;
-  if (ti == tj && M < 32 && N >= 32) return;
   double s = 0.0;
   for (int sp = 0; sp < nsplit; ++sp) s += part[((size_t)sp * ntiles + tile) * (SY_T * SY_T) + e];
   H[(size_t)gc * ldh + gr] = s;
@@ -249,39 +233,11 @@ __global__ void add_q_kernel(const AddQArgs a) {
 }
 
 // ---- host ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 int syrk_plan_create(bgp_model* m) {
   SyrkPlan* pl = new SyrkPlan();
   m->syrk_plan = pl;
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return BGP_ERR_CUDA;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)m->lda, (cuuint64_t)m->n};
-  const cuuint64_t gstr[1] = {(cuuint64_t)m->lda * 8};
-  const cuuint32_t box[2] = {16, (cuuint32_t)SY_KB};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)m->A, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (make_tensormap_f64(&pl->tmA, m->A, (uint64_t)m->lda, (uint64_t)m->n, (uint64_t)m->lda, 16, SY_KB) != 0) {
+    set_error("cuTensorMapEncodeTiled failed for the Hessian kernel");
     return BGP_ERR_CUDA;
   }
   pl->nt = (m->p + SY_T - 1) / SY_T;
@@ -323,7 +279,7 @@ void syrk_plan_destroy(bgp_model* m) {
 int launch_syrk(bgp_model* m) {
   SyrkPlan* pl = (SyrkPlan*)m->syrk_plan;
   syrk_kernel<<<pl->ntiles * pl->nsplit, SY_THREADS, SY_SMEM, m->stream>>>(pl->tmA, m->wobs, m->part_H, pl->tiles_dev,
-                                                                            pl->ntiles, m->n, pl->chunk);
+                                                                            pl->ntiles, m->n, pl->chunk, m->lda);
   count_launch();
   syrk_reduce_kernel<<<pl->ntiles * (SY_T * SY_T / 256), 256, 0, m->stream>>>(m->part_H, pl->tiles_dev, pl->ntiles,
                                                                                pl->nsplit, m->p, m->ldh, m->H);
