@@ -85,6 +85,13 @@ struct bgp_model {
   bool finalized = false;
   int p = 0, S = 0, J = 0;
   int lda = 0;          // row pitch of A in doubles (multiple of 16)
+  // Internal column order: the dense blocks first, [X_1..X_J | Xf_0..Xf_F | B_1..B_J], so that the always
+  // non-zero columns share column box 0 and the spline blocks keep their zero structure box-aligned.  The
+  // external (ABI) order is the W layout of src/BayesGP.cpp:76-127, [B | X | Xf]; vectors and matrices are
+  // rotated at the API boundary (io.cu).
+  int nD = 0;           // number of dense (boundary + fixed) columns
+  std::vector<double> qfix_host;   // theta-independent diagonal of Q, internal order (p)
+  double* xbuf = nullptr;          // device scratch for boundary rotations (max(lda, p*p) doubles)
   std::vector<bgp::RandomBlock> rnd;
   std::vector<int> bnd_dim, fix_dim;
   std::vector<double> bnd_prec, bnd_mean, fix_prec, fix_mean;
@@ -129,6 +136,12 @@ struct bgp_model {
   bgp::EvalScalars* sc_host = nullptr;   // pinned
   double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
   void* syrk_plan = nullptr;    // opaque (syrk.cu)
+  // {64-observation chunk} x {16-column box} occupancy (rowsort.cu): bit b of occ[c] set iff chunk c has a
+  // non-zero in columns 16b .. 16b+15
+  uint64_t* occ_dev = nullptr;
+  std::vector<uint64_t> occ_host;
+  int64_t nchunks = 0;
+  double hess_useful_flops = 0.0;   // structurally non-zero flops of one Hessian launch (syrk.cu)
   // ---- solver controls ---------------------------------------------------------------------
   double grad_tol = 1e-8, step_tol = 1e-8;
   int maxit = 100;
@@ -181,6 +194,8 @@ int lik_max_lda();
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
 double theta_constant(const bgp_model* m, const double* theta);
+// rowsort.cu: sort observations by zero pattern, build the occupancy map
+int build_row_order(bgp_model* m);
 // syrk.cu: H = A^T diag(w) A (+ allreduce when sharded) + Q(theta)
 int syrk_plan_create(bgp_model* m);
 void syrk_plan_destroy(bgp_model* m);
@@ -192,6 +207,11 @@ int launch_tangent(bgp_model* m, const double* theta);
 int launch_iwp_block(bgp_model* m, const double* x_dev, int64_t n, double x0, const double* kneg, int nneg,
                      const double* kpos, int npos, int order, double* dstB, int ldB, double* dstX, int ldX,
                      bool col_major, cudaStream_t st);
+// io.cu: external (ABI) <-> internal column order at the API boundary
+inline int ext2int(const bgp_model* m, int e) { return e < m->p - m->nD ? e + m->nD : e - (m->p - m->nD); }
+int copy_vec_in(bgp_model* m, const double* host_ext, double* dev_int);     // pads dev_int to lda with zeros
+int copy_vec_out(bgp_model* m, const double* dev_int, double* host_ext);
+int copy_H_out(bgp_model* m, double* host_ext);                             // from m->H (p x ldh) to p x p
 // newton.cu
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);

@@ -421,11 +421,8 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
       lp[j] = -v;
       if (keep && std::isfinite(v)) {
         // mode_j = last.par[random], H_j = spHess(last.par, random = TRUE)   (A.5)
-        BGP_CUDA(cudaMemcpyAsync(&f->modes[(size_t)j * p], m->Wmode, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost,
-                                 m->stream));
-        BGP_CUDA(cudaMemcpy2DAsync(&f->Hs[(size_t)j * p * p], (size_t)p * sizeof(double), m->H,
-                                   (size_t)m->ldh * sizeof(double), (size_t)p * sizeof(double), p,
-                                   cudaMemcpyDeviceToHost, m->stream));
+        BGP_TRY(copy_vec_out(m, m->Wmode, &f->modes[(size_t)j * p]));
+        BGP_TRY(copy_H_out(m, &f->Hs[(size_t)j * p * p]));
         BGP_CUDA(cudaStreamSynchronize(m->stream));
       }
     }

@@ -402,17 +402,9 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   if (gaussian) {
     const int k = m->S - 1;
     const double tau = std::exp(theta[k]);
-    int fix0 = 0;
-    for (auto& rb : m->rnd) fix0 += rb.d;
-    std::vector<double> qfix(p, 0.0);
-    {
-      int o = fix0;
-      for (size_t b = 0; b < m->bnd_dim.size(); ++b)
-        for (int c = 0; c < m->bnd_dim[b]; ++c) qfix[o++] = m->bnd_prec[b];
-      for (size_t b = 0; b < m->fix_dim.size(); ++b)
-        for (int c = 0; c < m->fix_dim[b]; ++c) qfix[o++] = m->fix_prec[b];
-    }
-    for (int c = fix0; c < p; ++c) {
+    const std::vector<double>& qfix = m->qfix_host;
+    for (int c = 0; c < p; ++c) {
+      if (qfix[c] == 0.0) continue;
       double s = 0.0;
       for (int i = c; i < p; ++i) {
         const double v = Li[(size_t)i * ldl + c];

@@ -312,12 +312,13 @@ int bgp_model_finalize(bgp_model* m) {
   m->J = (int)m->rnd.size();
   m->S = m->J + (m->family == BGP_FAMILY_GAUSSIAN ? 1 : 0);
   int p = 0;
+  for (int d : m->bnd_dim) p += d;
+  for (int d : m->fix_dim) p += d;
+  m->nD = p;                       // internal order: dense blocks first (bgp_internal.h)
   for (auto& rb : m->rnd) {
     rb.off = p;
     p += rb.d;
   }
-  for (int d : m->bnd_dim) p += d;
-  for (int d : m->fix_dim) p += d;
   m->p = p;
   m->lda = round_up(p, 16);
   m->ldh = round_up(p, 8);
@@ -350,9 +351,9 @@ int bgp_model_finalize(bgp_model* m) {
     }
     return BGP_OK;
   };
-  BGP_TRY(place(m->st_rnd));
   BGP_TRY(place(m->st_bnd));
   BGP_TRY(place(m->st_fix));
+  BGP_TRY(place(m->st_rnd));
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix}) {
     for (auto& s : *v)
@@ -362,7 +363,6 @@ int bgp_model_finalize(bgp_model* m) {
   // prior mean and the theta-independent diagonal of Q (src/BayesGP.cpp:222-238)
   std::vector<double> mu0((size_t)m->lda, 0.0), qfix((size_t)m->lda, 0.0);
   int o = 0;
-  for (auto& rb : m->rnd) o += rb.d;
   for (size_t b = 0; b < m->bnd_dim.size(); ++b)
     for (int c = 0; c < m->bnd_dim[b]; ++c, ++o) {
       mu0[o] = m->bnd_mean[b];
@@ -379,6 +379,8 @@ int bgp_model_finalize(bgp_model* m) {
     BGP_CUDA(cudaMemset(*ptr, 0, bytes));
     return BGP_OK;
   };
+  m->qfix_host.assign(qfix.begin(), qfix.begin() + m->p);
+  BGP_TRY(dalloc(&m->xbuf, std::max((size_t)m->lda, (size_t)m->p * m->p) * sizeof(double)));
   BGP_TRY(dalloc(&m->mu0, vb));
   BGP_TRY(dalloc(&m->qfix, vb));
   BGP_CUDA(cudaMemcpy(m->mu0, mu0.data(), vb, cudaMemcpyHostToDevice));
@@ -407,6 +409,7 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_CUDA(cudaMemset(m->sc_dev, 0, sizeof(EvalScalars)));
   BGP_CUDA(cudaMallocHost(&m->sc_host, sizeof(EvalScalars)));
   for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
+  BGP_TRY(build_row_order(m));
   BGP_TRY(syrk_plan_create(m));
   if (m->world > 1) {
     // the likelihood constant and n are global quantities
@@ -435,8 +438,9 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->Tan, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->xbuf, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
     if (ptr) cudaFree(ptr);
+  if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);
   for (int i = 0; i < 8; ++i)

@@ -204,13 +204,6 @@ using namespace bgp;
     BGP_CUDA(cudaSetDevice((m)->device));     \
   } while (0)
 
-static int copy_H_out(bgp_model* m, double* H) {
-  // device H is p x ldh column-major -> host p x p column-major
-  BGP_CUDA(cudaMemcpy2DAsync(H, (size_t)m->p * sizeof(double), m->H, (size_t)m->ldh * sizeof(double),
-                             (size_t)m->p * sizeof(double), m->p, cudaMemcpyDeviceToHost, m->stream));
-  return BGP_OK;
-}
-
 extern "C" {
 
 int bgp_objective(bgp_model* m, const double* W, const double* theta, double* f, double* grad, double* H) {
@@ -219,13 +212,12 @@ int bgp_objective(bgp_model* m, const double* W, const double* theta, double* f,
     set_error("bgp_objective: NULL W / theta");
     return BGP_ERR_ARG;
   }
-  BGP_CUDA(cudaMemsetAsync(m->Wtrial, 0, (size_t)m->lda * sizeof(double), m->stream));
-  BGP_CUDA(cudaMemcpyAsync(m->Wtrial, W, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  BGP_TRY(copy_vec_in(m, W, m->Wtrial));
   BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
   EvalScalars sc;
   BGP_TRY(read_scalars(m, &sc));
   if (f) *f = sc.nonfinite ? NAN : sc.f;
-  if (grad) BGP_CUDA(cudaMemcpyAsync(grad, m->g, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (grad) BGP_TRY(copy_vec_out(m, m->g, grad));
   if (H) {
     BGP_TRY(launch_hessian(m, theta));
     BGP_TRY(copy_H_out(m, H));
@@ -237,7 +229,7 @@ int bgp_objective(bgp_model* m, const double* W, const double* theta, double* f,
 int bgp_model_set_start(bgp_model* m, const double* W) {
   BGP_CHECK_READY(m);
   BGP_CUDA(cudaMemsetAsync(m->Wmode, 0, (size_t)m->lda * sizeof(double), m->stream));
-  if (W) BGP_CUDA(cudaMemcpyAsync(m->Wmode, W, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  if (W) BGP_TRY(copy_vec_in(m, W, m->Wmode));
   m->tan_valid = false;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   return BGP_OK;
@@ -274,8 +266,7 @@ int bgp_laplace_eval(bgp_model* m, const double* theta, double* value, double* g
   if (grad) {
     BGP_TRY(laplace_gradient(m, theta, grad));
   }
-  if (w_mode)
-    BGP_CUDA(cudaMemcpyAsync(w_mode, m->Wmode, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (w_mode) BGP_TRY(copy_vec_out(m, m->Wmode, w_mode));
   if (H) BGP_TRY(copy_H_out(m, H));
   cudaEventRecord(m->ev[1], m->stream);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
@@ -305,9 +296,7 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
       worst = st;
       continue;
     }
-    if (modes)
-      BGP_CUDA(cudaMemcpyAsync(modes + (size_t)j * m->p, m->Wmode, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost,
-                               m->stream));
+    if (modes) BGP_TRY(copy_vec_out(m, m->Wmode, modes + (size_t)j * m->p));
     if (Hs) BGP_TRY(copy_H_out(m, Hs + (size_t)j * m->p * m->p));
   }
   cudaEventRecord(m->ev[1], m->stream);
@@ -329,6 +318,16 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
   if (lik_launches) *lik_launches = m->n_lik;
   if (hess_launches) *hess_launches = m->n_hess;
   if (chol_launches) *chol_launches = m->n_chol;
+  return BGP_OK;
+}
+
+int bgp_model_hessian_flops(const bgp_model* m, double* dense, double* structural) {
+  if (!m || !m->finalized) {
+    set_error("model not finalized");
+    return BGP_ERR_STATE;
+  }
+  if (dense) *dense = (double)m->n * m->p * (m->p + 1.0);
+  if (structural) *structural = m->hess_useful_flops;
   return BGP_OK;
 }
 

@@ -161,6 +161,10 @@ int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, i
 int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,
                           int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches);
 
+/* flops of one Hessian launch H = A^T diag(w) A: dense (n p (p+1)) and the structurally non-zero part the
+ * kernel executes after skipping empty {64-observation x 16-column} cells (roofline reporting) */
+int bgp_model_hessian_flops(const bgp_model* m, double* dense, double* structural);
+
 #ifdef __cplusplus
 }
 #endif

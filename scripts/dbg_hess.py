@@ -16,3 +16,6 @@ R=np.abs(E)/np.maximum(1e-300,np.abs(o['H']))
 print('relative err per row max:', R.max(1))
 print('abs err matrix corner'); print(E[:8,:8]); print(E[30:,30:])
 print('nonzero err count', (np.abs(E)>1e-9*np.abs(o['H']).max()).sum())
+print('f err', f - o['f'], 'g relerr', np.abs(g - o['g']).max() / np.abs(o['g']).max())
+bad = np.abs(E) > 1e-9 * np.abs(o['H']).max()
+print('bad rows', np.where(bad.any(1))[0]); print('bad cols', np.where(bad.any(0))[0])

@@ -34,6 +34,8 @@ for rep in range(3):
 print(vals)
 p = ff.p
 flops = n * p * (p + 1)
+hf = ff.hessian_flops()
+print("hessian flops dense %.4e structural %.4e (%.1f%%) -> executed %.2f TFLOP/s" % (hf["dense"], hf["structural"], 100 * hf["structural"] / hf["dense"], hf["structural"] / (tm["hess_ms"] / tm["hess_launches"] * 1e-3) / 1e12))
 print("SYRK algorithmic flops %.3e -> %.2f TFLOP/s ; lik bytes %.3e -> %.1f GB/s" % (
     flops, flops / (tm["hess_ms"] / tm["hess_launches"] * 1e-3) / 1e12, 8.0 * n * (ff.p + 2),
     8.0 * n * (round((p + 15) // 16 * 16) + 2) / (tm["lik_ms"] / tm["lik_launches"] * 1e-3) / 1e9))
