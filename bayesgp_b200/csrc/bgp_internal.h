@@ -136,6 +136,7 @@ struct bgp_model {
   bgp::EvalScalars* sc_host = nullptr;   // pinned
   double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
   void* syrk_plan = nullptr;    // opaque (syrk.cu)
+  void* lik_plan = nullptr;     // opaque (lik.cu)
   // {64-observation chunk} x {16-column box} occupancy (rowsort.cu): bit b of occ[c] set iff chunk c has a
   // non-zero in columns 16b .. 16b+15
   uint64_t* occ_dev = nullptr;
@@ -191,6 +192,8 @@ namespace bgp {
 // rvec != NULL: only part_g = A^T rvec is produced (W_dev ignored)
 int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, const double* rvec = nullptr);
 int lik_max_lda();
+int lik_plan_create(bgp_model* m);
+void lik_plan_destroy(bgp_model* m);
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
 double theta_constant(const bgp_model* m, const double* theta);

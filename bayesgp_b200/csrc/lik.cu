@@ -6,20 +6,30 @@
 // and the first-order AD sweep TMB runs on them: r = d ll/d eta, w = -d2 ll/d eta2,
 // c3 = d w/d eta, g_lik = A^T r.
 //
-// Data layout: A is observation-major (n x lda, lda % 16 == 0, zero padded), so one warp
-// streams one observation row with fully coalesced 16-byte loads, keeps the row in registers,
-// reduces eta with warp shuffles, and accumulates its share of A^T r in registers: A is read
-// from HBM exactly once per evaluation (8*lda bytes / observation + 8..16 bytes of y/size).
-// Per-block partials are written out and reduced in a fixed order by finish.cu, so results are
-// bit-reproducible run to run.
+// Design (sm_100a): one persistent CTA per SM, 1 producer warp + 8 consumer warps.
+//   * A is observation-major (n x lda).  The producer streams it through a shared-memory ring with TMA:
+//     a stage is 8 or 16 observations, copied as {64 columns x rows} boxes (512-byte lines, no swizzle) plus
+//     the responses; up to ~160 KB per SM are in flight, which is what it takes to keep HBM3e busy.
+//   * Column groups whose {64-observation chunk x 16-column box} cells are all structurally zero
+//     (occupancy map of rowsort.cu) are neither copied nor multiplied: after the zero-pattern sort an
+//     O-spline design moves ~60 % of its bytes.
+//   * Consumer warp w owns observation w of every stage: lanes read the row as 16-byte words
+//     (conflict-free), reduce eta with warp shuffles, evaluate the likelihood terms, and accumulate
+//     their share of A^T r in registers.  A is read from HBM exactly once per evaluation.
+//   * Per-CTA partials are written out and reduced in a fixed order by finish.cu (bit-reproducible).
+#include <cuda.h>
+
 #include "bgp_internal.h"
+#include "ptx.cuh"
 
 namespace bgp {
 
+using namespace ptx;
+
 struct LikArgs {
-  const double* A;
   int lda;
   int64_t n;
+  int64_t nchunks;      // ceil(n / 64)
   const double* W;
   const double* y;
   const double* size;
@@ -31,15 +41,35 @@ struct LikArgs {
   double* part_g;   // [gridDim.x][lda]
   double* part_s;   // [gridDim.x][4] : ll, sumsq, nonfinite, unused
   const double* rvec;   // if set: skip the likelihood and accumulate A^T rvec only (leverage term)
+  const unsigned long long* occ;
 };
 
-constexpr int LIK_THREADS = 256;
-constexpr int LIK_WARPS = LIK_THREADS / 32;
+struct LikPlan {
+  CUtensorMap tmA;
+};
+
+constexpr int LK_CONSUMERS = 8;
+// consumer groups: a stage holds 8 * NG observations, one per consumer warp.  Two groups for narrow designs:
+// twice the bytes per TMA operation (the single producer thread issues ~1 operation per 100 clk) and twice
+// the rows in flight (the per-row chain dot -> shuffle tree -> exp -> A^T r is ~600 clk).
+__host__ __device__ constexpr int lk_groups(int NJ) { return NJ <= 6 ? 2 : 1; }
+__host__ __device__ constexpr int lk_kb(int NJ) { return 8 * lk_groups(NJ); }
+__host__ __device__ constexpr int lk_threads(int NJ) { return 32 * (LK_CONSUMERS * lk_groups(NJ) + 1); }
+constexpr int LK_SMEM_BUDGET = 200 * 1024;
+__host__ __device__ constexpr int lk_group_bytes(int NJ) { return lk_kb(NJ) * 64 * 8; }   // one {64 columns x KB rows} box
+__host__ __device__ constexpr int lk_stage_bytes(int NJ) { return NJ * lk_group_bytes(NJ) + 2 * lk_kb(NJ) * 8; }
+__host__ __device__ constexpr int lk_stages(int NJ) {
+  return (LK_SMEM_BUDGET - 4096 - NJ * 512 * 2) / lk_stage_bytes(NJ) > 10 ? 10
+                                                                         : (LK_SMEM_BUDGET - 4096 - NJ * 512 * 2) / lk_stage_bytes(NJ);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+__device__ __forceinline__ void lk_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // per-observation likelihood pieces; all lanes of the warp compute the same values
@@ -76,105 +106,173 @@ __device__ __forceinline__ void obs_terms(int family, double tau, double eta, do
   }
 }
 
-template <int NJ, int R>
-__global__ void __launch_bounds__(LIK_THREADS) lik_kernel(const LikArgs a) {
-  extern __shared__ double sm[];   // [LIK_WARPS][lda] partial g, then [LIK_WARPS][4] scalars
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// smem: [stages][ NJ boxes | y[8] | size[8] ] | W (NJ * 64) | meta[stages] | full[stages] | empty[stages]
+template <int NJ>
+__global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_constant__ CUtensorMap tmA, const LikArgs a) {
+  constexpr int STAGES = lk_stages(NJ);
+  constexpr int STAGE_BYTES = lk_stage_bytes(NJ);
+  constexpr int NG = lk_groups(NJ);
+  constexpr int NCW = LK_CONSUMERS * NG;       // consumer warps
+  constexpr int LK_KB = lk_kb(NJ);
+  constexpr int LK_GROUP_BYTES = lk_group_bytes(NJ);
+  constexpr int SPC = 64 / LK_KB;              // stages per 64-observation chunk
+  constexpr int LK_THREADS = lk_threads(NJ);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t w_base = base + STAGES * STAGE_BYTES;
+  const uint32_t meta_base = w_base + NJ * 512;
+  const uint32_t full_base = meta_base + 8 * STAGES;
+  const uint32_t empty_base = full_base + 8 * STAGES;
+  double* sm_gen = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lda = a.lda;
-  double2 wv[NJ], ga[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    wv[j] = c < lda ? *reinterpret_cast<const double2*>(a.W + c) : make_double2(0.0, 0.0);
-    ga[j] = make_double2(0.0, 0.0);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_base + 8 * s, 1);
+      mbar_init(empty_base + 8 * s, NCW);
+    }
+    mbar_fence_init();
   }
+  // W into shared memory (zero padded to NJ * 64)
+  for (int c = tid; c < NJ * 64; c += LK_THREADS) sm_gen[(w_base - base) / 8 + c] = (c < lda && a.W) ? a.W[c] : 0.0;
+  __syncthreads();
+
+  // 64-observation chunks (SPC stages) are dealt round-robin to the CTAs (cheap early chunks and dense late
+  // chunks mix); local stage `it` of a CTA is stage (it % SPC) of its chunk number (it / SPC)
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int64_t nchunks = a.nchunks;
+  const int64_t my_chunks = first < nchunks ? (nchunks - first + step - 1) / step : 0;
+  const int64_t my_stages = my_chunks * SPC;
+  if (warp == NCW) {
+    if (lane != 0) return;
+    unsigned long long o_next = my_chunks > 0 ? __ldg(a.occ + first) : 0ull;
+    uint32_t gm = 0;
+    for (int64_t it = 0; it < my_stages; ++it) {
+      const int slot = (int)(it % STAGES);
+      const int64_t chunk = first + (it / SPC) * step;
+      const int64_t row = chunk * 64 + (it % SPC) * LK_KB;
+      if ((it % SPC) == 0) {
+        const unsigned long long o = o_next;
+        if ((it / SPC) + 1 < my_chunks) o_next = __ldg(a.occ + chunk + step);   // prefetch: consumed a chunk later
+        gm = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if ((o >> (4 * j)) & 0xfull) gm |= 1u << j;
+      }
+      const uint32_t fb = full_base + 8 * slot;
+      const uint32_t sb = base + slot * STAGE_BYTES;
+      mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / STAGES) & 1) ^ 1));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta_base + 8 * slot), "r"(gm) : "memory");
+      const bool want_y = a.rvec == nullptr;
+      mbar_expect_tx(fb, (uint32_t)__popc(gm) * LK_GROUP_BYTES + (want_y ? LK_KB * 8 : 0) + (want_y && a.size ? LK_KB * 8 : 0));
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if ((gm >> j) & 1u) tma_load_2d(sb + j * LK_GROUP_BYTES, &tmA, 64 * j, (int)row, fb);
+      if (want_y) {
+        bulk_load_1d(sb + NJ * LK_GROUP_BYTES, a.y + row, LK_KB * 8, fb);
+        if (a.size) bulk_load_1d(sb + NJ * LK_GROUP_BYTES + LK_KB * 8, a.size + row, LK_KB * 8, fb);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: warp (g, w) handles observation w of the stages of group g -----------------------------
+  const int wrow = warp;                       // observation of the stage this warp owns
+  double2 ga[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) ga[j] = make_double2(0.0, 0.0);
   double ll = 0.0, sumsq = 0.0;
   int bad = 0;
-  const int64_t gw = (int64_t)blockIdx.x * LIK_WARPS + warp;
-  const int64_t stride = (int64_t)gridDim.x * LIK_WARPS * R;
-  for (int64_t base = gw * R; base < a.n; base += stride) {
-    double2 av[R][NJ];
+  for (int64_t it = 0; it < my_stages; ++it) {
+    const int slot = (int)(it % STAGES);
+    mbar_wait(full_base + 8 * slot, (uint32_t)((it / STAGES) & 1));
+    const int64_t row = (first + (it / SPC) * step) * 64 + (it % SPC) * LK_KB + wrow;
+    uint32_t gm;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gm) : "r"(meta_base + 8 * slot) : "memory");
+    const uint32_t sb = base + slot * STAGE_BYTES;
+    const uint32_t ra = sb + wrow * 512 + lane * 16;
+    if (row < a.n) {
+      double2 av[NJ];
+      double rr;
+      if (a.rvec) {
+        rr = __ldg(a.rvec + row);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = base + r;
-      const double* rp = a.A + row * (int64_t)lda;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int c = 2 * lane + 64 * j;
-        av[r][j] = (row < a.n && c < lda) ? __ldcs(reinterpret_cast<const double2*>(rp + c)) : make_double2(0.0, 0.0);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = base + r;
-      if (row < a.n) {
-        double rr;
-        if (a.rvec) {
-          rr = __ldg(a.rvec + row);
-        } else {
-          double s = 0.0;
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            s = fma(av[r][j].x, wv[j].x, s);
-            s = fma(av[r][j].y, wv[j].y, s);
-          }
-          s = warp_sum(s);
-          const double yv = __ldg(a.y + row);
-          const double sz = a.size ? __ldg(a.size + row) : 1.0;
-          double ww, cc;
-          obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
-          if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
-          if (lane == 0) {
-            a.eta[row] = s;
-            a.wobs[row] = ww;
-            if (a.c3) a.c3[row] = cc;
-          }
-        }
+        for (int j = 0; j < NJ; ++j) av[j] = ((gm >> j) & 1u) ? lds128(ra + j * LK_GROUP_BYTES) : make_double2(0.0, 0.0);
+      } else {
+        double s = 0.0, s2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          ga[j].x = fma(rr, av[r][j].x, ga[j].x);
-          ga[j].y = fma(rr, av[r][j].y, ga[j].y);
+          if ((gm >> j) & 1u) {
+            av[j] = lds128(ra + j * LK_GROUP_BYTES);
+            const double2 wv = lds128(w_base + j * 512 + lane * 16);
+            s = fma(av[j].x, wv.x, s);
+            s2 = fma(av[j].y, wv.y, s2);
+          } else {
+            av[j] = make_double2(0.0, 0.0);
+          }
+        }
+        s = warp_sum(s + s2);
+        const double yv = lds64(sb + NJ * LK_GROUP_BYTES + wrow * 8);
+        const double sz = a.size ? lds64(sb + NJ * LK_GROUP_BYTES + LK_KB * 8 + wrow * 8) : 1.0;
+        double ww, cc;
+        obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
+        if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
+        if (lane == 0) {
+          a.eta[row] = s;
+          a.wobs[row] = ww;
+          if (a.c3) a.c3[row] = cc;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if ((gm >> j) & 1u) {
+          ga[j].x = fma(rr, av[j].x, ga[j].x);
+          ga[j].y = fma(rr, av[j].y, ga[j].y);
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) lk_arrive(empty_base + 8 * slot);
   }
-  // ---- block reduction in a fixed order ------------------------------------------------------
-  double* sg = sm + (size_t)warp * lda;
+  // ---- block reduction in a fixed order (the ring is drained: reuse its memory) -------------------------
+  asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+  double* sg = sm_gen + (size_t)warp * (NJ * 64);
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    if (c < lda) *reinterpret_cast<double2*>(sg + c) = ga[j];
-  }
-  double* ss = sm + (size_t)LIK_WARPS * lda;
+  for (int j = 0; j < NJ; ++j) *reinterpret_cast<double2*>(sg + 64 * j + 2 * lane) = ga[j];
+  double* ss = sm_gen + (size_t)NCW * (NJ * 64);
   if (lane == 0) {
     ss[warp * 4 + 0] = ll;
     ss[warp * 4 + 1] = sumsq;
     ss[warp * 4 + 2] = (double)bad;
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < lda; c += LIK_THREADS) {
+  asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+  for (int c = tid; c < lda; c += NCW * 32) {
     double s = 0.0;
 #pragma unroll
-    for (int w8 = 0; w8 < LIK_WARPS; ++w8) s += sm[(size_t)w8 * lda + c];
+    for (int w8 = 0; w8 < NCW; ++w8) s += sm_gen[(size_t)w8 * (NJ * 64) + c];
     a.part_g[(size_t)blockIdx.x * lda + c] = s;
   }
-  if (threadIdx.x < 3) {
+  if (tid < 3) {
     double s = 0.0;
 #pragma unroll
-    for (int w8 = 0; w8 < LIK_WARPS; ++w8) s += ss[w8 * 4 + threadIdx.x];
-    a.part_s[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+    for (int w8 = 0; w8 < NCW; ++w8) s += ss[w8 * 4 + tid];
+    a.part_s[(size_t)blockIdx.x * 4 + tid] = s;
   }
 }
 
-template <int NJ, int R>
+template <int NJ>
 static int launch_lik_t(bgp_model* m, const LikArgs& a) {
-  const size_t smem = ((size_t)LIK_WARPS * a.lda + LIK_WARPS * 4) * sizeof(double);
+  constexpr int smem = lk_stages(NJ) * lk_stage_bytes(NJ) + NJ * 512 + 16 * lk_stages(NJ) + 256;
+  static_assert(lk_stages(NJ) >= 2, "likelihood ring needs at least two stages");
+  static_assert(LK_CONSUMERS * lk_groups(NJ) * (NJ * 64 * 8 + 32) <= lk_stages(NJ) * lk_stage_bytes(NJ), "reduction scratch must fit in the ring");
   static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  if (!attr_set) {
+    BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  lik_kernel<NJ, R><<<m->lik_blocks, LIK_THREADS, smem, m->stream>>>(a);
+  const LikPlan* pl = (const LikPlan*)m->lik_plan;
+  lik_kernel<NJ><<<m->lik_blocks, lk_threads(NJ), smem, m->stream>>>(pl->tmA, a);
   count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
@@ -182,12 +280,28 @@ static int launch_lik_t(bgp_model* m, const LikArgs& a) {
 
 int lik_max_lda() { return 1024; }
 
+int lik_plan_create(bgp_model* m) {
+  LikPlan* pl = new LikPlan();
+  m->lik_plan = pl;
+  if (make_tensormap_f64(&pl->tmA, m->A, (uint64_t)m->lda, (uint64_t)m->n, (uint64_t)m->lda, 64,
+                         (uint32_t)lk_kb((m->lda + 63) / 64), false) != 0) {
+    set_error("cuTensorMapEncodeTiled failed for the likelihood kernel");
+    return BGP_ERR_CUDA;
+  }
+  return BGP_OK;
+}
+
+void lik_plan_destroy(bgp_model* m) {
+  delete (LikPlan*)m->lik_plan;
+  m->lik_plan = nullptr;
+}
+
 int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, const double* rvec) {
   LikArgs a;
   a.rvec = rvec;
-  a.A = m->A;
   a.lda = m->lda;
   a.n = m->n;
+  a.nchunks = m->nchunks;
   a.W = W_dev;
   a.y = m->y;
   a.size = m->family == BGP_FAMILY_BINOMIAL ? m->size : nullptr;
@@ -198,20 +312,21 @@ int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, cons
   a.c3 = want_c3 ? m->c3 : nullptr;
   a.part_g = m->part_g;
   a.part_s = m->part_s;
+  a.occ = (const unsigned long long*)m->occ_dev;
   const int nj = (m->lda + 63) / 64;
   switch (nj) {
-    case 1: return launch_lik_t<1, 4>(m, a);
-    case 2: return launch_lik_t<2, 4>(m, a);
-    case 3: return launch_lik_t<3, 2>(m, a);
-    case 4: return launch_lik_t<4, 2>(m, a);
-    case 5: return launch_lik_t<5, 2>(m, a);
-    case 6: return launch_lik_t<6, 2>(m, a);
-    case 7: return launch_lik_t<7, 2>(m, a);
-    case 8: return launch_lik_t<8, 2>(m, a);
-    case 9: case 10: return launch_lik_t<10, 1>(m, a);
-    case 11: case 12: return launch_lik_t<12, 1>(m, a);
-    case 13: case 14: return launch_lik_t<14, 1>(m, a);
-    case 15: case 16: return launch_lik_t<16, 1>(m, a);
+    case 1: return launch_lik_t<1>(m, a);
+    case 2: return launch_lik_t<2>(m, a);
+    case 3: return launch_lik_t<3>(m, a);
+    case 4: return launch_lik_t<4>(m, a);
+    case 5: return launch_lik_t<5>(m, a);
+    case 6: return launch_lik_t<6>(m, a);
+    case 7: return launch_lik_t<7>(m, a);
+    case 8: return launch_lik_t<8>(m, a);
+    case 9: case 10: return launch_lik_t<10>(m, a);
+    case 11: case 12: return launch_lik_t<12>(m, a);
+    case 13: case 14: return launch_lik_t<14>(m, a);
+    case 15: case 16: return launch_lik_t<16>(m, a);
     default:
       set_error("latent dimension p = %d exceeds the supported maximum of %d", m->p, lik_max_lda());
       return BGP_ERR_ARG;

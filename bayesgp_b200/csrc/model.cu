@@ -104,10 +104,13 @@ int bgp_model_new(int64_t n, int family, const double* y, const double* size, in
   int st = [&]() -> int {
     BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     const size_t nb = (size_t)n * sizeof(double);
-    BGP_CUDA(cudaMalloc(&m->y, nb));
+    const size_t nb_pad = (size_t)(round_up64(n, 64) + 64) * sizeof(double);   // bulk copies read whole 8-row stages
+    BGP_CUDA(cudaMalloc(&m->y, nb_pad));
+    BGP_CUDA(cudaMemsetAsync(m->y, 0, nb_pad, m->stream));
     BGP_CUDA(cudaMemcpyAsync(m->y, y, nb, cudaMemcpyHostToDevice, m->stream));
     if (family == BGP_FAMILY_BINOMIAL) {
-      BGP_CUDA(cudaMalloc(&m->size, nb));
+      BGP_CUDA(cudaMalloc(&m->size, nb_pad));
+      BGP_CUDA(cudaMemsetAsync(m->size, 0, nb_pad, m->stream));
       if (size) {
         BGP_CUDA(cudaMemcpyAsync(m->size, size, nb, cudaMemcpyHostToDevice, m->stream));
       } else {
@@ -397,11 +400,7 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->Tan, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-  const int nj = (m->lda + 63) / 64;
-  const int rows_per_it = nj <= 2 ? 4 : (nj <= 8 ? 2 : 1);
-  int64_t blocks = (int64_t)sms * (nj <= 5 ? 4 : (nj <= 8 ? 3 : 1));
-  const int64_t max_blocks = (n + 8 * rows_per_it - 1) / (8 * rows_per_it);
-  m->lik_blocks = (int)std::max<int64_t>(1, std::min(blocks, max_blocks));
+  m->lik_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (n + 7) / 8));   // one persistent CTA per SM
   BGP_TRY(dalloc(&m->part_g, (size_t)m->lik_blocks * m->lda * sizeof(double)));
   BGP_TRY(dalloc(&m->part_s, (size_t)m->lik_blocks * 4 * sizeof(double)));
   BGP_TRY(dalloc(&m->red_buf, ((size_t)m->lda + 8) * sizeof(double)));
@@ -411,6 +410,7 @@ int bgp_model_finalize(bgp_model* m) {
   for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
   BGP_TRY(build_row_order(m));
   BGP_TRY(syrk_plan_create(m));
+  BGP_TRY(lik_plan_create(m));
   if (m->world > 1) {
     // the likelihood constant and n are global quantities
     double buf[2] = {m->ll_const, (double)m->n};
@@ -430,6 +430,7 @@ void bgp_model_destroy(bgp_model* m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   syrk_plan_destroy(m);
+  lik_plan_destroy(m);
   grad_plan_destroy(m);
   comm_destroy(m);
   for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix})

@@ -79,9 +79,9 @@ inline EncodeTiledFn get_tensormap_encoder() {
 }
 
 // FP64 2-D tensor map over a row-major matrix (rows x ld doubles), box = {box_cols (<=16), box_rows},
-// 128-byte swizzle, out-of-bounds elements read as zero.
+// 128-byte swizzle (box_cols <= 16) or none (box_cols <= 256), out-of-bounds elements read as zero.
 inline int make_tensormap_f64(CUtensorMap* tm, const double* base, uint64_t cols, uint64_t rows, uint64_t ld,
-                              uint32_t box_cols, uint32_t box_rows) {
+                              uint32_t box_cols, uint32_t box_rows, bool swizzle128 = true) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) return -1;
   const cuuint64_t gdim[2] = {cols, rows};
@@ -89,7 +89,8 @@ inline int make_tensormap_f64(CUtensorMap* tm, const double* base, uint64_t cols
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }

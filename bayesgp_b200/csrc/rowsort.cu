@@ -115,7 +115,9 @@ int build_row_order(bgp_model* m) {
       cudaFree(m->A);
       m->A = A2;
       double* v2 = nullptr;
-      BGP_CUDA(cudaMalloc(&v2, (size_t)n * sizeof(double)));
+      const size_t nb_pad = (size_t)(round_up64(n, 64) + 64) * sizeof(double);
+      BGP_CUDA(cudaMalloc(&v2, nb_pad));
+      BGP_CUDA(cudaMemsetAsync(v2, 0, nb_pad, m->stream));
       const unsigned vb = (unsigned)((n + 255) / 256);
       gather_vec_kernel<<<vb, 256, 0, m->stream>>>(m->y, idx2, n, v2);
       count_launch();

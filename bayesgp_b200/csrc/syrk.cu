@@ -174,12 +174,25 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     // ---------------- producer warp: one elected lane issues the TMA boxes and the weights ---------
     if (lane != 0) return;
     int it = 0;
+    // software prefetch: the entry two chunks ahead, its tile descriptor and occupancy word one chunk ahead
+    // (three dependent L2 round trips would otherwise sit in front of every chunk)
+    uint32_t ent_n = __ldg(entries + e_begin);
+    uint32_t ent_nn = e_begin + 1 < e_end ? __ldg(entries + e_begin + 1) : 0u;
+    SkTile t_n = tiles[ent_n >> 24];
+    unsigned long long occ_n = __ldg(occ + (ent_n & 0xffffffu));
     for (int e = e_begin; e < e_end; ++e) {
-      const uint32_t ent = __ldg(entries + e);
+      const uint32_t ent = ent_n;
       const int tile = (int)(ent >> 24), chunk = (int)(ent & 0xffffffu);
-      const SkTile t = tiles[tile];
+      const SkTile t = t_n;
+      const unsigned long long occ_c = occ_n;
+      if (e + 1 < e_end) {
+        ent_n = ent_nn;
+        t_n = tiles[ent_n >> 24];
+        occ_n = __ldg(occ + (ent_n & 0xffffffu));
+        if (e + 2 < e_end) ent_nn = __ldg(entries + e + 2);
+      }
       uint32_t act_m, load_m, need_n;
-      sk_chunk_masks(t, __ldg(occ + chunk), act_m, load_m, need_n);
+      sk_chunk_masks(t, occ_c, act_m, load_m, need_n);
       const uint32_t tx = (uint32_t)(__popc(load_m) + __popc(need_n)) * SK_BOX_BYTES + SK_W_BYTES;
       const int ncol0 = 4 * t.J * 16;
       for (int s = 0; s < SK_SPC; ++s, ++it) {
