@@ -22,9 +22,12 @@
 //     the list, single boxes by a per-stage 4-bit mask that selects a compile-time-specialised loop body
 //     (a predicated-off DMMA still occupies the pipe, so skipping has to be a branch).  Boxes above the
 //     diagonal or outside the lda x lda matrix are masked the same way.
-//   * Stream-K scheduling: the host cuts the cost-weighted work list into one contiguous slice per CTA;
-//     a CTA flushes its accumulators to a private partial slot whenever the tile changes.  Partials are
-//     summed in a fixed order (deterministic), mirrored to the upper triangle, then Q(theta) is added.
+//   * Scheduling: the work list is cut into units = (tile, range of chunks) of roughly equal cost, ordered
+//     range-major (units that read the same observations run at the same time and share them through L2),
+//     with finer units at the end of the queue.  Persistent CTAs take units from an atomic counter, so the
+//     load balances whatever the co-resident CTAs do; every unit owns a private partial slot and the
+//     slots of a tile are summed in a fixed order, so the result does not depend on which CTA ran what
+//     (bit-reproducible).  The sum is mirrored to the upper triangle, then Q(theta) is added.
 #include <cuda.h>
 
 #include <algorithm>
@@ -70,11 +73,16 @@ struct SyrkPlan {
   int ntiles = 0, G = 0, nslots = 0;
   SkTile* tiles_dev = nullptr;
   uint32_t* entries_dev = nullptr; // tile << 24 | chunk
-  int* cta_begin_dev = nullptr;    // G + 1
-  int* cta_slot_dev = nullptr;     // first partial slot of each CTA
+  int2* units_dev = nullptr;       // per unit: [entry begin, entry end)
+  int nunits = 0;
+  int* counter_dev = nullptr;      // work queue head (reset before every launch)
   int* tile_slots_dev = nullptr;   // CSR of partial slots per tile
   double useful_flops = 0.0;       // structurally non-zero flops per launch
   int64_t nentries = 0;
+  unsigned long long* dbg_dev = nullptr;   // BGP_SK_DEBUG: per-CTA start / end timestamps
+  std::vector<int64_t> unit_cost_dbg;
+  std::vector<int> unit_tile_dbg;
+  int dbg_left = 0;
 };
 
 using namespace ptx;
@@ -88,9 +96,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
-__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
 
@@ -147,18 +158,22 @@ __host__ __device__ __forceinline__ void sk_chunk_masks(const SkTile& t, unsigne
 
 __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     syrk_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ wobs, double* __restrict__ part,
-                const SkTile* __restrict__ tiles, const uint32_t* __restrict__ entries, const int* __restrict__ cta_begin,
-                const int* __restrict__ cta_slot, const unsigned long long* __restrict__ occ) {
+                const SkTile* __restrict__ tiles, const uint32_t* __restrict__ entries, const int2* __restrict__ units,
+                int nunits, int* __restrict__ counter, const unsigned long long* __restrict__ occ,
+                unsigned long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    dbg[2 * blockIdx.x] = t0;
+  }
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base + SK_STAGES * SK_STAGE_BYTES;
-  const uint32_t meta_base = w_base + SK_STAGES * SK_W_BYTES;      // 16 B per stage: {masks, tile}
+  const uint32_t meta_base = w_base + SK_STAGES * SK_W_BYTES;      // 16 B per stage: {masks, tile, unit, -}
   const uint32_t full_base = meta_base + 16 * SK_STAGES;
   const uint32_t empty_base = full_base + 8 * SK_STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int e_begin = cta_begin[blockIdx.x], e_end = cta_begin[blockIdx.x + 1];
-  const int nstage = (e_end - e_begin) * SK_SPC;
 
   if (tid == 0) {
     for (int s = 0; s < SK_STAGES; ++s) {
@@ -168,49 +183,68 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     mbar_fence_init();
   }
   __syncthreads();
-  if (nstage == 0) return;
 
   if (warp == SK_CONSUMERS) {
-    // ---------------- producer warp: one elected lane issues the TMA boxes and the weights ---------
+    // ---------------- producer warp: one elected lane takes units from the queue, issues the TMA boxes
     if (lane != 0) return;
     int it = 0;
-    // software prefetch: the entry two chunks ahead, its tile descriptor and occupancy word one chunk ahead
-    // (three dependent L2 round trips would otherwise sit in front of every chunk)
-    uint32_t ent_n = __ldg(entries + e_begin);
-    uint32_t ent_nn = e_begin + 1 < e_end ? __ldg(entries + e_begin + 1) : 0u;
-    SkTile t_n = tiles[ent_n >> 24];
-    unsigned long long occ_n = __ldg(occ + (ent_n & 0xffffffu));
-    for (int e = e_begin; e < e_end; ++e) {
-      const uint32_t ent = ent_n;
-      const int tile = (int)(ent >> 24), chunk = (int)(ent & 0xffffffu);
-      const SkTile t = t_n;
-      const unsigned long long occ_c = occ_n;
-      if (e + 1 < e_end) {
-        ent_n = ent_nn;
-        t_n = tiles[ent_n >> 24];
-        occ_n = __ldg(occ + (ent_n & 0xffffffu));
-        if (e + 2 < e_end) ent_nn = __ldg(entries + e + 2);
+    int unit = atomicAdd(counter, 1);
+    while (unit < nunits) {
+      const int unit_next = atomicAdd(counter, 1);      // in flight while this unit is being issued
+      if (dbg) {
+        unsigned long long tu;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tu));
+        dbg[2 * gridDim.x + 2 * unit] = tu;
+        dbg[2 * gridDim.x + 2 * unit + 1] = blockIdx.x;
       }
-      uint32_t act_m, load_m, need_n;
-      sk_chunk_masks(t, occ_c, act_m, load_m, need_n);
-      const uint32_t tx = (uint32_t)(__popc(load_m) + __popc(need_n)) * SK_BOX_BYTES + SK_W_BYTES;
-      const int ncol0 = 4 * t.J * 16;
-      for (int s = 0; s < SK_SPC; ++s, ++it) {
-        const int slot = it % SK_STAGES;
-        const uint32_t fb = full_base + 8 * slot;
-        const uint32_t sb = base + slot * SK_STAGE_BYTES;
-        mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
-        const int row = chunk * 64 + s * SK_KB;
-        sts64(meta_base + 16 * slot, act_m | (need_n << 8), (uint32_t)tile);   // rows present | N boxes present
-        mbar_expect_tx(fb, tx);
+      const int2 ur = units[unit];
+      const int e_begin = ur.x, e_end = ur.y;
+      // software prefetch: the entry two chunks ahead, its tile descriptor and occupancy word one chunk ahead
+      // (three dependent L2 round trips would otherwise sit in front of every chunk)
+      uint32_t ent_n = __ldg(entries + e_begin);
+      uint32_t ent_nn = e_begin + 1 < e_end ? __ldg(entries + e_begin + 1) : 0u;
+      SkTile t_n = tiles[ent_n >> 24];
+      unsigned long long occ_n = __ldg(occ + (ent_n & 0xffffffu));
+      for (int e = e_begin; e < e_end; ++e) {
+        const uint32_t ent = ent_n;
+        const int tile = (int)(ent >> 24), chunk = (int)(ent & 0xffffffu);
+        const SkTile t = t_n;
+        const unsigned long long occ_c = occ_n;
+        if (e + 1 < e_end) {
+          ent_n = ent_nn;
+          t_n = tiles[ent_n >> 24];
+          occ_n = __ldg(occ + (ent_n & 0xffffffu));
+          if (e + 2 < e_end) ent_nn = __ldg(entries + e + 2);
+        }
+        uint32_t act_m, load_m, need_n;
+        sk_chunk_masks(t, occ_c, act_m, load_m, need_n);
+        const uint32_t tx = (uint32_t)(__popc(load_m) + __popc(need_n)) * SK_BOX_BYTES + SK_W_BYTES;
+        const int ncol0 = 4 * t.J * 16;
+        for (int s = 0; s < SK_SPC; ++s, ++it) {
+          const int slot = it % SK_STAGES;
+          const uint32_t fb = full_base + 8 * slot;
+          const uint32_t sb = base + slot * SK_STAGE_BYTES;
+          mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
+          const int row = chunk * 64 + s * SK_KB;
+          sts128(meta_base + 16 * slot, act_m | (need_n << 8), (uint32_t)tile, (uint32_t)unit, 0u);   // rows | N boxes present
+          mbar_expect_tx(fb, tx);
 #pragma unroll
-        for (int b = 0; b < SK_MBOX; ++b)
-          if ((load_m >> b) & 1u) tma_load_2d(sb + b * SK_BOX_BYTES, &tmA, 16 * t.rows[b], row, fb);
+          for (int b = 0; b < SK_MBOX; ++b)
+            if ((load_m >> b) & 1u) tma_load_2d(sb + b * SK_BOX_BYTES, &tmA, 16 * t.rows[b], row, fb);
 #pragma unroll
-        for (int b = 0; b < SK_NBOX; ++b)
-          if ((need_n >> b) & 1u) tma_load_2d(sb + (SK_MBOX + b) * SK_BOX_BYTES, &tmA, ncol0 + b * 16, row, fb);
-        bulk_load_1d(w_base + slot * SK_W_BYTES, wobs + row, SK_W_BYTES, fb);
+          for (int b = 0; b < SK_NBOX; ++b)
+            if ((need_n >> b) & 1u) tma_load_2d(sb + (SK_MBOX + b) * SK_BOX_BYTES, &tmA, ncol0 + b * 16, row, fb);
+          bulk_load_1d(w_base + slot * SK_W_BYTES, wobs + row, SK_W_BYTES, fb);
+        }
       }
+      unit = unit_next;
+    }
+    // end of queue: one empty stage tells the consumers to flush and leave
+    {
+      const int slot = it % SK_STAGES;
+      mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
+      sts128(meta_base + 16 * slot, 0u, 0u, 0xffffffffu, 1u);
+      mbar_arrive(full_base + 8 * slot);
     }
     return;
   }
@@ -229,12 +263,12 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
         for (int c = 0; c < 2; ++c) acc[a][b][c][0] = acc[a][b][c][1] = 0.0;
   };
   zero_acc();
-  int cur_tile = -1, nflush = 0;
+  int cur_unit = -1;
   uint32_t smask_w = 0;       // bit s: box (rows[s], 4J + wc) belongs to the lower triangle
   uint32_t a_off[4] = {0, 0, 0, 0};
   auto flush = [&]() {
     // undo the column permutation, write this column strip of the partial tile (row-major [16 * s + m][n])
-    double* out = part + (size_t)(cta_slot[blockIdx.x] + nflush) * SK_TILE_ELEMS;
+    double* out = part + (size_t)cur_unit * SK_TILE_ELEMS;
 #pragma unroll
     for (int sr = 0; sr < 4; ++sr) {
       if (!((smask_w >> sr) & 1u)) continue;
@@ -250,20 +284,23 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
           }
       }
     }
-    ++nflush;
   };
-  for (int it = 0; it < nstage; ++it) {
+  for (int it = 0;; ++it) {
     const int slot = it % SK_STAGES;
     mbar_wait(full_base + 8 * slot, (uint32_t)((it / SK_STAGES) & 1));
-    const uint2 meta = lds_u2(meta_base + 16 * slot);
-    const int tile = (int)meta.y;
-    if (tile != cur_tile) {
-      if (cur_tile >= 0) {
+    const uint4 meta = lds_u4(meta_base + 16 * slot);
+    const int unit = (int)meta.z;
+    if (meta.w) {                 // end of queue
+      if (cur_unit >= 0) flush();
+      break;
+    }
+    if (unit != cur_unit) {
+      if (cur_unit >= 0) {
         flush();
         zero_acc();
       }
-      cur_tile = tile;
-      const SkTile* tp = tiles + tile;
+      cur_unit = unit;
+      const SkTile* tp = tiles + meta.y;
       const uint32_t sm = tp->smask;
       const int j4 = 4 * tp->J;
       smask_w = 0;
@@ -301,7 +338,11 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_base + 8 * slot);
   }
-  flush();
+  if (dbg && warp == 0 && lane == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    dbg[2 * blockIdx.x + 1] = t1;
+  }
 }
 
 // sum the partial slots of each tile in a fixed order, write the lower triangle and its mirror
@@ -418,65 +459,82 @@ int syrk_plan_create(bgp_model* m) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   pl->G = SK_CTAS_PER_SM * sms;
-  // work list: tile-major, chunks ascending; cost = fixed per-chunk overhead + DMMA work
-  int cost_mode = 1;
-  if (const char* e = getenv("BGP_SK_COST")) cost_mode = atoi(e);
-  std::vector<uint32_t> entries;
-  std::vector<uint8_t> cost;
-  entries.reserve((size_t)pl->ntiles * m->nchunks / 2);
-  cost.reserve((size_t)pl->ntiles * m->nchunks / 2);
+  // Work list.  A unit is (tile, run of chunks) of bounded cost; the queue walks the observations from the
+  // last block to the first (after the zero-pattern sort the late blocks are the densest) and visits every
+  // tile per block, so the CTAs that run at the same time read the same observations (L2 reuse).  Unit
+  // cost: total / (5 G) for the first 70 % of the work, then 1/2 and 1/4 of that (short queue tail).
+  // cost of a chunk = fixed overhead + DMMA time of the busiest consumer warp (warp b owns column box b).
+  auto chunk_cost = [&](const SkTile& t, uint64_t o, int& boxes) -> int {
+    uint32_t act_m, load_m, need_n;
+    sk_chunk_masks(t, o, act_m, load_m, need_n);
+    boxes = 0;
+    if (!act_m) return 0;
+    const uint32_t ncol = (uint32_t)(o >> (4 * t.J)) & 0xfu;
+    int mx = 0;
+    for (int b = 0; b < SK_NBOX; ++b) {
+      int bw = 0;
+      if ((ncol >> b) & 1u)
+        for (int w = 0; w < SK_MBOX; ++w) bw += (int)((act_m >> w) & 1u) & (int)((t.smask >> (4 * w + b)) & 1u);
+      boxes += bw;
+      mx = std::max(mx, bw);
+    }
+    return boxes ? 2 + 4 * mx : 0;
+  };
   double boxes_total = 0.0;
   int64_t cost_total = 0;
-  for (int ti = 0; ti < pl->ntiles; ++ti) {
-    const SkTile& t = tiles[ti];
+  for (int ti = 0; ti < pl->ntiles; ++ti)
     for (int64_t c = 0; c < m->nchunks; ++c) {
-      const uint64_t o = m->occ_host[(size_t)c];
-      uint32_t act_m, load_m, need_n;
-      sk_chunk_masks(t, o, act_m, load_m, need_n);
-      if (!act_m) continue;
-      const uint32_t ncol = (uint32_t)(o >> (4 * t.J)) & 0xfu;
-      // consumer warp b owns column box b: a chunk takes as long as the busiest warp
-      int boxes = 0, mx = 0;
-      for (int b = 0; b < SK_NBOX; ++b) {
-        int bw = 0;
-        if ((ncol >> b) & 1u)
-          for (int w = 0; w < SK_MBOX; ++w) bw += (int)((act_m >> w) & 1u) & (int)((t.smask >> (4 * w + b)) & 1u);
-        boxes += bw;
-        mx = std::max(mx, bw);
-      }
-      const int cst = 2 + (cost_mode == 0 ? boxes : (cost_mode == 1 ? 4 * mx : 2 * mx + boxes / 2));
-      entries.push_back(((uint32_t)ti << 24) | (uint32_t)c);
-      cost.push_back((uint8_t)cst);
+      int boxes;
+      cost_total += chunk_cost(tiles[ti], m->occ_host[(size_t)c], boxes);
       boxes_total += boxes;
-      cost_total += cst;
+    }
+  const int64_t unit_target = std::max<int64_t>(64, cost_total / ((int64_t)5 * pl->G));
+  const int64_t blk = 8;                                   // chunks per block of the walk
+  std::vector<uint32_t> entries;
+  std::vector<int2> units;
+  std::vector<int64_t> unit_cost_fine;
+  std::vector<int> unit_tile_fine;
+  entries.reserve((size_t)pl->ntiles * m->nchunks / 2);
+  std::vector<std::vector<uint32_t>> pend((size_t)pl->ntiles);
+  std::vector<int64_t> pend_cost((size_t)pl->ntiles, 0);
+  int64_t done_cost = 0;
+  auto emit = [&](int ti) {
+    if (pend[(size_t)ti].empty()) return;
+    const int e0 = (int)entries.size();
+    entries.insert(entries.end(), pend[(size_t)ti].begin(), pend[(size_t)ti].end());
+    units.push_back(make_int2(e0, (int)entries.size()));
+    unit_cost_fine.push_back(pend_cost[(size_t)ti]);
+    done_cost += pend_cost[(size_t)ti];
+    pend[(size_t)ti].clear();
+    pend_cost[(size_t)ti] = 0;
+  };
+  const int64_t nblk = (m->nchunks + blk - 1) / blk;
+  for (int64_t bk = nblk - 1; bk >= 0; --bk) {
+    const int64_t c0 = bk * blk, c1 = std::min<int64_t>(m->nchunks, c0 + blk);
+    for (int ti = 0; ti < pl->ntiles; ++ti) {
+      for (int64_t c = c0; c < c1; ++c) {
+        int boxes;
+        const int cst = chunk_cost(tiles[ti], m->occ_host[(size_t)c], boxes);
+        if (!cst) continue;
+        pend[(size_t)ti].push_back(((uint32_t)ti << 24) | (uint32_t)c);
+        pend_cost[(size_t)ti] += cst;
+      }
+      const int64_t target = done_cost * 100 < cost_total * 70 ? unit_target
+                             : (done_cost * 100 < cost_total * 85 ? unit_target / 2 : unit_target / 4);
+      if (pend_cost[(size_t)ti] >= target) emit(ti);
     }
   }
+  for (int ti = 0; ti < pl->ntiles; ++ti) emit(ti);
+  pl->nunits = (int)units.size();
+  pl->nslots = pl->nunits;
   pl->nentries = (int64_t)entries.size();
   pl->useful_flops = boxes_total * 64.0 * 16.0 * 16.0 * 2.0;
-  // stream-K: contiguous slices of equal cost
-  std::vector<int> cta_begin((size_t)pl->G + 1, 0), cta_slot((size_t)pl->G, 0);
+  // partial slot of a unit = its index; the slots of a tile are summed in queue order
   std::vector<std::vector<int>> slots_of_tile((size_t)pl->ntiles);
-  {
-    int64_t acc = 0;
-    size_t e = 0;
-    int nslots = 0;
-    for (int g = 0; g < pl->G; ++g) {
-      cta_begin[(size_t)g] = (int)e;
-      cta_slot[(size_t)g] = nslots;
-      const int64_t target = (cost_total * (int64_t)(g + 1)) / pl->G;
-      int last_tile = -1;
-      while (e < entries.size() && (acc < target || g == pl->G - 1)) {
-        const int ti = (int)(entries[e] >> 24);
-        if (ti != last_tile) {
-          slots_of_tile[(size_t)ti].push_back(nslots++);
-          last_tile = ti;
-        }
-        acc += cost[e];
-        ++e;
-      }
-    }
-    cta_begin[(size_t)pl->G] = (int)e;
-    pl->nslots = nslots;
+  for (int u = 0; u < pl->nunits; ++u) {
+    const int ti = (int)(entries[(size_t)units[(size_t)u].x] >> 24);
+    slots_of_tile[(size_t)ti].push_back(u);
+    unit_tile_fine.push_back(ti);
   }
   std::vector<int> tile_slots;
   for (int ti = 0; ti < pl->ntiles; ++ti) {
@@ -492,22 +550,29 @@ int syrk_plan_create(bgp_model* m) {
   };
   BGP_TRY(upload(&pl->tiles_dev, tiles));
   BGP_TRY(upload(&pl->entries_dev, entries));
-  BGP_TRY(upload(&pl->cta_begin_dev, cta_begin));
-  BGP_TRY(upload(&pl->cta_slot_dev, cta_slot));
+  BGP_TRY(upload(&pl->units_dev, units));
+  BGP_CUDA(cudaMalloc(&pl->counter_dev, sizeof(int)));
   BGP_TRY(upload(&pl->tile_slots_dev, tile_slots));
   m->part_H_bytes = (size_t)std::max(1, pl->nslots) * SK_TILE_ELEMS * sizeof(double);
   BGP_CUDA(cudaMalloc(&m->part_H, m->part_H_bytes));
   BGP_CUDA(cudaMemset(m->part_H, 0, m->part_H_bytes));
   BGP_CUDA(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
   m->hess_useful_flops = pl->useful_flops;
+  if (getenv("BGP_SK_DEBUG")) {
+    BGP_CUDA(cudaMalloc(&pl->dbg_dev, ((size_t)pl->G * 2 + (size_t)pl->nunits * 2) * sizeof(unsigned long long)));
+    pl->unit_cost_dbg = unit_cost_fine;
+    pl->unit_tile_dbg = unit_tile_fine;
+    pl->dbg_left = 3;
+    fprintf(stderr, "[syrk] tiles %d entries %lld units %d G %d\n", pl->ntiles, (long long)pl->nentries, pl->nunits, pl->G);
+  }
   return BGP_OK;
 }
 
 void syrk_plan_destroy(bgp_model* m) {
   SyrkPlan* pl = (SyrkPlan*)m->syrk_plan;
   if (!pl) return;
-  for (void* ptr : {(void*)pl->tiles_dev, (void*)pl->entries_dev, (void*)pl->cta_begin_dev, (void*)pl->cta_slot_dev,
-                    (void*)pl->tile_slots_dev})
+  for (void* ptr : {(void*)pl->tiles_dev, (void*)pl->entries_dev, (void*)pl->units_dev, (void*)pl->counter_dev,
+                    (void*)pl->tile_slots_dev, (void*)pl->dbg_dev})
     if (ptr) cudaFree(ptr);
   delete pl;
   m->syrk_plan = nullptr;
@@ -516,10 +581,62 @@ void syrk_plan_destroy(bgp_model* m) {
 // H_lik = A^T diag(w) A (both triangles); Q is added by launch_add_q after the optional allreduce
 int launch_syrk(bgp_model* m) {
   SyrkPlan* pl = (SyrkPlan*)m->syrk_plan;
+  BGP_CUDA(cudaMemsetAsync(pl->counter_dev, 0, sizeof(int), m->stream));
   syrk_kernel<<<pl->G, SK_THREADS, SK_SMEM, m->stream>>>(pl->tmA, m->wobs, m->part_H, pl->tiles_dev, pl->entries_dev,
-                                                        pl->cta_begin_dev, pl->cta_slot_dev,
-                                                        (const unsigned long long*)m->occ_dev);
+                                                        pl->units_dev, pl->nunits, pl->counter_dev,
+                                                        (const unsigned long long*)m->occ_dev, pl->dbg_dev);
   count_launch();
+  if (pl->dbg_dev && pl->dbg_left > 0) {
+    --pl->dbg_left;
+    std::vector<unsigned long long> h((size_t)pl->G * 2 + (size_t)pl->nunits * 2);
+    cudaStreamSynchronize(m->stream);
+    cudaMemcpy(h.data(), pl->dbg_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (int g = 0; g < pl->G; ++g) {
+      t0 = std::min(t0, h[2 * g]);
+      t1 = std::max(t1, h[2 * g + 1]);
+    }
+    std::vector<double> dur((size_t)pl->G), endt((size_t)pl->G);
+    for (int g = 0; g < pl->G; ++g) {
+      dur[g] = (double)(h[2 * g + 1] - h[2 * g]) * 1e-3;
+      endt[g] = (double)(h[2 * g + 1] - t0) * 1e-3;
+    }
+    std::vector<double> sd = dur, se = endt;
+    std::sort(sd.begin(), sd.end());
+    std::sort(se.begin(), se.end());
+    fprintf(stderr, "[syrk] span %.1f us; CTA duration min %.1f p10 %.1f med %.1f p90 %.1f max %.1f; end time p10 %.1f med %.1f p90 %.1f\n",
+            (double)(t1 - t0) * 1e-3, sd.front(), sd[sd.size() / 10], sd[sd.size() / 2], sd[sd.size() * 9 / 10], sd.back(),
+            se[se.size() / 10], se[se.size() / 2], se[se.size() * 9 / 10]);
+    if (pl->dbg_left == 0) {
+      // per-unit durations: next unit start on the same CTA (or CTA end) minus this unit's start
+      std::vector<std::vector<std::pair<unsigned long long, int>>> per_cta((size_t)pl->G);
+      for (int u = 0; u < pl->nunits; ++u)
+        per_cta[(size_t)h[2 * pl->G + 2 * u + 1]].push_back({h[2 * pl->G + 2 * u], u});
+      std::vector<double> tile_time((size_t)pl->ntiles, 0.0), tile_cost((size_t)pl->ntiles, 0.0);
+      double ttot = 0, ctot = 0;
+      for (int g = 0; g < pl->G; ++g) {
+        auto& v = per_cta[(size_t)g];
+        std::sort(v.begin(), v.end());
+        for (size_t i = 0; i < v.size(); ++i) {
+          const unsigned long long e = i + 1 < v.size() ? v[i + 1].first : h[2 * g + 1];
+          const double d = (double)(e - v[i].first) * 1e-3;
+          const int u = v[i].second;
+          tile_time[(size_t)pl->unit_tile_dbg[(size_t)u]] += d;
+          tile_cost[(size_t)pl->unit_tile_dbg[(size_t)u]] += (double)pl->unit_cost_dbg[(size_t)u];
+          ttot += d;
+          ctot += (double)pl->unit_cost_dbg[(size_t)u];
+        }
+      }
+      fprintf(stderr, "[syrk] per tile: time share / cost share (ratio):");
+      for (int t = 0; t < pl->ntiles; ++t)
+        fprintf(stderr, " %d:%.3f/%.3f(%.2f)", t, tile_time[t] / ttot, tile_cost[t] / ctot,
+                (tile_time[t] / ttot) / std::max(1e-12, tile_cost[t] / ctot));
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "[syrk] per-CTA duration by index (every 37th):");
+    for (int g = 0; g < pl->G; g += 37) fprintf(stderr, " %d:%.0f", g, dur[g]);
+    fprintf(stderr, "\n");
+  }
   syrk_reduce_kernel<<<pl->ntiles * (SK_TILE_ELEMS / 256), 256, 0, m->stream>>>(m->part_H, pl->tiles_dev,
                                                                                pl->tile_slots_dev, m->p, m->ldh, m->H);
   count_launch();
