@@ -118,7 +118,13 @@ struct bgp_model {
   double* Tan = nullptr;        // S x lda tangent d w_hat / d theta at the last mode (warm-start predictor)
   std::vector<double> theta_last;
   bool tan_valid = false;
+  // the evaluation before the last one (cubic Hermite extrapolation along collinear theta nodes)
+  double* Wmode_prev = nullptr;
+  double* Tan_prev = nullptr;
+  std::vector<double> theta_prev;
+  bool prev_valid = false;
   bool use_predictor = true;
+  bool use_hermite = true;
   double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)
   double* L = nullptr;          // Cholesky factor (lower, column-major p x ldh)
   double* Linv = nullptr;       // L^-1, row-major p x ldl (lower; allocated on first gradient call)

@@ -101,6 +101,7 @@ int bgp_model_new(int64_t n, int family, const double* y, const double* size, in
   m->family = family;
   m->device = device;
   if (const char* e = getenv("BGP_NO_PREDICTOR")) m->use_predictor = !(e[0] == '1');   // diagnostics only
+  if (const char* e = getenv("BGP_NO_HERMITE")) m->use_hermite = !(e[0] == '1');
   int st = [&]() -> int {
     BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     const size_t nb = (size_t)n * sizeof(double);
@@ -398,6 +399,8 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->L, hb));
   BGP_TRY(dalloc(&m->theta_dev, 64 * sizeof(double)));
   BGP_TRY(dalloc(&m->Tan, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
+  BGP_TRY(dalloc(&m->Tan_prev, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
+  BGP_TRY(dalloc(&m->Wmode_prev, vb));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   m->lik_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (n + 7) / 8));   // one persistent CTA per SM
@@ -439,7 +442,7 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->Tan, m->xbuf, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->Tan_prev, m->Wmode_prev, m->xbuf, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
     if (ptr) cudaFree(ptr);
   if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);

@@ -35,6 +35,26 @@ __global__ void predict_start_kernel(const PredictArgs a) {
   a.out[i] = v;
 }
 
+struct HermiteArgs {
+  const double *Wa, *Ta, *Wb, *Tb;   // a: the evaluation before the last, b: the last one
+  int S, lda;
+  double u[17];                      // theta_b - theta_a
+  double h00, h10, h01, h11;         // cubic Hermite basis at s = 1 + tau
+  double* out;
+};
+// cubic Hermite extrapolation of the mode along the line theta_a -> theta_b -> theta_c (values and
+// directional tangents at a and b): O(h^4) start instead of the O(h^2) of the tangent predictor
+__global__ void hermite_start_kernel(const HermiteArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.lda) return;
+  double ma = 0.0, mb = 0.0;
+  for (int k = 0; k < a.S; ++k) {
+    ma = fma(a.Ta[(size_t)k * a.lda + i], a.u[k], ma);
+    mb = fma(a.Tb[(size_t)k * a.lda + i], a.u[k], mb);
+  }
+  a.out[i] = a.h00 * a.Wa[i] + a.h10 * ma + a.h01 * a.Wb[i] + a.h11 * mb;
+}
+
 static inline double tau_of(const bgp_model* m, const double* theta) {
   return m->family == BGP_FAMILY_GAUSSIAN ? std::exp(theta[m->S - 1]) : 1.0;
 }
@@ -72,7 +92,43 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       pa.dtheta[k] = theta[k] - m->theta_last[k];
       dmax = std::max(dmax, std::fabs(pa.dtheta[k]));
     }
-    if (dmax > 0.0 && dmax <= 2.0) {
+    // collinear with the two previous nodes (grid rows, line searches): theta = theta_b + tau (theta_b - theta_a)
+    bool hermite = false;
+    double tau = 0.0;
+    if (m->use_hermite && m->prev_valid && (int)m->theta_prev.size() == m->S && dmax > 0.0 && dmax <= 2.0) {
+      double uu = 0.0, ud = 0.0;
+      for (int k = 0; k < m->S; ++k) {
+        const double u = m->theta_last[k] - m->theta_prev[k];
+        uu += u * u;
+        ud += u * pa.dtheta[k];
+      }
+      if (uu > 0.0) {
+        tau = ud / uu;
+        double dev = 0.0;
+        for (int k = 0; k < m->S; ++k)
+          dev = std::max(dev, std::fabs(pa.dtheta[k] - tau * (m->theta_last[k] - m->theta_prev[k])));
+        hermite = dev <= 1e-12 * std::max(1.0, dmax) && tau > 0.0 && tau <= 2.0;
+      }
+    }
+    if (hermite) {
+      HermiteArgs ha;
+      ha.Wa = m->Wmode_prev;
+      ha.Ta = m->Tan_prev;
+      ha.Wb = m->Wmode;
+      ha.Tb = m->Tan;
+      ha.S = m->S;
+      ha.lda = m->lda;
+      for (int k = 0; k < m->S; ++k) ha.u[k] = m->theta_last[k] - m->theta_prev[k];
+      const double s = 1.0 + tau, s2 = s * s, s3 = s2 * s;
+      ha.h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+      ha.h10 = s3 - 2.0 * s2 + s;
+      ha.h01 = -2.0 * s3 + 3.0 * s2;
+      ha.h11 = s3 - s2;
+      ha.out = m->W;
+      hermite_start_kernel<<<blocks, threads, 0, m->stream>>>(ha);
+      count_launch();
+      predicted = true;
+    } else if (dmax > 0.0 && dmax <= 2.0) {
       pa.Wmode = m->Wmode;
       pa.Tan = m->Tan;
       pa.S = m->S;
@@ -181,6 +237,13 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     }
     logdet = sc.logdet;
   }
+  if (m->use_predictor && m->S <= 17 && m->tan_valid) {
+    // the last evaluation becomes "the one before" (pointer swap, no copy)
+    std::swap(m->Wmode, m->Wmode_prev);
+    std::swap(m->Tan, m->Tan_prev);
+    m->theta_prev = m->theta_last;
+    m->prev_valid = true;
+  }
   BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   if (m->use_predictor && m->S <= 17) {
     BGP_TRY(launch_tangent(m, theta));      // uses the factor of H(w_hat) left in m->L
@@ -231,6 +294,7 @@ int bgp_model_set_start(bgp_model* m, const double* W) {
   BGP_CUDA(cudaMemsetAsync(m->Wmode, 0, (size_t)m->lda * sizeof(double), m->stream));
   if (W) BGP_TRY(copy_vec_in(m, W, m->Wmode));
   m->tan_valid = false;
+  m->prev_valid = false;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   return BGP_OK;
 }
