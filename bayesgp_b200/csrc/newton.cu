@@ -395,4 +395,21 @@ int bgp_model_hessian_flops(const bgp_model* m, double* dense, double* structura
   return BGP_OK;
 }
 
+int bgp_model_lik_bytes(const bgp_model* m, double* dense, double* structural) {
+  if (!m || !m->finalized) {
+    set_error("model not finalized");
+    return BGP_ERR_STATE;
+  }
+  const double vec = 24.0 * (double)m->n;            // y in, eta and w out
+  if (dense) *dense = 8.0 * (double)m->n * m->lda + vec;
+  if (structural) {
+    const int nj = (m->lda + 63) / 64;
+    double groups = 0.0;
+    for (uint64_t o : m->occ_host)
+      for (int j = 0; j < nj; ++j) groups += ((o >> (4 * j)) & 0xfull) ? 1.0 : 0.0;
+    *structural = groups * 64.0 * 512.0 + vec;
+  }
+  return BGP_OK;
+}
+
 }  // extern "C"

@@ -220,6 +220,11 @@ class LaplaceObjective:
                 "lik_launches": k[0].value, "hess_launches": k[1].value, "chol_launches": k[2].value}
 
 
+    def lik_bytes(self):
+        d, u = C.c_double(), C.c_double()
+        check(self._lib.bgp_model_lik_bytes(self._h, C.byref(d), C.byref(u)))
+        return {"dense": d.value, "structural": u.value}
+
     def hessian_flops(self):
         d, u = C.c_double(), C.c_double()
         check(self._lib.bgp_model_hessian_flops(self._h, C.byref(d), C.byref(u)))

@@ -200,10 +200,14 @@ def run_b200(args):
     except Exception as e:     # torch missing / OOM: keep the bench alive, say so
         fp64_peak = None
         peak_src += "; fp64 DGEMM peak unavailable (%s)" % type(e).__name__
-    flops = float(n) * p * (p + 1)
+    hf, lb = ff.hessian_flops(), ff.lik_bytes()
+    # Roofline numerators count the work on structurally non-zero {64-observation x 16-column} cells only
+    # (what the kernels execute after the zero-pattern sort); the dense-equivalent
+    # figures n p (p+1) / 8 n (lda+3) are given beside them.
+    flops = hf["structural"]
     achieved = flops / (hess_ms * 1e-3) / 1e12
-    lda = (p + 15) // 16 * 16
-    lik_bytes = 8.0 * n * (lda + 3)
+    lik_bytes = lb["structural"]
+    lik_gbs = lik_bytes / (lik_ms * 1e-3) / 1e9
     line = {
         "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300",
         "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -212,6 +216,7 @@ def run_b200(args):
         "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d), 1-D AGHQ 15 nodes per step "
                                "per GPU, warm-started inner Newton to max|g|<1e-8 + log-det" % (n, p),
                    "nodes_per_step": K_NODES, "newton_iters_per_eval": iters_tot / (K_NODES * args.steps),
+                   "hessians_per_eval": n_hess / (K_NODES * args.steps),
                    "theta_mode": mode, "theta_sd": sd, "l2_flush": "inputs (2.4 GB design matrix) exceed the 126 MB L2",
                    "parallelism": "node-sharded replicas x%d" % world, "model_build_s": t_build},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + K_NODES),
@@ -220,10 +225,15 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": achieved,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if fp64_peak else None,
                      "traffic": None, "ms_per_launch": hess_ms, "algorithmic_flops_per_launch": flops,
-                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
-        "roofline_lik": {"bound": "hbm", "kernel": "lik_kernel (eta, ll, r, w, A^T r)", "achieved": lik_bytes / (lik_ms * 1e-3) / 1e9,
+                     "dense_flops_per_launch": hf["dense"], "structural_fraction": hf["structural"] / hf["dense"],
+                     "dense_equivalent_tflops": hf["dense"] / (hess_ms * 1e-3) / 1e12,
+                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 "
+                                    "figure); DMMA.8x8x4 issue-rate peak 37.0 TFLOP/s (scripts/ubench/dmma_bench.cu)"},
+        "roofline_lik": {"bound": "hbm", "kernel": "lik_kernel (eta, ll, r, w, A^T r)", "achieved": lik_gbs,
                          "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                         "frac": lik_bytes / (lik_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "ms_per_launch": lik_ms,
+                         "frac": lik_gbs / peaks.get("hbm_gbs", 6650.0), "ms_per_launch": lik_ms,
+                         "algorithmic_bytes_per_launch": lik_bytes, "dense_bytes_per_launch": lb["dense"],
+                         "note": "ms_per_launch includes the partial-reduction and prior kernels that follow the pass",
                          "peak_source": peak_src},
         "chol_ms_per_launch": chol_ms,
         "clocks": clocks,
@@ -312,7 +322,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)

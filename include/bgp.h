@@ -164,6 +164,9 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
 /* flops of one Hessian launch H = A^T diag(w) A: dense (n p (p+1)) and the structurally non-zero part the
  * kernel executes after skipping empty {64-observation x 16-column} cells (roofline reporting) */
 int bgp_model_hessian_flops(const bgp_model* m, double* dense, double* structural);
+/* HBM bytes of one likelihood pass: dense (8 n (lda + 3)) and the part actually moved after skipping
+ * structurally empty {64-observation x 64-column} groups */
+int bgp_model_lik_bytes(const bgp_model* m, double* dense, double* structural);
 
 #ifdef __cplusplus
 }
