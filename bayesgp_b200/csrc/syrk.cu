@@ -62,9 +62,10 @@ constexpr int SK_SMEM = SK_STAGES * (SK_STAGE_BYTES + SK_W_BYTES + 16) + 16 * SK
 struct SkTile {
   int J;
   int slot_off, slot_cnt;   // partial slots of this tile in tile_slots
-  uint32_t smask;           // bit 4*w + b: box (rows[w], 4J + b) is on or below the diagonal and inside the matrix
-  int8_t rows[8];           // box row of strip w, -1 = unused
-  int pad[2];
+  uint32_t smask;           // bit 4*s + b: box (rows[s], 4J + b) is on or below the diagonal and inside the matrix
+  int8_t rows[8];           // box row of row slot s, -1 = unused
+  uint8_t wcol[4];          // consumer warp w works on column box wcol[w] of the N panel ...
+  uint8_t wrows[4];         // ... against the row slots in this mask (every live box has exactly one owner)
 };
 static_assert(sizeof(SkTile) == 32, "SkTile layout");
 
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
   }
 
   // ---------------- consumer warps: warp w owns column box w of the N panel ----------------------------
-  const int wc = warp;
+  int wc = warp;                 // column box of the N panel this warp works on (per tile)
   const int fj = lane >> 2, fk = lane & 3;
   const int ch = sy_chunk(fj);
   double acc[4][2][2][2];
@@ -301,12 +302,11 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
       }
       cur_unit = unit;
       const SkTile* tp = tiles + meta.y;
-      const uint32_t sm = tp->smask;
       const int j4 = 4 * tp->J;
-      smask_w = 0;
+      smask_w = tp->wrows[warp];
+      wc = tp->wcol[warp];
 #pragma unroll
       for (int sr = 0; sr < 4; ++sr) {
-        smask_w |= ((sm >> (4 * sr + wc)) & 1u) << sr;
         const int r = tp->rows[sr];
         // a row box is read from its private copy, or from the N panel's copy when it lies inside the panel
         a_off[sr] = (r >= j4 && r < j4 + 4) ? (uint32_t)(SK_MBOX + (r - j4)) * SK_BOX_BYTES : (uint32_t)sr * SK_BOX_BYTES;
@@ -345,22 +345,36 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
   }
 }
 
-// sum the partial slots of each tile in a fixed order, write the lower triangle and its mirror
-__global__ void __launch_bounds__(256)
+// sum the partial slots of each tile in a fixed order, write the lower triangle and its mirror.
+// 64 elements x 8 slot lanes per block: lane q adds slots q, q + 8, ... (independent loads in flight), the
+// eight partial sums are then combined in lane order, so the result is independent of the launch shape.
+constexpr int SR_ELEMS = 64, SR_LANES = 8;
+__global__ void __launch_bounds__(SR_ELEMS * SR_LANES)
     syrk_reduce_kernel(const double* __restrict__ part, const SkTile* __restrict__ tiles, const int* __restrict__ tile_slots,
                        int p, int ldh, double* __restrict__ H) {
-  const int tile = blockIdx.x / (SK_TILE_ELEMS / 256);
-  const int e = (blockIdx.x % (SK_TILE_ELEMS / 256)) * 256 + threadIdx.x;
+  __shared__ double sm[SR_LANES][SR_ELEMS + 1];
+  const int tile = blockIdx.x / (SK_TILE_ELEMS / SR_ELEMS);
+  const int el = threadIdx.x % SR_ELEMS, q = threadIdx.x / SR_ELEMS;
+  const int e = (blockIdx.x % (SK_TILE_ELEMS / SR_ELEMS)) * SR_ELEMS + el;
   const int M = e / (16 * SK_NBOX), N = e % (16 * SK_NBOX);
   const SkTile t = tiles[tile];
   const int r = t.rows[M / 16];
-  if (r < 0) return;
   const int gr = r * 16 + (M % 16), gc = t.J * 16 * SK_NBOX + N;
-  if (gr >= p || gc >= p || gc > gr) return;
+  const bool live = r >= 0 && gr < p && gc < p && gc <= gr;
   double s = 0.0;
-  for (int k = 0; k < t.slot_cnt; ++k) s += part[(size_t)tile_slots[t.slot_off + k] * SK_TILE_ELEMS + e];
-  H[(size_t)gc * ldh + gr] = s;
-  H[(size_t)gr * ldh + gc] = s;
+  if (live) {
+    const int* sl = tile_slots + t.slot_off;
+    for (int k = q; k < t.slot_cnt; k += SR_LANES) s += part[(size_t)sl[k] * SK_TILE_ELEMS + e];
+  }
+  sm[q][el] = s;
+  __syncthreads();
+  if (q == 0 && live) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < SR_LANES; ++k) tot += sm[k][el];
+    H[(size_t)gc * ldh + gr] = tot;
+    H[(size_t)gr * ldh + gc] = tot;
+  }
 }
 
 struct AddQArgs {
@@ -448,6 +462,32 @@ int syrk_plan_create(bgp_model* m) {
         }
       }
       if (getenv("BGP_SK_FULL")) t.smask = 0xffffu;   // diagnostics only
+      // box ownership: warp b takes column box b; while a warp is idle and another holds >= 2 boxes more,
+      // the idle warp takes over half of the busiest warp's row slots (same column box)
+      for (int b = 0; b < SK_NBOX; ++b) {
+        t.wcol[b] = (uint8_t)b;
+        t.wrows[b] = 0;
+        for (int w = 0; w < SK_MBOX; ++w) t.wrows[b] |= (uint8_t)(((t.smask >> (4 * w + b)) & 1u) << w);
+      }
+      for (int round = 0; round < 4; ++round) {
+        int lo = 0, hi = 0;
+        for (int b = 1; b < SK_NBOX; ++b) {
+          if (__builtin_popcount(t.wrows[b]) < __builtin_popcount(t.wrows[lo])) lo = b;
+          if (__builtin_popcount(t.wrows[b]) > __builtin_popcount(t.wrows[hi])) hi = b;
+        }
+        const int nhi = __builtin_popcount(t.wrows[hi]);
+        if (t.wrows[lo] != 0 || nhi < 2) break;
+        uint8_t moved = 0;
+        int left = nhi / 2;
+        for (int w = SK_MBOX - 1; w >= 0 && left > 0; --w)
+          if ((t.wrows[hi] >> w) & 1u) {
+            moved |= (uint8_t)(1u << w);
+            --left;
+          }
+        t.wrows[hi] &= (uint8_t)~moved;
+        t.wrows[lo] = moved;
+        t.wcol[lo] = t.wcol[hi];
+      }
       tiles.push_back(t);
     }
   }
@@ -462,7 +502,7 @@ int syrk_plan_create(bgp_model* m) {
   // Work list.  A unit is (tile, run of chunks) of bounded cost; the queue walks the observations from the
   // last block to the first (after the zero-pattern sort the late blocks are the densest) and visits every
   // tile per block, so the CTAs that run at the same time read the same observations (L2 reuse).  Unit
-  // cost: total / (5 G) for the first 70 % of the work, then 1/2 and 1/4 of that (short queue tail).
+  // cost: total / (4 G) for the first 70 % of the work, then 1/2 and 1/4 of that (short queue tail).
   // cost of a chunk = fixed overhead + DMMA time of the busiest consumer warp (warp b owns column box b).
   auto chunk_cost = [&](const SkTile& t, uint64_t o, int& boxes) -> int {
     uint32_t act_m, load_m, need_n;
@@ -471,10 +511,8 @@ int syrk_plan_create(bgp_model* m) {
     if (!act_m) return 0;
     const uint32_t ncol = (uint32_t)(o >> (4 * t.J)) & 0xfu;
     int mx = 0;
-    for (int b = 0; b < SK_NBOX; ++b) {
-      int bw = 0;
-      if ((ncol >> b) & 1u)
-        for (int w = 0; w < SK_MBOX; ++w) bw += (int)((act_m >> w) & 1u) & (int)((t.smask >> (4 * w + b)) & 1u);
+    for (int w = 0; w < SK_NBOX; ++w) {
+      const int bw = ((ncol >> t.wcol[w]) & 1u) ? __builtin_popcount(t.wrows[w] & act_m) : 0;
       boxes += bw;
       mx = std::max(mx, bw);
     }
@@ -488,7 +526,7 @@ int syrk_plan_create(bgp_model* m) {
       cost_total += chunk_cost(tiles[ti], m->occ_host[(size_t)c], boxes);
       boxes_total += boxes;
     }
-  const int64_t unit_target = std::max<int64_t>(64, cost_total / ((int64_t)5 * pl->G));
+  const int64_t unit_target = std::max<int64_t>(64, cost_total / ((int64_t)4 * pl->G));
   const int64_t blk = 8;                                   // chunks per block of the walk
   std::vector<uint32_t> entries;
   std::vector<int2> units;
@@ -637,7 +675,7 @@ int launch_syrk(bgp_model* m) {
     for (int g = 0; g < pl->G; g += 37) fprintf(stderr, " %d:%.0f", g, dur[g]);
     fprintf(stderr, "\n");
   }
-  syrk_reduce_kernel<<<pl->ntiles * (SK_TILE_ELEMS / 256), 256, 0, m->stream>>>(m->part_H, pl->tiles_dev,
+  syrk_reduce_kernel<<<pl->ntiles * (SK_TILE_ELEMS / SR_ELEMS), SR_ELEMS * SR_LANES, 0, m->stream>>>(m->part_H, pl->tiles_dev,
                                                                                pl->tile_slots_dev, m->p, m->ldh, m->H);
   count_launch();
   BGP_CUDA(cudaGetLastError());
