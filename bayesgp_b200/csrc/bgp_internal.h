@@ -127,6 +127,7 @@ struct bgp_model {
   bool use_hermite = true;
   double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)
   double* L = nullptr;          // Cholesky factor (lower, column-major p x ldh)
+  double* Ldinv = nullptr;      // 1 / L_jj (ldh)
   double* Linv = nullptr;       // L^-1, row-major p x ldl (lower; allocated on first gradient call)
   int ldl = 0;
   double* zobs = nullptr;       // c3 * leverage per observation

@@ -4,14 +4,21 @@
 // Hessian and the 1/2 logdet H term of the Laplace approximation (TMB::MakeADFun(random = "W"),
 // call site /root/reference/R/02_model_fit.R:276-284).
 //
-// One CTA (512 threads) owns one problem; H stays in global memory (L2-resident: <= 8 MB).
-// Right-looking blocked algorithm, panel width NB:
-//   1. the NB x NB diagonal block is factored in shared memory;
-//   2. the panel below it is solved one row per thread and kept in shared memory;
-//   3. the trailing update C -= P P^T runs on the FP64 tensor pipe (mma.sync m8n8k4 / DMMA),
-//      32x32 tiles per warp, fragments read conflict-free from the padded panel.
-// The same kernel then does the blocked forward/backward substitution for step = -H^-1 g.
+// One thread-block cluster (8 CTAs x 512 threads) owns one problem; H stays in global memory
+// (L2-resident: <= 8 MB).  Right-looking blocked algorithm, panel width NB, two cluster barriers per panel:
+//   1. every CTA factors the NB x NB diagonal block itself (one warp, rows in registers, shuffles —
+//      no CTA barrier inside the 32 dependent steps);
+//   2. the panel below it is solved one row per thread, 32-row blocks dealt round-robin to the CTAs;
+//   3. the trailing update C -= P P^T runs on the FP64 tensor pipe (mma.sync m8n8k4 / DMMA), 32x32
+//      tiles dealt round-robin to the (CTA, warp) pairs, fragments read conflict-free from a padded
+//      shared-memory copy of the panel.
+// Rank 0 then does the log-determinant and the blocked forward/backward substitution for step = -H^-1 g.
+// Every CTA performs the same operations on the same data in the same order: results do not depend on
+// the cluster size.
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "bgp_internal.h"
 
@@ -19,15 +26,19 @@ namespace bgp {
 
 struct CholArgs {
   double* L;         // p x ldh column-major; on entry a copy of H (lower triangle is used)
+  double* dinv;      // out: 1 / L_jj (p) — the substitutions multiply instead of divide
   int p, ldh;
   const double* g;   // gradient (p)
   double* step;      // out: -H^-1 g (p)
   EvalScalars* sc;
   int solve;
+  unsigned long long* dbg;   // BGP_CHOL_DEBUG: per-phase nanoseconds of rank 0 (9 slots)
 };
 
-constexpr int CH_THREADS = 512;   // 128 registers / thread for the 32x32 DMMA accumulators
+constexpr int CH_THREADS = 256;   // up to 255 registers / thread: row blocks and 32x32 DMMA accumulators stay in registers
 constexpr int CH_MAXP = 2048;
+constexpr int CH_CS = 8;          // CTAs per cluster (portable maximum)
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -38,20 +49,22 @@ __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, doubl
 
 // x <- (L L^T)^-1 x for the vector held in shared memory (blocked forward / backward substitution,
 // 32-wide diagonal blocks solved by warp 0 from a shared copy, off-diagonal updates by all threads)
-__device__ void tri_solve_inplace(const double* __restrict__ L, int p, int ldh, double* sv, double* sS, double* s_red) {
+__device__ void tri_solve_inplace(const double* L, const double* dinv, int p, int ldh, double* sv, double* sS,
+                                  double* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- forward substitution, blocks of 32
   for (int b0 = 0; b0 < p; b0 += 32) {
     const int bn = (p - b0) < 32 ? (p - b0) : 32;
     for (int t = tid; t < 1024; t += CH_THREADS) {
       const int i = t & 31, c = t >> 5;
-      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? __ldcg(L + (size_t)(b0 + c) * ldh + b0 + i) : 0.0;
     }
     __syncthreads();
     if (warp == 0) {
       double yv = lane < bn ? sv[b0 + lane] : 0.0;
+      const double di = lane < bn ? __ldcg(dinv + b0 + lane) : 0.0;
       for (int j = 0; j < bn; ++j) {
-        double yj = __shfl_sync(0xffffffffu, yv, j) / sS[j * 33 + j];
+        double yj = __shfl_sync(0xffffffffu, yv, j) * __shfl_sync(0xffffffffu, di, j);
         if (lane == j) yv = yj;
         else if (lane > j) yv = fma(-yj, sS[lane * 33 + j], yv);
       }
@@ -61,7 +74,7 @@ __device__ void tri_solve_inplace(const double* __restrict__ L, int p, int ldh, 
     for (int i = b0 + bn + tid; i < p; i += CH_THREADS) {
       double s = sv[i];
 #pragma unroll 8
-      for (int c = 0; c < bn; ++c) s = fma(-L[(size_t)(b0 + c) * ldh + i], sv[b0 + c], s);
+      for (int c = 0; c < bn; ++c) s = fma(-__ldcg(L + (size_t)(b0 + c) * ldh + i), sv[b0 + c], s);
       sv[i] = s;
     }
     __syncthreads();
@@ -75,20 +88,21 @@ __device__ void tri_solve_inplace(const double* __restrict__ L, int p, int ldh, 
     for (int c = warp; c < bn; c += CH_THREADS / 32) {
       const double* col = L + (size_t)(b0 + c) * ldh;
       double s = 0.0;
-      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(col[i], sv[i], s);
+      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(__ldcg(col + i), sv[i], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) s_red[c] = s;
     }
     for (int t = tid; t < 1024; t += CH_THREADS) {
       const int i = t & 31, c = t >> 5;
-      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? L[(size_t)(b0 + c) * ldh + b0 + i] : 0.0;
+      sS[i * 33 + c] = (i < bn && c < bn && i >= c) ? __ldcg(L + (size_t)(b0 + c) * ldh + b0 + i) : 0.0;
     }
     __syncthreads();
     if (warp == 0) {
       double xv = lane < bn ? sv[b0 + lane] - s_red[lane] : 0.0;
+      const double di = lane < bn ? __ldcg(dinv + b0 + lane) : 0.0;
       for (int j = bn - 1; j >= 0; --j) {
-        double xj = __shfl_sync(0xffffffffu, xv, j) / sS[j * 33 + j];
+        double xj = __shfl_sync(0xffffffffu, xv, j) * __shfl_sync(0xffffffffu, di, j);
         if (lane == j) xv = xj;
         else if (lane < j) xv = fma(-xj, sS[j * 33 + lane], xv);
       }
@@ -98,8 +112,47 @@ __device__ void tri_solve_inplace(const double* __restrict__ L, int p, int ldh, 
   }
 }
 
+// Cholesky of the NB x NB block in shared memory (working copy sD, row i at sD + i * DP, rows >= nb padded with
+// the identity) by the whole CTA: thread (i, q) owns row i and the columns c = j + 1 + q, j + 1 + q + Q, ...
+// of the rank-1 update, one CTA barrier per column.  The scaled column goes to a separate array sL, so the
+// unscaled working column can still be read by the other threads of the same step (no second barrier).
+// Columns are scaled with rsqrt of the pivot: L_jj = d * rsqrt(d) (within 2 ulp of sqrt(d)); 1 / L_jj =
+// rsqrt(d) goes to sInv for the substitutions.  Returns 0 or j + 1 for a non-positive pivot in column j.
 template <int NB>
-__global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
+__device__ __forceinline__ int block_chol(double* sD, double* sL, double* sInv, int tid) {
+  constexpr int DP = NB + 1;
+  constexpr int Q = CH_THREADS / 32;
+  const int i = tid & 31, q = tid >> 5;
+  int info = 0;
+  for (int j = 0; j < NB; ++j) {
+    const double d = sD[j * DP + j];
+    if (info == 0 && (!(d > 0.0) || !isfinite(d))) info = j + 1;
+    const double rs = rsqrt(d);
+    if (i < NB && i >= j) {
+      const double lij = sD[i * DP + j] * rs;
+      if (q == 0) {
+        sL[i * DP + j] = lij;
+        if (i == j) sInv[j] = rs;
+      }
+      for (int c = j + 1 + q; c <= i; c += Q) sD[i * DP + c] = fma(-lij, sD[c * DP + j] * rs, sD[i * DP + c]);
+    }
+    __syncthreads();
+  }
+  return info;
+}
+
+#define CH_MARK(slot)                                                    \
+  do {                                                                   \
+    if (a.dbg && rank == 0 && tid == 0) {                                \
+      unsigned long long _t;                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));             \
+      a.dbg[slot] += _t - t_last;                                        \
+      t_last = _t;                                                       \
+    }                                                                    \
+  } while (0)
+
+template <int NB>
+__global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
   extern __shared__ double sm[];
   constexpr int DP = NB + 1;        // pitch of the diagonal block
   constexpr int PP = NB + 4;        // pitch of the panel (conflict-free DMMA fragment loads)
@@ -109,76 +162,84 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
   double* sP = sv + CH_MAXP;        // panel rows x PP
   __shared__ int s_info;
   __shared__ double s_red[32];
+  __shared__ double s_inv[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = a.p, ldh = a.ldh;
   double* L = a.L;
   if (tid == 0) s_info = 0;
   __syncthreads();
+  unsigned long long t_last = 0;
+  if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
 
   for (int k0 = 0; k0 < p; k0 += NB) {
     const int nb = (p - k0) < NB ? (p - k0) : NB;
     const int m = p - k0 - nb;
-    // ---- 1. diagonal block -> shared, factor -----------------------------------------------
+    // ---- 1. diagonal block: every CTA factors its own copy (identical arithmetic) -------------------
     for (int t = tid; t < NB * NB; t += CH_THREADS) {
       const int i = t % NB, c = t / NB;
-      if (i < nb && c < nb && i >= c) sD[i * DP + c] = L[(size_t)(k0 + c) * ldh + k0 + i];
-    }
-    for (int j = 0; j < nb; ++j) {
-      __syncthreads();
-      const double d = sD[j * DP + j];
-      if (!(d > 0.0) || !isfinite(d)) {          // uniform across the CTA
-        if (tid == 0) s_info = k0 + j + 1;
-        break;
-      }
-      const double sq = sqrt(d);
-      __syncthreads();
-      for (int t = tid; t < NB; t += CH_THREADS) {
-        if (t == j) sD[j * DP + j] = sq;
-        else if (t > j && t < nb) sD[t * DP + j] /= sq;
-      }
-      __syncthreads();
-      for (int t = tid; t < NB * NB; t += CH_THREADS) {
-        const int i = t % NB, c = t / NB;
-        if (c > j && i >= c && i < nb) sD[i * DP + c] -= sD[i * DP + j] * sD[c * DP + j];
-      }
+      sD[i * DP + c] = (i < nb && c < nb && i >= c) ? __ldcg(L + (size_t)(k0 + c) * ldh + k0 + i) : (i == c ? 1.0 : 0.0);
     }
     __syncthreads();
-    if (s_info != 0) break;
-    for (int t = tid; t < NB * NB; t += CH_THREADS) {
-      const int i = t % NB, c = t / NB;
-      if (i < nb && c < nb && i >= c) L[(size_t)(k0 + c) * ldh + k0 + i] = sD[i * DP + c];
+    CH_MARK(0);
+    {
+      const int info = block_chol<NB>(sD, sS, s_inv, tid);       // every thread sees the same pivots
+      if (info != 0 && tid == 0) s_info = k0 + info;
     }
+    __syncthreads();
+    for (int t = tid; t < NB * NB; t += CH_THREADS) {             // factor back into sD for the panel solve
+      const int i = t % NB, c = t / NB;
+      if (c <= i) sD[i * DP + c] = sS[i * DP + c];
+    }
+    __syncthreads();
+    if (rank == 0 && s_info == 0) {
+      for (int t = tid; t < NB * NB; t += CH_THREADS) {
+        const int i = t % NB, c = t / NB;
+        if (i < nb && c <= i) __stcg(L + (size_t)(k0 + c) * ldh + k0 + i, sD[i * DP + c]);
+      }
+      if (tid < nb) __stcg(a.dinv + k0 + tid, s_inv[tid]);
+    }
+    CH_MARK(1);
+    if (s_info != 0) break;        // same decision in every CTA of the cluster
     if (m <= 0) break;
-    // ---- 2. panel solve: row r of L[k0+nb.., k0..k0+NB) <- row * L_kk^-T -----------------------
+    // ---- 2. panel solve: row r of L[k0+nb.., k0..k0+NB) <- row * L_kk^-T ; 32-row blocks round-robin ---
     const int mpad = (m + 31) & ~31;
-    for (int t = tid; t < mpad; t += CH_THREADS) {
-      double x[NB];
+    for (int blk = rank + CH_CS * warp; blk * 32 < m; blk += CH_CS * (CH_THREADS / 32)) {
+      const int t = blk * 32 + lane;
       if (t < m) {
+        double x[NB];
         const int r = k0 + nb + t;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) x[c] = L[(size_t)(k0 + c) * ldh + r];
+        for (int c = 0; c < NB; ++c) x[c] = c < nb ? __ldcg(L + (size_t)(k0 + c) * ldh + r) : 0.0;
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-          x[c] /= sD[c * DP + c];
+          x[c] *= s_inv[c];
 #pragma unroll
           for (int q = c + 1; q < NB; ++q) x[q] = fma(-x[c], sD[q * DP + c], x[q]);
         }
 #pragma unroll
-        for (int c = 0; c < NB; ++c) L[(size_t)(k0 + c) * ldh + r] = x[c];
-      } else {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) x[c] = 0.0;
+        for (int c = 0; c < NB; ++c)
+          if (c < nb) __stcg(L + (size_t)(k0 + c) * ldh + r, x[c]);
       }
-#pragma unroll
-      for (int c = 0; c < NB; ++c) sP[(size_t)t * PP + c] = x[c];
+    }
+    CH_MARK(2);
+    __threadfence();
+    cluster.sync();
+    CH_MARK(3);
+    // ---- 3. the whole panel into shared memory (zero padded) -----------------------------------------
+    for (int t = tid; t < mpad * NB; t += CH_THREADS) {
+      const int r = t % mpad, c = t / mpad;
+      sP[(size_t)r * PP + c] = (r < m && c < nb) ? __ldcg(L + (size_t)(k0 + c) * ldh + k0 + nb + r) : 0.0;
     }
     __syncthreads();
-    // ---- 3. trailing update on the FP64 tensor pipe ------------------------------------------
+    CH_MARK(4);
+    // ---- 4. trailing update on the FP64 tensor pipe, tiles round-robin over (CTA, warp) ---------------
     const int ntd = mpad / 32;
     const int ntile = ntd * (ntd + 1) / 2;
     const int fj = lane >> 2, fk = lane & 3;
-    for (int idx = warp; idx < ntile; idx += CH_THREADS / 32) {
+    for (int idx = rank + CH_CS * warp; idx < ntile; idx += CH_CS * (CH_THREADS / 32)) {
       // idx -> (ti >= tj)
       int ti = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
       while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
@@ -205,6 +266,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
           for (int ni = 0; ni < 4; ++ni) dmma884c(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
       }
       const int base = k0 + nb;
+      // read-modify-write of the 32 x 32 tile in two phases (all loads in flight, then all stores): the
+      // compiler must otherwise order every store before the next load (possible aliasing)
+      double cur[4][4][2];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
         const int row = ti * 32 + mi * 8 + fj;
@@ -213,13 +277,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int col = tj * 32 + ni * 8 + 2 * fk + e;
-            if (row < m && col <= row) L[(size_t)(base + col) * ldh + base + row] -= acc[mi][ni][e];
+            cur[mi][ni][e] = (row < m && col <= row) ? __ldcg(L + (size_t)(base + col) * ldh + base + row) : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int row = ti * 32 + mi * 8 + fj;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = tj * 32 + ni * 8 + 2 * fk + e;
+            if (row < m && col <= row) __stcg(L + (size_t)(base + col) * ldh + base + row, cur[mi][ni][e] - acc[mi][ni][e]);
           }
         }
       }
     }
-    __syncthreads();
+    CH_MARK(5);
+    __threadfence();
+    cluster.sync();
+    CH_MARK(6);
   }
+  // only rank 0 goes on; nobody waits on a cluster barrier any more
+  if (rank != 0) return;
   __syncthreads();
   if (s_info != 0) {
     if (tid == 0) {
@@ -232,7 +313,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
   // ---- log det H = 2 sum log L_jj (fixed-order tree) ------------------------------------------
   {
     double s = 0.0;
-    for (int j = tid; j < p; j += CH_THREADS) s += log(L[(size_t)j * ldh + j]);
+    for (int j = tid; j < p; j += CH_THREADS) s += log(__ldcg(L + (size_t)j * ldh + j));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_red[warp] = s;
@@ -245,10 +326,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
     }
     __syncthreads();
   }
+  CH_MARK(7);
   if (!a.solve) return;
   for (int i = tid; i < p; i += CH_THREADS) sv[i] = -a.g[i];
   __syncthreads();
-  tri_solve_inplace(L, p, ldh, sv, sS, s_red);
+  tri_solve_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
   double mx = 0.0;
   for (int i = tid; i < p; i += CH_THREADS) {
     const double x = sv[i];
@@ -264,6 +346,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
     for (int w = 0; w < CH_THREADS / 32; ++w) t = fmax(t, s_red[w]);
     a.sc->smax = t;
   }
+  CH_MARK(8);
 }
 
 template <int NB>
@@ -279,7 +362,7 @@ static int launch_chol_t(bgp_model* m, const CholArgs& a) {
     BGP_CUDA(cudaFuncSetAttribute(chol_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  chol_kernel<NB><<<1, CH_THREADS, smem, m->stream>>>(a);
+  chol_kernel<NB><<<CH_CS, CH_THREADS, smem, m->stream>>>(a);   // one cluster (compile-time __cluster_dims__)
   count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
@@ -290,12 +373,31 @@ int launch_chol_solve(bgp_model* m, bool solve) {
   BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   CholArgs a;
   a.L = m->L;
+  a.dinv = m->Ldinv;
   a.p = m->p;
   a.ldh = m->ldh;
   a.g = m->g;
   a.step = m->step;
   a.sc = m->sc_dev;
   a.solve = solve ? 1 : 0;
+  static unsigned long long* dbg_dev = nullptr;
+  static int dbg_calls = 0;
+  if (getenv("BGP_CHOL_DEBUG")) {
+    if (!dbg_dev) {
+      cudaMalloc(&dbg_dev, 16 * sizeof(unsigned long long));
+      cudaMemset(dbg_dev, 0, 16 * sizeof(unsigned long long));
+    }
+    if (++dbg_calls % 40 == 0) {
+      unsigned long long h[16];
+      cudaStreamSynchronize(m->stream);
+      cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[chol] %d calls, us/call: diag-load %.1f factor %.1f panel-solve %.1f sync1 %.1f panel-load %.1f update %.1f sync2 %.1f logdet %.1f trisolve %.1f\n",
+              dbg_calls - 1, h[0] * 1e-3 / (dbg_calls - 1), h[1] * 1e-3 / (dbg_calls - 1), h[2] * 1e-3 / (dbg_calls - 1),
+              h[3] * 1e-3 / (dbg_calls - 1), h[4] * 1e-3 / (dbg_calls - 1), h[5] * 1e-3 / (dbg_calls - 1),
+              h[6] * 1e-3 / (dbg_calls - 1), h[7] * 1e-3 / (dbg_calls - 1), h[8] * 1e-3 / (dbg_calls - 1));
+    }
+  }
+  a.dbg = dbg_dev;
   if (m->p > CH_MAXP) {
     set_error("p = %d exceeds the Cholesky kernel limit %d", m->p, CH_MAXP);
     return BGP_ERR_ARG;
@@ -315,6 +417,7 @@ struct TanBlock {
 };
 struct TangentArgs {
   const double* L;
+  const double* dinv;
   int p, ldh, lda;
   const double* W;      // the mode
   const double* mu0;
@@ -364,13 +467,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tangent_kernel(const TangentArg
     sv[i] = v;
   }
   __syncthreads();
-  tri_solve_inplace(a.L, a.p, a.ldh, sv, sS, s_red);
+  tri_solve_inplace(a.L, a.dinv, a.p, a.ldh, sv, sS, s_red);
   for (int i = tid; i < a.lda; i += CH_THREADS) a.T[(size_t)k * a.lda + i] = i < a.p ? -sv[i] : 0.0;
 }
 
 int launch_tangent(bgp_model* m, const double* theta) {
   TangentArgs a;
   a.L = m->L;
+  a.dinv = m->Ldinv;
   a.p = m->p;
   a.ldh = m->ldh;
   a.lda = m->lda;

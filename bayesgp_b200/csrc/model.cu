@@ -397,6 +397,7 @@ int bgp_model_finalize(bgp_model* m) {
   const size_t hb = (size_t)m->ldh * m->p * sizeof(double);
   BGP_TRY(dalloc(&m->H, hb));
   BGP_TRY(dalloc(&m->L, hb));
+  BGP_TRY(dalloc(&m->Ldinv, (size_t)m->ldh * sizeof(double)));
   BGP_TRY(dalloc(&m->theta_dev, 64 * sizeof(double)));
   BGP_TRY(dalloc(&m->Tan, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
   BGP_TRY(dalloc(&m->Tan_prev, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
@@ -442,7 +443,7 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->Tan, m->Tan_prev, m->Wmode_prev, m->xbuf, m->H, m->L, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->Tan_prev, m->Wmode_prev, m->xbuf, m->H, m->L, m->Ldinv, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
     if (ptr) cudaFree(ptr);
   if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);

@@ -84,3 +84,22 @@ def test_laplace_gradient(case):
         # designs must agree to 2e-7.
         tol = 1e-4 if name == "covid_poisson" else 2e-7
         assert np.max(np.abs(got - want)) <= tol * scale, (name, theta, got, want)
+
+
+def test_covid_against_40_digit_reference():
+    """README model: L(theta) from the GPU vs the mpmath values of tests/golden/covid_hp.json (north_star:
+    log marginal likelihood within 1e-8 relative).  cond(H) = 3.7e11 here, so this is the hardest case."""
+    import json
+    import os
+    from bayesgp_b200 import make_objective
+    from helpers import GOLDEN
+    hp = json.load(open(os.path.join(GOLDEN, "covid_hp.json")))
+    model = covid_model()[0]
+    ff = make_objective(tmbdata_from_oracle(model))
+    try:
+        for theta, want, mode in zip(hp["theta"], hp["value"], hp["mode"]):
+            got, _, w, _ = ff._eval(np.array([theta]))
+            assert abs(got - want) <= 1e-8 * abs(want), (theta, got, want, got - want)
+            assert relerr(w, np.array(mode)) < 1e-6
+    finally:
+        ff.close()

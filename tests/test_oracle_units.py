@@ -139,3 +139,18 @@ def test_binomial_gaussian_gradients_match_finite_differences():
             e[i] = 1e-5
             fd = (ff.fn(th + e) - ff.fn(th - e)) / 2e-5
             assert abs(g[i] - fd) < 2e-5 * max(1.0, abs(fd)), (i, g, fd)
+
+
+def test_oracle_against_40_digit_reference():
+    """The FP64 oracle itself vs the mpmath values (tests/golden/make_hp_covid.py): the oracle's own rounding
+    noise on the ill-conditioned README model is measured, not assumed."""
+    import json
+    import os
+    from helpers import GOLDEN, covid_model
+    from oracle.laplace import LaplaceObjective
+    hp = json.load(open(os.path.join(GOLDEN, "covid_hp.json")))
+    off = LaplaceObjective(covid_model()[0])
+    for theta, want, mode in zip(hp["theta"], hp["value"], hp["mode"]):
+        got = off.fn(np.array([theta]))
+        assert abs(got - want) <= 1e-8 * abs(want), (theta, got - want)
+        assert np.max(np.abs(off.last_par - np.array(mode))) <= 1e-6 * np.max(np.abs(mode))
