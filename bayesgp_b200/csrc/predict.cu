@@ -12,6 +12,8 @@
 #include <algorithm>
 
 #include "basis_dev.cuh"
+#include <mutex>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -157,77 +159,141 @@ struct SelectArgs {
   double* hi;
 };
 
+// One CTA per row.  Exact MSB radix select (8-bit digits) of the two order statistics, both in the same
+// sweeps: per-warp private histograms fed by warp-aggregated increments (the keys of a row share their
+// leading bytes, a single shared histogram serialises on one bin), a warp-parallel bin scan, and a start
+// digit chosen from the highest bit in which the row's keys differ.
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs a) {
   extern __shared__ unsigned long long skeys[];
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned long long s_prefix;
-  __shared__ long long s_below;
-  __shared__ unsigned int s_eq;
+  constexpr int NW = RS_THREADS / 32;
+  __shared__ unsigned int whist[2][NW][256];
+  __shared__ unsigned int hist[2][256];
+  __shared__ unsigned long long s_prefix[2];
+  __shared__ long long s_below[2];
+  __shared__ unsigned int s_eq[2];
   __shared__ double s_red[RS_THREADS];
-  __shared__ unsigned long long s_min[RS_THREADS];
-  const int tid = threadIdx.x;
+  __shared__ unsigned long long s_min[RS_THREADS], s_max[RS_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* row = a.F + (size_t)blockIdx.x * a.ldF;
   const int64_t M = a.M;
-  // mean (fixed-order tree) and, when the row fits, the sortable keys in shared memory
+  // mean (fixed-order tree), key range and, when the row fits, the sortable keys in shared memory
   double sum = 0.0;
+  unsigned long long kmin = ~0ull, kmax = 0ull;
   for (int64_t i = tid; i < M; i += RS_THREADS) {
     const double v = row[i];
     sum += v;
-    if (IN_SMEM) skeys[i] = dkey(v);
+    const unsigned long long k = dkey(v);
+    kmin = k < kmin ? k : kmin;
+    kmax = k > kmax ? k : kmax;
+    if (IN_SMEM) skeys[i] = k;
   }
   s_red[tid] = sum;
+  s_min[tid] = kmin;
+  s_max[tid] = kmax;
   __syncthreads();
   for (int o = RS_THREADS / 2; o > 0; o >>= 1) {
-    if (tid < o) s_red[tid] += s_red[tid + o];
+    if (tid < o) {
+      s_red[tid] += s_red[tid + o];
+      if (s_min[tid + o] < s_min[tid]) s_min[tid] = s_min[tid + o];
+      if (s_max[tid + o] > s_max[tid]) s_max[tid] = s_max[tid + o];
+    }
     __syncthreads();
   }
   const double mean = s_red[0] / (double)M;
+  kmin = s_min[0];
+  kmax = s_max[0];
+  __syncthreads();
   auto key_at = [&](int64_t i) -> unsigned long long { return IN_SMEM ? skeys[i] : dkey(row[i]); };
 
+  // all keys agree above byte `top`: start there
+  const unsigned long long diff = kmin ^ kmax;
+  const int top = diff ? (63 - __clzll((long long)diff)) / 8 : 0;
+  const unsigned long long hi_mask = top == 7 ? 0ull : (~0ull << (8 * (top + 1)));
+  unsigned long long prefix[2] = {kmin & hi_mask, kmin & hi_mask}, mask = hi_mask;
+  long long below[2] = {0, 0};
+  unsigned int eq[2] = {(unsigned)M, (unsigned)M};
+  const int64_t rk[2] = {a.r1, a.r2};
+  for (int pass = top; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    const bool same = prefix[0] == prefix[1];          // both quantiles still in the same bucket: one histogram
+    for (int t = tid; t < 2 * NW * 256; t += RS_THREADS) (&whist[0][0][0])[t] = 0;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < M; i0 += RS_THREADS) {
+      const int64_t i = i0 + tid;
+      const bool in = i < M;
+      const unsigned long long k = in ? key_at(i) : 0ull;
+      const unsigned digit = (unsigned)(k >> shift) & 255u;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && same) break;
+        const bool hit = in && (k & mask) == prefix[q];
+        const unsigned act = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const unsigned peers = __match_any_sync(act, digit);
+          if (lane == __ffs(peers) - 1) whist[q][warp][digit] += __popc(peers);
+        }
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * 256; t += RS_THREADS) {
+      const int q = t >> 8, bin = t & 255;
+      unsigned s = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += whist[same ? 0 : q][w][bin];
+      hist[q][bin] = s;
+    }
+    __syncthreads();
+    if (warp < 2) {
+      // warp q finds the bin of rank rk[q]: 8 bins per lane, exclusive scan across lanes
+      const int q = warp;
+      unsigned loc[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[q][lane * 8 + j];
+        tot += loc[j];
+      }
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      long long cum = below[q] + (long long)(inc - tot);
+      const bool mine = cum <= rk[q] && rk[q] < cum + (long long)tot;
+      if (mine) {
+        int j = 0;
+        for (; j < 7; ++j) {
+          if (cum + (long long)loc[j] > rk[q]) break;
+          cum += loc[j];
+        }
+        s_below[q] = cum;
+        s_prefix[q] = prefix[q] | ((unsigned long long)(lane * 8 + j) << shift);
+        s_eq[q] = loc[j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      below[q] = s_below[q];
+      prefix[q] = s_prefix[q];
+      eq[q] = s_eq[q];
+    }
+    mask |= 0xFFull << shift;
+    __syncthreads();
+  }
   double qv[2];
   for (int which = 0; which < 2; ++which) {
-    const int64_t r = which == 0 ? a.r1 : a.r2;
+    const int64_t r = rk[which];
     const double h = which == 0 ? a.h1 : a.h2;
-    unsigned long long prefix = 0ull, mask = 0ull;
-    long long below = 0;
-    unsigned int eq = 0;
-    for (int pass = 7; pass >= 0; --pass) {
-      const int shift = pass * 8;
-      hist[tid] = 0;
-      __syncthreads();
-      for (int64_t i = tid; i < M; i += RS_THREADS) {
-        const unsigned long long k = key_at(i);
-        if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        long long cum = below;
-        int b = 0;
-        for (; b < 256; ++b) {
-          if (cum + (long long)hist[b] > r) break;
-          cum += hist[b];
-        }
-        if (b > 255) b = 255;
-        s_below = cum;
-        s_prefix = prefix | ((unsigned long long)b << shift);
-        s_eq = hist[b];
-      }
-      __syncthreads();
-      below = s_below;
-      prefix = s_prefix;
-      eq = s_eq;
-      mask |= 0xFFull << shift;
-      __syncthreads();
-    }
-    const double x_lo = dunkey(prefix);
+    const double x_lo = dunkey(prefix[which]);
     double x_hi = x_lo;
-    if (h != 0.0 && below + (long long)eq <= r + 1) {
+    if (h != 0.0 && below[which] + (long long)eq[which] <= r + 1) {
       // next order statistic = smallest key strictly above
       unsigned long long mn = ~0ull;
       for (int64_t i = tid; i < M; i += RS_THREADS) {
         const unsigned long long k = key_at(i);
-        if (k > prefix && k < mn) mn = k;
+        if (k > prefix[which] && k < mn) mn = k;
       }
       s_min[tid] = mn;
       __syncthreads();
@@ -250,13 +316,54 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
 }
 
 // ---- host orchestration ---------------------------------------------------------------------------------
+// Scratch buffers of the predict / basis entry points.  Every entry point is blocking (its stream is drained
+// before it returns), so a released block can be handed to the next call as is: a small per-device free list
+// replaces cudaMalloc / cudaFree (several milliseconds per call for the 100 MB strips).
+struct ScratchPool {
+  struct Block { size_t bytes; void* p; int dev; };
+  std::vector<Block> free_blocks;
+  size_t cached = 0;
+  std::mutex mu;
+  ~ScratchPool() {}   // blocks are returned to the driver at process exit
+};
+static ScratchPool g_scratch;
+
 struct DevBuf {
   void* p = nullptr;
+  size_t bytes = 0;
+  int dev = 0;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_scratch.mu);
+    if (g_scratch.free_blocks.size() < 32 && g_scratch.cached + bytes <= ((size_t)4 << 30)) {
+      g_scratch.free_blocks.push_back({bytes, p, dev});
+      g_scratch.cached += bytes;
+    } else {
+      cudaFree(p);
+    }
   }
-  int alloc(size_t bytes) {
-    BGP_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+  int alloc(size_t want) {
+    want = want ? want : 8;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(g_scratch.mu);
+      int best = -1;
+      for (int i = 0; i < (int)g_scratch.free_blocks.size(); ++i) {
+        const auto& b = g_scratch.free_blocks[(size_t)i];
+        if (b.dev == dev && b.bytes >= want && b.bytes <= 2 * want + 4096 &&
+            (best < 0 || b.bytes < g_scratch.free_blocks[(size_t)best].bytes))
+          best = i;
+      }
+      if (best >= 0) {
+        p = g_scratch.free_blocks[(size_t)best].p;
+        bytes = g_scratch.free_blocks[(size_t)best].bytes;
+        g_scratch.cached -= bytes;
+        g_scratch.free_blocks.erase(g_scratch.free_blocks.begin() + best);
+        return BGP_OK;
+      }
+    }
+    bytes = want;
+    BGP_CUDA(cudaMalloc(&p, bytes));
     return BGP_OK;
   }
   template <class T>

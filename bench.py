@@ -239,12 +239,44 @@ def run_b200(args):
         "clocks": clocks,
         "wall_s_timed_region": region_s,
     }
+    if world == 1 and not args.no_predict:
+        line["predict"] = predict_leg(local, fp64_peak)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(x, y, thetas, w_mode, budget_s=args.cpu_budget)
     print(json.dumps(line), flush=True)
     ff.close()
     if dist:
         dist.destroy_process_group()
+
+
+def predict_leg(device, fp64_peak, G=100_000, M=10_000):
+    """Second half of the BASELINE metric: predict GFLOP/s for the sample -> function evaluation
+    (compute_post_fun_IWP + extract_mean_interval_given_samps, /root/reference/R/03_post_fit.R:200-241,287-296)
+    at the C3 term shape (IWP3, k = 300: 299 spline + 2 boundary + intercept columns), M = 1e4 posterior samples,
+    a G = 1e5 point grid: F = [X | B](x_new) [global; coef] is a (G x 302) x (302 x M) FP64 product that is never
+    materialised (L2-sized strips), each row reduced to mean + two type-7 quantiles by an exact radix select.
+    Timed through the public call with host buffers (coefficient samples in, 3 G-vectors out)."""
+    from bayesgp_b200.api import compute_post_fun_IWP
+    rng = np.random.default_rng(20243)
+    knots = np.linspace(0.0, 1.0, P_KNOTS)
+    coef = 0.05 * rng.standard_normal((P_KNOTS - 1, M))
+    glob = rng.standard_normal((ORDER - 1, M))
+    icpt = rng.standard_normal(M)
+    xg = np.linspace(0.0, 1.0, G)
+    kw = dict(global_samps=glob, knots=knots, refined_x=xg, p=ORDER, degree=0, intercept_samps=icpt, device=device)
+    compute_post_fun_IWP(coef, **kw)                     # warm-up (allocations, attributes)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = compute_post_fun_IWP(coef, **kw)
+        best = min(best, time.perf_counter() - t0)
+    K = (P_KNOTS - 1) + ORDER
+    flops = 2.0 * G * K * M
+    return {"workload": "IWP3 k=%d term, G=%d grid points x M=%d samples, degree 0, mean + 2.5/97.5 %% type-7 quantiles"
+                        % (P_KNOTS, G, M), "ms": best * 1e3, "gflops": flops / best / 1e9,
+            "dgemm_flops": flops, "frac_of_fp64_peak": (flops / best / 1e12 / fp64_peak) if fp64_peak else None,
+            "timing": "wall clock of the public call, host buffers in and out, best of 3",
+            "h2d_bytes": 8 * (K * M + G), "d2h_bytes": 24 * G, "checksum_mean": float(np.sum(out["mean"]))}
 
 
 def oracle_model(x, y):
@@ -327,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-predict", action="store_true", help="skip the predict GFLOP/s leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-nodes", type=int, default=1)
     args = ap.parse_args()
