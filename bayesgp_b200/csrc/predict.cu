@@ -328,6 +328,9 @@ struct ScratchPool {
 };
 static ScratchPool g_scratch;
 
+// device time of the last predict call on this thread (CUDA events on its stream): GEMM, select, whole call
+static thread_local double g_pred_ms[3] = {0.0, 0.0, 0.0};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -430,6 +433,14 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   const bool in_smem = key_bytes <= 200 * 1024;
   if (in_smem && key_bytes > 40 * 1024)
     BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_bytes));
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    evs.push_back(e);
+  };
+  mark();                                             // evs[0]: start
   for (int64_t g0 = 0; g0 < G; g0 += strip) {
     const int64_t rows = std::min(strip, G - g0);
     if (ds.iwp) {
@@ -464,8 +475,10 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     }
     count_launch();
     BGP_CUDA(cudaGetLastError());
+    mark();                                           // per strip: [gemm start, gemm end, select end]
     BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Fb.as<double>(), ldF, false,
                          nullptr, st));
+    mark();
     if (samples)   // G x M column-major copy for only.samples = TRUE
       BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
                            true, nullptr, st));
@@ -474,6 +487,7 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     else row_select_kernel<false><<<(unsigned)rows, RS_THREADS, 0, st>>>(sa);
     count_launch();
     BGP_CUDA(cudaGetLastError());
+    mark();
   }
   if (mean) BGP_CUDA(cudaMemcpyAsync(mean, o_mean, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (plower) BGP_CUDA(cudaMemcpyAsync(plower, o_lo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -481,6 +495,20 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   if (samples)
     BGP_CUDA(cudaMemcpyAsync(samples, Sb.p, (size_t)G * M * sizeof(double), cudaMemcpyDeviceToHost, st));
   BGP_CUDA(cudaStreamSynchronize(st));
+  g_pred_ms[0] = g_pred_ms[1] = g_pred_ms[2] = 0.0;
+  for (size_t i = 1; i + 2 < evs.size(); i += 3) {
+    float a_ms = 0, b_ms = 0;
+    cudaEventElapsedTime(&a_ms, evs[i], evs[i + 1]);
+    cudaEventElapsedTime(&b_ms, evs[i + 1], evs[i + 2]);
+    g_pred_ms[0] += a_ms;
+    g_pred_ms[1] += b_ms;
+  }
+  if (evs.size() >= 2) {
+    float t_ms = 0;
+    cudaEventElapsedTime(&t_ms, evs.front(), evs.back());
+    g_pred_ms[2] = t_ms;
+  }
+  for (cudaEvent_t e : evs) cudaEventDestroy(e);
   return BGP_OK;
 }
 
@@ -633,6 +661,13 @@ int bgp_predict_sgp(const double* coef, const double* global, const double* icpt
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   return rc;
+}
+
+int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms) {
+  if (gemm_ms) *gemm_ms = g_pred_ms[0];
+  if (select_ms) *select_ms = g_pred_ms[1];
+  if (total_ms) *total_ms = g_pred_ms[2];
+  return BGP_OK;
 }
 
 int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, int64_t G, int device, double* out) {

@@ -272,9 +272,17 @@ def predict_leg(device, fp64_peak, G=100_000, M=10_000):
         best = min(best, time.perf_counter() - t0)
     K = (P_KNOTS - 1) + ORDER
     flops = 2.0 * G * K * M
+    import ctypes as C
+    from bayesgp_b200 import _lib
+    tg, ts, tt = C.c_double(), C.c_double(), C.c_double()
+    _lib.load().bgp_predict_last_timing(C.byref(tg), C.byref(ts), C.byref(tt))
+    gemm_tflops = flops / (tg.value * 1e-3) / 1e12 if tg.value > 0 else None
     return {"workload": "IWP3 k=%d term, G=%d grid points x M=%d samples, degree 0, mean + 2.5/97.5 %% type-7 quantiles"
                         % (P_KNOTS, G, M), "ms": best * 1e3, "gflops": flops / best / 1e9,
             "dgemm_flops": flops, "frac_of_fp64_peak": (flops / best / 1e12 / fp64_peak) if fp64_peak else None,
+            "device_ms": {"gemm": tg.value, "select": ts.value, "total": tt.value},
+            "gemm_tflops": gemm_tflops,
+            "gemm_frac_of_fp64_peak": (gemm_tflops / fp64_peak) if (fp64_peak and gemm_tflops) else None,
             "timing": "wall clock of the public call, host buffers in and out, best of 3",
             "h2d_bytes": 8 * (K * M + G), "d2h_bytes": 24 * G, "checksum_mean": float(np.sum(out["mean"]))}
 

@@ -154,6 +154,9 @@ int bgp_predict_iwp(const double* coef, const double* global, const double* icpt
 int bgp_predict_sgp(const double* coef, const double* global, const double* icpt, int64_t M, double a, int k, int m,
                     const double* region /* 2 */, int boundary, const double* x, int64_t G, double level, int device,
                     double* mean, double* plower, double* pupper, double* samples);
+/* device time (CUDA events on the call's stream, ms) of the last bgp_predict_* call on this thread: the FP64
+ * tensor-pipe GEMM strips, the per-row quantile selection, and the whole device sequence */
+int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms);
 /* basis evaluators on the device (R/01_utility.R:378-401, :413-419, :198-208): out is G x ncol col-major */
 int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, int64_t G, int device, double* out);
 
