@@ -36,6 +36,16 @@ def _binom():
     return y, x1, x2, size
 
 
+def _three_terms():
+    """C5 in miniature: Poisson, three IWP smoothing terms on three covariates (S = 3, 3-D AGHQ grid)."""
+    rng = np.random.default_rng(20245)
+    n = 4000
+    x1, x2, x3 = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    eta = 0.5 + np.sin(2 * np.pi * x1) + 0.5 * x2 ** 2 - 0.7 * np.cos(3 * x3)
+    y = rng.poisson(np.exp(eta)).astype(np.float64)
+    return y, x1, x2, x3
+
+
 def _both(case):
     """returns (oracle fit pieces, product fit) built from the same raw data."""
     import bayesgp_b200 as bg
@@ -50,6 +60,13 @@ def _both(case):
         oargs = dict(y=y, terms=[ofit.Term("IWP", "exposure", x, order=3, k=50)], fixed={}, family="Gaussian")
         pargs = dict(y=y, terms=[bg.Term("IWP", "exposure", x, order=3, k=50)], fixed={}, family="Gaussian")
         k = 4
+    elif case == "three_iwp":
+        y, x1, x2, x3 = _three_terms()
+        mk = lambda T: [T("IWP", "x1", x1, order=3, k=14), T("IWP", "x2", x2, order=2, k=10),
+                        T("IWP", "x3", x3, order=3, k=12)]
+        oargs = dict(y=y, terms=mk(ofit.Term), fixed={}, family="Poisson")
+        pargs = dict(y=y, terms=mk(bg.Term), fixed={}, family="Poisson")
+        k = 3
     else:
         y, x1, x2, size = _binom()
         mk = lambda T: [T("IWP", "x1", x1, order=2, k=16),
@@ -60,7 +77,7 @@ def _both(case):
     return oargs, pargs, k
 
 
-@pytest.fixture(scope="module", params=["covid", "sim1_gaussian", "binomial_sgp"])
+@pytest.fixture(scope="module", params=["covid", "sim1_gaussian", "binomial_sgp", "three_iwp"])
 def fits(request):
     import bayesgp_b200 as bg
     from oracle import fit as ofit

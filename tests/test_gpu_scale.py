@@ -1,0 +1,146 @@
+"""GPU tests at BASELINE.json's full size (C3: n = 1e6, IWP3 k = 300, p = 302): one direct comparison with the
+oracle at a size it finishes in seconds, and size-independent properties of the hot path at n = 1e6
+(row-order invariance, linearity over observation blocks, batch == single, determinism)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _c3(n):
+    from bayesgp_b200.workloads import c3_data, iwp_knots
+    x, y = c3_data(n)
+    x0, knots = iwp_knots(x, 300)
+    return x, y, x0, knots
+
+
+def _build(x, y, x0, knots, sort=True):
+    from bayesgp_b200.objective import LaplaceObjective
+    old = os.environ.get("BGP_NO_SORT")
+    if not sort:
+        os.environ["BGP_NO_SORT"] = "1"
+    try:
+        ff = LaplaceObjective(y=y, family="Poisson")
+        ff.add_iwp(x, x0, knots, 3)
+        ff.add_fixed(np.ones(len(y)))
+        ff.finalize()
+    finally:
+        if not sort:
+            if old is None:
+                del os.environ["BGP_NO_SORT"]
+            else:
+                os.environ["BGP_NO_SORT"] = old
+    return ff
+
+
+def test_c3_200k_matches_oracle():
+    """Same generator as the bench at n = 2e5 (the oracle needs ~10 s): Laplace value 1e-8, mode / Hessian 1e-6."""
+    from oracle.fit import Term, build_model
+    from oracle.laplace import LaplaceObjective as OFF
+    x, y, x0, knots = _c3(200_000)
+    model = build_model(y, [Term("IWP", "x", x, order=3, k=300)], {}, family="Poisson")[0]
+    off = OFF(model)
+    ff = _build(x, y, x0, knots)
+    try:
+        assert ff.p == model.p == 302
+        for theta in (np.array([-9.0]), np.array([-10.5])):
+            want = off.fn(theta)
+            got, _, w, H = ff._eval(theta, want_hess=True)
+            assert abs(got - want) <= 1e-8 * abs(want), (theta, got, want)
+            assert relerr(w, off.last_par) < 1e-6
+            assert relerr(H, off.sp_hess()) < 1e-6
+    finally:
+        ff.close()
+
+
+@pytest.fixture(scope="module")
+def c3_full():
+    x, y, x0, knots = _c3(1_000_000)
+    ff = _build(x, y, x0, knots)
+    yield x, y, x0, knots, ff
+    ff.close()
+
+
+def test_full_size_row_order_invariance(c3_full):
+    """f, g, H are sums over observations: the zero-pattern sort (and the skipping of empty cells it enables)
+    must not change them beyond summation-order rounding."""
+    x, y, x0, knots, ff = c3_full
+    ff2 = _build(x, y, x0, knots, sort=False)
+    try:
+        hf, hf2 = ff.hessian_flops(), ff2.hessian_flops()
+        assert hf["structural"] < 0.5 * hf["dense"] and hf2["structural"] > 0.9 * hf2["dense"]
+        rng = np.random.default_rng(3)
+        W = 0.02 * rng.standard_normal(ff.p)
+        theta = np.array([-10.0])
+        f1, g1, H1 = ff.objective(W, theta, want_grad=True, want_hess=True)
+        f2, g2, H2 = ff2.objective(W, theta, want_grad=True, want_hess=True)
+        assert abs(f1 - f2) <= 1e-12 * abs(f2)
+        assert relerr(g1, g2) < 1e-10
+        assert relerr(H1, H2) < 1e-11
+        assert np.array_equal(H1, H1.T)
+        v1, v2 = ff.fn(np.array([-10.5])), ff2.fn(np.array([-10.5]))
+        assert abs(v1 - v2) <= 1e-11 * abs(v2)
+    finally:
+        ff2.close()
+
+
+def test_full_size_linearity_over_observation_blocks(c3_full):
+    """H(all) - Q = (H(first half) - Q) + (H(second half) - Q) and the same for g and the log-likelihood part."""
+    x, y, x0, knots, ff = c3_full
+    n = len(y)
+    h = n // 2
+    # same knots / location for the halves so the designs are row blocks of the full design
+    fa = _build(x[:h], y[:h], x0, knots)
+    fb = _build(x[h:], y[h:], x0, knots)
+    try:
+        rng = np.random.default_rng(4)
+        W = 0.02 * rng.standard_normal(ff.p)
+        theta = np.array([-10.0])
+        f, g, H = ff.objective(W, theta, want_grad=True, want_hess=True)
+        f_a, g_a, H_a = fa.objective(W, theta, want_grad=True, want_hess=True)
+        f_b, g_b, H_b = fb.objective(W, theta, want_grad=True, want_hess=True)
+        # prior terms (Q, Q (W - mu0), -lpW - lpT) appear once in the full model and once in each half
+        f0, g0, H0 = _prior_only(W, theta, x0, knots)
+        assert relerr(H_a + H_b - H0, H) < 1e-11
+        assert relerr(g_a + g_b - g0, g) < 1e-10
+        assert abs((f_a + f_b - f0) - f) <= 1e-11 * abs(f)
+    finally:
+        fa.close()
+        fb.close()
+
+
+def _prior_only(W, theta, x0, knots):
+    """f, g, H of the same model with the likelihood switched off (family "none", src/BayesGP.cpp:212-214)."""
+    from bayesgp_b200.objective import LaplaceObjective
+    x = x0 + np.linspace(0.0, float(knots[-1]), 64)
+    y = np.zeros(64)
+    f0 = LaplaceObjective(y=y, family="none")
+    f0.add_iwp(x, x0, knots, 3)
+    f0.add_fixed(np.ones(len(y)))
+    f0.finalize()
+    try:
+        return f0.objective(W, theta, want_grad=True, want_hess=True)
+    finally:
+        f0.close()
+
+
+def test_full_size_batch_equals_single_and_is_deterministic(c3_full):
+    x, y, x0, knots, ff = c3_full
+    thetas = np.array([[-10.8], [-10.5], [-10.2]])
+    ff.set_start(None)
+    v1, m1, H1, _ = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+    ff.set_start(None)
+    v2, m2, H2, _ = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+    assert np.array_equal(v1, v2) and np.array_equal(m1, m2) and np.array_equal(H1, H2)      # bit-reproducible
+    ff.set_start(None)
+    singles = [ff.fn(t) for t in thetas]
+    assert np.max(np.abs(np.array(singles) - v1) / np.abs(v1)) < 1e-12
+    # the gradient of the Laplace objective against a central difference of its values
+    g = ff.gr(thetas[1])
+    eps = 1e-4
+    fd = (ff.fn(thetas[1] + eps) - ff.fn(thetas[1] - eps)) / (2 * eps)
+    assert abs(g[0] - fd) <= 1e-5 * max(1.0, abs(fd)), (g, fd)
