@@ -130,8 +130,10 @@ class FitResult:
 
 
 def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]] = None, family="Gaussian", size=None,
-                    control_family=None, control_fixed=None, device=0):
-    """get_result_by_method up to MakeADFun (R/02_model_fit.R:1-183,249-282): returns (ff, index maps)."""
+                    control_family=None, control_fixed=None, device=0, shard=None):
+    """get_result_by_method up to MakeADFun (R/02_model_fit.R:1-183,249-282): returns (ff, index maps).
+    ``shard = (rank, world, nccl_unique_id)``: y / x / fixed are this rank's rows of an observation-sharded
+    problem (terms must then carry the GLOBAL knots and initial_location)."""
     if family not in FAMILY_CODES:
         raise ValueError("family %r is outside the B200 hot path (Gaussian / Poisson / Binomial / none)" % family)
     fixed = fixed or {}
@@ -162,6 +164,8 @@ def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]]
             ff.add_fixed(np.asarray(col, dtype=np.float64), cf.get("prec", 0.01), cf.get("mean", 0.0))
         if FAMILY_CODES[family] == 0:
             ff.set_noise_prior(control_family.get("u", 1.0), control_family.get("alpha", 0.5))
+        if shard is not None:
+            ff.set_shard(*shard)
         ff.finalize()
     except Exception:
         ff.close()
@@ -270,6 +274,8 @@ def predict(object: FitResult, newdata=None, variable=None, degree=0, include_in
     if newdata is None:
         refined_x = term.observed_x
     else:
+        if isinstance(newdata, dict):          # R: newdata[[variable]]  (R/03_post_fit.R:73)
+            newdata = newdata[variable]
         refined_x = np.sort(np.asarray(newdata, dtype=np.float64) - term.initial_location)
     intercept = samps[object.fixed_samp_indexes["intercept"], :] if include_intercept else None
     dev = object.ff.device

@@ -172,6 +172,7 @@ struct bgp_fit {
   int S = 0, K = 0, p = 0, k = 0;
   std::vector<double> mode, hessian;   // S, S*S (column-major)
   int convergence = 0, fn_count = 0, gr_count = 0;
+  int hessian_fallback = 0;            // number of Richardson retries with a larger step (0 = numDeriv default)
   std::vector<double> nodes;           // K x S column-major
   std::vector<double> weights, logpost, logpost_norm;
   double lognormconst = 0.0;

@@ -9,6 +9,8 @@
 #include <functional>
 #include <limits>
 
+#include <cstdlib>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -156,9 +158,10 @@ static int vmmin(FF& ff, std::vector<double>& b, double* Fmin_out, int* fail, in
 }
 
 // ---- numDeriv::jacobian(ff$gr, theta), method "Richardson" (A.3) ------------------------------------------
-static int richardson_jacobian(FF& ff, const std::vector<double>& x, std::vector<double>& J /* S x S col-major */) {
+static int richardson_jacobian(FF& ff, const std::vector<double>& x, std::vector<double>& J /* S x S col-major */,
+                               double d = 1e-4) {
   const int n = (int)x.size(), r = 4;
-  const double d = 1e-4, eps = 1e-4, v = 2.0;
+  const double eps = 1e-4, v = 2.0;
   const double zero_tol = std::sqrt(std::numeric_limits<double>::epsilon() / 7e-7);
   std::vector<double> f0(n), h(n), gp(n), gm(n), xx(x);
   BGP_TRY(ff.gr(x.data(), f0.data()));
@@ -401,6 +404,32 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   } else {
     int st = richardson_jacobian(ff, f->mode, f->hessian);
     if (st != BGP_OK) return fail(st);
+    // numDeriv's default step (d = 1e-4) differentiates a gradient that carries ~cond(H) * eps * |L| of rounding
+    // noise; at large n the result can come out indefinite, where aghq would stop with a chol() error.  Retry with
+    // 10x / 100x larger steps (less noise amplification), recorded in hessian_fallback.
+    auto is_pd = [&](const std::vector<double>& H) {
+      std::vector<double> C;
+      if (!invert_general(H, S, C)) return false;
+      for (int i = 0; i < S; ++i)
+        for (int j = i + 1; j < S; ++j) C[(size_t)i * S + j] = C[(size_t)j * S + i];
+      return chol_lower(C, S);
+    };
+    const bool dbg = getenv("BGP_FIT_DEBUG") != nullptr;
+    auto dump = [&](const char* tag) {
+      if (!dbg) return;
+      fprintf(stderr, "[fit] %s mode:", tag);
+      for (int i = 0; i < S; ++i) fprintf(stderr, " %.8f", f->mode[i]);
+      fprintf(stderr, " hessian:");
+      for (int i = 0; i < S * S; ++i) fprintf(stderr, " %.6g", f->hessian[i]);
+      fprintf(stderr, "\n");
+    };
+    dump("richardson d=1e-4");
+    for (double d = 1e-3; !is_pd(f->hessian) && d <= 1.001e-2; d *= 10.0) {
+      st = richardson_jacobian(ff, f->mode, f->hessian, d);
+      if (st != BGP_OK) return fail(st);
+      ++f->hessian_fallback;
+      dump("richardson retry");
+    }
   }
   std::vector<int> ord(S);
   for (int i = 0; i < S; ++i) ord[i] = i;

@@ -1,0 +1,82 @@
+"""End-to-end model_fit() + predict() on BASELINE.json's large synthetic configs:
+   c4: Binomial n = 1e6, IWP2 k=440 + sGP (a = 2 pi 5, k = 20, m = 1) + intercept (p = 497), 2-D AGHQ 7^2
+       (SURVEY 8d proposed IWP2 k=200 + sGP k=100 for the same p; the sGP precision of Compute_Q_sB is
+       numerically singular beyond k ~ 30 at this frequency — cond(H) 2e13 at k=40, not positive definite in
+       FP64 at k>=60, measured — so the columns are moved to the IWP term)
+   c5: Poisson  n = 1e7, three IWP3 k = 334 terms + intercept (p = 1006), 3-D AGHQ 5^3, M = 1e5, G = 1e5
+   Under torchrun the observations are sharded over the ranks (NCCL all-reduce of g and H per Newton iteration).
+   usage: run_config.py c4|c5 [n] [aghq_k] [M] [G]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
+import numpy as np
+import bayesgp_b200 as bg
+from bayesgp_b200 import api
+from bayesgp_b200.distributed import broadcast_unique_id, nccl_unique_id, shard_bounds
+
+cfg = sys.argv[1]
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+dist = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+arg = lambda i, d: type(d)(float(sys.argv[i])) if len(sys.argv) > i else d
+t_all = time.time()
+if cfg == "c4":
+    n, k, M, G = arg(2, 1_000_000), arg(3, 7), arg(4, 10_000), arg(5, 1000)
+    rng = np.random.default_rng(20244)
+    x1, x2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    eta = -0.3 + np.sin(2 * np.pi * x1) + 0.6 * np.cos(2 * np.pi * 5 * x2)
+    size = 1.0 + rng.poisson(9, n)
+    y = rng.binomial(size.astype(int), 1 / (1 + np.exp(-eta))).astype(np.float64)
+    cols = {"x1": x1, "x2": x2}
+    mk = lambda sl: [bg.Term("IWP", "x1", x1[sl], order=2, knots=np.linspace(0, x1.max() - x1.min(), 440), initial_location=float(x1.min())),
+                     bg.Term("sGP", "x2", x2[sl], a=2 * np.pi * 5, k=20, m=1, region=np.array([0.0, 1.0]), accuracy=0.01)]
+    family = "Binomial"
+else:
+    n, k, M, G = arg(2, 10_000_000), arg(3, 5), arg(4, 100_000), arg(5, 100_000)
+    rng = np.random.default_rng(20245)
+    xs = [rng.uniform(0, 1, n) for _ in range(3)]
+    # none of the three effects lies in the null space of its IWP3 penalty (a quadratic would send theta -> +inf)
+    eta = 0.5 + np.sin(2 * np.pi * xs[0]) + 0.4 * np.sin(3 * np.pi * xs[1]) + 0.6 * np.sin(2.5 * np.pi * xs[2] + 1.0)
+    y = rng.poisson(np.exp(eta)).astype(np.float64)
+    size = None
+    cols = {"x%d" % (i + 1): xs[i] for i in range(3)}
+    mk = lambda sl: [bg.Term("IWP", "x%d" % (i + 1), xs[i][sl], order=3, knots=np.linspace(0, xs[i].max() - xs[i].min(), 334),
+                             initial_location=float(xs[i].min())) for i in range(3)]
+    family = "Poisson"
+lo, hi = shard_bounds(n, rank, world)
+sl = slice(lo, hi)
+shard = (rank, world, broadcast_unique_id(nccl_unique_id, rank)) if world > 1 else None
+t0 = time.time()
+ff, terms, rand_idx, bnd_idx, fix_idx = api.build_objective(y[sl], mk(sl), {}, family, None if size is None else size[sl],
+                                                            device=local, shard=shard)
+t_build = time.time() - t0
+hf = ff.hessian_flops()
+t0 = time.time()
+mod = api.marginal_laplace_tmb(ff, k, np.zeros(ff.S))
+t_fit = time.time() - t0
+out = {"config": cfg, "n": n, "p": ff.p, "S": ff.S, "K": mod.K, "gpus": world, "build_s": t_build, "fit_s": t_fit,
+       "data_s": t0 - t_all - t_build, "hessian_structural_fraction": hf["structural"] / hf["dense"],
+       "theta_mode": mod.optresults["mode"].tolist(), "convergence": mod.optresults["convergence"],
+       "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"], "lognormconst": mod.lognormconst,
+       "laplace_evals": ff.n_fn, "gradient_evals": ff.n_gr, "newton_iters": ff.newton_iters}
+if rank == 0:
+    t0 = time.time()
+    samps = api.sample_marginal(mod, M, seed=1)
+    out["sample_s"] = time.time() - t0
+    res = api.FitResult(terms, mod, ff, bnd_idx, rand_idx, fix_idx, family)
+    res.samps = samps
+    out["predict_s"] = {}
+    for t in terms:
+        xg = np.linspace(cols[t.name].min(), cols[t.name].max(), G)
+        t0 = time.time()
+        pr = api.predict(res, newdata={t.name: xg}, variable=t.name, degree=0)
+        out["predict_s"][t.name] = time.time() - t0
+        out.setdefault("predict_mean_range", {})[t.name] = [float(np.min(pr["mean"])), float(np.max(pr["mean"]))]
+    out["total_s"] = time.time() - t_all
+    print("RUN_CONFIG " + json.dumps(out), flush=True)
+if dist:
+    dist.barrier()
+    dist.destroy_process_group()
