@@ -30,6 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K_NODES = 15
+# DRAM bytes (read + write) of one syrk_kernel launch on C3, from the committed `ncu --set full` capture
+# (profiles/r01_ncu_full_metrics.txt: dram__bytes_read.sum 3.983 GB + dram__bytes_write.sum 85 MB); the
+# algorithmic minimum is one pass over the occupied boxes of A (1.5 GB) — units of different tiles re-read
+# the observations they share, L2 serves a third of those reads.
+SYRK_DRAM_TRAFFIC_BYTES = 4.068e9
 # centre / scale of the C3 theta grid (seed 20243, n = 1e6), located by the b200 arm's untimed golden-section
 # search (bench.py prints them as config.theta_mode / theta_sd); used by the CPU arm to skip that search.
 C3_THETA_MODE, C3_THETA_SD = -10.5, 0.1
@@ -224,7 +229,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": achieved,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if fp64_peak else None,
-                     "traffic": None, "ms_per_launch": hess_ms, "algorithmic_flops_per_launch": flops,
+                     "traffic": SYRK_DRAM_TRAFFIC_BYTES if n == 1_000_000 else None, "traffic_unit": "bytes",
+                     "ms_per_launch": hess_ms, "algorithmic_flops_per_launch": flops,
                      "dense_flops_per_launch": hf["dense"], "structural_fraction": hf["structural"] / hf["dense"],
                      "dense_equivalent_tflops": hf["dense"] / (hess_ms * 1e-3) / 1e12,
                      "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 "
