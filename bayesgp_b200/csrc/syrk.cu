@@ -46,8 +46,8 @@ constexpr int SK_MBOX = SK_MBOX_N;         // strips (16-row boxes of H) per CTA
 constexpr int SK_NBOX = 4;                 // N panel: 4 boxes = 64 columns of H
 constexpr int SK_KB = 16;                  // observations per pipeline stage
 constexpr int SK_SPC = 4;                  // stages per 64-observation chunk
-constexpr int SK_STAGES = SK_MBOX == 4 ? 3 : 4;
-constexpr int SK_CTAS_PER_SM = SK_MBOX == 4 ? 4 : 2;
+constexpr int SK_STAGES = 4;
+constexpr int SK_CTAS_PER_SM = 3;
 constexpr int SK_CONSUMERS = SK_NBOX;     // one consumer warp per box of the N panel
 constexpr int SK_THREADS = 32 * (SK_CONSUMERS + 1);
 constexpr int SK_BOX_BYTES = 16 * SK_KB * 8;                       // 2048
