@@ -118,11 +118,17 @@ struct bgp_model {
   double* Tan = nullptr;        // S x lda tangent d w_hat / d theta at the last mode (warm-start predictor)
   std::vector<double> theta_last;
   bool tan_valid = false;
-  // the evaluation before the last one (cubic Hermite extrapolation along collinear theta nodes)
-  double* Wmode_prev = nullptr;
-  double* Tan_prev = nullptr;
-  std::vector<double> theta_prev;
-  bool prev_valid = false;
+  // recent evaluations (theta, mode, tangent) for the warm-start predictor: cubic Hermite through the two
+  // nearest entries collinear with the new theta (grid rows, line searches), else first order from the nearest
+  static constexpr int NHIST = 8;
+  struct Hist {
+    std::vector<double> theta;
+    double* W = nullptr;      // lda
+    double* T = nullptr;      // S x lda
+    uint64_t stamp = 0;       // 0 = empty
+  };
+  Hist hist[NHIST];
+  uint64_t hist_clock = 0;
   bool use_predictor = true;
   bool use_hermite = true;
   double* H = nullptr;          // p x ldh column-major (full symmetric after reduce)

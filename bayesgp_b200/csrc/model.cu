@@ -400,8 +400,10 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->Ldinv, (size_t)m->ldh * sizeof(double)));
   BGP_TRY(dalloc(&m->theta_dev, 64 * sizeof(double)));
   BGP_TRY(dalloc(&m->Tan, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
-  BGP_TRY(dalloc(&m->Tan_prev, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
-  BGP_TRY(dalloc(&m->Wmode_prev, vb));
+  for (auto& h : m->hist) {
+    BGP_TRY(dalloc(&h.T, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
+    BGP_TRY(dalloc(&h.W, vb));
+  }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   m->lik_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (n + 7) / 8));   // one persistent CTA per SM
@@ -443,8 +445,12 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->Tan, m->Tan_prev, m->Wmode_prev, m->xbuf, m->H, m->L, m->Ldinv, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->xbuf, m->H, m->L, m->Ldinv, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
     if (ptr) cudaFree(ptr);
+  for (auto& h : m->hist) {
+    if (h.W) cudaFree(h.W);
+    if (h.T) cudaFree(h.T);
+  }
   if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);

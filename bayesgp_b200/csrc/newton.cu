@@ -85,58 +85,80 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   // start from the previous mode (TMB last.par.best), moved along the tangent d w_hat / d theta when the
   // step in theta is moderate; fall back to the plain warm start, then to W = 0, if that point is non-finite
   bool predicted = false;
-  if (m->use_predictor && m->tan_valid && (int)m->theta_last.size() == m->S && m->S <= 17) {
-    PredictArgs pa;
-    double dmax = 0.0;
-    for (int k = 0; k < m->S; ++k) {
-      pa.dtheta[k] = theta[k] - m->theta_last[k];
-      dmax = std::max(dmax, std::fabs(pa.dtheta[k]));
-    }
-    // collinear with the two previous nodes (grid rows, line searches): theta = theta_b + tau (theta_b - theta_a)
-    bool hermite = false;
-    double tau = 0.0;
-    if (m->use_hermite && m->prev_valid && (int)m->theta_prev.size() == m->S && dmax > 0.0 && dmax <= 2.0) {
-      double uu = 0.0, ud = 0.0;
-      for (int k = 0; k < m->S; ++k) {
-        const double u = m->theta_last[k] - m->theta_prev[k];
-        uu += u * u;
-        ud += u * pa.dtheta[k];
-      }
-      if (uu > 0.0) {
-        tau = ud / uu;
-        double dev = 0.0;
-        for (int k = 0; k < m->S; ++k)
-          dev = std::max(dev, std::fabs(pa.dtheta[k] - tau * (m->theta_last[k] - m->theta_prev[k])));
-        hermite = dev <= 1e-12 * std::max(1.0, dmax) && tau > 0.0 && tau <= 2.0;
+  if (m->use_predictor && m->S <= 17) {
+    // nearest history entry (max-norm in theta)
+    int e1 = -1;
+    double d1 = 0.0;
+    for (int i = 0; i < bgp_model::NHIST; ++i) {
+      const auto& h = m->hist[i];
+      if (!h.stamp) continue;
+      double d = 0.0;
+      for (int k = 0; k < m->S; ++k) d = std::max(d, std::fabs(theta[k] - h.theta[k]));
+      if (e1 < 0 || d < d1 || (d == d1 && h.stamp > m->hist[e1].stamp)) {
+        e1 = i;
+        d1 = d;
       }
     }
-    if (hermite) {
-      HermiteArgs ha;
-      ha.Wa = m->Wmode_prev;
-      ha.Ta = m->Tan_prev;
-      ha.Wb = m->Wmode;
-      ha.Tb = m->Tan;
-      ha.S = m->S;
-      ha.lda = m->lda;
-      for (int k = 0; k < m->S; ++k) ha.u[k] = m->theta_last[k] - m->theta_prev[k];
-      const double s = 1.0 + tau, s2 = s * s, s3 = s2 * s;
-      ha.h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
-      ha.h10 = s3 - 2.0 * s2 + s;
-      ha.h01 = -2.0 * s3 + 3.0 * s2;
-      ha.h11 = s3 - s2;
-      ha.out = m->W;
-      hermite_start_kernel<<<blocks, threads, 0, m->stream>>>(ha);
-      count_launch();
-      predicted = true;
-    } else if (dmax > 0.0 && dmax <= 2.0) {
-      pa.Wmode = m->Wmode;
-      pa.Tan = m->Tan;
-      pa.S = m->S;
-      pa.lda = m->lda;
-      pa.out = m->W;
-      predict_start_kernel<<<blocks, threads, 0, m->stream>>>(pa);
-      count_launch();
-      predicted = true;
+    if (e1 >= 0 && d1 <= 2.0) {
+      const auto& hb = m->hist[e1];
+      // second entry: collinear with (theta, e1), the closest such to e1; theta = theta_b + tau (theta_b - theta_a)
+      int e2 = -1;
+      double tau2 = 0.0, u2 = 0.0;
+      if (m->use_hermite && d1 > 0.0) {
+        for (int i = 0; i < bgp_model::NHIST; ++i) {
+          const auto& ha = m->hist[i];
+          if (!ha.stamp || i == e1) continue;
+          double uu = 0.0, ud = 0.0, umax = 0.0;
+          for (int k = 0; k < m->S; ++k) {
+            const double u = hb.theta[k] - ha.theta[k];
+            uu += u * u;
+            ud += u * (theta[k] - hb.theta[k]);
+            umax = std::max(umax, std::fabs(u));
+          }
+          if (!(uu > 0.0)) continue;
+          const double tau = ud / uu;
+          double dev = 0.0;
+          for (int k = 0; k < m->S; ++k)
+            dev = std::max(dev, std::fabs((theta[k] - hb.theta[k]) - tau * (hb.theta[k] - ha.theta[k])));
+          // inside [a, b] (tau in (-1, 0)) or at most two intervals beyond b
+          if (dev <= 1e-12 * std::max(1.0, d1) && tau > -1.0 && tau <= 2.0 && (e2 < 0 || umax < u2)) {
+            e2 = i;
+            tau2 = tau;
+            u2 = umax;
+          }
+        }
+      }
+      if (e2 >= 0) {
+        const auto& hA = m->hist[e2];
+        HermiteArgs ha;
+        ha.Wa = hA.W;
+        ha.Ta = hA.T;
+        ha.Wb = hb.W;
+        ha.Tb = hb.T;
+        ha.S = m->S;
+        ha.lda = m->lda;
+        for (int k = 0; k < m->S; ++k) ha.u[k] = hb.theta[k] - hA.theta[k];
+        const double s = 1.0 + tau2, s2 = s * s, s3 = s2 * s;
+        ha.h00 = 2.0 * s3 - 3.0 * s2 + 1.0;
+        ha.h10 = s3 - 2.0 * s2 + s;
+        ha.h01 = -2.0 * s3 + 3.0 * s2;
+        ha.h11 = s3 - s2;
+        ha.out = m->W;
+        hermite_start_kernel<<<blocks, threads, 0, m->stream>>>(ha);
+        count_launch();
+        predicted = true;
+      } else {
+        PredictArgs pa;
+        for (int k = 0; k < m->S; ++k) pa.dtheta[k] = theta[k] - hb.theta[k];
+        pa.Wmode = hb.W;
+        pa.Tan = hb.T;
+        pa.S = m->S;
+        pa.lda = m->lda;
+        pa.out = m->W;
+        predict_start_kernel<<<blocks, threads, 0, m->stream>>>(pa);
+        count_launch();
+        predicted = true;
+      }
     }
   }
   if (!predicted)
@@ -237,18 +259,25 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     }
     logdet = sc.logdet;
   }
-  if (m->use_predictor && m->S <= 17 && m->tan_valid) {
-    // the last evaluation becomes "the one before" (pointer swap, no copy)
-    std::swap(m->Wmode, m->Wmode_prev);
-    std::swap(m->Tan, m->Tan_prev);
-    m->theta_prev = m->theta_last;
-    m->prev_valid = true;
-  }
   BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   if (m->use_predictor && m->S <= 17) {
     BGP_TRY(launch_tangent(m, theta));      // uses the factor of H(w_hat) left in m->L
     m->theta_last.assign(theta, theta + m->S);
     m->tan_valid = true;
+    // record (theta, mode, tangent): same theta => overwrite, else replace the oldest entry
+    int slot = -1;
+    for (int i = 0; i < bgp_model::NHIST && slot < 0; ++i)
+      if (m->hist[i].stamp && m->hist[i].theta == m->theta_last) slot = i;
+    if (slot < 0) {
+      slot = 0;
+      for (int i = 1; i < bgp_model::NHIST; ++i)
+        if (m->hist[i].stamp < m->hist[slot].stamp) slot = i;
+    }
+    auto& h = m->hist[slot];
+    h.theta = m->theta_last;
+    h.stamp = ++m->hist_clock;
+    BGP_CUDA(cudaMemcpyAsync(h.W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    BGP_CUDA(cudaMemcpyAsync(h.T, m->Tan, (size_t)m->S * m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   }
   *value = f + 0.5 * logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
   return BGP_OK;
@@ -294,7 +323,7 @@ int bgp_model_set_start(bgp_model* m, const double* W) {
   BGP_CUDA(cudaMemsetAsync(m->Wmode, 0, (size_t)m->lda * sizeof(double), m->stream));
   if (W) BGP_TRY(copy_vec_in(m, W, m->Wmode));
   m->tan_valid = false;
-  m->prev_valid = false;
+  for (auto& h : m->hist) h.stamp = 0;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   return BGP_OK;
 }
@@ -349,7 +378,49 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
   }
   int total = 0, worst = BGP_OK;
   cudaEventRecord(m->ev[0], m->stream);
-  for (int j = 0; j < K; ++j) {
+  // Evaluation order (results go back to the caller's slots): start next to what is already known — the
+  // nearest history entry, or the node closest to the centroid when the history is empty (the warm start is
+  // the mode at the grid centre in aghq's flow) — then always the node nearest to an evaluated one, so every
+  // inner solve starts from a close, usually collinear, pair of neighbours.
+  const int S = m->S;
+  std::vector<int> order;
+  {
+    std::vector<char> done((size_t)K, 0);
+    std::vector<double> known;                          // thetas with a mode on record
+    for (const auto& h : m->hist)
+      if (h.stamp && (int)h.theta.size() == S) known.insert(known.end(), h.theta.begin(), h.theta.end());
+    if (known.empty()) {
+      std::vector<double> c((size_t)S, 0.0);
+      for (int j = 0; j < K; ++j)
+        for (int k = 0; k < S; ++k) c[k] += theta[(size_t)j * S + k] / K;
+      known = c;
+    }
+    for (int it = 0; it < K; ++it) {
+      int best = -1;
+      double bd = 0.0;
+      for (int j = 0; j < K; ++j) {
+        if (done[j]) continue;
+        double dj = INFINITY;
+        for (size_t e = 0; e + S <= known.size(); e += S) {
+          double d = 0.0;
+          for (int k = 0; k < S; ++k) {
+            const double t = theta[(size_t)j * S + k] - known[e + k];
+            d += t * t;
+          }
+          dj = std::min(dj, d);
+        }
+        if (best < 0 || dj < bd) {
+          best = j;
+          bd = dj;
+        }
+      }
+      done[best] = 1;
+      order.push_back(best);
+      known.insert(known.end(), theta + (size_t)best * S, theta + (size_t)best * S + S);
+    }
+  }
+  for (int oi = 0; oi < K; ++oi) {
+    const int j = order[oi];
     int iters = 0;
     double v = NAN;
     int st = laplace_inner(m, theta + (size_t)j * m->S, &v, &iters);

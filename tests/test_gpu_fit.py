@@ -135,7 +135,10 @@ def test_own_optimisation_matches_oracle_procedure(fits):
         # L - L_min < 6e-5, i.e. |dtheta| < sqrt(2 * 6e-5 / 12.9) = 3e-3, is a valid stop (the oracle, the README
         # run and the 80-bit optimum differ by 1e-4 among themselves).  The Richardson Hessian is
         # noise-dominated there as well.  Well-conditioned fixtures keep the 1e-6 target.
-        tol_mode, tol_hess = (1e-3, 5e-2) if name == "covid" else (1e-6, 1e-5)
+        # Elsewhere the Richardson Hessian inherits the inner tolerance: each ff$gr carries up to ~1e-8 (max|g| <
+        # 1e-8 stop) and is divided by 2h = 2e-4 |theta|, i.e. ~1e-4 absolute per entry, whichever start the
+        # inner solve had; relative to the largest entry that is a few 1e-5.
+        tol_mode, tol_hess = (1e-3, 5e-2) if name == "covid" else (1e-6, 5e-5)
         assert np.max(np.abs(mode - omod.mode)) <= tol_mode * max(1.0, np.max(np.abs(omod.mode))), (mode, omod.mode)
         assert relerr(hess, omod.hessian) <= tol_hess, (hess, omod.hessian)
         assert abs(own.mod.lognormconst - omod.lognormconst) <= 2e-7 * abs(omod.lognormconst)
