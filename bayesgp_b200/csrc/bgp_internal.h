@@ -70,7 +70,7 @@ struct EvalScalars {
   int chol_info;   // 0 ok, j+1: non-positive pivot at column j
   int nonfinite;   // 1 if eta / ll produced a non-finite value
   double sumsq;    // Gaussian: sum (y-eta)^2
-  double pad;
+  double pad;      // max |eta - previous eta| of the last likelihood pass (single-device models)
 };
 
 struct Comm;   // NCCL communicator wrapper (comm.cpp)
@@ -159,6 +159,13 @@ struct bgp_model {
   // ---- solver controls ---------------------------------------------------------------------
   double grad_tol = 1e-8, step_tol = 1e-8;
   int maxit = 100;
+  // Certified reuse of the last Newton factorisation for the log-determinant (newton.cu): allowed when the
+  // accepted full step moved the linear predictor by delta = max |d eta| with delta <= reuse_eta_tol and
+  // p * delta / 2 <= reuse_rel_tol * |value|  (|logdet H(w1) - logdet H(w0)| <= p * delta).
+  bool allow_reuse = true;
+  double reuse_eta_tol = 1e-7, reuse_rel_tol = 1e-10;
+  bool factor_is_exact = true;   // H / L in memory were formed at the mode itself
+  int64_t n_evals = 0, n_newton = 0, n_reuse = 0;
   // ---- sharding ------------------------------------------------------------------------------
   int rank = 0, world = 1;
   int64_t n_total = 0;

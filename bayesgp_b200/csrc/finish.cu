@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __rest
     for (int b = 0; b < nblocks; ++b) t += part_s[(size_t)b * 4 + k];
     red[lda + k] = t;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 67) red[lda + 3] = 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 67) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t = fmax(t, part_s[(size_t)b * 4 + 3]);
+    red[lda + 3] = t;            // max |eta - previous eta| (local rows; not meaningful after a SUM all-reduce)
+  }
 }
 
 __global__ void __launch_bounds__(1024) finish_prior_kernel(const PriorArgs a) {
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(1024) finish_prior_kernel(const PriorArgs a) {
     a.sc->gmax = s_gmax[0];
     a.sc->quad = s_quad[0];
     a.sc->sumsq = sumsq;
+    a.sc->pad = a.red[a.lda + 3];
     a.sc->nonfinite = (bad != 0.0 || !isfinite(f)) ? 1 : 0;
   }
 }

@@ -314,6 +314,13 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   const bool has_c3 = m->family == BGP_FAMILY_POISSON || m->family == BGP_FAMILY_BINOMIAL;
   // exact per-observation quantities at the mode (also fixes sumsq for the Gaussian noise theta)
   BGP_TRY(eval_fg_async(m, m->Wmode, theta, true));
+  if (!m->factor_is_exact) {
+    // the inner solve kept the factor of its last Newton iteration (newton.cu); the gradient differentiates
+    // through H^-1, so it gets the factor at the mode itself
+    BGP_TRY(launch_hessian(m, theta));
+    BGP_TRY(launch_chol_solve(m, false));
+    m->factor_is_exact = true;
+  }
   // 1. L^-1
   BGP_TRY(launch_trtri(m, m->Linv, ldl, nullptr));
   // 2./3. leverage term v = A^T (c3 * q)

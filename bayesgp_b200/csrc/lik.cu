@@ -39,7 +39,7 @@ struct LikArgs {
   double* wobs;
   double* c3;
   double* part_g;   // [gridDim.x][lda]
-  double* part_s;   // [gridDim.x][4] : ll, sumsq, nonfinite, unused
+  double* part_s;   // [gridDim.x][4] : ll, sumsq, nonfinite, max |eta - previous eta|
   const double* rvec;   // if set: skip the likelihood and accumulate A^T rvec only (leverage term)
   const unsigned long long* occ;
 };
@@ -57,7 +57,7 @@ __host__ __device__ constexpr int lk_kb(int NJ) { return 8 * lk_groups(NJ); }
 __host__ __device__ constexpr int lk_threads(int NJ) { return 32 * (LK_CONSUMERS * lk_groups(NJ) + 1); }
 constexpr int LK_SMEM_BUDGET = 200 * 1024;
 __host__ __device__ constexpr int lk_group_bytes(int NJ) { return lk_kb(NJ) * 64 * 8; }   // one {64 columns x KB rows} box
-__host__ __device__ constexpr int lk_stage_bytes(int NJ) { return NJ * lk_group_bytes(NJ) + 2 * lk_kb(NJ) * 8; }
+__host__ __device__ constexpr int lk_stage_bytes(int NJ) { return NJ * lk_group_bytes(NJ) + 4 * lk_kb(NJ) * 8; }   // boxes | y | size | previous eta | pad
 __host__ __device__ constexpr int lk_stages(int NJ) {
   return (LK_SMEM_BUDGET - 4096 - NJ * 512 * 2) / lk_stage_bytes(NJ) > 10 ? 10
                                                                          : (LK_SMEM_BUDGET - 4096 - NJ * 512 * 2) / lk_stage_bytes(NJ);
@@ -165,13 +165,14 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
       mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / STAGES) & 1) ^ 1));
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta_base + 8 * slot), "r"(gm) : "memory");
       const bool want_y = a.rvec == nullptr;
-      mbar_expect_tx(fb, (uint32_t)__popc(gm) * LK_GROUP_BYTES + (want_y ? LK_KB * 8 : 0) + (want_y && a.size ? LK_KB * 8 : 0));
+      mbar_expect_tx(fb, (uint32_t)__popc(gm) * LK_GROUP_BYTES + (want_y ? 2 * LK_KB * 8 : 0) + (want_y && a.size ? LK_KB * 8 : 0));
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
         if ((gm >> j) & 1u) tma_load_2d(sb + j * LK_GROUP_BYTES, &tmA, 64 * j, (int)row, fb);
       if (want_y) {
         bulk_load_1d(sb + NJ * LK_GROUP_BYTES, a.y + row, LK_KB * 8, fb);
         if (a.size) bulk_load_1d(sb + NJ * LK_GROUP_BYTES + LK_KB * 8, a.size + row, LK_KB * 8, fb);
+        bulk_load_1d(sb + NJ * LK_GROUP_BYTES + 2 * LK_KB * 8, a.eta + row, LK_KB * 8, fb);   // previous eta
       }
     }
     return;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
   double2 ga[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) ga[j] = make_double2(0.0, 0.0);
-  double ll = 0.0, sumsq = 0.0;
+  double ll = 0.0, sumsq = 0.0, dmax = 0.0;
   int bad = 0;
   for (int64_t it = 0; it < my_stages; ++it) {
     const int slot = (int)(it % STAGES);
@@ -218,7 +219,10 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
         double ww, cc;
         obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
         if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
+        const double eta_old = lds64(sb + NJ * LK_GROUP_BYTES + 2 * LK_KB * 8 + wrow * 8);
         if (lane == 0) {
+          const double d = fabs(s - eta_old);           // change of the linear predictor since the last pass
+          dmax = d > dmax || !(d == d) ? (d == d ? d : INFINITY) : dmax;
           a.eta[row] = s;
           a.wobs[row] = ww;
           if (a.c3) a.c3[row] = cc;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
     ss[warp * 4 + 0] = ll;
     ss[warp * 4 + 1] = sumsq;
     ss[warp * 4 + 2] = (double)bad;
+    ss[warp * 4 + 3] = dmax;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
   for (int c = tid; c < lda; c += NCW * 32) {
@@ -258,6 +263,12 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
 #pragma unroll
     for (int w8 = 0; w8 < NCW; ++w8) s += ss[w8 * 4 + tid];
     a.part_s[(size_t)blockIdx.x * 4 + tid] = s;
+  }
+  if (tid == 3) {
+    double s = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < NCW; ++w8) s = fmax(s, ss[w8 * 4 + 3]);
+    a.part_s[(size_t)blockIdx.x * 4 + 3] = s;
   }
 }
 

@@ -182,7 +182,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   double f = sc.f, gmax = sc.gmax;
   int iters = 0;
-  bool converged = false, have_factor = false;
+  bool converged = false, have_factor = false, reused = false;
   double logdet = NAN;
   for (int it = 0; it < m->maxit; ++it) {
     if (gmax < m->grad_tol) {
@@ -218,14 +218,16 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       // less than step_tol and are not used again for this theta.
       break;
     }
+    const double deta_full = sc.pad;      // max |eta(W + step) - eta(W)|: W is where H was formed
     double t = 1.0;
-    bool accepted = false;
+    bool accepted = false, full_step = true;
     for (int h = 0; h < 40; ++h) {
       if (!sc.nonfinite && (sc.f <= f || sc.gmax < gmax)) {
         accepted = true;
         break;
       }
       t *= 0.5;
+      full_step = false;
       axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, t, m->p, m->lda, m->Wtrial);
       count_launch();
       BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
@@ -236,6 +238,21 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     f = sc.f;
     gmax = sc.gmax;
     ++iters;
+    if (gmax < m->grad_tol && full_step && m->allow_reuse && m->world == 1 && std::isfinite(sc.logdet)) {
+      // Converged by a full Newton step from the point where H was factored.  |logdet H(w1) - logdet H(w0)| <=
+      // p * delta (delta = max |d eta|; Gaussian: H does not depend on W at all), so when that is far inside
+      // the tolerances the factor of the last iteration serves as the factor at the mode.
+      const double val = f + 0.5 * sc.logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
+      const bool tiny = m->family == BGP_FAMILY_GAUSSIAN ||
+                        (deta_full <= m->reuse_eta_tol && 0.5 * m->p * deta_full <= m->reuse_rel_tol * std::fabs(val));
+      if (tiny) {
+        converged = true;
+        have_factor = true;
+        reused = true;
+        logdet = sc.logdet;
+        break;
+      }
+    }
   }
   *iters_out = iters;
   if (!converged) {
@@ -279,6 +296,10 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     BGP_CUDA(cudaMemcpyAsync(h.W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
     BGP_CUDA(cudaMemcpyAsync(h.T, m->Tan, (size_t)m->S * m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   }
+  m->factor_is_exact = !reused;
+  ++m->n_evals;
+  m->n_newton += iters;
+  m->n_reuse += reused ? 1 : 0;
   *value = f + 0.5 * logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
   return BGP_OK;
 }
@@ -453,6 +474,22 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
   if (lik_launches) *lik_launches = m->n_lik;
   if (hess_launches) *hess_launches = m->n_hess;
   if (chol_launches) *chol_launches = m->n_chol;
+  return BGP_OK;
+}
+
+int bgp_model_counters(const bgp_model* m, int64_t* laplace_evals, int64_t* newton_iters, int64_t* factor_reuses) {
+  if (!m) return BGP_ERR_ARG;
+  if (laplace_evals) *laplace_evals = m->n_evals;
+  if (newton_iters) *newton_iters = m->n_newton;
+  if (factor_reuses) *factor_reuses = m->n_reuse;
+  return BGP_OK;
+}
+
+int bgp_model_set_factor_reuse(bgp_model* m, int allow, double eta_tol, double rel_tol) {
+  if (!m) return BGP_ERR_ARG;
+  m->allow_reuse = allow != 0;
+  if (eta_tol > 0) m->reuse_eta_tol = eta_tol;
+  if (rel_tol > 0) m->reuse_rel_tol = rel_tol;
   return BGP_OK;
 }
 

@@ -220,6 +220,14 @@ class LaplaceObjective:
                 "lik_launches": k[0].value, "hess_launches": k[1].value, "chol_launches": k[2].value}
 
 
+    def counters(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._lib.bgp_model_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"laplace_evals": a.value, "newton_iters": b.value, "factor_reuses": c.value}
+
+    def set_factor_reuse(self, allow=True, eta_tol=1e-7, rel_tol=1e-10):
+        check(self._lib.bgp_model_set_factor_reuse(self._h, int(allow), float(eta_tol), float(rel_tol)))
+
     def lik_bytes(self):
         d, u = C.c_double(), C.c_double()
         check(self._lib.bgp_model_lik_bytes(self._h, C.byref(d), C.byref(u)))

@@ -163,6 +163,7 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         vals, iters, _, _ = step()
     tm0 = ff.last_timing()
+    cnt0 = ff.counters()
     launches0 = lib.bgp_kernel_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -185,6 +186,7 @@ def run_b200(args):
     region_s = time.perf_counter() - t_region
     clocks = sampler.stop() if sampler else None
     tm1 = ff.last_timing()
+    cnt1 = ff.counters()
     launches = lib.bgp_kernel_launch_count() - launches0
     if rank != 0:
         ff.close()
@@ -222,6 +224,10 @@ def run_b200(args):
                                "per GPU, warm-started inner Newton to max|g|<1e-8 + log-det" % (n, p),
                    "nodes_per_step": K_NODES, "newton_iters_per_eval": iters_tot / (K_NODES * args.steps),
                    "hessians_per_eval": n_hess / (K_NODES * args.steps),
+                   "logdet_from_last_newton_factor": "%d of %d evaluations (certified |d logdet| <= p max|d eta| <= 2e-10 |L|; "
+                                                     "bgp_model_set_factor_reuse, DESIGN.md section 5)"
+                                                     % (cnt1["factor_reuses"] - cnt0["factor_reuses"],
+                                                        cnt1["laplace_evals"] - cnt0["laplace_evals"]),
                    "theta_mode": mode, "theta_sd": sd, "l2_flush": "inputs (2.4 GB design matrix) exceed the 126 MB L2",
                    "parallelism": "node-sharded replicas x%d" % world, "model_build_s": t_build},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + K_NODES),

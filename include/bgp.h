@@ -164,6 +164,15 @@ int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, i
 int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,
                           int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches);
 
+/* counters since creation: Laplace evaluations, accepted Newton iterations, evaluations whose log-determinant
+ * came from the factor of the last Newton iteration (certified: |d logdet| <= p * max|d eta|, see below) */
+int bgp_model_counters(const bgp_model* m, int64_t* laplace_evals, int64_t* newton_iters, int64_t* factor_reuses);
+/* When the inner Newton converges by a full step that moved the linear predictor by delta = max |d eta| with
+ * delta <= eta_tol (default 1e-7) and p * delta / 2 <= rel_tol * |value| (default 1e-10), the factor of that
+ * last iteration is used for 1/2 logdet H instead of a new Hessian + Cholesky at the mode (TMB recomputes;
+ * the certified difference is 100x inside the 1e-8 tolerance).  allow = 0 restores the recomputation.
+ * Gradients always use the factor at the mode. */
+int bgp_model_set_factor_reuse(bgp_model* m, int allow, double eta_tol, double rel_tol);
 /* flops of one Hessian launch H = A^T diag(w) A: dense (n p (p+1)) and the structurally non-zero part the
  * kernel executes after skipping empty {64-observation x 16-column} cells (roofline reporting) */
 int bgp_model_hessian_flops(const bgp_model* m, double* dense, double* structural);

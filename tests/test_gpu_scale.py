@@ -128,6 +128,26 @@ def _prior_only(W, theta, x0, knots):
         f0.close()
 
 
+def test_full_size_factor_reuse_is_within_its_certificate(c3_full):
+    """log det from the last Newton factor vs the recomputed one: |difference| <= 1e-10 |L| (library default)."""
+    x, y, x0, knots, ff = c3_full
+    thetas = np.array([[-10.9], [-10.7], [-10.5], [-10.3], [-10.1]])
+    ff.set_start(None)
+    c0 = ff.counters()
+    v_reuse, m_reuse, H_reuse, _ = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+    c1 = ff.counters()
+    ff.set_factor_reuse(False)
+    try:
+        ff.set_start(None)
+        v_exact, m_exact, H_exact, _ = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+    finally:
+        ff.set_factor_reuse(True)
+    assert c1["factor_reuses"] - c0["factor_reuses"] >= 1          # the shortcut was actually exercised
+    assert np.max(np.abs(v_reuse - v_exact) / np.abs(v_exact)) <= 1e-10
+    assert relerr(m_reuse, m_exact) < 1e-8
+    assert relerr(H_reuse, H_exact) < 1e-6
+
+
 def test_full_size_batch_equals_single_and_is_deterministic(c3_full):
     x, y, x0, knots, ff = c3_full
     thetas = np.array([[-10.8], [-10.5], [-10.2]])
@@ -142,5 +162,9 @@ def test_full_size_batch_equals_single_and_is_deterministic(c3_full):
     # the gradient of the Laplace objective against a central difference of its values
     g = ff.gr(thetas[1])
     eps = 1e-4
-    fd = (ff.fn(thetas[1] + eps) - ff.fn(thetas[1] - eps)) / (2 * eps)
+    ff.set_factor_reuse(False)       # a difference of values 2e-4 apart needs them to ~1e-11 relative, not 1e-10
+    try:
+        fd = (ff.fn(thetas[1] + eps) - ff.fn(thetas[1] - eps)) / (2 * eps)
+    finally:
+        ff.set_factor_reuse(True)
     assert abs(g[0] - fd) <= 1e-5 * max(1.0, abs(fd)), (g, fd)
