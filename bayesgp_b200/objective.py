@@ -163,6 +163,8 @@ class LaplaceObjective:
 
     # -- ff$fn / ff$gr ------------------------------------------------------------------------------
     def _eval(self, theta, want_grad=False, want_mode=True, want_hess=False):
+        if not self._finalized:
+            raise BgpError(7, "model not finalized")          # BGP_ERR_STATE, as the C entry points answer
         theta = fvec(np.atleast_1d(theta))
         val = C.c_double()
         iters = C.c_int()

@@ -1,0 +1,121 @@
+"""GPU parity on the edge cases of the path: IWP order 1 (no boundary columns, R/02_model_fit.R:460,651-652),
+mixed-sign knots (mirrored O-spline blocks, R/01_utility.R:378-401), an IID term (one-hot design with
+structural zeros, R/01_utility.R:214-219), Binomial with the default size = 1 (R/02_model_fit.R:176-183),
+n and p that are not multiples of any tile size, derivatives in predict, and the error behaviour of the ABI."""
+import numpy as np
+import pytest
+
+from helpers import relerr, tmbdata_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(model, thetas, tol_val=1e-8):
+    from bayesgp_b200 import make_objective
+    from oracle.laplace import LaplaceObjective as OFF
+    off = OFF(model)
+    ff = make_objective(tmbdata_from_oracle(model))
+    try:
+        rng = np.random.default_rng(5)
+        W = 0.05 * rng.standard_normal(model.p)
+        o = model.objective(W, thetas[0], "fgH")
+        f, g, H = ff.objective(W, thetas[0], want_grad=True, want_hess=True)
+        assert abs(f - o["f"]) <= 1e-11 * abs(o["f"])
+        assert relerr(g, o["g"]) < 1e-10 and relerr(H, o["H"]) < 1e-10
+        for th in thetas:
+            want = off.fn(th)
+            got, _, w, Hm = ff._eval(th, want_hess=True)
+            assert abs(got - want) <= tol_val * abs(want), (th, got, want)
+            assert relerr(w, off.last_par) < 1e-6 and relerr(Hm, off.sp_hess()) < 1e-6
+            gw, gg = off.gr(th), ff.gr(th)
+            assert np.max(np.abs(gw - gg)) <= 2e-6 * max(1.0, np.max(np.abs(gw))), (th, gw, gg)
+    finally:
+        ff.close()
+
+
+def test_iwp_order_one_has_no_boundary_block():
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(11)
+    n = 1237                                     # not a multiple of 8 / 16 / 64
+    x = rng.uniform(0, 3, n)
+    y = rng.poisson(np.exp(0.3 + np.sin(x))).astype(np.float64)
+    model = build_model(y, [Term("IWP", "x", x, order=1, k=23)], {}, family="Poisson")[0]
+    assert model.X[0].shape[1] == 0 and model.p == 22 + 1
+    _compare(model, [np.array([0.0]), np.array([2.5])])
+
+
+def test_mixed_sign_knots_and_fixed_effects():
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(12)
+    n = 3001
+    x = rng.uniform(-1.0, 2.0, n)
+    z = rng.standard_normal(n)
+    y = rng.poisson(np.exp(0.2 + 0.5 * np.cos(2 * x) + 0.1 * z)).astype(np.float64)
+    knots = np.array([-1.0, -0.6, -0.3, -0.1, 0.0, 0.2, 0.5, 0.9, 1.4, 2.0])
+    model = build_model(y, [Term("IWP", "x", x, order=3, knots=knots, initial_location=0.0)], {"z": z}, family="Poisson")[0]
+    _compare(model, [np.array([0.0]), np.array([-1.5])])
+
+
+def test_iid_term_and_default_binomial_size():
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(13)
+    n = 2500
+    grp = rng.integers(0, 37, n).astype(np.float64)
+    x = rng.uniform(0, 1, n)
+    eff = rng.standard_normal(37) * 0.7
+    eta = -0.2 + eff[grp.astype(int)] + np.sin(3 * x)
+    y = rng.binomial(1, 1 / (1 + np.exp(-eta))).astype(np.float64)
+    model = build_model(y, [Term("IID", "g", grp), Term("IWP", "x", x, order=2, k=12)], {}, family="Binomial")[0]
+    assert model.size is not None and np.all(model.size == 1.0)
+    _compare(model, [np.array([0.0, 0.0]), np.array([1.0, 2.0])])
+
+
+def test_predict_derivatives_match_oracle():
+    """f, f', f'' from the same samples (degree < order, R/03_post_fit.R:201-203 rejects the rest)."""
+    import bayesgp_b200 as bg
+    from oracle import fit as ofit
+    rng = np.random.default_rng(14)
+    knots = np.linspace(0, 2.0, 17)
+    M, G, order = 700, 333, 3
+    coef = rng.standard_normal((16, M)) * 0.3
+    glob = rng.standard_normal((order - 1, M))
+    icpt = rng.standard_normal(M)
+    xg = np.sort(rng.uniform(0, 2.0, G))
+    for degree in (0, 1, 2):
+        out = bg.compute_post_fun_IWP(coef, glob, knots, xg, order, degree, icpt)
+        F = ofit.compute_post_fun_IWP(coef, glob, knots, xg, order, degree, icpt)
+        lo, hi, mean = ofit.extract_mean_interval_given_samps(F)
+        assert relerr(out["mean"], mean) < 1e-10
+        assert relerr(out["plower"], lo) < 1e-10 and relerr(out["pupper"], hi) < 1e-10
+    assert bg.compute_post_fun_IWP(coef, glob, knots, xg, order, 3, icpt) is None      # degree >= order
+
+
+def test_abi_error_behaviour():
+    import ctypes as C
+    from bayesgp_b200 import _lib
+    from bayesgp_b200.objective import LaplaceObjective
+    lib = _lib.load()
+    y = np.arange(10, dtype=np.float64)
+    with pytest.raises(_lib.BgpError):
+        LaplaceObjective(y=y, family=3)                         # Coxph: outside the path
+    ff = LaplaceObjective(y=y, family="Poisson")
+    with pytest.raises(_lib.BgpError):
+        ff.fn(np.array([0.0]))                                  # not finalized
+    with pytest.raises(_lib.BgpError):
+        ff.finalize()                                           # no design columns
+    ff.close()
+    # latent dimension above the supported maximum is refused, not truncated
+    ff = LaplaceObjective(y=np.zeros(40), family="Poisson")
+    ff.add_fixed(np.ones(40))
+    ff.add_random(np.zeros((40, 1100)), np.ones(1100), 0.0)
+    with pytest.raises(_lib.BgpError) as ei:
+        ff.finalize()
+    assert "exceeds" in str(ei.value)
+    ff.close()
+    # a non positive definite inner Hessian comes back as NaN (TMB behaviour), not as an exception
+    ff = LaplaceObjective(y=np.array([1.0, 2.0, 0.0, 3.0]), family="Poisson")
+    ff.add_random(np.zeros((4, 2)), np.array([-1.0, 1.0]), 0.0)    # indefinite prior precision, no data information
+    ff.add_fixed(np.ones(4))
+    ff.finalize()
+    assert np.isnan(ff.fn(np.array([0.0])))
+    ff.close()
