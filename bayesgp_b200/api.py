@@ -53,6 +53,15 @@ class AGHQ:
     def lognormconst(self):
         return self.normalized_posterior["lognormconst"]
 
+    def theta_moments(self):
+        """Posterior mean and sd of theta by the quadrature itself, as ``summary(mod)`` prints them
+        (aghq::compute_moment on ``normalized_posterior``; /root/reference/README.md:83-85)."""
+        nw = self.normalized_posterior["nodesandweights"]
+        lam = nw["weights"] * np.exp(nw["logpost_normalized"])
+        mean = lam @ nw["theta"]
+        var = lam @ (nw["theta"] - mean[None, :]) ** 2
+        return mean, np.sqrt(var)
+
     @property
     def modesandhessians(self):
         if self._modes is None:

@@ -203,3 +203,30 @@ def test_library_side_draws(fits):
     var = lam @ (np.array([np.linalg.inv(H)[j, j] for H in omod.hessians]) + (omod.modes[:, j] - mu[j]) ** 2)
     assert abs(s1["samps"][j].mean() - mu[j]) < 6 * np.sqrt(var / 4000)
     assert abs(s1["samps"][j].var() / var - 1) < 0.2
+
+
+def test_readme_goldens_through_the_cuda_path():
+    """External pin of the PRODUCT (not only of the oracle): with the README's own grid centre and scale
+    (/root/reference/README.md:75-81) the CUDA path reproduces the printed log normalising constant and the theta
+    posterior mean / sd (README.md:77,85) to printed precision, and the fixed-effect sample moments (README.md:90-96)
+    within Monte-Carlo error of 3000 draws."""
+    import json
+    import bayesgp_b200 as bg
+    g = json.load(open(os.path.join(GOLDEN, "readme_golden.json")))
+    y, t, fixed = _covid()
+    fit = bg.model_fit(y, [bg.Term("IWP", "t", t, order=3, k=30)], fixed, family="Poisson", aghq_k=4, M=3000, seed=7,
+                       optresults={"mode": np.array([g["theta_mode"]]), "hessian": np.array([[1.0 / g["quad_cov"]]])})
+    try:
+        assert fit.mod.p == g["latent_dim"] == 38
+        assert abs(fit.mod.lognormconst - g["lognormconst"]) < 6e-4
+        mean, sd = fit.mod.theta_moments()
+        assert abs(mean[0] - g["theta_mean"]) < 5e-6
+        assert abs(sd[0] - g["theta_sd"]) < 5e-6
+        names = list(g["fixed"])
+        fe = bg.sample_fixed_effect(fit, names)
+        for j, nm in enumerate(names):
+            se = g["fixed"][nm]["sd"] / np.sqrt(g["M"])
+            assert abs(fe[:, j].mean() - g["fixed"][nm]["mean"]) < 6 * se * np.sqrt(2), nm
+            assert abs(fe[:, j].std(ddof=1) / g["fixed"][nm]["sd"] - 1.0) < 0.08, nm
+    finally:
+        fit.close()
