@@ -225,7 +225,9 @@ int syrk_plan_create(bgp_model* m);
 void syrk_plan_destroy(bgp_model* m);
 int launch_hessian(bgp_model* m, const double* theta);
 // chol.cu: L = chol(H), logdet, optionally step = -H^-1 g and max|step|
-int launch_chol_solve(bgp_model* m, bool solve);
+// theta_tan / W_tan != NULL: also form the tangents d w_hat / d theta (at W_tan) into m->Tan on the cluster's idle ranks
+int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan = nullptr, const double* W_tan = nullptr);
+constexpr int CHOL_TANGENT_MAX_S = 7;
 int launch_tangent(bgp_model* m, const double* theta);
 // basis.cu
 int launch_iwp_block(bgp_model* m, const double* x_dev, int64_t n, double x0, const double* kneg, int nneg,

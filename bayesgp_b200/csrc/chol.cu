@@ -141,6 +141,64 @@ __device__ __forceinline__ int block_chol(double* sD, double* sL, double* sInv, 
   return info;
 }
 
+// ---- tangent predictor: T_k = d w_hat / d theta_k = -H^-1 c_k, c_k = d2 f / dW dtheta_k -------------------
+// (same closed form as the implicit term of the Laplace gradient, SURVEY.md A.1.3).  Used only to
+// warm-start the next inner Newton solve; results do not depend on it.
+struct TanBlock {
+  int off, d, diag;
+  const double* P;
+  double etheta;
+};
+struct TangentArgs {
+  const double* L;
+  const double* dinv;
+  int p, ldh, lda;
+  const double* W;      // the mode
+  const double* mu0;
+  const double* qfix;
+  int nrnd, S;
+  TanBlock rnd[16];
+  double* T;            // S x lda
+};
+
+// right-hand side c_k = d2 f / dW dtheta_k of tangent k into sv (length p)
+__device__ __forceinline__ void tangent_rhs(const TangentArgs& a, int k, double* sv) {
+  for (int i = threadIdx.x; i < a.p; i += CH_THREADS) {
+    double v = 0.0;
+    if (k < a.nrnd) {
+      const TanBlock& rb = a.rnd[k];
+      if (i >= rb.off && i < rb.off + rb.d) {
+        const int r = i - rb.off;
+        if (rb.diag) {
+          v = rb.etheta * rb.P[r] * a.W[i];
+        } else {
+          double s = 0.0;
+          for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
+          v = rb.etheta * s;
+        }
+      }
+    } else {
+      // Gaussian noise theta: c = -A^T r = -Q (w_hat - mu0) at the mode
+      double q = a.qfix[i] * (a.W[i] - a.mu0[i]);
+      for (int b = 0; b < a.nrnd; ++b) {
+        const TanBlock& rb = a.rnd[b];
+        if (i >= rb.off && i < rb.off + rb.d) {
+          const int r = i - rb.off;
+          if (rb.diag) {
+            q = rb.etheta * rb.P[r] * a.W[i];
+          } else {
+            double s = 0.0;
+            for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
+            q = rb.etheta * s;
+          }
+        }
+      }
+      v = -q;
+    }
+    sv[i] = v;
+  }
+}
+
 #define CH_MARK(slot)                                                    \
   do {                                                                   \
     if (a.dbg && rank == 0 && tid == 0) {                                \
@@ -152,7 +210,8 @@ __device__ __forceinline__ int block_chol(double* sD, double* sL, double* sInv, 
   } while (0)
 
 template <int NB>
-__global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1) chol_kernel(const CholArgs a) {
+__global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
+    chol_kernel(const CholArgs a, const TangentArgs ta, const int ntan) {
   extern __shared__ double sm[];
   constexpr int DP = NB + 1;        // pitch of the diagonal block
   constexpr int PP = NB + 4;        // pitch of the panel (conflict-free DMMA fragment loads)
@@ -299,8 +358,17 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1) c
     cluster.sync();
     CH_MARK(6);
   }
-  // only rank 0 goes on; nobody waits on a cluster barrier any more
-  if (rank != 0) return;
+  // no cluster barrier from here on.  Rank 0: log-determinant and Newton step; ranks 1 .. ntan: one tangent
+  // d w_hat / d theta_k each (warm-start predictor), solved at the same time on their own SMs
+  if (rank != 0) {
+    if (rank - 1 < ntan && s_info == 0) {
+      tangent_rhs(ta, rank - 1, sv);
+      __syncthreads();
+      tri_solve_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
+      for (int i = tid; i < ta.lda; i += CH_THREADS) ta.T[(size_t)(rank - 1) * ta.lda + i] = i < p ? -sv[i] : 0.0;
+    }
+    return;
+  }
   __syncthreads();
   if (s_info != 0) {
     if (tid == 0) {
@@ -350,7 +418,7 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1) c
 }
 
 template <int NB>
-static int launch_chol_t(bgp_model* m, const CholArgs& a) {
+static int launch_chol_t(bgp_model* m, const CholArgs& a, const TangentArgs& ta, int ntan) {
   const int mpad = round_up(std::max(0, a.p - NB), 32);
   const size_t smem = (size_t)(2 * 32 * 33 + CH_MAXP + (size_t)mpad * (NB + 4)) * sizeof(double);
   if (smem > 227 * 1024) {
@@ -362,14 +430,16 @@ static int launch_chol_t(bgp_model* m, const CholArgs& a) {
     BGP_CUDA(cudaFuncSetAttribute(chol_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  chol_kernel<NB><<<CH_CS, CH_THREADS, smem, m->stream>>>(a);   // one cluster (compile-time __cluster_dims__)
+  chol_kernel<NB><<<CH_CS, CH_THREADS, smem, m->stream>>>(a, ta, ntan);   // one cluster (compile-time __cluster_dims__)
   count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
 }
 
+static void fill_tangent_args(bgp_model* m, const double* theta, const double* W, TangentArgs& a);
+
 // L <- chol(H) (H is left untouched), logdet, optionally step = -H^-1 g
-int launch_chol_solve(bgp_model* m, bool solve) {
+int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan, const double* W_tan) {
   BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   CholArgs a;
   a.L = m->L;
@@ -402,83 +472,37 @@ int launch_chol_solve(bgp_model* m, bool solve) {
     set_error("p = %d exceeds the Cholesky kernel limit %d", m->p, CH_MAXP);
     return BGP_ERR_ARG;
   }
-  if (m->p <= 512) return launch_chol_t<32>(m, a);
-  if (m->p <= 1200) return launch_chol_t<16>(m, a);
-  return launch_chol_t<8>(m, a);
+  // tangents ride along on the idle ranks of the cluster when there is one rank per theta
+  TangentArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  int ntan = 0;
+  if (theta_tan && W_tan && m->S <= CH_CS - 1) {
+    fill_tangent_args(m, theta_tan, W_tan, ta);
+    ntan = m->S;
+  }
+  if (m->p <= 512) return launch_chol_t<32>(m, a, ta, ntan);
+  if (m->p <= 1200) return launch_chol_t<16>(m, a, ta, ntan);
+  return launch_chol_t<8>(m, a, ta, ntan);
 }
-
-// ---- tangent predictor: T_k = d w_hat / d theta_k = -H^-1 c_k, c_k = d2 f / dW dtheta_k -------------------
-// (same closed form as the implicit term of the Laplace gradient, SURVEY.md A.1.3).  Used only to
-// warm-start the next inner Newton solve; results do not depend on it.
-struct TanBlock {
-  int off, d, diag;
-  const double* P;
-  double etheta;
-};
-struct TangentArgs {
-  const double* L;
-  const double* dinv;
-  int p, ldh, lda;
-  const double* W;      // the mode
-  const double* mu0;
-  const double* qfix;
-  int nrnd, S;
-  TanBlock rnd[16];
-  double* T;            // S x lda
-};
 
 __global__ void __launch_bounds__(CH_THREADS, 1) tangent_kernel(const TangentArgs a) {
   __shared__ double sS[32 * 33];
   __shared__ double sv[CH_MAXP];
   __shared__ double s_red[32];
   const int k = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < a.p; i += CH_THREADS) {
-    double v = 0.0;
-    if (k < a.nrnd) {
-      const TanBlock& rb = a.rnd[k];
-      if (i >= rb.off && i < rb.off + rb.d) {
-        const int r = i - rb.off;
-        if (rb.diag) {
-          v = rb.etheta * rb.P[r] * a.W[i];
-        } else {
-          double s = 0.0;
-          for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
-          v = rb.etheta * s;
-        }
-      }
-    } else {
-      // Gaussian noise theta: c = -A^T r = -Q (w_hat - mu0) at the mode
-      double q = a.qfix[i] * (a.W[i] - a.mu0[i]);
-      for (int b = 0; b < a.nrnd; ++b) {
-        const TanBlock& rb = a.rnd[b];
-        if (i >= rb.off && i < rb.off + rb.d) {
-          const int r = i - rb.off;
-          if (rb.diag) {
-            q = rb.etheta * rb.P[r] * a.W[i];
-          } else {
-            double s = 0.0;
-            for (int c = 0; c < rb.d; ++c) s = fma(rb.P[(size_t)c * rb.d + r], a.W[rb.off + c], s);
-            q = rb.etheta * s;
-          }
-        }
-      }
-      v = -q;
-    }
-    sv[i] = v;
-  }
+  tangent_rhs(a, k, sv);
   __syncthreads();
   tri_solve_inplace(a.L, a.dinv, a.p, a.ldh, sv, sS, s_red);
   for (int i = tid; i < a.lda; i += CH_THREADS) a.T[(size_t)k * a.lda + i] = i < a.p ? -sv[i] : 0.0;
 }
 
-int launch_tangent(bgp_model* m, const double* theta) {
-  TangentArgs a;
+static void fill_tangent_args(bgp_model* m, const double* theta, const double* W, TangentArgs& a) {
   a.L = m->L;
   a.dinv = m->Ldinv;
   a.p = m->p;
   a.ldh = m->ldh;
   a.lda = m->lda;
-  a.W = m->Wmode;
+  a.W = W;
   a.mu0 = m->mu0;
   a.qfix = m->qfix;
   a.nrnd = m->J;
@@ -491,6 +515,11 @@ int launch_tangent(bgp_model* m, const double* theta) {
     a.rnd[j].etheta = std::exp(theta[j]);
   }
   a.T = m->Tan;
+}
+
+int launch_tangent(bgp_model* m, const double* theta) {
+  TangentArgs a;
+  fill_tangent_args(m, theta, m->Wmode, a);
   tangent_kernel<<<m->S, CH_THREADS, 0, m->stream>>>(a);
   count_launch();
   BGP_CUDA(cudaGetLastError());

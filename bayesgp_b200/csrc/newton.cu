@@ -193,7 +193,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     BGP_TRY(launch_hessian(m, theta));
     m->n_hess++;
     phase_mark(m, PH_CHOL);
-    BGP_TRY(launch_chol_solve(m, true));
+    const bool tan_in_chol = m->use_predictor && m->S <= CHOL_TANGENT_MAX_S;
+    BGP_TRY(launch_chol_solve(m, true, tan_in_chol ? theta : nullptr, m->W));
     m->n_chol++;
     phase_mark(m, PH_OTHER);
     // speculative full step: evaluate the trial point before reading anything back
@@ -266,7 +267,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     BGP_TRY(launch_hessian(m, theta));
     m->n_hess++;
     phase_mark(m, PH_CHOL);
-    BGP_TRY(launch_chol_solve(m, false));
+    const bool tan_in_chol = m->use_predictor && m->S <= CHOL_TANGENT_MAX_S;
+    BGP_TRY(launch_chol_solve(m, false, tan_in_chol ? theta : nullptr, m->W));
     m->n_chol++;
     BGP_TRY(read_scalars(m, &sc));
     if (sc.chol_info != 0) {
@@ -278,7 +280,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   if (m->use_predictor && m->S <= 17) {
-    BGP_TRY(launch_tangent(m, theta));      // uses the factor of H(w_hat) left in m->L
+    // the tangent came out of the last Cholesky launch (idle cluster ranks) unless there are too many thetas
+    if (m->S > CHOL_TANGENT_MAX_S) BGP_TRY(launch_tangent(m, theta));
     m->theta_last.assign(theta, theta + m->S);
     m->tan_valid = true;
     // record (theta, mode, tangent): same theta => overwrite, else replace the oldest entry
