@@ -47,7 +47,9 @@ def _rank_world():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: one long-running `nvidia-smi -lms 50`
+    (a fresh nvidia-smi per sample takes ~0.3 s, longer than a bench step); rows are stamped on arrival and
+    only those inside [mark_start, mark_stop] are summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -56,32 +58,44 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._halt = threading.Event()
+        self.proc = None
+        self.t0 = self.t1 = None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [s.strip() for s in line.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+                    self.rows.append((time.perf_counter(), parts))
+        except Exception:
+            pass
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        self.t1 = time.perf_counter()
+        time.sleep(0.12)                      # let the sample that covers the end of the region arrive
+        try:
+            if self.proc:
+                self.proc.terminate()
+        except Exception:
+            pass
+        self.join(timeout=3)
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.1]
+        rows = inside if inside else [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(rows), "samples_inside_timed_region": len(inside)}
 
 
 def measured_peaks():
@@ -168,9 +182,12 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)                       # nvidia-smi is up and streaming before the region starts
     if dist:
         dist.barrier()
     dev_ms, wall_s, iters_tot = 0.0, 0.0, 0
+    if sampler:
+        sampler.mark_start()
     t_region = time.perf_counter()
     for _ in range(args.steps):
         vals, iters, wall, ms = step()
@@ -374,7 +391,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
