@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "basis_dev.cuh"
+#include <cstdlib>
 #include <mutex>
 
 #include "bgp_internal.h"
@@ -154,6 +155,8 @@ struct SelectArgs {
   int64_t g0;
   int64_t r1, r2;     // 0-based ranks floor(index) - 1 of the two probabilities
   double h1, h2;      // interpolation weights (0 => no second order statistic needed)
+  double z_lo, z_hi;  // candidate cuts in standard deviations from the row mean (fast path)
+  int cap;            // candidate capacity per tail (power of two, 0 => radix path only)
   double* mean;
   double* lo;
   double* hi;
@@ -167,8 +170,10 @@ template <bool IN_SMEM>
 __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs a) {
   extern __shared__ unsigned long long skeys[];
   constexpr int NW = RS_THREADS / 32;
-  __shared__ unsigned int whist[2][NW][256];
+  // the per-warp histograms of the radix path live in the candidate area of the fast path (never both at once)
+  unsigned int (*whist)[NW][256] = reinterpret_cast<unsigned int (*)[NW][256]>(skeys + (IN_SMEM ? a.M : 0));
   __shared__ unsigned int hist[2][256];
+  __shared__ unsigned int s_cnt[2];
   __shared__ unsigned long long s_prefix[2];
   __shared__ long long s_below[2];
   __shared__ unsigned int s_eq[2];
@@ -178,33 +183,141 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
   const double* row = a.F + (size_t)blockIdx.x * a.ldF;
   const int64_t M = a.M;
   // mean (fixed-order tree), key range and, when the row fits, the sortable keys in shared memory
-  double sum = 0.0;
+  double sum = 0.0, sumsq = 0.0;
   unsigned long long kmin = ~0ull, kmax = 0ull;
-  for (int64_t i = tid; i < M; i += RS_THREADS) {
-    const double v = row[i];
-    sum += v;
-    const unsigned long long k = dkey(v);
-    kmin = k < kmin ? k : kmin;
-    kmax = k > kmax ? k : kmax;
-    if (IN_SMEM) skeys[i] = k;
+  for (int64_t i0 = tid; i0 < M; i0 += 8 * RS_THREADS) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                         // eight L2 loads in flight per thread
+      const int64_t i = i0 + (int64_t)u * RS_THREADS;
+      v[u] = i < M ? row[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + (int64_t)u * RS_THREADS;
+      if (i < M) {
+        sum += v[u];
+        sumsq = fma(v[u], v[u], sumsq);
+        const unsigned long long k = dkey(v[u]);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+        if (IN_SMEM) skeys[i] = k;
+      }
+    }
   }
-  s_red[tid] = sum;
-  s_min[tid] = kmin;
-  s_max[tid] = kmax;
+  // fixed-order reductions: shuffle tree inside each warp, then the warp results in warp order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+    const unsigned long long mn = __shfl_xor_sync(0xffffffffu, kmin, o), mx = __shfl_xor_sync(0xffffffffu, kmax, o);
+    kmin = mn < kmin ? mn : kmin;
+    kmax = mx > kmax ? mx : kmax;
+  }
+  if (lane == 0) {
+    s_red[warp] = sum;
+    s_red[NW + warp] = sumsq;
+    s_min[warp] = kmin;
+    s_max[warp] = kmax;
+  }
   __syncthreads();
-  for (int o = RS_THREADS / 2; o > 0; o >>= 1) {
-    if (tid < o) {
-      s_red[tid] += s_red[tid + o];
-      if (s_min[tid + o] < s_min[tid]) s_min[tid] = s_min[tid + o];
-      if (s_max[tid + o] > s_max[tid]) s_max[tid] = s_max[tid + o];
+  sum = 0.0;
+  sumsq = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    sum += s_red[w];
+    sumsq += s_red[NW + w];
+    kmin = s_min[w] < kmin ? s_min[w] : kmin;
+    kmax = s_max[w] > kmax ? s_max[w] : kmax;
+  }
+  const double mean = sum / (double)M;
+  __syncthreads();
+  auto key_at = [&](int64_t i) -> unsigned long long { return IN_SMEM ? skeys[i] : dkey(row[i]); };
+  const int64_t rk[2] = {a.r1, a.r2};
+
+  // ---- fast path: the few keys beyond mean +- z sigma hold the wanted order statistics -------------------------
+  // (exact: the counts are exact and the candidates are sorted; anything unexpected — too few or too many
+  // candidates, NaNs — falls through to the radix select below)
+  bool done[2] = {false, false};
+  double qv[2] = {0.0, 0.0};
+  if (a.cap > 0) {
+    unsigned long long* cand = skeys + (IN_SMEM ? M : 0);      // [2][cap]
+    const int cap = a.cap;
+    const double var = fmax(sumsq / (double)M - mean * mean, 0.0);
+    const double sd = sqrt(var);
+    const unsigned long long cut_lo = dkey(mean + a.z_lo * sd), cut_hi = dkey(mean + a.z_hi * sd);
+    if (tid < 2) s_cnt[tid] = 0;
+    for (int t = tid; t < 2 * cap; t += RS_THREADS) cand[t] = ~0ull;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < M; i0 += RS_THREADS) {
+      const int64_t i = i0 + tid;
+      const bool in = i < M;
+      const unsigned long long k = in ? key_at(i) : 0ull;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool hit = in && (q == 0 ? k < cut_lo : k > cut_hi);
+        const unsigned act = __ballot_sync(0xffffffffu, hit);
+        if (act) {
+          unsigned base = 0;
+          if (lane == __ffs(act) - 1) base = atomicAdd(&s_cnt[q], (unsigned)__popc(act));
+          base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
+          if (hit) {
+            const unsigned pos = base + __popc(act & ((1u << lane) - 1u));
+            if (pos < (unsigned)cap) cand[q * cap + pos] = q == 0 ? k : ~k;      // upper tail sorted descending
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const long long n_lo = s_cnt[0], n_hi = s_cnt[1];
+    const long long need_lo = rk[0] + (a.h1 != 0.0 ? 2 : 1);
+    const long long top2 = M - 1 - rk[1];                        // position of rank r2 counted from the top
+    const bool ok_lo = n_lo >= need_lo && n_lo <= cap;
+    const bool ok_hi = n_hi >= top2 + 1 && n_hi <= cap && (a.h2 == 0.0 || top2 >= 1);
+    if (ok_lo || ok_hi) {
+      // bitonic sort of both lists (padded with the maximal key; the order of equal keys is irrelevant)
+      for (int ksz = 2; ksz <= cap; ksz <<= 1) {
+        for (int j = ksz >> 1; j > 0; j >>= 1) {
+          for (int t = tid; t < cap; t += RS_THREADS) {          // cap / 2 pairs per list, two lists
+            const int q = t >= cap / 2 ? 1 : 0;
+            const int pr = t - q * (cap / 2);
+            const int lo_i = 2 * j * (pr / j) + (pr % j);
+            const int hi_i = lo_i + j;
+            const bool up = ((lo_i & ksz) == 0);
+            unsigned long long* c = cand + q * cap;
+            const unsigned long long x = c[lo_i], y = c[hi_i];
+            if ((x > y) == up) {
+              c[lo_i] = y;
+              c[hi_i] = x;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (ok_lo) {
+        const double x_lo = dunkey(cand[rk[0]]);
+        const double x_hi = a.h1 != 0.0 ? dunkey(cand[rk[0] + 1]) : x_lo;
+        qv[0] = (a.h1 != 0.0 && x_hi != x_lo) ? (1.0 - a.h1) * x_lo + a.h1 * x_hi : x_lo;
+        done[0] = true;
+      }
+      if (ok_hi) {
+        const double x_lo = dunkey(~cand[cap + top2]);
+        const double x_hi = a.h2 != 0.0 ? dunkey(~cand[cap + top2 - 1]) : x_lo;
+        qv[1] = (a.h2 != 0.0 && x_hi != x_lo) ? (1.0 - a.h2) * x_lo + a.h2 * x_hi : x_lo;
+        done[1] = true;
+      }
     }
     __syncthreads();
   }
-  const double mean = s_red[0] / (double)M;
-  kmin = s_min[0];
-  kmax = s_max[0];
-  __syncthreads();
-  auto key_at = [&](int64_t i) -> unsigned long long { return IN_SMEM ? skeys[i] : dkey(row[i]); };
+  if (done[0] && done[1]) {
+    if (tid == 0) {
+      const int64_t g = a.g0 + blockIdx.x;
+      if (a.mean) a.mean[g] = mean;
+      if (a.lo) a.lo[g] = qv[0];
+      if (a.hi) a.hi[g] = qv[1];
+    }
+    return;
+  }
 
   // all keys agree above byte `top`: start there
   const unsigned long long diff = kmin ^ kmax;
@@ -213,7 +326,6 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
   unsigned long long prefix[2] = {kmin & hi_mask, kmin & hi_mask}, mask = hi_mask;
   long long below[2] = {0, 0};
   unsigned int eq[2] = {(unsigned)M, (unsigned)M};
-  const int64_t rk[2] = {a.r1, a.r2};
   for (int pass = top; pass >= 0; --pass) {
     const int shift = pass * 8;
     const bool same = prefix[0] == prefix[1];          // both quantiles still in the same bucket: one histogram
@@ -282,8 +394,8 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
     mask |= 0xFFull << shift;
     __syncthreads();
   }
-  double qv[2];
   for (int which = 0; which < 2; ++which) {
+    if (done[which]) continue;
     const int64_t r = rk[which];
     const double h = which == 0 ? a.h1 : a.h2;
     const double x_lo = dunkey(prefix[which]);
@@ -429,10 +541,51 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   sa.mean = o_mean;
   sa.lo = o_lo;
   sa.hi = o_hi;
+  // candidate cuts of the fast path: expected tail fraction 1.5 q + 5 sqrt(q / M) (Gaussian-ish rows hold the
+  // wanted ranks with a wide margin), capacity = power of two >= twice the expected count
+  auto norm_inv = [](double pr) {                 // Acklam's rational approximation, |error| < 1.2e-9
+    static const double a_[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                                 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b_[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                                 6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c_[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                                 -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d_[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                                 3.754408661907416e+00};
+    if (pr < 0.02425) {
+      const double q = std::sqrt(-2.0 * std::log(pr));
+      return (((((c_[0] * q + c_[1]) * q + c_[2]) * q + c_[3]) * q + c_[4]) * q + c_[5]) /
+             ((((d_[0] * q + d_[1]) * q + d_[2]) * q + d_[3]) * q + 1.0);
+    }
+    const double q = pr - 0.5, r = q * q;
+    return (((((a_[0] * r + a_[1]) * r + a_[2]) * r + a_[3]) * r + a_[4]) * r + a_[5]) * q /
+           (((((b_[0] * r + b_[1]) * r + b_[2]) * r + b_[3]) * r + b_[4]) * r + 1.0);
+  };
+  const double qt = std::max(q1, 1.0 - q2);
+  const double frac = 1.5 * qt + 5.0 * std::sqrt(qt / (double)M);
+  sa.cap = 0;
+  sa.z_lo = sa.z_hi = 0.0;
+  size_t cand_bytes = 0;
+  if (std::min(q1, 1.0 - q2) > 0.0 && frac < 0.45 && M >= 64 && !getenv("BGP_SELECT_RADIX")) {   // env: diagnostics
+    int cap = 64;
+    while ((double)cap < 2.0 * frac * (double)M) cap <<= 1;
+    if (cap <= 8192) {
+      sa.cap = cap;
+      sa.z_lo = norm_inv(frac);
+      sa.z_hi = -sa.z_lo;
+      cand_bytes = (size_t)2 * cap * sizeof(unsigned long long);
+    }
+  }
+  cand_bytes = std::max<size_t>(cand_bytes, (size_t)2 * (RS_THREADS / 32) * 256 * sizeof(unsigned int));   // radix histograms
   const size_t key_bytes = (size_t)M * sizeof(unsigned long long);
-  const bool in_smem = key_bytes <= 200 * 1024;
-  if (in_smem && key_bytes > 40 * 1024)
-    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_bytes));
+  const bool in_smem = key_bytes + cand_bytes <= 190 * 1024;
+  const size_t dyn_bytes = (in_smem ? key_bytes : 0) + cand_bytes;
+  if (dyn_bytes > 40 * 1024) {
+    if (in_smem)
+      BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+    else
+      BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  }
   std::vector<cudaEvent_t> evs;
   auto mark = [&]() {
     cudaEvent_t e;
@@ -483,8 +636,8 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
       BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
                            true, nullptr, st));
     sa.g0 = g0;
-    if (in_smem) row_select_kernel<true><<<(unsigned)rows, RS_THREADS, key_bytes, st>>>(sa);
-    else row_select_kernel<false><<<(unsigned)rows, RS_THREADS, 0, st>>>(sa);
+    if (in_smem) row_select_kernel<true><<<(unsigned)rows, RS_THREADS, dyn_bytes, st>>>(sa);
+    else row_select_kernel<false><<<(unsigned)rows, RS_THREADS, dyn_bytes, st>>>(sa);
     count_launch();
     BGP_CUDA(cudaGetLastError());
     mark();
