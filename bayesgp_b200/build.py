@@ -11,10 +11,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbgp.so")
 STAMP = os.path.join(HERE, ".libbgp.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "--use_fast_math=false".replace("=false", "") if False else "-DBGP_BUILD",
-]
+# per-file compile flags (each translation unit is compiled in parallel, then linked)
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def sources():
@@ -27,7 +25,7 @@ def _digest():
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(CFLAGS).encode())
     return h.hexdigest()
 
 
@@ -41,8 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-x", "cu", "-c", src, "-o", obj]
+        cmd = [NVCC] + CFLAGS + ["-x", "cu", "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

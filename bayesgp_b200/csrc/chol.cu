@@ -425,11 +425,8 @@ static int launch_chol_t(bgp_model* m, const CholArgs& a, const TangentArgs& ta,
     set_error("Cholesky panel does not fit shared memory (p = %d)", a.p);
     return BGP_ERR_ARG;
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    BGP_CUDA(cudaFuncSetAttribute(chol_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  // per device and cheap: set on every launch (a process may drive models on several devices)
+  BGP_CUDA(cudaFuncSetAttribute(chol_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   chol_kernel<NB><<<CH_CS, CH_THREADS, smem, m->stream>>>(a, ta, ntan);   // one cluster (compile-time __cluster_dims__)
   count_launch();
   BGP_CUDA(cudaGetLastError());

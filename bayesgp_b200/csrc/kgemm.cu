@@ -147,11 +147,8 @@ int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64
     set_error("cuTensorMapEncodeTiled failed in kgemm");
     return BGP_ERR_CUDA;
   }
-  static bool attr = false;
-  if (!attr) {
-    BGP_CUDA(cudaFuncSetAttribute(kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KG_SMEM));
-    attr = true;
-  }
+  // per device and cheap: set on every launch (a process may drive several devices)
+  BGP_CUDA(cudaFuncSetAttribute(kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KG_SMEM));
   KgemmArgs a;
   a.M = M;
   a.N = N;

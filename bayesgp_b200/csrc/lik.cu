@@ -277,11 +277,8 @@ static int launch_lik_t(bgp_model* m, const LikArgs& a) {
   constexpr int smem = lk_stages(NJ) * lk_stage_bytes(NJ) + NJ * 512 + 16 * lk_stages(NJ) + 256;
   static_assert(lk_stages(NJ) >= 2, "likelihood ring needs at least two stages");
   static_assert(LK_CONSUMERS * lk_groups(NJ) * (NJ * 64 * 8 + 32) <= lk_stages(NJ) * lk_stage_bytes(NJ), "reduction scratch must fit in the ring");
-  static bool attr_set = false;
-  if (!attr_set) {
-    BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  // per device and cheap: set on every launch (a process may drive models on several devices)
+  BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const LikPlan* pl = (const LikPlan*)m->lik_plan;
   lik_kernel<NJ><<<m->lik_blocks, lk_threads(NJ), smem, m->stream>>>(pl->tmA, a);
   count_launch();
