@@ -73,6 +73,8 @@ SIGNATURES = {
     "bgp_predict_last_timing": (C.c_int, [c_double_p, c_double_p, c_double_p]),
     "bgp_model_counters": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
     "bgp_model_set_factor_reuse": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    "bgp_model_add_sgp": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p,
+                                    C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "bgp_model_last_timing": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int64_p,
                                         c_int64_p, c_int64_p]),
 }

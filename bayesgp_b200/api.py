@@ -158,10 +158,10 @@ def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]]
                 # random + boundary block generated on the device (blocks keep the order of the calls)
                 ff.add_iwp(t.x, t.initial_location, t.knots, t.order, t.u, t.alpha, t.boundary_prec, t.boundary_mean)
             elif t.kind == "sGP":
-                B, X = sgp_design(t)
+                # design on the device from the covariate; the (d x d) precision Compute_Q_sB stays on the host
                 P = sgp_precision(t)
-                ff.add_random(B, P, float(np.linalg.slogdet(P)[1]), t.u, t.alpha)
-                ff.add_boundary(X, t.boundary_prec, t.boundary_mean)
+                ff.add_sgp(t.x, t.initial_location, t.a, t.k, t.m, [float(t.region.min()), float(t.region.max())], P,
+                           float(np.linalg.slogdet(P)[1]), t.u, t.alpha, t.boundary_prec, t.boundary_mean)
             else:
                 B, Pd = iid_design(t)
                 ff.add_random(B, Pd, 0.0, t.u, t.alpha)

@@ -238,6 +238,8 @@ inline int ext2int(const bgp_model* m, int e) { return e < m->p - m->nD ? e + m-
 int copy_vec_in(bgp_model* m, const double* host_ext, double* dev_int);     // pads dev_int to lda with zeros
 int copy_vec_out(bgp_model* m, const double* dev_int, double* host_ext);
 int copy_H_out(bgp_model* m, double* host_ext);                             // from m->H (p x ldh) to p x p
+int launch_sgp_block(const double* x_dev, int64_t n, double x0, double a, int k, int m, double lo, double hi, double* dstB,
+                     double* dstX, cudaStream_t st);
 // newton.cu
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);

@@ -293,6 +293,50 @@ int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, co
   return BGP_OK;
 }
 
+int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm, const double* region,
+                      const double* P, double logPdet, double u, double alpha, double boundary_prec, double boundary_mean) {
+  BGP_CHECK_BUILDING(m);
+  if (!x || !region || !P || k < 5 || nharm < 1 || !(region[1] > region[0])) {
+    set_error("bgp_model_add_sgp: bad arguments (k must be >= 5, m >= 1, region increasing)");
+    return BGP_ERR_ARG;
+  }
+  if ((int)m->rnd.size() >= 16) {
+    set_error("at most 16 smoothing terms are supported");
+    return BGP_ERR_ARG;
+  }
+  const int d = 3 * (k - 2) * nharm;
+  double* x_dev = nullptr;
+  const size_t nb = (size_t)m->n * sizeof(double);
+  BGP_CUDA(cudaMalloc(&x_dev, nb));
+  BGP_CUDA(cudaMemcpyAsync(x_dev, x, nb, cudaMemcpyHostToDevice, m->stream));
+  bgp_model::Staged sB, sX;
+  sB.ncol = d;
+  sX.ncol = 2 * nharm;
+  sB.dev = sX.dev = nullptr;
+  BGP_CUDA(cudaMalloc(&sB.dev, (size_t)m->n * d * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&sX.dev, (size_t)m->n * sX.ncol * sizeof(double)));
+  BGP_TRY(launch_sgp_block(x_dev, m->n, initial_location, a, k, nharm, region[0], region[1], sB.dev, sX.dev, m->stream));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(x_dev);
+  m->st_rnd.push_back(sB);
+  m->st_bnd.push_back(sX);
+  RandomBlock rb;
+  rb.d = d;
+  rb.diag = false;
+  rb.logPdet = logPdet;
+  rb.u = u;
+  rb.alpha = alpha;
+  const size_t pb = (size_t)d * d * sizeof(double);
+  BGP_CUDA(cudaMalloc(&rb.P_dev, pb));
+  BGP_CUDA(cudaMemcpy(rb.P_dev, P, pb, cudaMemcpyHostToDevice));
+  rb.P_host.assign(P, P + (size_t)d * d);
+  m->rnd.push_back(rb);
+  m->bnd_dim.push_back(2 * nharm);
+  m->bnd_prec.push_back(boundary_prec);
+  m->bnd_mean.push_back(boundary_mean);
+  return BGP_OK;
+}
+
 int bgp_nccl_unique_id(void* id128) { return comm_unique_id(id128); }
 
 int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_unique_id) {

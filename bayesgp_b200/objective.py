@@ -116,6 +116,16 @@ class LaplaceObjective:
                                           int(order), float(u), float(alpha), float(boundary_prec),
                                           float(boundary_mean)))
 
+    def add_sgp(self, x, initial_location, a, k, m, region, P, logPdet, u=1.0, alpha=0.5, boundary_prec=0.01,
+                boundary_mean=0.0):
+        """Device-side construction of an sGP design (B and X) from the covariate; P comes from the host."""
+        x = fvec(x)
+        reg = fvec(np.asarray(region, dtype=np.float64)[:2])
+        Pm = fmat(P)
+        check(self._lib.bgp_model_add_sgp(self._h, dptr(x), float(initial_location), float(a), int(k), int(m), dptr(reg),
+                                          dptr(Pm), float(logPdet), float(u), float(alpha), float(boundary_prec),
+                                          float(boundary_mean)))
+
     def set_noise_prior(self, u=1.0, alpha=0.5):
         check(self._lib.bgp_model_set_noise_prior(self._h, float(u), float(alpha)))
 

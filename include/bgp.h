@@ -71,6 +71,14 @@ int bgp_model_set_noise_prior(bgp_model* m, double u, double alpha);
  * boundary block of the term (boundary blocks of generated terms keep the order of the calls). */
 int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, const double* knots, int nknots,
                       int order, double u, double alpha, double boundary_prec, double boundary_mean);
+/* GPU-side constructor of an sGP term from the covariate: B = cbind over harmonics i = 1..m of
+ * [B cos(i a x), B sin(i a x), B] with the cubic B-spline basis on `region` minus its first two functions
+ * (Compute_B_sB with boundary = TRUE, as the fit always uses), X = cbind(cos(i a x), sin(i a x))
+ * (/root/reference/R/01_utility.R:177-195,224-239,301-312; R/02_model_fit.R:493-569).  P (d x d dense,
+ * d = 3 (k-2) m, Compute_Q_sB) and logPdet come from the caller.  Adds the random AND the boundary block. */
+int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm,
+                      const double* region /* 2 */, const double* P, double logPdet, double u, double alpha,
+                      double boundary_prec, double boundary_mean);
 /* observation sharding: this process holds rows [row0, row0 + n) of a global problem of n_total rows and
  * joins an NCCL communicator of `world` ranks (nccl_unique_id: the 128-byte ncclUniqueId produced by
  * bgp_nccl_unique_id on rank 0 and broadcast by the launcher). Must precede finalize. */
