@@ -106,6 +106,71 @@ __device__ __forceinline__ void obs_terms(int family, double tau, double eta, do
   }
 }
 
+// One observation, one warp.  MASKED = false: the occupied column groups are the G leading ones (the usual
+// case after the zero-pattern sort) — straight-line code over exactly those groups; MASKED = true: arbitrary
+// group mask gm over all NJ groups.
+struct RowCtx {
+  uint32_t ra, w_base, aux;     // shared addresses: this lane's 16 bytes of the row / of W; y | size | previous eta
+  int wrow, lane;
+  int64_t row;
+};
+template <int NJ, int G, bool MASKED>
+__device__ __forceinline__ void lik_row(const LikArgs& a, const RowCtx& c, uint32_t gm, int group_bytes, int kb, double2 (&ga)[NJ],
+                                        double& ll, double& sumsq, double& dmax, int& bad) {
+  double2 av[G];
+  double rr;
+  if (a.rvec) {
+    rr = __ldg(a.rvec + c.row);
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+      av[j] = (!MASKED || ((gm >> j) & 1u)) ? lds128(c.ra + j * group_bytes) : make_double2(0.0, 0.0);
+  } else {
+    double s = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (!MASKED || ((gm >> j) & 1u)) {
+        av[j] = lds128(c.ra + j * group_bytes);
+        const double2 wv = lds128(c.w_base + j * 512 + c.lane * 16);
+        s = fma(av[j].x, wv.x, s);
+        s2 = fma(av[j].y, wv.y, s2);
+      } else {
+        av[j] = make_double2(0.0, 0.0);
+      }
+    }
+    s = warp_sum(s + s2);
+    const double yv = lds64(c.aux + c.wrow * 8);
+    const double sz = a.size ? lds64(c.aux + kb * 8 + c.wrow * 8) : 1.0;
+    double ww, cc;
+    obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
+    if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
+    const double eta_old = lds64(c.aux + 2 * kb * 8 + c.wrow * 8);
+    if (c.lane == 0) {
+      const double d = fabs(s - eta_old);           // change of the linear predictor since the last pass
+      dmax = d > dmax || !(d == d) ? (d == d ? d : INFINITY) : dmax;
+      a.eta[c.row] = s;
+      a.wobs[c.row] = ww;
+      if (a.c3) a.c3[c.row] = cc;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    if (!MASKED || ((gm >> j) & 1u)) {
+      ga[j].x = fma(rr, av[j].x, ga[j].x);
+      ga[j].y = fma(rr, av[j].y, ga[j].y);
+    }
+  }
+}
+
+// dispatch on the number of leading occupied groups (1 .. NJ); anything else takes the masked body
+template <int NJ, int G>
+__device__ __forceinline__ void lik_row_dispatch(int g, const LikArgs& a, const RowCtx& c, int group_bytes, int kb,
+                                                 double2 (&ga)[NJ], double& ll, double& sumsq, double& dmax, int& bad) {
+  if constexpr (G >= 1) {
+    if (g == G) lik_row<NJ, G, false>(a, c, 0u, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+    else lik_row_dispatch<NJ, G - 1>(g, a, c, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+  }
+}
+
 // smem: [stages][ NJ boxes | y[8] | size[8] ] | W (NJ * 64) | meta[stages] | full[stages] | empty[stages]
 template <int NJ>
 __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_constant__ CUtensorMap tmA, const LikArgs a) {
@@ -194,47 +259,18 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
     const uint32_t sb = base + slot * STAGE_BYTES;
     const uint32_t ra = sb + wrow * 512 + lane * 16;
     if (row < a.n) {
-      double2 av[NJ];
-      double rr;
-      if (a.rvec) {
-        rr = __ldg(a.rvec + row);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) av[j] = ((gm >> j) & 1u) ? lds128(ra + j * LK_GROUP_BYTES) : make_double2(0.0, 0.0);
-      } else {
-        double s = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          if ((gm >> j) & 1u) {
-            av[j] = lds128(ra + j * LK_GROUP_BYTES);
-            const double2 wv = lds128(w_base + j * 512 + lane * 16);
-            s = fma(av[j].x, wv.x, s);
-            s2 = fma(av[j].y, wv.y, s2);
-          } else {
-            av[j] = make_double2(0.0, 0.0);
-          }
-        }
-        s = warp_sum(s + s2);
-        const double yv = lds64(sb + NJ * LK_GROUP_BYTES + wrow * 8);
-        const double sz = a.size ? lds64(sb + NJ * LK_GROUP_BYTES + LK_KB * 8 + wrow * 8) : 1.0;
-        double ww, cc;
-        obs_terms(a.family, a.tau, s, yv, sz, ll, sumsq, rr, ww, cc);
-        if (!(isfinite(ww) && isfinite(rr) && isfinite(ll))) bad = 1;
-        const double eta_old = lds64(sb + NJ * LK_GROUP_BYTES + 2 * LK_KB * 8 + wrow * 8);
-        if (lane == 0) {
-          const double d = fabs(s - eta_old);           // change of the linear predictor since the last pass
-          dmax = d > dmax || !(d == d) ? (d == d ? d : INFINITY) : dmax;
-          a.eta[row] = s;
-          a.wobs[row] = ww;
-          if (a.c3) a.c3[row] = cc;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if ((gm >> j) & 1u) {
-          ga[j].x = fma(rr, av[j].x, ga[j].x);
-          ga[j].y = fma(rr, av[j].y, ga[j].y);
-        }
-      }
+      RowCtx c;
+      c.ra = ra;
+      c.w_base = w_base;
+      c.aux = sb + NJ * LK_GROUP_BYTES;
+      c.wrow = wrow;
+      c.lane = lane;
+      c.row = row;
+      const int g = 32 - __clz(gm);                       // groups 0 .. g-1 occupied <=> gm == 2^g - 1
+      if (NJ <= 8 && gm != 0u && gm == ((1u << g) - 1u))
+        lik_row_dispatch<NJ, (NJ <= 8 ? NJ : 1)>(g, a, c, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
+      else
+        lik_row<NJ, NJ, true>(a, c, gm, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
     }
     __syncwarp();
     if (lane == 0) lk_arrive(empty_base + 8 * slot);
