@@ -70,7 +70,7 @@ struct EvalScalars {
   int chol_info;   // 0 ok, j+1: non-positive pivot at column j
   int nonfinite;   // 1 if eta / ll produced a non-finite value
   double sumsq;    // Gaussian: sum (y-eta)^2
-  double pad;      // max |eta - previous eta| of the last likelihood pass (single-device models)
+  double pad;      // max |eta - previous eta| of the last likelihood pass (sharded: sum of the ranks' maxima, an upper bound)
 };
 
 struct Comm;   // NCCL communicator wrapper (comm.cpp)

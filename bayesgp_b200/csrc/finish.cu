@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __rest
   if (blockIdx.x == 0 && threadIdx.x == 67) {
     double t = 0.0;
     for (int b = 0; b < nblocks; ++b) t = fmax(t, part_s[(size_t)b * 4 + 3]);
-    red[lda + 3] = t;            // max |eta - previous eta| (local rows; not meaningful after a SUM all-reduce)
+    red[lda + 3] = t;            // max |eta - previous eta| over the local rows; the SUM all-reduce of sharded
+                                 // models turns it into an upper bound of the global maximum
   }
 }
 

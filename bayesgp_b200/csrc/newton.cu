@@ -239,9 +239,10 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     f = sc.f;
     gmax = sc.gmax;
     ++iters;
-    if (gmax < m->grad_tol && full_step && m->allow_reuse && m->world == 1 && std::isfinite(sc.logdet)) {
+    if (gmax < m->grad_tol && full_step && m->allow_reuse && std::isfinite(sc.logdet)) {
       // Converged by a full Newton step from the point where H was factored.  |logdet H(w1) - logdet H(w0)| <=
-      // p * delta (delta = max |d eta|; Gaussian: H does not depend on W at all), so when that is far inside
+      // p * delta (delta = max |d eta|; sharded models carry the SUM over ranks of the local maxima, an upper
+      // bound every rank sees identically; Gaussian: H does not depend on W at all), so when that is far inside
       // the tolerances the factor of the last iteration serves as the factor at the mode.
       const double val = f + 0.5 * sc.logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
       const bool tiny = m->family == BGP_FAMILY_GAUSSIAN ||
