@@ -101,3 +101,54 @@ def test_workload_generators_are_seeded():
     assert len(kn) == 30 and kn[0] == 0.0 and x0 == x1.min()
     from oracle.aghq import gh_rule
     assert np.allclose(gh_nodes(15), gh_rule(15)[0], atol=1e-13)
+
+
+def _header_arity():
+    """name -> number of parameters, parsed from include/bgp.h."""
+    src = open(os.path.join(ROOT, "include", "bgp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(bgp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def _call_arity(text, name):
+    """argument counts of every call of `name(` in C source text (balanced parentheses)."""
+    counts = []
+    for m in re.finditer(r"\b%s\s*\(" % re.escape(name), text):
+        depth, i, commas, seen = 1, m.end(), 0, False
+        while depth and i < len(text):
+            ch = text[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            elif not ch.isspace():
+                seen = True
+            i += 1
+        counts.append(commas + 1 if seen else 0)
+    return counts
+
+
+def test_r_shim_binds_only_declared_entry_points_with_matching_arity():
+    """integration/r/bgp_rcall.c cannot be compiled here (no R headers); at least every bgp_* it calls must exist in
+    include/bgp.h with the same number of arguments, and its .Call table must match its own definitions."""
+    shim = open(os.path.join(ROOT, "integration", "r", "bgp_rcall.c")).read()
+    code = re.sub(r"/\*.*?\*/", "", shim, flags=re.S)
+    arity = _header_arity()
+    used = sorted(set(re.findall(r"\b(bgp_[a-z0-9_]+)\s*\(", code)))
+    assert len(used) >= 12
+    for nm in used:
+        assert nm in arity, "%s is not declared in include/bgp.h" % nm
+        for k in _call_arity(code, nm):
+            assert k == arity[nm], (nm, k, arity[nm])
+    table = dict((n, int(k)) for n, k in re.findall(r'\{"(bgpR_[a-z_]+)",\s*\(DL_FUNC\)&\1,\s*(\d+)\}', code))
+    defs = dict((m.group(1), m.group(2).count("SEXP")) for m in re.finditer(r"^SEXP (bgpR_[a-z_]+)\(([^)]*)\)", code, flags=re.M))
+    assert table and table == defs, (table, defs)
+    rglue = open(os.path.join(ROOT, "integration", "r", "bgp_shim.R")).read()
+    for nm in set(re.findall(r'\.Call\("(bgpR_[a-z_]+)"', rglue)):
+        assert nm in table, nm
