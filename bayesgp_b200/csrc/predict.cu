@@ -8,7 +8,8 @@
 //   F (G x M) = [X_deg(x) | B(x)] [global rows; coef]          fitted_samps_deriv, :235 / :272
 // is never materialised: rows are processed in strips; per strip the design rows are generated on
 // the device, multiplied on the FP64 tensor pipe (kgemm.cu) into an L2-sized scratch strip, and each
-// row is reduced to (mean, two type-7 quantiles) by an exact MSB radix select (one CTA per row).
+// row is reduced to (mean, two type-7 quantiles) by an exact selection (one CTA per row: candidate cuts
+// + value buckets, MSB radix select as the assumption-free fallback).
 #include <algorithm>
 
 #include "basis_dev.cuh"
@@ -137,7 +138,7 @@ __global__ void build_coef_kernel(const CoefArgs a) {
   }
 }
 
-// ---- per-row mean and type-7 quantiles by exact radix select --------------------------------------------
+// ---- per-row mean and type-7 quantiles ------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long dkey(double x) {
   const long long b = __double_as_longlong(x);
   return (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
@@ -148,6 +149,9 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
 }
 
 constexpr int RS_THREADS = 256;
+constexpr int RS_LIST = 128;      // keys of one target bucket, ranked by a single warp
+constexpr int RS_OVF = 256;       // shared overflow list behind the per-thread candidate slots
+constexpr int RS_PC_MIN = 8;      // the slot area doubles as the per-warp histograms of the radix path (16 KB)
 
 struct SelectArgs {
   const double* F;
@@ -156,69 +160,95 @@ struct SelectArgs {
   int64_t r1, r2;     // 0-based ranks floor(index) - 1 of the two probabilities
   double h1, h2;      // interpolation weights (0 => no second order statistic needed)
   double z_lo, z_hi;  // candidate cuts in standard deviations from the row mean (fast path)
-  int cap;            // candidate capacity per tail (power of two, 0 => radix path only)
+  int pc;             // candidate slots per thread (0 => radix path only)
+  int nb;             // value buckets per tail (power of two, multiple of 128)
   double* mean;
   double* lo;
   double* hi;
 };
 
-// One CTA per row.  Exact MSB radix select (8-bit digits) of the two order statistics, both in the same
-// sweeps: per-warp private histograms fed by warp-aggregated increments (the keys of a row share their
-// leading bytes, a single shared histogram serialises on one bin), a warp-parallel bin scan, and a start
-// digit chosen from the highest bit in which the row's keys differ.
+// One CTA per row, four steps, each a few instructions per value:
+//   A  stream the row once (128-bit loads, eight in flight per thread): sum, sum of squares, copy to shared memory;
+//   B  every thread re-reads its own values and keeps those beyond mean +- z sigma (about 1.8 x the wanted tail) in
+//      private slots — no ballots or atomics; the rare thread with more hits than slots spills to a shared list;
+//   C  the kept values are counted into nb buckets per tail by distance from the cut (a monotone map, so bucket
+//      order is value order); a scan from the extreme end finds the bucket holding each wanted order statistic and
+//      the exact number of values beyond it;
+//   D  the handful of values of that bucket are collected and ranked by one warp.
+// Every count is exact, so the result is the exact order statistic.  Anything unexpected — cuts that miss the rank
+// (heavy tails, constant rows), NaN / Inf, a crowded bucket, a full overflow list — drops the whole row to the MSB
+// radix select below, which needs no assumption about the values.
 template <bool IN_SMEM>
-__global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs a) {
-  extern __shared__ unsigned long long skeys[];
+__global__ void __launch_bounds__(RS_THREADS, 2) row_select_kernel(const SelectArgs a) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
   constexpr int NW = RS_THREADS / 32;
-  // the per-warp histograms of the radix path live in the candidate area of the fast path (never both at once)
-  unsigned int (*whist)[NW][256] = reinterpret_cast<unsigned int (*)[NW][256]>(skeys + (IN_SMEM ? a.M : 0));
-  __shared__ unsigned int hist[2][256];
-  __shared__ unsigned int s_cnt[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t M = a.M;
+  const int64_t Mpad = (M + 1) & ~(int64_t)1;
+  const int pc = a.pc, nb = a.nb;
+  double* vals = reinterpret_cast<double*>(rs_smem);
+  double* priv = vals + (IN_SMEM ? Mpad : 0);                                  // [slot][thread]
+  double* ovf = priv + (size_t)(pc > RS_PC_MIN ? pc : RS_PC_MIN) * RS_THREADS;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(ovf + RS_OVF);          // [2][nb]
+  double* lists = reinterpret_cast<double*>(hist + 2 * nb);                    // [2 tails][2 ranks][RS_LIST]
+  __shared__ double s_red[2 * NW];
+  __shared__ unsigned long long s_kmin[NW], s_kmax[NW];
+  __shared__ unsigned int s_novf, s_wtot[NW], s_n[2], s_lcnt[2][2];
+  __shared__ int s_bsel[2][2];
+  __shared__ unsigned int s_before[2][2];
+  __shared__ double s_val[2][2];
   __shared__ unsigned long long s_prefix[2];
   __shared__ long long s_below[2];
   __shared__ unsigned int s_eq[2];
-  __shared__ double s_red[RS_THREADS];
-  __shared__ unsigned long long s_min[RS_THREADS], s_max[RS_THREADS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* row = a.F + (size_t)blockIdx.x * a.ldF;
-  const int64_t M = a.M;
-  // mean (fixed-order tree), key range and, when the row fits, the sortable keys in shared memory
+  const double2* row2 = reinterpret_cast<const double2*>(row);                 // rows are 16-byte aligned (ldF even)
+  const int64_t npair = M >> 1;
+
+  // ---- A: mean (fixed-order tree) and the row into shared memory ----------------------------------------------
+  // (squares are taken about the first value of the row: the variance only places the cuts, but a row whose
+  // spread is tiny against its level must not lose it to cancellation)
+  const double shift = row[0];
   double sum = 0.0, sumsq = 0.0;
-  unsigned long long kmin = ~0ull, kmax = 0ull;
-  for (int64_t i0 = tid; i0 < M; i0 += 8 * RS_THREADS) {
-    double v[8];
+  for (int64_t p0 = tid; p0 < npair; p0 += 8 * RS_THREADS) {
+    double2 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {                         // eight L2 loads in flight per thread
-      const int64_t i = i0 + (int64_t)u * RS_THREADS;
-      v[u] = i < M ? row[i] : 0.0;
+    for (int u = 0; u < 8; ++u) {
+      const int64_t p = p0 + (int64_t)u * RS_THREADS;
+      v[u] = p < npair ? row2[p] : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int64_t i = i0 + (int64_t)u * RS_THREADS;
-      if (i < M) {
-        sum += v[u];
-        sumsq = fma(v[u], v[u], sumsq);
-        const unsigned long long k = dkey(v[u]);
-        kmin = k < kmin ? k : kmin;
-        kmax = k > kmax ? k : kmax;
-        if (IN_SMEM) skeys[i] = k;
+      const int64_t p = p0 + (int64_t)u * RS_THREADS;
+      if (p < npair) {
+        const double dx = v[u].x - shift, dy = v[u].y - shift;
+        sum += v[u].x;
+        sumsq = fma(dx, dx, sumsq);
+        sum += v[u].y;
+        sumsq = fma(dy, dy, sumsq);
+        if (IN_SMEM) reinterpret_cast<double2*>(vals)[p] = v[u];
       }
     }
   }
-  // fixed-order reductions: shuffle tree inside each warp, then the warp results in warp order
+  if ((M & 1) && tid == 0) {
+    const double v = row[M - 1];
+    sum += v;
+    sumsq = fma(v - shift, v - shift, sumsq);
+    if (IN_SMEM) vals[M - 1] = v;
+  }
+  for (int t = tid; t < 2 * nb; t += RS_THREADS) hist[t] = 0;
+  if (tid < 4) {
+    s_lcnt[tid >> 1][tid & 1] = 0;
+    s_bsel[tid >> 1][tid & 1] = -1;
+  }
+  if (tid == 0) s_novf = 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
     sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
-    const unsigned long long mn = __shfl_xor_sync(0xffffffffu, kmin, o), mx = __shfl_xor_sync(0xffffffffu, kmax, o);
-    kmin = mn < kmin ? mn : kmin;
-    kmax = mx > kmax ? mx : kmax;
   }
   if (lane == 0) {
     s_red[warp] = sum;
     s_red[NW + warp] = sumsq;
-    s_min[warp] = kmin;
-    s_max[warp] = kmax;
   }
   __syncthreads();
   sum = 0.0;
@@ -227,98 +257,227 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
   for (int w = 0; w < NW; ++w) {
     sum += s_red[w];
     sumsq += s_red[NW + w];
-    kmin = s_min[w] < kmin ? s_min[w] : kmin;
-    kmax = s_max[w] > kmax ? s_max[w] : kmax;
   }
   const double mean = sum / (double)M;
-  __syncthreads();
-  auto key_at = [&](int64_t i) -> unsigned long long { return IN_SMEM ? skeys[i] : dkey(row[i]); };
-  const int64_t rk[2] = {a.r1, a.r2};
+  double q_lo = 0.0, q_hi = 0.0;
+  bool done = false;
 
-  // ---- fast path: the few keys beyond mean +- z sigma hold the wanted order statistics -------------------------
-  // (exact: the counts are exact and the candidates are sorted; anything unexpected — too few or too many
-  // candidates, NaNs — falls through to the radix select below)
-  bool done[2] = {false, false};
-  double qv[2] = {0.0, 0.0};
-  if (a.cap > 0) {
-    unsigned long long* cand = skeys + (IN_SMEM ? M : 0);      // [2][cap]
-    const int cap = a.cap;
-    const double var = fmax(sumsq / (double)M - mean * mean, 0.0);
-    const double sd = sqrt(var);
-    const unsigned long long cut_lo = dkey(mean + a.z_lo * sd), cut_hi = dkey(mean + a.z_hi * sd);
-    if (tid < 2) s_cnt[tid] = 0;
-    for (int t = tid; t < 2 * cap; t += RS_THREADS) cand[t] = ~0ull;
-    __syncthreads();
-    for (int64_t i0 = 0; i0 < M; i0 += RS_THREADS) {
-      const int64_t i = i0 + tid;
-      const bool in = i < M;
-      const unsigned long long k = in ? key_at(i) : 0ull;
+  const double sd = sqrt(fmax(sumsq / (double)M - (mean - shift) * (mean - shift), 0.0));
+  if (pc > 0 && sd > 0.0 && isfinite(sd) && isfinite(mean)) {                  // CTA-uniform
+    const double cut_lo = mean + a.z_lo * sd, cut_hi = mean + a.z_hi * sd;
+    const double scale = (double)nb / (3.0 * sd);                              // buckets span three sigma beyond a cut
+    bool ok = true;
+    // ---- B: candidates into private slots -------------------------------------------------------------------
+    int c = 0;
+    auto visit = [&](double v) {
+      if (v < cut_lo || v > cut_hi) {
+        if (c < pc) {
+          priv[c * RS_THREADS + tid] = v;
+        } else {
+          const unsigned pos = atomicAdd(&s_novf, 1u);
+          if (pos < (unsigned)RS_OVF) ovf[pos] = v;
+        }
+        ++c;
+      }
+    };
+    if (IN_SMEM) {
+      for (int64_t p = tid; p < npair; p += RS_THREADS) {
+        const double2 v = reinterpret_cast<const double2*>(vals)[p];          // written by this thread in step A
+        visit(v.x);
+        visit(v.y);
+      }
+      if ((M & 1) && tid == 0) visit(vals[M - 1]);
+    } else {
+      for (int64_t p0 = tid; p0 < npair; p0 += 4 * RS_THREADS) {
+        double2 v[4];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const bool hit = in && (q == 0 ? k < cut_lo : k > cut_hi);
-        const unsigned act = __ballot_sync(0xffffffffu, hit);
-        if (act) {
-          unsigned base = 0;
-          if (lane == __ffs(act) - 1) base = atomicAdd(&s_cnt[q], (unsigned)__popc(act));
-          base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
-          if (hit) {
-            const unsigned pos = base + __popc(act & ((1u << lane) - 1u));
-            if (pos < (unsigned)cap) cand[q * cap + pos] = q == 0 ? k : ~k;      // upper tail sorted descending
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int64_t p = p0 + (int64_t)u * RS_THREADS;
+          v[u] = p < npair ? row2[p] : make_double2(mean, mean);               // the mean is never a candidate
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          visit(v[u].x);
+          visit(v[u].y);
         }
       }
+      if ((M & 1) && tid == 0) visit(row[M - 1]);
+    }
+    // ---- C: bucket counts, extreme end first ----------------------------------------------------------------
+    // tail 0 = below cut_lo, tail 1 = above cut_hi; bucket nb - 1 is the far end.  v1 <= v2 implies
+    // bucket(v1) >= bucket(v2) in tail 0 (and the mirror image in tail 1): subtraction, the scaling and the
+    // floor are all monotone, so the buckets partition the candidates in value order.
+    auto bucket_of = [&](double v, int& q) {
+      q = v > cut_hi ? 1 : 0;
+      const double d = q ? v - cut_hi : cut_lo - v;
+      const int b = __double2int_rd(d * scale);                                // saturating; d > 0
+      return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+    };
+    const int cp = c < pc ? c : pc;
+    for (int j = 0; j < cp; ++j) {
+      int q;
+      const int b = bucket_of(priv[j * RS_THREADS + tid], q);
+      atomicAdd(&hist[q * nb + b], 1u);
     }
     __syncthreads();
-    const long long n_lo = s_cnt[0], n_hi = s_cnt[1];
-    const long long need_lo = rk[0] + (a.h1 != 0.0 ? 2 : 1);
-    const long long top2 = M - 1 - rk[1];                        // position of rank r2 counted from the top
-    const bool ok_lo = n_lo >= need_lo && n_lo <= cap;
-    const bool ok_hi = n_hi >= top2 + 1 && n_hi <= cap && (a.h2 == 0.0 || top2 >= 1);
-    if (ok_lo || ok_hi) {
-      // bitonic sort of both lists (padded with the maximal key; the order of equal keys is irrelevant)
-      for (int ksz = 2; ksz <= cap; ksz <<= 1) {
-        for (int j = ksz >> 1; j > 0; j >>= 1) {
-          for (int t = tid; t < cap; t += RS_THREADS) {          // cap / 2 pairs per list, two lists
-            const int q = t >= cap / 2 ? 1 : 0;
-            const int pr = t - q * (cap / 2);
-            const int lo_i = 2 * j * (pr / j) + (pr % j);
-            const int hi_i = lo_i + j;
-            const bool up = ((lo_i & ksz) == 0);
-            unsigned long long* c = cand + q * cap;
-            const unsigned long long x = c[lo_i], y = c[hi_i];
-            if ((x > y) == up) {
-              c[lo_i] = y;
-              c[hi_i] = x;
+    const unsigned novf = s_novf;
+    if (novf > (unsigned)RS_OVF) ok = false;
+    const unsigned novf_c = novf > (unsigned)RS_OVF ? 0u : novf;
+    for (unsigned i = tid; i < novf_c; i += RS_THREADS) {
+      int q;
+      const int b = bucket_of(ovf[i], q);
+      atomicAdd(&hist[q * nb + b], 1u);
+    }
+    __syncthreads();
+    // 128 threads per tail, nb / 128 consecutive buckets each, walking inwards from the far end
+    const int q = tid >> 7, u = tid & 127, w = nb >> 7;
+    const unsigned int* hq = hist + q * nb;
+    const int btop = nb - 1 - u * w;
+    unsigned tot = 0;
+    for (int j = 0; j < w; ++j) tot += hq[btop - j];
+    unsigned inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
+    __syncthreads();
+    unsigned base = 0;
+    for (int ww = q * 4; ww < warp; ++ww) base += s_wtot[ww];
+    const long long cum0 = (long long)base + (long long)(inc - tot);         // candidates beyond this thread's buckets
+    if (u == 127) s_n[q] = base + inc;
+    // wanted positions counted from the extreme end: P0 = rank r (x_lo of the interpolation), P1 = rank r + 1
+    const long long top2 = M - 1 - a.r2;
+    const bool need_lo = a.h1 != 0.0, need_hi = a.h2 != 0.0;
+    {
+      const long long P0 = q == 0 ? a.r1 : top2, P1 = q == 0 ? a.r1 + 1 : top2 - 1;
+      const bool need1 = q == 0 ? need_lo : need_hi;
+#pragma unroll
+      for (int wch = 0; wch < 2; ++wch) {
+        if (wch == 1 && !need1) continue;
+        const long long P = wch == 0 ? P0 : P1;
+        if (P >= cum0 && P < cum0 + (long long)tot) {
+          long long cum = cum0;
+          for (int j = 0; j < w; ++j) {
+            const unsigned cnt = hq[btop - j];
+            if (P < cum + (long long)cnt) {
+              s_bsel[q][wch] = btop - j;
+              s_before[q][wch] = (unsigned)cum;
+              break;
             }
+            cum += cnt;
           }
-          __syncthreads();
         }
-      }
-      if (ok_lo) {
-        const double x_lo = dunkey(cand[rk[0]]);
-        const double x_hi = a.h1 != 0.0 ? dunkey(cand[rk[0] + 1]) : x_lo;
-        qv[0] = (a.h1 != 0.0 && x_hi != x_lo) ? (1.0 - a.h1) * x_lo + a.h1 * x_hi : x_lo;
-        done[0] = true;
-      }
-      if (ok_hi) {
-        const double x_lo = dunkey(~cand[cap + top2]);
-        const double x_hi = a.h2 != 0.0 ? dunkey(~cand[cap + top2 - 1]) : x_lo;
-        qv[1] = (a.h2 != 0.0 && x_hi != x_lo) ? (1.0 - a.h2) * x_lo + a.h2 * x_hi : x_lo;
-        done[1] = true;
       }
     }
     __syncthreads();
+    // the cuts must not have missed a wanted rank
+    if ((need_lo ? a.r1 + 1 : a.r1) >= (long long)s_n[0]) ok = false;
+    if (top2 >= (long long)s_n[1] || (need_hi && top2 < 1)) ok = false;
+    // ---- D: collect the target buckets, rank inside them -------------------------------------------------------
+    const int b00 = s_bsel[0][0], b01 = s_bsel[0][1], b10 = s_bsel[1][0], b11 = s_bsel[1][1];
+    if (ok) {
+      auto collect = [&](double v) {
+        int qq;
+        const int b = bucket_of(v, qq);
+        const int t0 = qq ? b10 : b00, t1 = qq ? b11 : b01;
+        if (b == t0) {
+          const unsigned pos = atomicAdd(&s_lcnt[qq][0], 1u);
+          if (pos < (unsigned)RS_LIST) lists[(qq * 2) * RS_LIST + pos] = v;
+        } else if (b == t1) {
+          const unsigned pos = atomicAdd(&s_lcnt[qq][1], 1u);
+          if (pos < (unsigned)RS_LIST) lists[(qq * 2 + 1) * RS_LIST + pos] = v;
+        }
+      };
+      for (int j = 0; j < cp; ++j) collect(priv[j * RS_THREADS + tid]);
+      for (unsigned i = tid; i < novf_c; i += RS_THREADS) collect(ovf[i]);
+    }
+    __syncthreads();
+    if (ok) {
+      if (s_lcnt[0][0] > (unsigned)RS_LIST || s_lcnt[0][1] > (unsigned)RS_LIST || s_lcnt[1][0] > (unsigned)RS_LIST ||
+          s_lcnt[1][1] > (unsigned)RS_LIST)
+        ok = false;                                                            // crowded bucket
+    }
+    if (ok && warp < 4) {
+      const int qq = warp >> 1, wch = warp & 1;
+      if (wch == 0 || (qq == 0 ? need_lo : need_hi)) {
+        const int bsel0 = qq ? b10 : b00, bsel1 = qq ? b11 : b01;
+        const int src = (wch == 1 && bsel1 == bsel0) ? 0 : wch;
+        const int n = (int)s_lcnt[qq][src];
+        const double* L = lists + (qq * 2 + src) * RS_LIST;
+        const long long P = qq == 0 ? (wch == 0 ? a.r1 : a.r1 + 1) : (wch == 0 ? top2 : top2 - 1);
+        const long long t = P - (long long)s_before[qq][wch];                  // position inside the bucket
+        for (int e = lane; e < n; e += 32) {
+          const double x = L[e];
+          int r = 0;
+          for (int j = 0; j < n; ++j) {
+            const double y = L[j];
+            r += ((qq == 0 ? y < x : y > x) || (y == x && j < e)) ? 1 : 0;
+          }
+          if ((long long)r == t) s_val[qq][wch] = x;
+        }
+      }
+    }
+    __syncthreads();
+    if (ok) {
+      // R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]
+      {
+        const double x_lo = s_val[0][0];
+        const double x_hi = need_lo ? s_val[0][1] : x_lo;
+        q_lo = (need_lo && x_hi != x_lo) ? (1.0 - a.h1) * x_lo + a.h1 * x_hi : x_lo;
+      }
+      {
+        const double x_lo = s_val[1][0];
+        const double x_hi = need_hi ? s_val[1][1] : x_lo;
+        q_hi = (need_hi && x_hi != x_lo) ? (1.0 - a.h2) * x_lo + a.h2 * x_hi : x_lo;
+      }
+      done = true;
+    }
   }
-  if (done[0] && done[1]) {
+  if (done) {
     if (tid == 0) {
       const int64_t g = a.g0 + blockIdx.x;
       if (a.mean) a.mean[g] = mean;
-      if (a.lo) a.lo[g] = qv[0];
-      if (a.hi) a.hi[g] = qv[1];
+      if (a.lo) a.lo[g] = q_lo;
+      if (a.hi) a.hi[g] = q_hi;
     }
     return;
   }
 
+  // ---- fallback: exact MSB radix select (8-bit digits) of both order statistics in the same sweeps ---------------
+  // per-warp private histograms fed by warp-aggregated increments (the keys of a row share their leading bytes, a
+  // single shared histogram serialises on one bin), a warp-parallel bin scan, and a start digit chosen from the
+  // highest bit in which the row's keys differ.  The histograms live in the candidate-slot area.
+  __syncthreads();
+  const int64_t rk[2] = {a.r1, a.r2};
+  double qv[2] = {0.0, 0.0};
+  unsigned int (*whist)[NW][256] = reinterpret_cast<unsigned int (*)[NW][256]>(priv);
+  unsigned int (*rhist)[256] = reinterpret_cast<unsigned int (*)[256]>(hist);  // [2][256] (nb >= 256)
+  auto key_at = [&](int64_t i) -> unsigned long long { return dkey(IN_SMEM ? vals[i] : row[i]); };
+  unsigned long long kmin = ~0ull, kmax = 0ull;
+  for (int64_t i = tid; i < M; i += RS_THREADS) {
+    const unsigned long long k = key_at(i);
+    kmin = k < kmin ? k : kmin;
+    kmax = k > kmax ? k : kmax;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long mn = __shfl_xor_sync(0xffffffffu, kmin, o), mx = __shfl_xor_sync(0xffffffffu, kmax, o);
+    kmin = mn < kmin ? mn : kmin;
+    kmax = mx > kmax ? mx : kmax;
+  }
+  if (lane == 0) {
+    s_kmin[warp] = kmin;
+    s_kmax[warp] = kmax;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    kmin = s_kmin[w] < kmin ? s_kmin[w] : kmin;
+    kmax = s_kmax[w] > kmax ? s_kmax[w] : kmax;
+  }
+  __syncthreads();
   // all keys agree above byte `top`: start there
   const unsigned long long diff = kmin ^ kmax;
   const int top = diff ? (63 - __clzll((long long)diff)) / 8 : 0;
@@ -353,7 +512,7 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
       unsigned s = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) s += whist[same ? 0 : q][w][bin];
-      hist[q][bin] = s;
+      rhist[q][bin] = s;
     }
     __syncthreads();
     if (warp < 2) {
@@ -362,7 +521,7 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
       unsigned loc[8], tot = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        loc[j] = hist[q][lane * 8 + j];
+        loc[j] = rhist[q][lane * 8 + j];
         tot += loc[j];
       }
       unsigned inc = tot;
@@ -395,7 +554,6 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
     __syncthreads();
   }
   for (int which = 0; which < 2; ++which) {
-    if (done[which]) continue;
     const int64_t r = rk[which];
     const double h = which == 0 ? a.h1 : a.h2;
     const double x_lo = dunkey(prefix[which]);
@@ -407,13 +565,16 @@ __global__ void __launch_bounds__(RS_THREADS) row_select_kernel(const SelectArgs
         const unsigned long long k = key_at(i);
         if (k > prefix[which] && k < mn) mn = k;
       }
-      s_min[tid] = mn;
-      __syncthreads();
-      for (int o = RS_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o && s_min[tid + o] < s_min[tid]) s_min[tid] = s_min[tid + o];
-        __syncthreads();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mn, o);
+        mn = t < mn ? t : mn;
       }
-      x_hi = dunkey(s_min[0]);
+      if (lane == 0) s_kmin[warp] = mn;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mn = s_kmin[w] < mn ? s_kmin[w] : mn;
+      x_hi = dunkey(mn);
       __syncthreads();
     }
     // R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]
@@ -542,7 +703,8 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   sa.lo = o_lo;
   sa.hi = o_hi;
   // candidate cuts of the fast path: expected tail fraction 1.5 q + 5 sqrt(q / M) (Gaussian-ish rows hold the
-  // wanted ranks with a wide margin), capacity = power of two >= twice the expected count
+  // wanted ranks with a wide margin).  Per-thread slots for the expected hits plus 1.5 sigma (the shared overflow
+  // list takes the rest), value buckets of about 16 / M of a tail each.
   auto norm_inv = [](double pr) {                 // Acklam's rational approximation, |error| < 1.2e-9
     static const double a_[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
                                  1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
@@ -563,29 +725,41 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   };
   const double qt = std::max(q1, 1.0 - q2);
   const double frac = 1.5 * qt + 5.0 * std::sqrt(qt / (double)M);
-  sa.cap = 0;
+  sa.pc = 0;
+  sa.nb = 256;
   sa.z_lo = sa.z_hi = 0.0;
-  size_t cand_bytes = 0;
+  while (sa.nb < 2048 && (int64_t)sa.nb * 16 < M) sa.nb <<= 1;
+  const size_t key_bytes = (size_t)round_up64(M, 2) * sizeof(double);
+  const size_t fixed_bytes = (size_t)RS_OVF * sizeof(double) + (size_t)2 * sa.nb * sizeof(unsigned int) +
+                             (size_t)4 * RS_LIST * sizeof(double);
+  const size_t slot_bytes = (size_t)RS_THREADS * sizeof(double);               // one candidate slot of every thread
+  const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;              // dynamic bytes for 2 / 1 CTAs per SM
+  bool in_smem = key_bytes + fixed_bytes + RS_PC_MIN * slot_bytes <= one_per_sm;
   if (std::min(q1, 1.0 - q2) > 0.0 && frac < 0.45 && M >= 64 && !getenv("BGP_SELECT_RADIX")) {   // env: diagnostics
-    int cap = 64;
-    while ((double)cap < 2.0 * frac * (double)M) cap <<= 1;
-    if (cap <= 8192) {
-      sa.cap = cap;
+    const double e = (double)M / RS_THREADS * 2.0 * frac;                     // expected candidates per thread
+    int want = std::max(RS_PC_MIN, (int)std::ceil(e + 1.5 * std::sqrt(e) + 2.0));
+    // room for the slots: beside the row when that still leaves two CTAs per SM, else within one CTA per SM, else
+    // with the row left in global memory / L2
+    const size_t base = fixed_bytes + (in_smem ? key_bytes : 0);
+    size_t budget = base + (size_t)RS_PC_MIN * slot_bytes <= two_per_sm ? two_per_sm : one_per_sm;
+    if (base + (size_t)want * slot_bytes > budget && (size_t)want * slot_bytes > (budget - base) * 2) {
+      // the slots would mostly overflow: keep the row out of shared memory instead
+      in_smem = false;
+      budget = fixed_bytes + (size_t)want * slot_bytes <= two_per_sm ? two_per_sm : one_per_sm;
+    }
+    const size_t base2 = fixed_bytes + (in_smem ? key_bytes : 0);
+    const int fit = (int)((budget - base2) / slot_bytes);
+    if (fit >= RS_PC_MIN && (double)fit >= e + 2.0) {
+      sa.pc = std::min(want, fit);
       sa.z_lo = norm_inv(frac);
       sa.z_hi = -sa.z_lo;
-      cand_bytes = (size_t)2 * cap * sizeof(unsigned long long);
     }
   }
-  cand_bytes = std::max<size_t>(cand_bytes, (size_t)2 * (RS_THREADS / 32) * 256 * sizeof(unsigned int));   // radix histograms
-  const size_t key_bytes = (size_t)M * sizeof(unsigned long long);
-  const bool in_smem = key_bytes + cand_bytes <= 190 * 1024;
-  const size_t dyn_bytes = (in_smem ? key_bytes : 0) + cand_bytes;
-  if (dyn_bytes > 40 * 1024) {
-    if (in_smem)
-      BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
-    else
-      BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
-  }
+  const size_t dyn_bytes = (in_smem ? key_bytes : 0) + (size_t)std::max(sa.pc, RS_PC_MIN) * slot_bytes + fixed_bytes;
+  if (in_smem)
+    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  else
+    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
   std::vector<cudaEvent_t> evs;
   auto mark = [&]() {
     cudaEvent_t e;
