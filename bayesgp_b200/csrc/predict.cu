@@ -17,6 +17,7 @@
 #include <mutex>
 
 #include "bgp_internal.h"
+#include "ptx.cuh"
 
 namespace bgp {
 
@@ -148,10 +149,19 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-constexpr int RS_THREADS = 256;
+// R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]   (stats::quantile type 7).
+// Spelled with explicit roundings: a contracted FMA would differ from R by one ulp, and differently per call site.
+__device__ __forceinline__ double type7_interp(double h, double x_lo, double x_hi) {
+  return (h != 0.0 && x_hi != x_lo) ? __dadd_rn(__dmul_rn(1.0 - h, x_lo), __dmul_rn(h, x_hi)) : x_lo;
+}
+
 constexpr int RS_LIST = 128;      // keys of one target bucket, ranked by a single warp
 constexpr int RS_OVF = 256;       // shared overflow list behind the per-thread candidate slots
-constexpr int RS_PC_MIN = 8;      // the slot area doubles as the per-warp histograms of the radix path (16 KB)
+constexpr int RS_BATCH = 10;      // 128-bit loads in flight per thread
+constexpr int RS_RH = 8;          // radix path: histogram copies (warps w and w + 8 share one), 16 KB
+constexpr int RS_SLOT_AREA_MIN = 2 * RS_RH * 256 * 4;   // the slot area doubles as those histograms
+constexpr int RS_DBG_POINTS = 8;
+constexpr int RS_PCREG = 16;      // 256-thread CTAs: bucket codes of up to this many private candidates stay in registers
 
 struct SelectArgs {
   const double* F;
@@ -161,27 +171,35 @@ struct SelectArgs {
   double h1, h2;      // interpolation weights (0 => no second order statistic needed)
   double z_lo, z_hi;  // candidate cuts in standard deviations from the row mean (fast path)
   int pc;             // candidate slots per thread (0 => radix path only)
-  int nb;             // value buckets per tail (power of two, multiple of 128)
+  int nb;             // value buckets per tail (power of two, multiple of 256)
   double* mean;
   double* lo;
   double* hi;
+  long long* dbg;     // BGP_SEL_DEBUG: clock64 at RS_DBG_POINTS points of every row of the first strip
+  int64_t rows;       // rows of this strip
+  unsigned int* counter;   // next row to hand out (zeroed before the launch)
 };
 
-// One CTA per row, four steps, each a few instructions per value:
-//   A  stream the row once (128-bit loads, eight in flight per thread): sum, sum of squares, copy to shared memory;
-//   B  every thread re-reads its own values and keeps those beyond mean +- z sigma (about 1.8 x the wanted tail) in
-//      private slots — no ballots or atomics; the rare thread with more hits than slots spills to a shared list;
+// Persistent CTAs (two per SM), rows handed out by an atomic counter.  Per row, four steps, each a few
+// instructions per value:
+//   A  the row arrives in shared memory by one bulk copy (cp.async.bulk + mbarrier) that was started while the
+//      previous row was still being ranked; one pass over it gives the sum and the sum of squares;
+//   B  every thread goes over its own values again and keeps those further than z sigma from the mean (about 1.8 x
+//      the wanted tail) in private slots — one FP64 subtraction and an integer compare per value, no ballots or
+//      atomics; the rare thread with more hits than slots makes a second pass and spills to a shared list;
 //   C  the kept values are counted into nb buckets per tail by distance from the cut (a monotone map, so bucket
 //      order is value order); a scan from the extreme end finds the bucket holding each wanted order statistic and
 //      the exact number of values beyond it;
 //   D  the handful of values of that bucket are collected and ranked by one warp.
 // Every count is exact, so the result is the exact order statistic.  Anything unexpected — cuts that miss the rank
 // (heavy tails, constant rows), NaN / Inf, a crowded bucket, a full overflow list — drops the whole row to the MSB
-// radix select below, which needs no assumption about the values.
-template <bool IN_SMEM>
+// radix select at the end of the loop body, which needs no assumption about the values.
+template <bool IN_SMEM, int RS_THREADS>
 __global__ void __launch_bounds__(RS_THREADS, 2) row_select_kernel(const SelectArgs a) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
-  constexpr int NW = RS_THREADS / 32;
+  constexpr int NW = RS_THREADS / 32, RS_HALF = RS_THREADS / 2;
+  constexpr int RS_PC_MIN = RS_SLOT_AREA_MIN / (RS_THREADS * 8);
+  constexpr int PCREG = RS_THREADS == 256 ? RS_PCREG : 1;                      // candidates cached in registers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t M = a.M;
   const int64_t Mpad = (M + 1) & ~(int64_t)1;
@@ -190,7 +208,9 @@ __global__ void __launch_bounds__(RS_THREADS, 2) row_select_kernel(const SelectA
   double* priv = vals + (IN_SMEM ? Mpad : 0);                                  // [slot][thread]
   double* ovf = priv + (size_t)(pc > RS_PC_MIN ? pc : RS_PC_MIN) * RS_THREADS;
   unsigned int* hist = reinterpret_cast<unsigned int*>(ovf + RS_OVF);          // [2][nb]
-  double* lists = reinterpret_cast<double*>(hist + 2 * nb);                    // [2 tails][2 ranks][RS_LIST]
+  double* lists = reinterpret_cast<double*>(hist);     // [2 tails][2 ranks][RS_LIST]: used once the scan is done with hist
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ long long s_rowix[2];
   __shared__ double s_red[2 * NW];
   __shared__ unsigned long long s_kmin[NW], s_kmax[NW];
   __shared__ unsigned int s_novf, s_wtot[NW], s_n[2], s_lcnt[2][2];
@@ -200,391 +220,506 @@ __global__ void __launch_bounds__(RS_THREADS, 2) row_select_kernel(const SelectA
   __shared__ unsigned long long s_prefix[2];
   __shared__ long long s_below[2];
   __shared__ unsigned int s_eq[2];
-  const double* row = a.F + (size_t)blockIdx.x * a.ldF;
-  const double2* row2 = reinterpret_cast<const double2*>(row);                 // rows are 16-byte aligned (ldF even)
   const int64_t npair = M >> 1;
+  const uint32_t bar = ptx::smem_u32(&s_bar), vals_addr = ptx::smem_u32(vals);
+  const uint32_t row_bytes = (uint32_t)(Mpad * sizeof(double));
 
-  // ---- A: mean (fixed-order tree) and the row into shared memory ----------------------------------------------
-  // (squares are taken about the first value of the row: the variance only places the cuts, but a row whose
-  // spread is tiny against its level must not lose it to cancellation)
-  const double shift = row[0];
-  double sum = 0.0, sumsq = 0.0;
-  for (int64_t p0 = tid; p0 < npair; p0 += 8 * RS_THREADS) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t p = p0 + (int64_t)u * RS_THREADS;
-      v[u] = p < npair ? row2[p] : make_double2(0.0, 0.0);
+  // thread 0: claim the next row and, when rows are staged in shared memory, start its copy
+  auto fetch = [&](int slot, unsigned claimed) {
+    const long long r = (long long)claimed;
+    s_rowix[slot] = r;
+    if (IN_SMEM && r < a.rows) {
+      ptx::mbar_expect_tx(bar, row_bytes);
+      ptx::bulk_load_1d(vals_addr, a.F + (size_t)r * a.ldF, row_bytes, bar);   // 16-byte aligned: ldF is even
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t p = p0 + (int64_t)u * RS_THREADS;
-      if (p < npair) {
-        const double dx = v[u].x - shift, dy = v[u].y - shift;
-        sum += v[u].x;
-        sumsq = fma(dx, dx, sumsq);
-        sum += v[u].y;
-        sumsq = fma(dy, dy, sumsq);
-        if (IN_SMEM) reinterpret_cast<double2*>(vals)[p] = v[u];
-      }
+  };
+  if (tid == 0) {
+    if (IN_SMEM) {
+      ptx::mbar_init(bar, 1);
+      ptx::mbar_fence_init();
     }
-  }
-  if ((M & 1) && tid == 0) {
-    const double v = row[M - 1];
-    sum += v;
-    sumsq = fma(v - shift, v - shift, sumsq);
-    if (IN_SMEM) vals[M - 1] = v;
-  }
-  for (int t = tid; t < 2 * nb; t += RS_THREADS) hist[t] = 0;
-  if (tid < 4) {
-    s_lcnt[tid >> 1][tid & 1] = 0;
-    s_bsel[tid >> 1][tid & 1] = -1;
-  }
-  if (tid == 0) s_novf = 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
-  }
-  if (lane == 0) {
-    s_red[warp] = sum;
-    s_red[NW + warp] = sumsq;
+    fetch(0, atomicAdd(a.counter, 1u));
   }
   __syncthreads();
-  sum = 0.0;
-  sumsq = 0.0;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) {
-    sum += s_red[w];
-    sumsq += s_red[NW + w];
-  }
-  const double mean = sum / (double)M;
-  double q_lo = 0.0, q_hi = 0.0;
-  bool done = false;
+  uint32_t parity = 0;
+  for (int slot = 0;; slot ^= 1) {
+    const long long rix = s_rowix[slot];
+    if (rix >= a.rows) break;
+    const double* row = a.F + (size_t)rix * a.ldF;
+    const double2* row2 = reinterpret_cast<const double2*>(row);
+    bool fetched = false;                          // next row's copy started: `vals` no longer holds this row
+    // the next row is claimed now and used at the hand-over: the atomic's round trip hides behind steps A and B
+    unsigned claimed = 0;
+    if (tid == 0) claimed = atomicAdd(a.counter, 1u);
+    auto stamp = [&](int k) {
+      if (a.dbg && tid == 0) a.dbg[(size_t)rix * RS_DBG_POINTS + k] = clock64();
+    };
+    stamp(0);
 
-  const double sd = sqrt(fmax(sumsq / (double)M - (mean - shift) * (mean - shift), 0.0));
-  if (pc > 0 && sd > 0.0 && isfinite(sd) && isfinite(mean)) {                  // CTA-uniform
-    const double cut_lo = mean + a.z_lo * sd, cut_hi = mean + a.z_hi * sd;
-    const double scale = (double)nb / (3.0 * sd);                              // buckets span three sigma beyond a cut
-    bool ok = true;
-    // ---- B: candidates into private slots -------------------------------------------------------------------
-    int c = 0;
-    auto visit = [&](double v) {
-      if (v < cut_lo || v > cut_hi) {
-        if (c < pc) {
-          priv[c * RS_THREADS + tid] = v;
-        } else {
-          const unsigned pos = atomicAdd(&s_novf, 1u);
-          if (pos < (unsigned)RS_OVF) ovf[pos] = v;
-        }
-        ++c;
-      }
-    };
+    // ---- A: mean (fixed-order tree) and spread -------------------------------------------------------------
+    // (squares are taken about the first value of the row: the variance only places the cuts, but a row whose
+    // spread is tiny against its level must not lose it to cancellation)
+    double sum = 0.0, sumsq = 0.0;
+    double shift;
     if (IN_SMEM) {
-      for (int64_t p = tid; p < npair; p += RS_THREADS) {
-        const double2 v = reinterpret_cast<const double2*>(vals)[p];          // written by this thread in step A
-        visit(v.x);
-        visit(v.y);
+      ptx::mbar_wait(bar, parity);
+      parity ^= 1u;
+      shift = vals[0];
+      const double2* vals2 = reinterpret_cast<const double2*>(vals);
+      double sum1 = 0.0, sumsq1 = 0.0;                   // second chain: the FP64 adds are latency bound otherwise
+      auto acc = [&](const double2 v) {
+        const double dx = v.x - shift, dy = v.y - shift;
+        sum += v.x;
+        sumsq = fma(dx, dx, sumsq);
+        sum1 += v.y;
+        sumsq1 = fma(dy, dy, sumsq1);
+      };
+      int64_t p = tid;
+      for (; p + 3 * RS_THREADS < npair; p += 4 * RS_THREADS) {
+        const double2 v0 = vals2[p], v1 = vals2[p + RS_THREADS], v2 = vals2[p + 2 * RS_THREADS],
+                      v3 = vals2[p + 3 * RS_THREADS];
+        acc(v0);
+        acc(v1);
+        acc(v2);
+        acc(v3);
       }
-      if ((M & 1) && tid == 0) visit(vals[M - 1]);
+      for (; p < npair; p += RS_THREADS) acc(vals2[p]);
+      sum += sum1;
+      sumsq += sumsq1;
+      if ((M & 1) && tid == 0) {
+        const double v = vals[M - 1];
+        sum += v;
+        sumsq = fma(v - shift, v - shift, sumsq);
+      }
     } else {
-      for (int64_t p0 = tid; p0 < npair; p0 += 4 * RS_THREADS) {
-        double2 v[4];
+      shift = row[0];
+      for (int64_t p0 = tid; p0 < npair; p0 += RS_BATCH * RS_THREADS) {
+        double2 v[RS_BATCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RS_BATCH; ++u) {
           const int64_t p = p0 + (int64_t)u * RS_THREADS;
-          v[u] = p < npair ? row2[p] : make_double2(mean, mean);               // the mean is never a candidate
+          v[u] = p < npair ? row2[p] : make_double2(shift, shift);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          visit(v[u].x);
-          visit(v[u].y);
-        }
-      }
-      if ((M & 1) && tid == 0) visit(row[M - 1]);
-    }
-    // ---- C: bucket counts, extreme end first ----------------------------------------------------------------
-    // tail 0 = below cut_lo, tail 1 = above cut_hi; bucket nb - 1 is the far end.  v1 <= v2 implies
-    // bucket(v1) >= bucket(v2) in tail 0 (and the mirror image in tail 1): subtraction, the scaling and the
-    // floor are all monotone, so the buckets partition the candidates in value order.
-    auto bucket_of = [&](double v, int& q) {
-      q = v > cut_hi ? 1 : 0;
-      const double d = q ? v - cut_hi : cut_lo - v;
-      const int b = __double2int_rd(d * scale);                                // saturating; d > 0
-      return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
-    };
-    const int cp = c < pc ? c : pc;
-    for (int j = 0; j < cp; ++j) {
-      int q;
-      const int b = bucket_of(priv[j * RS_THREADS + tid], q);
-      atomicAdd(&hist[q * nb + b], 1u);
-    }
-    __syncthreads();
-    const unsigned novf = s_novf;
-    if (novf > (unsigned)RS_OVF) ok = false;
-    const unsigned novf_c = novf > (unsigned)RS_OVF ? 0u : novf;
-    for (unsigned i = tid; i < novf_c; i += RS_THREADS) {
-      int q;
-      const int b = bucket_of(ovf[i], q);
-      atomicAdd(&hist[q * nb + b], 1u);
-    }
-    __syncthreads();
-    // 128 threads per tail, nb / 128 consecutive buckets each, walking inwards from the far end
-    const int q = tid >> 7, u = tid & 127, w = nb >> 7;
-    const unsigned int* hq = hist + q * nb;
-    const int btop = nb - 1 - u * w;
-    unsigned tot = 0;
-    for (int j = 0; j < w; ++j) tot += hq[btop - j];
-    unsigned inc = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_wtot[warp] = inc;
-    __syncthreads();
-    unsigned base = 0;
-    for (int ww = q * 4; ww < warp; ++ww) base += s_wtot[ww];
-    const long long cum0 = (long long)base + (long long)(inc - tot);         // candidates beyond this thread's buckets
-    if (u == 127) s_n[q] = base + inc;
-    // wanted positions counted from the extreme end: P0 = rank r (x_lo of the interpolation), P1 = rank r + 1
-    const long long top2 = M - 1 - a.r2;
-    const bool need_lo = a.h1 != 0.0, need_hi = a.h2 != 0.0;
-    {
-      const long long P0 = q == 0 ? a.r1 : top2, P1 = q == 0 ? a.r1 + 1 : top2 - 1;
-      const bool need1 = q == 0 ? need_lo : need_hi;
-#pragma unroll
-      for (int wch = 0; wch < 2; ++wch) {
-        if (wch == 1 && !need1) continue;
-        const long long P = wch == 0 ? P0 : P1;
-        if (P >= cum0 && P < cum0 + (long long)tot) {
-          long long cum = cum0;
-          for (int j = 0; j < w; ++j) {
-            const unsigned cnt = hq[btop - j];
-            if (P < cum + (long long)cnt) {
-              s_bsel[q][wch] = btop - j;
-              s_before[q][wch] = (unsigned)cum;
-              break;
-            }
-            cum += cnt;
+        for (int u = 0; u < RS_BATCH; ++u) {
+          const int64_t p = p0 + (int64_t)u * RS_THREADS;
+          if (p < npair) {
+            const double dx = v[u].x - shift, dy = v[u].y - shift;
+            sum += v[u].x;
+            sumsq = fma(dx, dx, sumsq);
+            sum += v[u].y;
+            sumsq = fma(dy, dy, sumsq);
           }
         }
       }
+      if ((M & 1) && tid == 0) {
+        const double v = row[M - 1];
+        sum += v;
+        sumsq = fma(v - shift, v - shift, sumsq);
+      }
+    }
+    for (int t = tid; t < 2 * nb; t += RS_THREADS) hist[t] = 0;
+    if (tid < 4) {
+      s_lcnt[tid >> 1][tid & 1] = 0;
+      s_bsel[tid >> 1][tid & 1] = -1;
+    }
+    if (tid == 0) s_novf = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+    }
+    if (lane == 0) {
+      s_red[warp] = sum;
+      s_red[NW + warp] = sumsq;
     }
     __syncthreads();
-    // the cuts must not have missed a wanted rank
-    if ((need_lo ? a.r1 + 1 : a.r1) >= (long long)s_n[0]) ok = false;
-    if (top2 >= (long long)s_n[1] || (need_hi && top2 < 1)) ok = false;
-    // ---- D: collect the target buckets, rank inside them -------------------------------------------------------
-    const int b00 = s_bsel[0][0], b01 = s_bsel[0][1], b10 = s_bsel[1][0], b11 = s_bsel[1][1];
-    if (ok) {
-      auto collect = [&](double v) {
-        int qq;
-        const int b = bucket_of(v, qq);
-        const int t0 = qq ? b10 : b00, t1 = qq ? b11 : b01;
-        if (b == t0) {
-          const unsigned pos = atomicAdd(&s_lcnt[qq][0], 1u);
-          if (pos < (unsigned)RS_LIST) lists[(qq * 2) * RS_LIST + pos] = v;
-        } else if (b == t1) {
-          const unsigned pos = atomicAdd(&s_lcnt[qq][1], 1u);
-          if (pos < (unsigned)RS_LIST) lists[(qq * 2 + 1) * RS_LIST + pos] = v;
+    sum = 0.0;
+    sumsq = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      sum += s_red[w];
+      sumsq += s_red[NW + w];
+    }
+    const double mean = sum / (double)M;
+    double q_lo = 0.0, q_hi = 0.0;
+    bool done = false;
+    stamp(1);
+
+    const double sd = sqrt(fmax(sumsq / (double)M - (mean - shift) * (mean - shift), 0.0));
+    if (pc > 0 && sd > 0.0 && isfinite(sd) && isfinite(mean)) {                // CTA-uniform
+      // a value is a candidate when the high word of |v - mean| exceeds that of z sd: v -> fl(v - mean) is monotone,
+      // so each tail's candidates are exactly the values beyond some threshold, whatever the rounding
+      const double rad = a.z_hi * sd;
+      const int rad_hi = __double2hiint(rad);
+      const double scale = (double)nb / (3.0 * sd);                            // buckets span three sigma beyond the cut
+      bool ok = true;
+      // ---- B: candidates into private slots ---------------------------------------------------------------
+      auto is_hit = [&](double v) { return (__double2hiint(v - mean) & 0x7fffffff) > rad_hi; };
+      auto for_own = [&](auto&& f) {
+        if (IN_SMEM) {
+          const double2* vals2 = reinterpret_cast<const double2*>(vals);
+          int64_t p = tid;
+          for (; p + 3 * RS_THREADS < npair; p += 4 * RS_THREADS) {            // loads first: four in flight
+            const double2 v0 = vals2[p], v1 = vals2[p + RS_THREADS], v2 = vals2[p + 2 * RS_THREADS],
+                          v3 = vals2[p + 3 * RS_THREADS];
+            f(v0.x);
+            f(v0.y);
+            f(v1.x);
+            f(v1.y);
+            f(v2.x);
+            f(v2.y);
+            f(v3.x);
+            f(v3.y);
+          }
+          for (; p < npair; p += RS_THREADS) {
+            const double2 v = vals2[p];
+            f(v.x);
+            f(v.y);
+          }
+          if ((M & 1) && tid == 0) f(vals[M - 1]);
+        } else {
+          for (int64_t p0 = tid; p0 < npair; p0 += 4 * RS_THREADS) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int64_t p = p0 + (int64_t)u * RS_THREADS;
+              v[u] = p < npair ? row2[p] : make_double2(mean, mean);           // the mean is never a candidate
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              f(v[u].x);
+              f(v[u].y);
+            }
+          }
+          if ((M & 1) && tid == 0) f(row[M - 1]);
         }
       };
-      for (int j = 0; j < cp; ++j) collect(priv[j * RS_THREADS + tid]);
-      for (unsigned i = tid; i < novf_c; i += RS_THREADS) collect(ovf[i]);
-    }
-    __syncthreads();
-    if (ok) {
-      if (s_lcnt[0][0] > (unsigned)RS_LIST || s_lcnt[0][1] > (unsigned)RS_LIST || s_lcnt[1][0] > (unsigned)RS_LIST ||
-          s_lcnt[1][1] > (unsigned)RS_LIST)
-        ok = false;                                                            // crowded bucket
-    }
-    if (ok && warp < 4) {
-      const int qq = warp >> 1, wch = warp & 1;
-      if (wch == 0 || (qq == 0 ? need_lo : need_hi)) {
-        const int bsel0 = qq ? b10 : b00, bsel1 = qq ? b11 : b01;
-        const int src = (wch == 1 && bsel1 == bsel0) ? 0 : wch;
-        const int n = (int)s_lcnt[qq][src];
-        const double* L = lists + (qq * 2 + src) * RS_LIST;
-        const long long P = qq == 0 ? (wch == 0 ? a.r1 : a.r1 + 1) : (wch == 0 ? top2 : top2 - 1);
-        const long long t = P - (long long)s_before[qq][wch];                  // position inside the bucket
-        for (int e = lane; e < n; e += 32) {
-          const double x = L[e];
-          int r = 0;
-          for (int j = 0; j < n; ++j) {
-            const double y = L[j];
-            r += ((qq == 0 ? y < x : y > x) || (y == x && j < e)) ? 1 : 0;
+      // (a predicated store, spelled out: the compiler otherwise branches around every candidate)
+      const uint32_t priv_addr = ptx::smem_u32(priv) + (uint32_t)tid * 8u;
+      int c = 0;
+      for_own([&](double v) {
+        const int hit = is_hit(v) ? 1 : 0;
+        const int keep = (hit != 0 && c < pc) ? 1 : 0;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %2, 0;\n"
+            "@p st.shared.f64 [%0], %1;\n"
+            "}\n" ::"r"(priv_addr + (uint32_t)c * (uint32_t)(RS_THREADS * 8)),
+            "d"(v), "r"(keep)
+            : "memory");
+        c += hit;
+      });
+      if (c > pc) {
+        int k = 0;
+        for_own([&](double v) {
+          k += is_hit(v) ? 1 : 0;
+          if (k > pc && is_hit(v)) {                       // rare: only the excess takes the branch
+            const unsigned pos = atomicAdd(&s_novf, 1u);
+            if (pos < (unsigned)RS_OVF) ovf[pos] = v;
           }
-          if ((long long)r == t) s_val[qq][wch] = x;
+        });
+      }
+      stamp(2);
+      // ---- C: bucket counts, extreme end first -------------------------------------------------------------
+      // tail 0 = below the mean, tail 1 = above; bucket nb - 1 is the far end.  |v1 - mean| <= |v2 - mean| implies
+      // bucket(v1) <= bucket(v2) within a tail: subtraction, scaling and floor are all monotone, so the buckets
+      // partition the candidates of a tail in value order.  code = tail * nb + bucket.
+      auto code_of = [&](double v) {
+        const double d = v - mean;
+        const int q = __double2hiint(d) < 0 ? 0 : 1;
+        const int b = __double2int_rd((fabs(d) - rad) * scale);                // saturating; |d| > rad for a candidate
+        return q * nb + (b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b));
+      };
+      const int cp = c < pc ? c : pc;
+      const bool in_regs = pc <= PCREG;                                        // CTA-uniform
+      int code[PCREG];
+      if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < PCREG; ++j) {
+          const bool act = j < cp;
+          const double v = priv[(act ? j : 0) * RS_THREADS + tid];             // slot 0 of an idle lane: stale, unused
+          const int cd = code_of(v);
+          code[j] = act ? cd : -1;
+          if (act) atomicAdd(&hist[cd], 1u);
+        }
+      } else {
+        for (int j = 0; j < cp; ++j) atomicAdd(&hist[code_of(priv[j * RS_THREADS + tid])], 1u);
+      }
+      __syncthreads();
+      // every thread is past step B: the row buffer is free for the next row
+      if (tid == 0) fetch(slot ^ 1, claimed);
+      fetched = true;
+      const unsigned novf = s_novf;
+      if (novf > (unsigned)RS_OVF) ok = false;
+      const unsigned novf_c = novf > (unsigned)RS_OVF ? 0u : novf;
+      for (unsigned i = tid; i < novf_c; i += RS_THREADS) atomicAdd(&hist[code_of(ovf[i])], 1u);
+      __syncthreads();
+      stamp(3);
+      // half of the threads per tail, nb / RS_HALF consecutive buckets each, walking inwards from the far end
+      const int q = tid / RS_HALF, u = tid % RS_HALF, w = nb / RS_HALF;
+      const unsigned int* hq = hist + q * nb;
+      const int btop = nb - 1 - u * w;
+      unsigned tot = 0;
+      for (int j = 0; j < w; ++j) tot += hq[btop - j];
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_wtot[warp] = inc;
+      __syncthreads();
+      unsigned base = 0;
+      for (int ww = q * (NW / 2); ww < warp; ++ww) base += s_wtot[ww];
+      const long long cum0 = (long long)base + (long long)(inc - tot);       // candidates beyond this thread's buckets
+      if (u == RS_HALF - 1) s_n[q] = base + inc;
+      // wanted positions counted from the extreme end: P0 = rank r (x_lo of the interpolation), P1 = rank r + 1
+      const long long top2 = M - 1 - a.r2;
+      const bool need_lo = a.h1 != 0.0, need_hi = a.h2 != 0.0;
+      {
+        const long long P0 = q == 0 ? a.r1 : top2, P1 = q == 0 ? a.r1 + 1 : top2 - 1;
+        const bool need1 = q == 0 ? need_lo : need_hi;
+#pragma unroll
+        for (int wch = 0; wch < 2; ++wch) {
+          if (wch == 1 && !need1) continue;
+          const long long P = wch == 0 ? P0 : P1;
+          if (P >= cum0 && P < cum0 + (long long)tot) {
+            long long cum = cum0;
+            for (int j = 0; j < w; ++j) {
+              const unsigned cnt = hq[btop - j];
+              if (P < cum + (long long)cnt) {
+                s_bsel[q][wch] = btop - j;
+                s_before[q][wch] = (unsigned)cum;
+                break;
+              }
+              cum += cnt;
+            }
+          }
         }
       }
-    }
-    __syncthreads();
-    if (ok) {
-      // R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]
-      {
-        const double x_lo = s_val[0][0];
-        const double x_hi = need_lo ? s_val[0][1] : x_lo;
-        q_lo = (need_lo && x_hi != x_lo) ? (1.0 - a.h1) * x_lo + a.h1 * x_hi : x_lo;
+      __syncthreads();
+      stamp(4);
+      // the cuts must not have missed a wanted rank
+      if ((need_lo ? a.r1 + 1 : a.r1) >= (long long)s_n[0]) ok = false;
+      if (top2 >= (long long)s_n[1] || (need_hi && top2 < 1)) ok = false;
+      // ---- D: collect the target buckets, rank inside them -----------------------------------------------------
+      const int b00 = s_bsel[0][0], b01 = s_bsel[0][1], b10 = s_bsel[1][0], b11 = s_bsel[1][1];
+      if (ok) {
+        // bucket codes of the four wanted order statistics (-1: not wanted, -2: same bucket as the first of the tail)
+        const int c00 = b00, c01 = b01 < 0 ? -1 : (b01 == b00 ? -2 : b01);
+        const int c10 = nb + b10, c11 = b11 < 0 ? -1 : (b11 == b10 ? -2 : nb + b11);
+        auto collect = [&](int cd, double v) {
+          int l = -1;
+          if (cd == c00) l = 0;
+          else if (cd == c01) l = 1;
+          else if (cd == c10) l = 2;
+          else if (cd == c11) l = 3;
+          if (l >= 0) {
+            const unsigned pos = atomicAdd(&s_lcnt[l >> 1][l & 1], 1u);
+            if (pos < (unsigned)RS_LIST) lists[l * RS_LIST + pos] = v;
+          }
+        };
+        if (in_regs) {
+#pragma unroll
+          for (int j = 0; j < PCREG; ++j)
+            if (code[j] >= 0 && (code[j] == c00 || code[j] == c01 || code[j] == c10 || code[j] == c11))
+              collect(code[j], priv[j * RS_THREADS + tid]);
+        } else {
+          for (int j = 0; j < cp; ++j) {
+            const double v = priv[j * RS_THREADS + tid];
+            collect(code_of(v), v);
+          }
+        }
+        for (unsigned i = tid; i < novf_c; i += RS_THREADS) collect(code_of(ovf[i]), ovf[i]);
       }
-      {
-        const double x_lo = s_val[1][0];
-        const double x_hi = need_hi ? s_val[1][1] : x_lo;
-        q_hi = (need_hi && x_hi != x_lo) ? (1.0 - a.h2) * x_lo + a.h2 * x_hi : x_lo;
+      __syncthreads();
+      stamp(5);
+      if (ok) {
+        if (s_lcnt[0][0] > (unsigned)RS_LIST || s_lcnt[0][1] > (unsigned)RS_LIST || s_lcnt[1][0] > (unsigned)RS_LIST ||
+            s_lcnt[1][1] > (unsigned)RS_LIST)
+          ok = false;                                                          // crowded bucket
       }
-      done = true;
+      if (ok && warp < 4) {
+        const int qq = warp >> 1, wch = warp & 1;
+        if (wch == 0 || (qq == 0 ? need_lo : need_hi)) {
+          const int bsel0 = qq ? b10 : b00, bsel1 = qq ? b11 : b01;
+          const int src = (wch == 1 && bsel1 == bsel0) ? 0 : wch;
+          const int n = (int)s_lcnt[qq][src];
+          const double* L = lists + (qq * 2 + src) * RS_LIST;
+          const long long P = qq == 0 ? (wch == 0 ? a.r1 : a.r1 + 1) : (wch == 0 ? top2 : top2 - 1);
+          const long long t = P - (long long)s_before[qq][wch];                // position inside the bucket
+          for (int e = lane; e < n; e += 32) {
+            const double x = L[e];
+            int r = 0;
+            for (int j = 0; j < n; ++j) {
+              const double y = L[j];
+              r += ((qq == 0 ? y < x : y > x) || (y == x && j < e)) ? 1 : 0;
+            }
+            if ((long long)r == t) s_val[qq][wch] = x;
+          }
+        }
+      }
+      __syncthreads();
+      stamp(6);
+      if (ok) {
+        q_lo = type7_interp(a.h1, s_val[0][0], need_lo ? s_val[0][1] : s_val[0][0]);
+        q_hi = type7_interp(a.h2, s_val[1][0], need_hi ? s_val[1][1] : s_val[1][0]);
+        done = true;
+      }
     }
-  }
-  if (done) {
+    if (!done) {
+      // ---- fallback: exact MSB radix select (8-bit digits) of both order statistics in the same sweeps -------------
+      // per-warp histograms fed by warp-aggregated increments (the keys of a row share their leading bytes, a
+      // single shared histogram serialises on one bin), a warp-parallel bin scan, and a start digit chosen from the
+      // highest bit in which the row's keys differ.  The histograms live in the candidate-slot area; the keys come
+      // from shared memory while it still holds this row, else from global memory / L2.
+      __syncthreads();
+      const bool from_smem = IN_SMEM && !fetched;
+      const int64_t rk[2] = {a.r1, a.r2};
+      double qv[2] = {0.0, 0.0};
+      unsigned int (*whist)[RS_RH][256] = reinterpret_cast<unsigned int (*)[RS_RH][256]>(priv);
+      unsigned int (*rhist)[256] = reinterpret_cast<unsigned int (*)[256]>(hist);  // [2][256] (nb >= 256)
+      auto key_at = [&](int64_t i) -> unsigned long long { return dkey(from_smem ? vals[i] : row[i]); };
+      unsigned long long kmin = ~0ull, kmax = 0ull;
+      for (int64_t i = tid; i < M; i += RS_THREADS) {
+        const unsigned long long k = key_at(i);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long mn = __shfl_xor_sync(0xffffffffu, kmin, o), mx = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = mn < kmin ? mn : kmin;
+        kmax = mx > kmax ? mx : kmax;
+      }
+      if (lane == 0) {
+        s_kmin[warp] = kmin;
+        s_kmax[warp] = kmax;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        kmin = s_kmin[w] < kmin ? s_kmin[w] : kmin;
+        kmax = s_kmax[w] > kmax ? s_kmax[w] : kmax;
+      }
+      __syncthreads();
+      // all keys agree above byte `top`: start there
+      const unsigned long long diff = kmin ^ kmax;
+      const int top = diff ? (63 - __clzll((long long)diff)) / 8 : 0;
+      const unsigned long long hi_mask = top == 7 ? 0ull : (~0ull << (8 * (top + 1)));
+      unsigned long long prefix[2] = {kmin & hi_mask, kmin & hi_mask}, mask = hi_mask;
+      long long below[2] = {0, 0};
+      unsigned int eq[2] = {(unsigned)M, (unsigned)M};
+      for (int pass = top; pass >= 0; --pass) {
+        const int shift_bits = pass * 8;
+        const bool same = prefix[0] == prefix[1];        // both quantiles still in the same bucket: one histogram
+        for (int t = tid; t < 2 * RS_RH * 256; t += RS_THREADS) (&whist[0][0][0])[t] = 0;
+        __syncthreads();
+        for (int64_t i0 = 0; i0 < M; i0 += RS_THREADS) {
+          const int64_t i = i0 + tid;
+          const bool in = i < M;
+          const unsigned long long k = in ? key_at(i) : 0ull;
+          const unsigned digit = (unsigned)(k >> shift_bits) & 255u;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q == 1 && same) break;
+            const bool hit = in && (k & mask) == prefix[q];
+            const unsigned act = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+              const unsigned peers = __match_any_sync(act, digit);
+              if (lane == __ffs(peers) - 1) atomicAdd(&whist[q][warp % RS_RH][digit], (unsigned)__popc(peers));
+            }
+          }
+        }
+        __syncthreads();
+        for (int t = tid; t < 2 * 256; t += RS_THREADS) {
+          const int q = t >> 8, bin = t & 255;
+          unsigned s = 0;
+#pragma unroll
+          for (int w = 0; w < RS_RH; ++w) s += whist[same ? 0 : q][w][bin];
+          rhist[q][bin] = s;
+        }
+        __syncthreads();
+        if (warp < 2) {
+          // warp q finds the bin of rank rk[q]: 8 bins per lane, exclusive scan across lanes
+          const int q = warp;
+          unsigned loc[8], tot = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            loc[j] = rhist[q][lane * 8 + j];
+            tot += loc[j];
+          }
+          unsigned inc = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+          }
+          long long cum = below[q] + (long long)(inc - tot);
+          const bool mine = cum <= rk[q] && rk[q] < cum + (long long)tot;
+          if (mine) {
+            int j = 0;
+            for (; j < 7; ++j) {
+              if (cum + (long long)loc[j] > rk[q]) break;
+              cum += loc[j];
+            }
+            s_below[q] = cum;
+            s_prefix[q] = prefix[q] | ((unsigned long long)(lane * 8 + j) << shift_bits);
+            s_eq[q] = loc[j];
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          below[q] = s_below[q];
+          prefix[q] = s_prefix[q];
+          eq[q] = s_eq[q];
+        }
+        mask |= 0xFFull << shift_bits;
+        __syncthreads();
+      }
+      for (int which = 0; which < 2; ++which) {
+        const int64_t r = rk[which];
+        const double h = which == 0 ? a.h1 : a.h2;
+        const double x_lo = dunkey(prefix[which]);
+        double x_hi = x_lo;
+        if (h != 0.0 && below[which] + (long long)eq[which] <= r + 1) {
+          // next order statistic = smallest key strictly above
+          unsigned long long mn = ~0ull;
+          for (int64_t i = tid; i < M; i += RS_THREADS) {
+            const unsigned long long k = key_at(i);
+            if (k > prefix[which] && k < mn) mn = k;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, mn, o);
+            mn = t < mn ? t : mn;
+          }
+          if (lane == 0) s_kmin[warp] = mn;
+          __syncthreads();
+#pragma unroll
+          for (int w = 0; w < NW; ++w) mn = s_kmin[w] < mn ? s_kmin[w] : mn;
+          x_hi = dunkey(mn);
+          __syncthreads();
+        }
+        qv[which] = type7_interp(h, x_lo, x_hi);
+      }
+      q_lo = qv[0];
+      q_hi = qv[1];
+    }
     if (tid == 0) {
-      const int64_t g = a.g0 + blockIdx.x;
+      const int64_t g = a.g0 + rix;
       if (a.mean) a.mean[g] = mean;
       if (a.lo) a.lo[g] = q_lo;
       if (a.hi) a.hi[g] = q_hi;
     }
-    return;
-  }
-
-  // ---- fallback: exact MSB radix select (8-bit digits) of both order statistics in the same sweeps ---------------
-  // per-warp private histograms fed by warp-aggregated increments (the keys of a row share their leading bytes, a
-  // single shared histogram serialises on one bin), a warp-parallel bin scan, and a start digit chosen from the
-  // highest bit in which the row's keys differ.  The histograms live in the candidate-slot area.
-  __syncthreads();
-  const int64_t rk[2] = {a.r1, a.r2};
-  double qv[2] = {0.0, 0.0};
-  unsigned int (*whist)[NW][256] = reinterpret_cast<unsigned int (*)[NW][256]>(priv);
-  unsigned int (*rhist)[256] = reinterpret_cast<unsigned int (*)[256]>(hist);  // [2][256] (nb >= 256)
-  auto key_at = [&](int64_t i) -> unsigned long long { return dkey(IN_SMEM ? vals[i] : row[i]); };
-  unsigned long long kmin = ~0ull, kmax = 0ull;
-  for (int64_t i = tid; i < M; i += RS_THREADS) {
-    const unsigned long long k = key_at(i);
-    kmin = k < kmin ? k : kmin;
-    kmax = k > kmax ? k : kmax;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long mn = __shfl_xor_sync(0xffffffffu, kmin, o), mx = __shfl_xor_sync(0xffffffffu, kmax, o);
-    kmin = mn < kmin ? mn : kmin;
-    kmax = mx > kmax ? mx : kmax;
-  }
-  if (lane == 0) {
-    s_kmin[warp] = kmin;
-    s_kmax[warp] = kmax;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int w = 0; w < NW; ++w) {
-    kmin = s_kmin[w] < kmin ? s_kmin[w] : kmin;
-    kmax = s_kmax[w] > kmax ? s_kmax[w] : kmax;
-  }
-  __syncthreads();
-  // all keys agree above byte `top`: start there
-  const unsigned long long diff = kmin ^ kmax;
-  const int top = diff ? (63 - __clzll((long long)diff)) / 8 : 0;
-  const unsigned long long hi_mask = top == 7 ? 0ull : (~0ull << (8 * (top + 1)));
-  unsigned long long prefix[2] = {kmin & hi_mask, kmin & hi_mask}, mask = hi_mask;
-  long long below[2] = {0, 0};
-  unsigned int eq[2] = {(unsigned)M, (unsigned)M};
-  for (int pass = top; pass >= 0; --pass) {
-    const int shift = pass * 8;
-    const bool same = prefix[0] == prefix[1];          // both quantiles still in the same bucket: one histogram
-    for (int t = tid; t < 2 * NW * 256; t += RS_THREADS) (&whist[0][0][0])[t] = 0;
+    if (done) stamp(7);
+    // hand-over to the next row: every read of this row's shared state is behind this barrier
     __syncthreads();
-    for (int64_t i0 = 0; i0 < M; i0 += RS_THREADS) {
-      const int64_t i = i0 + tid;
-      const bool in = i < M;
-      const unsigned long long k = in ? key_at(i) : 0ull;
-      const unsigned digit = (unsigned)(k >> shift) & 255u;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 1 && same) break;
-        const bool hit = in && (k & mask) == prefix[q];
-        const unsigned act = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-          const unsigned peers = __match_any_sync(act, digit);
-          if (lane == __ffs(peers) - 1) whist[q][warp][digit] += __popc(peers);
-        }
-      }
-    }
+    if (!fetched && tid == 0) fetch(slot ^ 1, claimed);
     __syncthreads();
-    for (int t = tid; t < 2 * 256; t += RS_THREADS) {
-      const int q = t >> 8, bin = t & 255;
-      unsigned s = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) s += whist[same ? 0 : q][w][bin];
-      rhist[q][bin] = s;
-    }
-    __syncthreads();
-    if (warp < 2) {
-      // warp q finds the bin of rank rk[q]: 8 bins per lane, exclusive scan across lanes
-      const int q = warp;
-      unsigned loc[8], tot = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        loc[j] = rhist[q][lane * 8 + j];
-        tot += loc[j];
-      }
-      unsigned inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      long long cum = below[q] + (long long)(inc - tot);
-      const bool mine = cum <= rk[q] && rk[q] < cum + (long long)tot;
-      if (mine) {
-        int j = 0;
-        for (; j < 7; ++j) {
-          if (cum + (long long)loc[j] > rk[q]) break;
-          cum += loc[j];
-        }
-        s_below[q] = cum;
-        s_prefix[q] = prefix[q] | ((unsigned long long)(lane * 8 + j) << shift);
-        s_eq[q] = loc[j];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      below[q] = s_below[q];
-      prefix[q] = s_prefix[q];
-      eq[q] = s_eq[q];
-    }
-    mask |= 0xFFull << shift;
-    __syncthreads();
-  }
-  for (int which = 0; which < 2; ++which) {
-    const int64_t r = rk[which];
-    const double h = which == 0 ? a.h1 : a.h2;
-    const double x_lo = dunkey(prefix[which]);
-    double x_hi = x_lo;
-    if (h != 0.0 && below[which] + (long long)eq[which] <= r + 1) {
-      // next order statistic = smallest key strictly above
-      unsigned long long mn = ~0ull;
-      for (int64_t i = tid; i < M; i += RS_THREADS) {
-        const unsigned long long k = key_at(i);
-        if (k > prefix[which] && k < mn) mn = k;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mn, o);
-        mn = t < mn ? t : mn;
-      }
-      if (lane == 0) s_kmin[warp] = mn;
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < NW; ++w) mn = s_kmin[w] < mn ? s_kmin[w] : mn;
-      x_hi = dunkey(mn);
-      __syncthreads();
-    }
-    // R: qs <- x[lo]; where (index > lo & x[hi] != qs): qs <- (1 - h) * qs + h * x[hi]
-    qv[which] = (h != 0.0 && x_hi != x_lo) ? (1.0 - h) * x_lo + h * x_hi : x_lo;
-  }
-  if (tid == 0) {
-    const int64_t g = a.g0 + blockIdx.x;
-    if (a.mean) a.mean[g] = mean;
-    if (a.lo) a.lo[g] = qv[0];
-    if (a.hi) a.hi[g] = qv[1];
   }
 }
 
@@ -728,38 +863,77 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   sa.pc = 0;
   sa.nb = 256;
   sa.z_lo = sa.z_hi = 0.0;
-  while (sa.nb < 2048 && (int64_t)sa.nb * 16 < M) sa.nb <<= 1;
+  sa.dbg = nullptr;
+  while (sa.nb < 2048 && (int64_t)sa.nb * 32 < M) sa.nb <<= 1;
+  // CTA width: per-row fixed work (scans, barriers) grows with the thread count, the latency hidden too
+  int threads = M > 16384 ? 512 : 256;
+  if (const char* e = getenv("BGP_SEL_THREADS")) threads = atoi(e) == 512 ? 512 : 256;       // env: diagnostics
   const size_t key_bytes = (size_t)round_up64(M, 2) * sizeof(double);
-  const size_t fixed_bytes = (size_t)RS_OVF * sizeof(double) + (size_t)2 * sa.nb * sizeof(unsigned int) +
-                             (size_t)4 * RS_LIST * sizeof(double);
-  const size_t slot_bytes = (size_t)RS_THREADS * sizeof(double);               // one candidate slot of every thread
+  const size_t fixed_bytes = (size_t)RS_OVF * sizeof(double) +          // overflow list, then bucket counts / rank lists
+                             std::max((size_t)2 * sa.nb * sizeof(unsigned int), (size_t)4 * RS_LIST * sizeof(double));
+  const size_t slot_bytes = (size_t)threads * sizeof(double);                  // one candidate slot of every thread
+  const int pc_min = (int)(RS_SLOT_AREA_MIN / slot_bytes);
   const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;              // dynamic bytes for 2 / 1 CTAs per SM
-  bool in_smem = key_bytes + fixed_bytes + RS_PC_MIN * slot_bytes <= one_per_sm;
+  bool in_smem = key_bytes + fixed_bytes + RS_SLOT_AREA_MIN <= one_per_sm;
   if (std::min(q1, 1.0 - q2) > 0.0 && frac < 0.45 && M >= 64 && !getenv("BGP_SELECT_RADIX")) {   // env: diagnostics
-    const double e = (double)M / RS_THREADS * 2.0 * frac;                     // expected candidates per thread
-    int want = std::max(RS_PC_MIN, (int)std::ceil(e + 1.5 * std::sqrt(e) + 2.0));
-    // room for the slots: beside the row when that still leaves two CTAs per SM, else within one CTA per SM, else
-    // with the row left in global memory / L2
-    const size_t base = fixed_bytes + (in_smem ? key_bytes : 0);
-    size_t budget = base + (size_t)RS_PC_MIN * slot_bytes <= two_per_sm ? two_per_sm : one_per_sm;
-    if (base + (size_t)want * slot_bytes > budget && (size_t)want * slot_bytes > (budget - base) * 2) {
-      // the slots would mostly overflow: keep the row out of shared memory instead
-      in_smem = false;
-      budget = fixed_bytes + (size_t)want * slot_bytes <= two_per_sm ? two_per_sm : one_per_sm;
-    }
-    const size_t base2 = fixed_bytes + (in_smem ? key_bytes : 0);
-    const int fit = (int)((budget - base2) / slot_bytes);
-    if (fit >= RS_PC_MIN && (double)fit >= e + 2.0) {
-      sa.pc = std::min(want, fit);
-      sa.z_lo = norm_inv(frac);
-      sa.z_hi = -sa.z_lo;
+    const double e = (double)M / threads * 2.0 * frac;                        // expected candidates per thread
+    const int want = std::max(pc_min, (int)std::ceil(e + 3.5 * std::sqrt(e) + 1.0));
+    const int least = std::max(pc_min, (int)std::ceil(e + 2.0));
+    // slots that fit beside (row in shared memory?) under a budget
+    auto fit = [&](bool row_in, size_t budget) {
+      const size_t base = fixed_bytes + (row_in ? key_bytes : 0);
+      return base >= budget ? 0 : (int)((budget - base) / slot_bytes);
+    };
+    // preference: row in shared memory at two CTAs per SM, row re-read from L2 at two CTAs per SM, then one CTA per SM
+    const bool row_opts[4] = {true, false, true, false};
+    const size_t budgets[4] = {two_per_sm, two_per_sm, one_per_sm, one_per_sm};
+    for (int o = 0; o < 4; ++o) {
+      if (row_opts[o] && !in_smem) continue;
+      const int f = fit(row_opts[o], budgets[o]);
+      if (f >= least) {
+        in_smem = row_opts[o];
+        sa.pc = std::min(want, f);
+        sa.z_lo = norm_inv(frac);
+        sa.z_hi = -sa.z_lo;
+        break;
+      }
     }
   }
-  const size_t dyn_bytes = (in_smem ? key_bytes : 0) + (size_t)std::max(sa.pc, RS_PC_MIN) * slot_bytes + fixed_bytes;
-  if (in_smem)
-    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
-  else
-    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  const size_t dyn_bytes = (in_smem ? key_bytes : 0) + std::max((size_t)sa.pc * slot_bytes, (size_t)RS_SLOT_AREA_MIN) +
+                           fixed_bytes;
+  DevBuf cntb;
+  BGP_TRY(cntb.alloc(sizeof(unsigned int)));
+  sa.counter = cntb.as<unsigned int>();
+  int n_sm = 0, cur_dev = 0;
+  BGP_CUDA(cudaGetDevice(&cur_dev));
+  BGP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev));
+  // persistent CTAs: as many as are resident at once, rows handed out by the counter
+  auto launch_select = [&](unsigned rows) -> int {
+    sa.rows = rows;
+    BGP_CUDA(cudaMemsetAsync(sa.counter, 0, sizeof(unsigned int), st));
+#define BGP_RS_LAUNCH(IS, T)                                                                                        \
+  do {                                                                                                              \
+    BGP_CUDA(cudaFuncSetAttribute(row_select_kernel<IS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  (int)dyn_bytes));                                                                 \
+    int per_sm = 0;                                                                                                 \
+    BGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_select_kernel<IS, T>, T, dyn_bytes));       \
+    const unsigned grid = std::min<unsigned>(rows, (unsigned)std::max(1, per_sm) * (unsigned)n_sm);                 \
+    row_select_kernel<IS, T><<<grid, T, dyn_bytes, st>>>(sa);                                                       \
+  } while (0)
+    if (in_smem) {
+      if (threads == 512) BGP_RS_LAUNCH(true, 512);
+      else BGP_RS_LAUNCH(true, 256);
+    } else {
+      if (threads == 512) BGP_RS_LAUNCH(false, 512);
+      else BGP_RS_LAUNCH(false, 256);
+    }
+#undef BGP_RS_LAUNCH
+    count_launch();
+    BGP_CUDA(cudaGetLastError());
+    return BGP_OK;
+  };
+  DevBuf dbgb;
+  const bool sel_debug = getenv("BGP_SEL_DEBUG") != nullptr;
   std::vector<cudaEvent_t> evs;
   auto mark = [&]() {
     cudaEvent_t e;
@@ -810,10 +984,32 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
       BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
                            true, nullptr, st));
     sa.g0 = g0;
-    if (in_smem) row_select_kernel<true><<<(unsigned)rows, RS_THREADS, dyn_bytes, st>>>(sa);
-    else row_select_kernel<false><<<(unsigned)rows, RS_THREADS, dyn_bytes, st>>>(sa);
-    count_launch();
-    BGP_CUDA(cudaGetLastError());
+    sa.dbg = nullptr;
+    if (sel_debug && g0 == 0) {
+      BGP_TRY(dbgb.alloc((size_t)rows * RS_DBG_POINTS * sizeof(long long)));
+      BGP_CUDA(cudaMemsetAsync(dbgb.p, 0, (size_t)rows * RS_DBG_POINTS * sizeof(long long), st));
+      sa.dbg = dbgb.as<long long>();
+    }
+    BGP_TRY(launch_select((unsigned)rows));
+    if (sa.dbg) {
+      std::vector<long long> h((size_t)rows * RS_DBG_POINTS);
+      BGP_CUDA(cudaMemcpyAsync(h.data(), dbgb.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+      BGP_CUDA(cudaStreamSynchronize(st));
+      double acc[RS_DBG_POINTS] = {0};
+      int64_t nfast = 0;
+      for (int64_t r = 0; r < rows; ++r) {
+        const long long* t = h.data() + (size_t)r * RS_DBG_POINTS;
+        if (!t[7]) continue;                                     // row went to the radix path
+        ++nfast;
+        for (int k = 1; k < RS_DBG_POINTS; ++k) acc[k] += (double)(t[k] - t[k - 1]);
+      }
+      fprintf(stderr, "[select] M %lld threads %d in_smem %d pc %d nb %d dyn %zu B; %lld of %lld rows on the fast path; "
+              "mean clocks: load+stats %.0f, cuts %.0f, candidates %.0f, buckets %.0f, scan %.0f, collect %.0f, rank %.0f\n",
+              (long long)M, threads, (int)in_smem, sa.pc, sa.nb, dyn_bytes, (long long)nfast, (long long)rows,
+              acc[1] / std::max<int64_t>(nfast, 1), 0.0, acc[2] / std::max<int64_t>(nfast, 1),
+              acc[3] / std::max<int64_t>(nfast, 1), acc[4] / std::max<int64_t>(nfast, 1),
+              acc[5] / std::max<int64_t>(nfast, 1), (acc[6] + acc[7]) / std::max<int64_t>(nfast, 1));
+    }
     mark();
   }
   if (mean) BGP_CUDA(cudaMemcpyAsync(mean, o_mean, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
