@@ -19,6 +19,8 @@
 //   * Per-CTA partials are written out and reduced in a fixed order by finish.cu (bit-reproducible).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "bgp_internal.h"
 #include "ptx.cuh"
 
@@ -54,7 +56,11 @@ constexpr int LK_CONSUMERS = 8;
 // the rows in flight (the per-row chain dot -> shuffle tree -> exp -> A^T r is ~600 clk).
 __host__ __device__ constexpr int lk_groups(int NJ) { return NJ <= 6 ? 2 : 1; }
 __host__ __device__ constexpr int lk_kb(int NJ) { return 8 * lk_groups(NJ); }
-__host__ __device__ constexpr int lk_threads(int NJ) { return 32 * (LK_CONSUMERS * lk_groups(NJ) + 1); }
+// R = observations per consumer warp and stage.  R = 2 (narrow designs): the two dot products are reduced with a
+// transposing butterfly (5 adds instead of 10) and the likelihood terms — the exp / log1p chains — are evaluated
+// once per pair, even lanes for the first observation, odd lanes for the second.
+__host__ __device__ constexpr int lk_rows_per_warp(int NJ) { return NJ <= 6 ? 2 : 1; }
+__host__ __device__ constexpr int lk_threads(int NJ, int R) { return 32 * (lk_kb(NJ) / R + 1); }
 constexpr int LK_SMEM_BUDGET = 200 * 1024;
 __host__ __device__ constexpr int lk_group_bytes(int NJ) { return lk_kb(NJ) * 64 * 8; }   // one {64 columns x KB rows} box
 __host__ __device__ constexpr int lk_stage_bytes(int NJ) { return NJ * lk_group_bytes(NJ) + 4 * lk_kb(NJ) * 8; }   // boxes | y | size | previous eta | pad
@@ -161,27 +167,106 @@ __device__ __forceinline__ void lik_row(const LikArgs& a, const RowCtx& c, uint3
   }
 }
 
+
+// Two observations (stage rows wrow, wrow + 1), one warp: see lk_rows_per_warp.  ll / sumsq / dmax / bad are
+// per-lane accumulators here: lane 0 carries the first observation's terms, lane 1 the second's.
+template <int NJ, int G, bool MASKED>
+__device__ __forceinline__ void lik_row2(const LikArgs& a, const RowCtx& c, uint32_t gm, int group_bytes, int kb,
+                                         double2 (&ga)[NJ], double& ll, double& sumsq, double& dmax, int& bad) {
+  double2 av0[G], av1[G];
+  double r0, r1;
+  const int odd = c.lane & 1;
+  if (a.rvec) {
+    r0 = __ldg(a.rvec + c.row);
+    r1 = c.row + 1 < a.n ? __ldg(a.rvec + c.row + 1) : 0.0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const bool on = !MASKED || ((gm >> j) & 1u);
+      av0[j] = on ? lds128(c.ra + j * group_bytes) : make_double2(0.0, 0.0);
+      av1[j] = on ? lds128(c.ra + 512 + j * group_bytes) : make_double2(0.0, 0.0);
+    }
+  } else {
+    double s0 = 0.0, t0 = 0.0, s1 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (!MASKED || ((gm >> j) & 1u)) {
+        av0[j] = lds128(c.ra + j * group_bytes);
+        av1[j] = lds128(c.ra + 512 + j * group_bytes);
+        const double2 wv = lds128(c.w_base + j * 512 + c.lane * 16);
+        s0 = fma(av0[j].x, wv.x, s0);
+        t0 = fma(av0[j].y, wv.y, t0);
+        s1 = fma(av1[j].x, wv.x, s1);
+        t1 = fma(av1[j].y, wv.y, t1);
+      } else {
+        av0[j] = make_double2(0.0, 0.0);
+        av1[j] = make_double2(0.0, 0.0);
+      }
+    }
+    s0 += t0;
+    s1 += t1;
+    // transposing butterfly: after the first exchange even lanes hold the first observation, odd lanes the second
+    double s = (odd ? s1 : s0) + __shfl_xor_sync(0xffffffffu, odd ? s0 : s1, 1);
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int mine = c.wrow + odd;
+    const bool valid = c.row + odd < a.n;
+    const double yv = lds64(c.aux + mine * 8);
+    const double sz = a.size ? lds64(c.aux + kb * 8 + mine * 8) : 1.0;
+    double ll_t = 0.0, sq_t = 0.0, rr, ww, cc;
+    obs_terms(a.family, a.tau, s, yv, sz, ll_t, sq_t, rr, ww, cc);
+    if (valid) {
+      ll += ll_t;
+      sumsq += sq_t;
+      if (!(isfinite(ww) && isfinite(rr) && isfinite(ll_t))) bad = 1;
+    } else {
+      rr = 0.0;
+    }
+    const double eta_old = lds64(c.aux + 2 * kb * 8 + mine * 8);
+    if (c.lane < 2 && valid) {
+      const double d = fabs(s - eta_old);           // change of the linear predictor since the last pass
+      dmax = d > dmax || !(d == d) ? (d == d ? d : INFINITY) : dmax;
+      a.eta[c.row + odd] = s;
+      a.wobs[c.row + odd] = ww;
+      if (a.c3) a.c3[c.row + odd] = cc;
+    }
+    r0 = __shfl_sync(0xffffffffu, rr, 0);
+    r1 = __shfl_sync(0xffffffffu, rr, 1);
+  }
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    if (!MASKED || ((gm >> j) & 1u)) {
+      ga[j].x = fma(r0, av0[j].x, ga[j].x);
+      ga[j].y = fma(r0, av0[j].y, ga[j].y);
+      ga[j].x = fma(r1, av1[j].x, ga[j].x);
+      ga[j].y = fma(r1, av1[j].y, ga[j].y);
+    }
+  }
+}
+
 // dispatch on the number of leading occupied groups (1 .. NJ); anything else takes the masked body
-template <int NJ, int G>
+template <int NJ, int G, int R>
 __device__ __forceinline__ void lik_row_dispatch(int g, const LikArgs& a, const RowCtx& c, int group_bytes, int kb,
                                                  double2 (&ga)[NJ], double& ll, double& sumsq, double& dmax, int& bad) {
   if constexpr (G >= 1) {
-    if (g == G) lik_row<NJ, G, false>(a, c, 0u, group_bytes, kb, ga, ll, sumsq, dmax, bad);
-    else lik_row_dispatch<NJ, G - 1>(g, a, c, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+    if (g == G) {
+      if constexpr (R == 2) lik_row2<NJ, G, false>(a, c, 0u, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+      else lik_row<NJ, G, false>(a, c, 0u, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+    } else {
+      lik_row_dispatch<NJ, G - 1, R>(g, a, c, group_bytes, kb, ga, ll, sumsq, dmax, bad);
+    }
   }
 }
 
 // smem: [stages][ NJ boxes | y[8] | size[8] ] | W (NJ * 64) | meta[stages] | full[stages] | empty[stages]
-template <int NJ>
-__global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_constant__ CUtensorMap tmA, const LikArgs a) {
+template <int NJ, int R>
+__global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_constant__ CUtensorMap tmA, const LikArgs a) {
   constexpr int STAGES = lk_stages(NJ);
   constexpr int STAGE_BYTES = lk_stage_bytes(NJ);
-  constexpr int NG = lk_groups(NJ);
-  constexpr int NCW = LK_CONSUMERS * NG;       // consumer warps
   constexpr int LK_KB = lk_kb(NJ);
+  constexpr int NCW = LK_KB / R;               // consumer warps
   constexpr int LK_GROUP_BYTES = lk_group_bytes(NJ);
   constexpr int SPC = 64 / LK_KB;              // stages per 64-observation chunk
-  constexpr int LK_THREADS = lk_threads(NJ);
+  constexpr int LK_THREADS = lk_threads(NJ, R);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t w_base = base + STAGES * STAGE_BYTES;
@@ -243,8 +328,8 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
     return;
   }
 
-  // ---- consumers: warp (g, w) handles observation w of the stages of group g -----------------------------
-  const int wrow = warp;                       // observation of the stage this warp owns
+  // ---- consumers: warp w handles observations w * R .. w * R + R - 1 of every stage ----------------------------
+  const int wrow = warp * R;                   // first observation of the stage this warp owns
   double2 ga[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) ga[j] = make_double2(0.0, 0.0);
@@ -268,7 +353,9 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
       c.row = row;
       const int g = 32 - __clz(gm);                       // groups 0 .. g-1 occupied <=> gm == 2^g - 1
       if (NJ <= 8 && gm != 0u && gm == ((1u << g) - 1u))
-        lik_row_dispatch<NJ, (NJ <= 8 ? NJ : 1)>(g, a, c, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
+        lik_row_dispatch<NJ, (NJ <= 8 ? NJ : 1), R>(g, a, c, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
+      else if constexpr (R == 2)
+        lik_row2<NJ, NJ, true>(a, c, gm, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
       else
         lik_row<NJ, NJ, true>(a, c, gm, LK_GROUP_BYTES, LK_KB, ga, ll, sumsq, dmax, bad);
     }
@@ -281,6 +368,12 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
 #pragma unroll
   for (int j = 0; j < NJ; ++j) *reinterpret_cast<double2*>(sg + 64 * j + 2 * lane) = ga[j];
   double* ss = sm_gen + (size_t)NCW * (NJ * 64);
+  if (R == 2) {                                // lane 0: first observations, lane 1: second ones (fixed order)
+    ll += __shfl_sync(0xffffffffu, ll, 1);
+    sumsq += __shfl_sync(0xffffffffu, sumsq, 1);
+    bad |= __shfl_sync(0xffffffffu, bad, 1);
+    dmax = fmax(dmax, __shfl_sync(0xffffffffu, dmax, 1));
+  }
   if (lane == 0) {
     ss[warp * 4 + 0] = ll;
     ss[warp * 4 + 1] = sumsq;
@@ -308,18 +401,26 @@ __global__ void __launch_bounds__(lk_threads(NJ), 1) lik_kernel(const __grid_con
   }
 }
 
-template <int NJ>
-static int launch_lik_t(bgp_model* m, const LikArgs& a) {
+template <int NJ, int R>
+static int launch_lik_tr(bgp_model* m, const LikArgs& a) {
   constexpr int smem = lk_stages(NJ) * lk_stage_bytes(NJ) + NJ * 512 + 16 * lk_stages(NJ) + 256;
   static_assert(lk_stages(NJ) >= 2, "likelihood ring needs at least two stages");
   static_assert(LK_CONSUMERS * lk_groups(NJ) * (NJ * 64 * 8 + 32) <= lk_stages(NJ) * lk_stage_bytes(NJ), "reduction scratch must fit in the ring");
   // per device and cheap: set on every launch (a process may drive models on several devices)
-  BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  BGP_CUDA(cudaFuncSetAttribute(lik_kernel<NJ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const LikPlan* pl = (const LikPlan*)m->lik_plan;
-  lik_kernel<NJ><<<m->lik_blocks, lk_threads(NJ), smem, m->stream>>>(pl->tmA, a);
+  lik_kernel<NJ, R><<<m->lik_blocks, lk_threads(NJ, R), smem, m->stream>>>(pl->tmA, a);
   count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
+}
+template <int NJ>
+static int launch_lik_t(bgp_model* m, const LikArgs& a) {
+  static const bool one_row = getenv("BGP_LIK_R1") != nullptr;      // env: diagnostics (one observation per warp)
+  if constexpr (lk_rows_per_warp(NJ) == 2) {
+    if (!one_row) return launch_lik_tr<NJ, 2>(m, a);
+  }
+  return launch_lik_tr<NJ, 1>(m, a);
 }
 
 int lik_max_lda() { return 1024; }

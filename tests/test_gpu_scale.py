@@ -161,10 +161,13 @@ def test_full_size_batch_equals_single_and_is_deterministic(c3_full):
     assert np.max(np.abs(np.array(singles) - v1) / np.abs(v1)) < 1e-12
     # the gradient of the Laplace objective against a central difference of its values
     g = ff.gr(thetas[1])
-    eps = 1e-4
-    ff.set_factor_reuse(False)       # a difference of values 2e-4 apart needs them to ~1e-11 relative, not 1e-10
+    # five-point stencil: the values (~1e6 in magnitude) carry ~1e-8 of summation noise, so the step has to be wide
+    # (noise / step ~ 1e-5) and the truncation error of a wide step has to be of fourth order
+    eps = 2e-3
+    ff.set_factor_reuse(False)       # a difference of close values needs them to ~1e-11 relative, not 1e-10
     try:
-        fd = (ff.fn(thetas[1] + eps) - ff.fn(thetas[1] - eps)) / (2 * eps)
+        f = {k: ff.fn(thetas[1] + k * eps) for k in (-2, -1, 1, 2)}
     finally:
         ff.set_factor_reuse(True)
+    fd = (f[-2] - 8.0 * f[-1] + 8.0 * f[1] - f[2]) / (12.0 * eps)
     assert abs(g[0] - fd) <= 1e-5 * max(1.0, abs(fd)), (g, fd)
