@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/bgp.h"
@@ -145,8 +146,17 @@ struct bgp_model {
   int lik_blocks = 0;
   double* part_H = nullptr;     // split-K partial tiles
   size_t part_H_bytes = 0;
-  bgp::EvalScalars* sc_dev = nullptr;
-  bgp::EvalScalars* sc_host = nullptr;   // pinned
+  bgp::EvalScalars* sc_dev = nullptr;    // [2]: [1] = snapshot of the scalars of the starting point (speculative Newton)
+  bgp::EvalScalars* sc_host = nullptr;   // pinned, [2]
+  // The first Newton iteration is enqueued without waiting for the scalars of the starting point (a predicted start
+  // is practically never converged or non-finite): one host round trip per evaluation instead of two.
+  bool speculate = true;
+  // batch evaluations: modes / Hessians leave through two pinned slots; the copy into the caller's arrays is
+  // deferred to the moment the next evaluation's kernels are in flight (host_hook runs there, once)
+  double* pin_out[2] = {nullptr, nullptr};
+  size_t pin_out_elems = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  std::function<void()> host_hook;
   double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
   void* syrk_plan = nullptr;    // opaque (syrk.cu)
   void* lik_plan = nullptr;     // opaque (lik.cu)

@@ -454,9 +454,10 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->part_g, (size_t)m->lik_blocks * m->lda * sizeof(double)));
   BGP_TRY(dalloc(&m->part_s, (size_t)m->lik_blocks * 4 * sizeof(double)));
   BGP_TRY(dalloc(&m->red_buf, ((size_t)m->lda + 8) * sizeof(double)));
-  BGP_CUDA(cudaMalloc(&m->sc_dev, sizeof(EvalScalars)));
-  BGP_CUDA(cudaMemset(m->sc_dev, 0, sizeof(EvalScalars)));
-  BGP_CUDA(cudaMallocHost(&m->sc_host, sizeof(EvalScalars)));
+  BGP_CUDA(cudaMalloc(&m->sc_dev, 2 * sizeof(EvalScalars)));
+  BGP_CUDA(cudaMemset(m->sc_dev, 0, 2 * sizeof(EvalScalars)));
+  BGP_CUDA(cudaMallocHost(&m->sc_host, 2 * sizeof(EvalScalars)));
+  if (const char* e = getenv("BGP_NO_SPECULATION")) m->speculate = !(e[0] == '1');   // diagnostics only
   for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
   BGP_TRY(build_row_order(m));
   BGP_TRY(syrk_plan_create(m));
@@ -498,6 +499,10 @@ void bgp_model_destroy(bgp_model* m) {
   if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);
+  for (int i = 0; i < 2; ++i) {
+    if (m->pin_out[i]) cudaFreeHost(m->pin_out[i]);
+    if (m->pin_ev[i]) cudaEventDestroy(m->pin_ev[i]);
+  }
   for (int i = 0; i < 8; ++i)
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);

@@ -8,6 +8,7 @@
 // maxit 100; a step is accepted when the objective is finite and either it or max|g| decreased.
 // One device->host read of 80 bytes of scalars per Newton iteration is the only synchronisation.
 #include <algorithm>
+#include <cstring>
 
 #include "bgp_internal.h"
 
@@ -62,9 +63,28 @@ static inline double tau_of(const bgp_model* m, const double* theta) {
 static int read_scalars(bgp_model* m, EvalScalars* out) {
   BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
   phase_mark(m, PH_OTHER);
+  if (m->host_hook) {                       // deferred host work of the previous evaluation: the GPU is busy now
+    m->host_hook();
+    m->host_hook = nullptr;
+  }
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   phase_harvest(m);
   *out = *m->sc_host;
+  return BGP_OK;
+}
+
+// the scalars of the speculative first iteration: [1] = starting point (snapshot), [0] = Cholesky + trial point
+static int read_scalars2(bgp_model* m, EvalScalars* start, EvalScalars* out) {
+  BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, 2 * sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
+  phase_mark(m, PH_OTHER);
+  if (m->host_hook) {                       // deferred host work of the previous evaluation: the GPU is busy now
+    m->host_hook();
+    m->host_hook = nullptr;
+  }
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  phase_harvest(m);
+  *out = m->sc_host[0];
+  *start = m->sc_host[1];
   return BGP_OK;
 }
 
@@ -85,6 +105,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   // start from the previous mode (TMB last.par.best), moved along the tangent d w_hat / d theta when the
   // step in theta is moderate; fall back to the plain warm start, then to W = 0, if that point is non-finite
   bool predicted = false;
+  double start_dist = INFINITY;          // max-norm distance in theta to the history entry the start came from
   if (m->use_predictor && m->S <= 17) {
     // nearest history entry (max-norm in theta)
     int e1 = -1;
@@ -100,6 +121,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       }
     }
     if (e1 >= 0 && d1 <= 2.0) {
+      start_dist = d1;
       const auto& hb = m->hist[e1];
       // second entry: collinear with (theta, e1), the closest such to e1; theta = theta_b + tau (theta_b - theta_a)
       int e2 = -1;
@@ -164,7 +186,17 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   if (!predicted)
     BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   BGP_TRY(eval_fg_async(m, m->W, theta, false));
-  BGP_TRY(read_scalars(m, &sc));
+  // Speculation: a start predicted from a different theta is practically never converged or non-finite, so the
+  // first Newton iteration is enqueued behind it at once and the starting point's scalars are read together with
+  // the iteration's (one host round trip less; a wrong guess costs one likelihood pass or is redone below).
+  bool spec = m->speculate && predicted && start_dist > 0.0;
+  if (spec) {
+    BGP_CUDA(cudaMemcpyAsync(m->sc_dev + 1, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToDevice, m->stream));
+    sc.nonfinite = 0;
+    sc.f = sc.gmax = NAN;
+  } else {
+    BGP_TRY(read_scalars(m, &sc));
+  }
   if (sc.nonfinite && predicted) {
     BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
     BGP_TRY(eval_fg_async(m, m->W, theta, false));
@@ -185,7 +217,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   bool converged = false, have_factor = false, reused = false;
   double logdet = NAN;
   for (int it = 0; it < m->maxit; ++it) {
-    if (gmax < m->grad_tol) {
+    const bool spec_now = spec && it == 0;
+    if (!spec_now && gmax < m->grad_tol) {
       converged = true;
       break;
     }
@@ -203,7 +236,43 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     // the Cholesky scalars must be captured before the trial evaluation overwrites f / gmax:
     // they live in different fields of EvalScalars, so one read after the trial eval suffices.
     BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
-    BGP_TRY(read_scalars(m, &sc));
+    if (spec_now) {
+      EvalScalars sc0;
+      BGP_TRY(read_scalars2(m, &sc0, &sc));
+      spec = false;
+      if (sc0.nonfinite) {
+        // the predicted start was not finite: what was enqueued behind it is void; redo from the plain warm start
+        BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+        BGP_TRY(eval_fg_async(m, m->W, theta, false));
+        BGP_TRY(read_scalars(m, &sc));
+        if (sc.nonfinite) {
+          BGP_CUDA(cudaMemsetAsync(m->W, 0, (size_t)m->lda * sizeof(double), m->stream));
+          BGP_TRY(eval_fg_async(m, m->W, theta, false));
+          BGP_TRY(read_scalars(m, &sc));
+          if (sc.nonfinite) {
+            set_error("objective is not finite at the starting point");
+            *value = NAN;
+            return BGP_ERR_NONFINITE;
+          }
+        }
+        f = sc.f;
+        gmax = sc.gmax;
+        it = -1;
+        continue;
+      }
+      f = sc0.f;
+      gmax = sc0.gmax;
+      if (gmax < m->grad_tol && sc.chol_info == 0) {
+        // already converged at the start: H, L and logdet were formed there (the trial evaluation was not needed;
+        // eta / wobs on the device are those of W + step, closer to the mode still)
+        converged = true;
+        have_factor = true;
+        logdet = sc.logdet;
+        break;
+      }
+    } else {
+      BGP_TRY(read_scalars(m, &sc));
+    }
     if (sc.chol_info != 0) {
       set_error("Hessian not positive definite (pivot %d) at Newton iteration %d", sc.chol_info, it);
       *value = NAN;
@@ -220,6 +289,10 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       break;
     }
     const double deta_full = sc.pad;      // max |eta(W + step) - eta(W)|: W is where H was formed
+    static const bool newton_debug = getenv("BGP_NEWTON_DEBUG") != nullptr;     // env: diagnostics
+    if (newton_debug)
+      fprintf(stderr, "[newton] it %d  gmax %.3e -> %.3e  max|step| %.3e  max|d eta| %.3e  f %.15g -> %.15g (%.3e)\n", it,
+              gmax, sc.gmax, sc.smax, deta_full, f, sc.f, sc.f - f);
     double t = 1.0;
     bool accepted = false, full_step = true;
     for (int h = 0; h < 40; ++h) {
@@ -402,6 +475,12 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
     return BGP_ERR_ARG;
   }
   int total = 0, worst = BGP_OK;
+  // the deferred copies point into the caller's arrays: none may outlive this call, whichever way it returns
+  struct HookGuard {
+    bgp_model* m;
+    ~HookGuard() { m->host_hook = nullptr; }
+  } hook_guard{m};
+  m->host_hook = nullptr;
   cudaEventRecord(m->ev[0], m->stream);
   // Evaluation order (results go back to the caller's slots): start next to what is already known — the
   // nearest history entry, or the node closest to the centroid when the history is empty (the warm start is
@@ -456,8 +535,41 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
       worst = st;
       continue;
     }
-    if (modes) BGP_TRY(copy_vec_out(m, m->Wmode, modes + (size_t)j * m->p));
-    if (Hs) BGP_TRY(copy_H_out(m, Hs + (size_t)j * m->p * m->p));
+    if (modes || Hs) {
+      // device -> pinned slot now (asynchronous); pinned slot -> caller's arrays while the next evaluation runs
+      const size_t pp = (size_t)m->p * m->p, need = pp + (size_t)m->p;
+      if (m->pin_out_elems < need) {
+        for (int i = 0; i < 2; ++i) {
+          if (m->pin_out[i]) cudaFreeHost(m->pin_out[i]);
+          m->pin_out[i] = nullptr;
+          BGP_CUDA(cudaMallocHost(&m->pin_out[i], need * sizeof(double)));
+          if (!m->pin_ev[i]) BGP_CUDA(cudaEventCreateWithFlags(&m->pin_ev[i], cudaEventDisableTiming));
+        }
+        m->pin_out_elems = need;
+      }
+      if (m->host_hook) {                   // the slot's previous tenant (two evaluations ago at the latest)
+        m->host_hook();
+        m->host_hook = nullptr;
+      }
+      const int slot = oi & 1;
+      double* pin = m->pin_out[slot];
+      if (modes) BGP_TRY(copy_vec_out(m, m->Wmode, pin + pp));
+      if (Hs) BGP_TRY(copy_H_out(m, pin));
+      BGP_CUDA(cudaEventRecord(m->pin_ev[slot], m->stream));
+      double* mode_dst = modes ? modes + (size_t)j * m->p : nullptr;
+      double* H_dst = Hs ? Hs + (size_t)j * pp : nullptr;
+      cudaEvent_t ev = m->pin_ev[slot];
+      const size_t pn = (size_t)m->p;
+      m->host_hook = [pin, pp, pn, mode_dst, H_dst, ev]() {
+        cudaEventSynchronize(ev);
+        if (mode_dst) memcpy(mode_dst, pin + pp, pn * sizeof(double));
+        if (H_dst) memcpy(H_dst, pin, pp * sizeof(double));
+      };
+    }
+  }
+  if (m->host_hook) {
+    m->host_hook();
+    m->host_hook = nullptr;
   }
   cudaEventRecord(m->ev[1], m->stream);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
