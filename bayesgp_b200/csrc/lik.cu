@@ -60,7 +60,9 @@ __host__ __device__ constexpr int lk_kb(int NJ) { return 8 * lk_groups(NJ); }
 // transposing butterfly (5 adds instead of 10) and the likelihood terms — the exp / log1p chains — are evaluated
 // once per pair, even lanes for the first observation, odd lanes for the second.
 __host__ __device__ constexpr int lk_rows_per_warp(int NJ) { return NJ <= 6 ? 2 : 1; }
-__host__ __device__ constexpr int lk_threads(int NJ, int R) { return 32 * (lk_kb(NJ) / R + 1); }
+// With R = 2 the consumer warps form two teams that take alternate stages, so the warp count (and with it the
+// latency the SM can hide) stays what it is with one observation per warp.
+__host__ __device__ constexpr int lk_threads(int NJ, int R) { return 32 * (lk_kb(NJ) + 1) + 0 * R; }
 constexpr int LK_SMEM_BUDGET = 200 * 1024;
 __host__ __device__ constexpr int lk_group_bytes(int NJ) { return lk_kb(NJ) * 64 * 8; }   // one {64 columns x KB rows} box
 __host__ __device__ constexpr int lk_stage_bytes(int NJ) { return NJ * lk_group_bytes(NJ) + 4 * lk_kb(NJ) * 8; }   // boxes | y | size | previous eta | pad
@@ -263,7 +265,8 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
   constexpr int STAGES = lk_stages(NJ);
   constexpr int STAGE_BYTES = lk_stage_bytes(NJ);
   constexpr int LK_KB = lk_kb(NJ);
-  constexpr int NCW = LK_KB / R;               // consumer warps
+  constexpr int TEAM = LK_KB / R;              // warps that share a stage
+  constexpr int NCW = TEAM * R;                // consumer warps: R teams on alternate stages
   constexpr int LK_GROUP_BYTES = lk_group_bytes(NJ);
   constexpr int SPC = 64 / LK_KB;              // stages per 64-observation chunk
   constexpr int LK_THREADS = lk_threads(NJ, R);
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_base + 8 * s, 1);
-      mbar_init(empty_base + 8 * s, NCW);
+      mbar_init(empty_base + 8 * s, TEAM);
     }
     mbar_fence_init();
   }
@@ -328,14 +331,15 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
     return;
   }
 
-  // ---- consumers: warp w handles observations w * R .. w * R + R - 1 of every stage ----------------------------
-  const int wrow = warp * R;                   // first observation of the stage this warp owns
+  // ---- consumers: warp w of team t handles observations w * R .. w * R + R - 1 of stages t, t + R, ... ----------
+  const int team = warp / TEAM;
+  const int wrow = (warp % TEAM) * R;          // first observation of the stage this warp owns
   double2 ga[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) ga[j] = make_double2(0.0, 0.0);
   double ll = 0.0, sumsq = 0.0, dmax = 0.0;
   int bad = 0;
-  for (int64_t it = 0; it < my_stages; ++it) {
+  for (int64_t it = team; it < my_stages; it += R) {
     const int slot = (int)(it % STAGES);
     mbar_wait(full_base + 8 * slot, (uint32_t)((it / STAGES) & 1));
     const int64_t row = (first + (it / SPC) * step) * 64 + (it % SPC) * LK_KB + wrow;

