@@ -293,18 +293,21 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
 
   // 64-observation chunks (SPC stages) are dealt round-robin to the CTAs (cheap early chunks and dense late
   // chunks mix); local stage `it` of a CTA is stage (it % SPC) of its chunk number (it / SPC)
-  const int64_t first = blockIdx.x, step = gridDim.x;
-  const int64_t nchunks = a.nchunks;
-  const int64_t my_chunks = first < nchunks ? (nchunks - first + step - 1) / step : 0;
-  const int64_t my_stages = my_chunks * SPC;
+  // (32-bit counters: chunk numbers and a CTA's stage count are far below 2^31, and 64-bit div / mod by the ring
+  // constants would cost more integer instructions per stage than the likelihood terms)
+  const int first = (int)blockIdx.x, step = (int)gridDim.x;
+  const int nchunks = (int)a.nchunks;
+  const int my_chunks = first < nchunks ? (nchunks - first + step - 1) / step : 0;
+  const int my_stages = my_chunks * SPC;
   if (warp == NCW) {
     if (lane != 0) return;
     unsigned long long o_next = my_chunks > 0 ? __ldg(a.occ + first) : 0ull;
     uint32_t gm = 0;
-    for (int64_t it = 0; it < my_stages; ++it) {
-      const int slot = (int)(it % STAGES);
-      const int64_t chunk = first + (it / SPC) * step;
-      const int64_t row = chunk * 64 + (it % SPC) * LK_KB;
+    int slot = 0;
+    uint32_t par = 1;                         // parity to wait for on the empty barrier of `slot`
+    for (int it = 0; it < my_stages; ++it) {
+      const int chunk = first + (it / SPC) * step;
+      const int64_t row = (int64_t)chunk * 64 + (it % SPC) * LK_KB;
       if ((it % SPC) == 0) {
         const unsigned long long o = o_next;
         if ((it / SPC) + 1 < my_chunks) o_next = __ldg(a.occ + chunk + step);   // prefetch: consumed a chunk later
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
       }
       const uint32_t fb = full_base + 8 * slot;
       const uint32_t sb = base + slot * STAGE_BYTES;
-      mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / STAGES) & 1) ^ 1));
+      mbar_wait(empty_base + 8 * slot, par);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta_base + 8 * slot), "r"(gm) : "memory");
       const bool want_y = a.rvec == nullptr;
       mbar_expect_tx(fb, (uint32_t)__popc(gm) * LK_GROUP_BYTES + (want_y ? 2 * LK_KB * 8 : 0) + (want_y && a.size ? LK_KB * 8 : 0));
@@ -326,6 +329,10 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
         bulk_load_1d(sb + NJ * LK_GROUP_BYTES, a.y + row, LK_KB * 8, fb);
         if (a.size) bulk_load_1d(sb + NJ * LK_GROUP_BYTES + LK_KB * 8, a.size + row, LK_KB * 8, fb);
         bulk_load_1d(sb + NJ * LK_GROUP_BYTES + 2 * LK_KB * 8, a.eta + row, LK_KB * 8, fb);   // previous eta
+      }
+      if (++slot == STAGES) {
+        slot = 0;
+        par ^= 1u;
       }
     }
     return;
@@ -339,10 +346,12 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
   for (int j = 0; j < NJ; ++j) ga[j] = make_double2(0.0, 0.0);
   double ll = 0.0, sumsq = 0.0, dmax = 0.0;
   int bad = 0;
-  for (int64_t it = team; it < my_stages; it += R) {
-    const int slot = (int)(it % STAGES);
-    mbar_wait(full_base + 8 * slot, (uint32_t)((it / STAGES) & 1));
-    const int64_t row = (first + (it / SPC) * step) * 64 + (it % SPC) * LK_KB + wrow;
+  static_assert(R <= STAGES, "a team's first stage must lie in the first lap of the ring");
+  int slot = team;
+  uint32_t par = 0;                           // parity to wait for on the full barrier of `slot`
+  for (int it = team; it < my_stages; it += R) {
+    mbar_wait(full_base + 8 * slot, par);
+    const int64_t row = (int64_t)(first + (it / SPC) * step) * 64 + (it % SPC) * LK_KB + wrow;
     uint32_t gm;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gm) : "r"(meta_base + 8 * slot) : "memory");
     const uint32_t sb = base + slot * STAGE_BYTES;
@@ -365,6 +374,11 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
     }
     __syncwarp();
     if (lane == 0) lk_arrive(empty_base + 8 * slot);
+    slot += R;
+    if (slot >= STAGES) {
+      slot -= STAGES;
+      par ^= 1u;
+    }
   }
   // ---- block reduction in a fixed order (the ring is drained: reuse its memory) -------------------------
   asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
