@@ -71,12 +71,6 @@ class AGHQ:
             self._modes, self._Hs = modes, Hs
         return {"theta": self.normalized_posterior["nodesandweights"]["theta"], "mode": self._modes, "H": self._Hs}
 
-    def theta_moments(self):
-        nw = self.normalized_posterior["nodesandweights"]
-        lam = nw["weights"] * np.exp(nw["logpost_normalized"])
-        mean = lam @ nw["theta"]
-        return mean, np.sqrt(lam @ (nw["theta"] - mean[None, :]) ** 2)
-
     def close(self):
         if self._h:
             self._lib.bgp_fit_destroy(self._h)
@@ -209,6 +203,7 @@ def model_fit(y, terms: List[Term], fixed=None, method="aghq", family="Gaussian"
         raise ValueError("For model with no hyper-parameter, the method cannot be aghq or MCMC.")
     mod = marginal_laplace_tmb(ff, aghq_k, np.zeros(ff.S), optresults)
     res = FitResult(terms, mod, ff, bnd_idx, rand_idx, fix_idx, family)
+    res.control_family = dict(control_family) if control_family else {"u": 1.0, "alpha": 0.5}   # sd.prior of the noise
     if M:
         res.samps = sample_marginal(mod, M, Z, node_idx, seed)
     return res
