@@ -120,21 +120,36 @@ __device__ void tri_solve_inplace(const double* L, const double* dinv, int p, in
 // rsqrt(d) goes to sInv for the substitutions.  Returns 0 or j + 1 for a non-positive pivot in column j.
 template <int NB>
 __device__ __forceinline__ int block_chol(double* sD, double* sL, double* sInv, int tid) {
+  // Two columns per barrier: every thread forms the 2 x 2 pivot block (L_jj, L_j+1,j, L_j+1,j+1) itself, scales its
+  // row's two entries and applies both rank-1 updates to its trailing entries in the order the one-column
+  // algorithm would (same roundings), so 16 barriers instead of 32 sit on the critical path of a panel.
+  static_assert(NB % 2 == 0, "columns are eliminated in pairs");
   constexpr int DP = NB + 1;
   constexpr int Q = CH_THREADS / 32;
   const int i = tid & 31, q = tid >> 5;
   int info = 0;
-  for (int j = 0; j < NB; ++j) {
-    const double d = sD[j * DP + j];
-    if (info == 0 && (!(d > 0.0) || !isfinite(d))) info = j + 1;
-    const double rs = rsqrt(d);
+  for (int j = 0; j < NB; j += 2) {
+    const double d00 = sD[j * DP + j], d10 = sD[(j + 1) * DP + j], d11 = sD[(j + 1) * DP + j + 1];
+    if (info == 0 && (!(d00 > 0.0) || !isfinite(d00))) info = j + 1;
+    const double rs0 = rsqrt(d00);
+    const double l10 = d10 * rs0;
+    const double e11 = fma(-l10, l10, d11);
+    if (info == 0 && (!(e11 > 0.0) || !isfinite(e11))) info = j + 2;
+    const double rs1 = rsqrt(e11);
     if (i < NB && i >= j) {
-      const double lij = sD[i * DP + j] * rs;
+      const double li0 = sD[i * DP + j] * rs0;
+      const double li1 = i > j ? fma(-li0, l10, sD[i * DP + j + 1]) * rs1 : 0.0;
       if (q == 0) {
-        sL[i * DP + j] = lij;
-        if (i == j) sInv[j] = rs;
+        sL[i * DP + j] = li0;
+        if (i > j) sL[i * DP + j + 1] = li1;
+        if (i == j) sInv[j] = rs0;
+        if (i == j + 1) sInv[j + 1] = rs1;
       }
-      for (int c = j + 1 + q; c <= i; c += Q) sD[i * DP + c] = fma(-lij, sD[c * DP + j] * rs, sD[i * DP + c]);
+      for (int c = j + 2 + q; c <= i; c += Q) {
+        const double lc0 = sD[c * DP + j] * rs0;
+        const double lc1 = fma(-lc0, l10, sD[c * DP + j + 1]) * rs1;
+        sD[i * DP + c] = fma(-li1, lc1, fma(-li0, lc0, sD[i * DP + c]));
+      }
     }
     __syncthreads();
   }

@@ -41,8 +41,16 @@ __global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __rest
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double s = 0.0;
-  if (c < lda)
-    for (int b = warp; b < nblocks; b += 8) s += part_g[(size_t)b * lda + c];
+  if (c < lda) {
+    // four loads in flight, added in ascending block order (the order of the sum is what makes it reproducible)
+    for (int b = warp; b < nblocks; b += 32) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = b + 8 * u < nblocks ? part_g[(size_t)(b + 8 * u) * lda + c] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s += v[u];
+    }
+  }
   sm[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && c < lda) {
@@ -51,17 +59,26 @@ __global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __rest
     for (int w = 0; w < 8; ++w) t += sm[w][lane];
     red[c] = t;
   }
-  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 67) {
-    const int k = threadIdx.x - 64;
-    double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += part_s[(size_t)b * 4 + k];
-    red[lda + k] = t;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 67) {
-    double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t = fmax(t, part_s[(size_t)b * 4 + 3]);
-    red[lda + 3] = t;            // max |eta - previous eta| over the local rows; the SUM all-reduce of sharded
-                                 // models turns it into an upper bound of the global maximum
+  if (blockIdx.x == 0 && warp == 2) {
+    // the four scalars: lane l takes blocks l, l + 32, ...; lanes are combined by a fixed shuffle tree
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = lane; b < nblocks; b += 32) {
+      const double4 q = *reinterpret_cast<const double4*>(part_s + (size_t)b * 4);
+      t[0] += q.x;
+      t[1] += q.y;
+      t[2] += q.z;
+      t[3] = fmax(t[3], q.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t[0] += __shfl_xor_sync(0xffffffffu, t[0], o);
+      t[1] += __shfl_xor_sync(0xffffffffu, t[1], o);
+      t[2] += __shfl_xor_sync(0xffffffffu, t[2], o);
+      t[3] = fmax(t[3], __shfl_xor_sync(0xffffffffu, t[3], o));
+    }
+    // [3]: max |eta - previous eta| over the local rows; the SUM all-reduce of sharded models turns it into an
+    // upper bound of the global maximum
+    if (lane < 4) red[lda + lane] = lane == 0 ? t[0] : (lane == 1 ? t[1] : (lane == 2 ? t[2] : t[3]));
   }
 }
 
