@@ -49,8 +49,7 @@ __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, doubl
 
 // x <- (L L^T)^-1 x for the vector held in shared memory (blocked forward / backward substitution,
 // 32-wide diagonal blocks solved by warp 0 from a shared copy, off-diagonal updates by all threads)
-__device__ void tri_solve_inplace(const double* L, const double* dinv, int p, int ldh, double* sv, double* sS,
-                                  double* s_red) {
+__device__ void tri_forward_inplace(const double* L, const double* dinv, int p, int ldh, double* sv, double* sS) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- forward substitution, blocks of 32
   for (int b0 = 0; b0 < p; b0 += 32) {
@@ -79,7 +78,12 @@ __device__ void tri_solve_inplace(const double* L, const double* dinv, int p, in
     }
     __syncthreads();
   }
-  // ---- backward substitution L^T x = y ---------------------------------------------------------------
+}
+
+// ---- backward substitution L^T x = y (y in sv) -------------------------------------------------------
+__device__ void tri_backward_inplace(const double* L, const double* dinv, int p, int ldh, double* sv, double* sS,
+                                     double* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (p + 31) / 32;
   for (int bi = nblk - 1; bi >= 0; --bi) {
     const int b0 = bi * 32;
@@ -110,6 +114,12 @@ __device__ void tri_solve_inplace(const double* L, const double* dinv, int p, in
     }
     __syncthreads();
   }
+}
+
+__device__ void tri_solve_inplace(const double* L, const double* dinv, int p, int ldh, double* sv, double* sS,
+                                  double* s_red) {
+  tri_forward_inplace(L, dinv, p, ldh, sv, sS);
+  tri_backward_inplace(L, dinv, p, ldh, sv, sS, s_red);
 }
 
 // Cholesky of the NB x NB block in shared memory (working copy sD, row i at sD + i * DP, rows >= nb padded with
@@ -248,6 +258,20 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
   unsigned long long t_last = 0;
   if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
 
+  // The forward substitution rides along with the factorisation: this CTA's right-hand side (rank 0: -g for the
+  // Newton step; rank r: tangent r - 1) sits in shared memory, block k is solved against L_kk by an otherwise idle
+  // warp as soon as the diagonal block is factored, and the rest of the vector is updated from the panel while it
+  // is in shared memory for the trailing update.  Same operations in the same order as tri_forward_inplace.
+  const bool has_rhs = rank == 0 ? a.solve != 0 : (rank - 1 < ntan);
+  if (has_rhs) {
+    if (rank == 0) {
+      for (int i = tid; i < p; i += CH_THREADS) sv[i] = -a.g[i];
+    } else {
+      tangent_rhs(ta, rank - 1, sv);
+    }
+  }
+  __syncthreads();
+
   for (int k0 = 0; k0 < p; k0 += NB) {
     const int nb = (p - k0) < NB ? (p - k0) : NB;
     const int m = p - k0 - nb;
@@ -277,6 +301,17 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
     }
     CH_MARK(1);
     if (s_info != 0) break;        // same decision in every CTA of the cluster
+    if (has_rhs && warp == CH_THREADS / 32 - 1) {
+      // y_k = L_kk^-1 b_k (the last warp has no share in the panel solve or the trailing tiles at these sizes)
+      double yv = lane < nb ? sv[k0 + lane] : 0.0;
+      const double di = lane < nb ? s_inv[lane] : 0.0;
+      for (int j = 0; j < nb; ++j) {
+        const double yj = __shfl_sync(0xffffffffu, yv, j) * __shfl_sync(0xffffffffu, di, j);
+        if (lane == j) yv = yj;
+        else if (lane > j) yv = fma(-yj, sD[lane * DP + j], yv);
+      }
+      if (lane < nb) sv[k0 + lane] = yv;
+    }
     if (m <= 0) break;
     // ---- 2. panel solve: row r of L[k0+nb.., k0..k0+NB) <- row * L_kk^-T ; 32-row blocks round-robin ---
     const int mpad = (m + 31) & ~31;
@@ -308,6 +343,15 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
       sP[(size_t)r * PP + c] = (r < m && c < nb) ? __ldcg(L + (size_t)(k0 + c) * ldh + k0 + nb + r) : 0.0;
     }
     __syncthreads();
+    if (has_rhs) {
+      // b_trail -= L_trail,k y_k from the panel in shared memory (y_k was written before the barriers above)
+      for (int i = tid; i < m; i += CH_THREADS) {
+        double sacc = sv[k0 + nb + i];
+#pragma unroll 8
+        for (int c = 0; c < nb; ++c) sacc = fma(-sP[(size_t)i * PP + c], sv[k0 + c], sacc);
+        sv[k0 + nb + i] = sacc;
+      }
+    }
     CH_MARK(4);
     // ---- 4. trailing update on the FP64 tensor pipe, tiles round-robin over (CTA, warp) ---------------
     const int ntd = mpad / 32;
@@ -377,9 +421,8 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
   // d w_hat / d theta_k each (warm-start predictor), solved at the same time on their own SMs
   if (rank != 0) {
     if (rank - 1 < ntan && s_info == 0) {
-      tangent_rhs(ta, rank - 1, sv);
       __syncthreads();
-      tri_solve_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
+      tri_backward_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
       for (int i = tid; i < ta.lda; i += CH_THREADS) ta.T[(size_t)(rank - 1) * ta.lda + i] = i < p ? -sv[i] : 0.0;
     }
     return;
@@ -411,9 +454,8 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
   }
   CH_MARK(7);
   if (!a.solve) return;
-  for (int i = tid; i < p; i += CH_THREADS) sv[i] = -a.g[i];
   __syncthreads();
-  tri_solve_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
+  tri_backward_inplace(L, a.dinv, p, ldh, sv, sS, s_red);
   double mx = 0.0;
   for (int i = tid; i < p; i += CH_THREADS) {
     const double x = sv[i];
