@@ -6,16 +6,18 @@
 // and the first-order AD sweep TMB runs on them: r = d ll/d eta, w = -d2 ll/d eta2,
 // c3 = d w/d eta, g_lik = A^T r.
 //
-// Design (sm_100a): one persistent CTA per SM, 1 producer warp + 8 consumer warps.
+// Design (sm_100a): one persistent CTA per SM, 1 producer warp + 8 or 16 consumer warps.
 //   * A is observation-major (n x lda).  The producer streams it through a shared-memory ring with TMA:
 //     a stage is 8 or 16 observations, copied as {64 columns x rows} boxes (512-byte lines, no swizzle) plus
 //     the responses; up to ~160 KB per SM are in flight, which is what it takes to keep HBM3e busy.
 //   * Column groups whose {64-observation chunk x 16-column box} cells are all structurally zero
 //     (occupancy map of rowsort.cu) are neither copied nor multiplied: after the zero-pattern sort an
 //     O-spline design moves ~60 % of its bytes.
-//   * Consumer warp w owns observation w of every stage: lanes read the row as 16-byte words
-//     (conflict-free), reduce eta with warp shuffles, evaluate the likelihood terms, and accumulate
-//     their share of A^T r in registers.  A is read from HBM exactly once per evaluation.
+//   * Narrow designs (p <= 384): a consumer warp owns two observations of a stage — lanes read the rows as
+//     16-byte words (conflict-free), the two dot products are reduced with one transposing butterfly, the
+//     likelihood terms are evaluated once per pair (even lanes: first observation, odd lanes: second), and the
+//     warp accumulates its share of A^T r in registers; the 16 warps form two teams on alternate stages.
+//     Wider designs: one observation per warp.  A is read from HBM exactly once per evaluation.
 //   * Per-CTA partials are written out and reduced in a fixed order by finish.cu (bit-reproducible).
 #include <cuda.h>
 
