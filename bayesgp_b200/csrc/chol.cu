@@ -88,14 +88,30 @@ __device__ void tri_backward_inplace(const double* L, const double* dinv, int p,
   for (int bi = nblk - 1; bi >= 0; --bi) {
     const int b0 = bi * 32;
     const int bn = (p - b0) < 32 ? (p - b0) : 32;
-    // y_block[c] -= sum_{i >= b0+bn} L[i][b0+c] x[i]   (warp c owns column c)
-    for (int c = warp; c < bn; c += CH_THREADS / 32) {
-      const double* col = L + (size_t)(b0 + c) * ldh;
-      double s = 0.0;
-      for (int i = b0 + bn + lane; i < p; i += 32) s = fma(__ldcg(col + i), sv[i], s);
+    // y_block[c] -= sum_{i >= b0+bn} L[i][b0+c] x[i]   (warp w owns columns w, w + 8, w + 16, w + 24; the four
+    // dot products advance together so their loads and shuffle trees overlap, each in its own order)
+    {
+      constexpr int NWARP = CH_THREADS / 32;
+      static_assert(4 * NWARP >= 32, "four columns per warp cover a 32-wide block");
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = b0 + bn + lane; i < p; i += 32) {
+        const double xv = sv[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) s_red[c] = s;
+        for (int u = 0; u < 4; ++u) {
+          const int c = warp + NWARP * u;
+          if (c < bn) s[u] = fma(__ldcg(L + (size_t)(b0 + c) * ldh + i), xv, s[u]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (warp + NWARP * u < bn) s_red[warp + NWARP * u] = s[u];
+      }
     }
     for (int t = tid; t < 1024; t += CH_THREADS) {
       const int i = t & 31, c = t >> 5;

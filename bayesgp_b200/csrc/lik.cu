@@ -13,7 +13,7 @@
 //   * Column groups whose {64-observation chunk x 16-column box} cells are all structurally zero
 //     (occupancy map of rowsort.cu) are neither copied nor multiplied: after the zero-pattern sort an
 //     O-spline design moves ~60 % of its bytes.
-//   * Narrow designs (p <= 384): a consumer warp owns two observations of a stage — lanes read the rows as
+//   * Designs up to 512 columns: a consumer warp owns two observations of a stage — lanes read the rows as
 //     16-byte words (conflict-free), the two dot products are reduced with one transposing butterfly, the
 //     likelihood terms are evaluated once per pair (even lanes: first observation, odd lanes: second), and the
 //     warp accumulates its share of A^T r in registers; the 16 warps form two teams on alternate stages.
@@ -61,7 +61,7 @@ __host__ __device__ constexpr int lk_kb(int NJ) { return 8 * lk_groups(NJ); }
 // R = observations per consumer warp and stage.  R = 2 (narrow designs): the two dot products are reduced with a
 // transposing butterfly (5 adds instead of 10) and the likelihood terms — the exp / log1p chains — are evaluated
 // once per pair, even lanes for the first observation, odd lanes for the second.
-__host__ __device__ constexpr int lk_rows_per_warp(int NJ) { return NJ <= 6 ? 2 : 1; }
+__host__ __device__ constexpr int lk_rows_per_warp(int NJ) { return NJ <= 8 ? 2 : 1; }
 // With R = 2 the consumer warps form two teams that take alternate stages, so the warp count (and with it the
 // latency the SM can hide) stays what it is with one observation per warp.
 __host__ __device__ constexpr int lk_threads(int NJ, int R) { return 32 * (lk_kb(NJ) + 1) + 0 * R; }

@@ -56,6 +56,16 @@ def test_mixed_sign_knots_and_fixed_effects():
     _compare(model, [np.array([0.0]), np.array([-1.5])])
 
 
+@pytest.mark.parametrize("k", [400, 470])
+def test_designs_of_seven_and_eight_column_groups(k):
+    """384 < p <= 512: the likelihood pass with two observations per warp on 8-observation stages (ring depths 6
+    and 5, the odd one included), the Hessian and Cholesky at panel counts that are not a power of two."""
+    from helpers import synth_poisson
+    model = synth_poisson(n=15001, k=k, order=3, seed=77 + k)[0]
+    assert (model.p + 63) // 64 in (7, 8)
+    _compare(model, [np.array([-4.0]), np.array([-4.6])])
+
+
 def test_iid_term_and_default_binomial_size():
     from oracle.fit import Term, build_model
     rng = np.random.default_rng(13)
