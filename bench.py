@@ -31,10 +31,11 @@ sys.path.insert(0, ROOT)
 
 K_NODES = 15
 # DRAM bytes (read + write) of one syrk_kernel launch on C3, from the committed `ncu --set full` capture
-# (profiles/r01_ncu_full_metrics.txt: dram__bytes_read.sum 3.983 GB + dram__bytes_write.sum 85 MB); the
+# (profiles/r01_ncu_full_metrics.txt, launch id 3: dram__bytes_read.sum 3.766 GB + dram__bytes_write.sum 63 MB;
+# launch id 7 of the same report: 3.672 GB + 63 MB); the
 # algorithmic minimum is one pass over the occupied boxes of A (1.5 GB) — units of different tiles re-read
 # the observations they share, L2 serves a third of those reads.
-SYRK_DRAM_TRAFFIC_BYTES = 4.068e9
+SYRK_DRAM_TRAFFIC_BYTES = 3.829e9
 # centre / scale of the C3 theta grid (seed 20243, n = 1e6), located by the b200 arm's untimed golden-section
 # search (bench.py prints them as config.theta_mode / theta_sd); used by the CPU arm to skip that search.
 C3_THETA_MODE, C3_THETA_SD = -10.5, 0.1
