@@ -69,3 +69,20 @@ def test_frozen_oracle_outputs(covid_fit):
     assert np.allclose(z["theta_mode"], covid_fit.mod.mode, rtol=0, atol=1e-9)
     assert abs(float(z["lognormconst"]) - covid_fit.mod.lognormconst) < 1e-7
     assert np.allclose(z["modes"], covid_fit.mod.modes, rtol=1e-7, atol=1e-9)
+
+
+def test_fixed_effect_quartiles_within_monte_carlo_error(readme, covid_fit):
+    """The fixed-effect table of summary.FitResult (README.md:88-96: 1st Qu., Median, 3rd Qu.): sample quartiles
+    of 3000 draws, so agreement is up to the Monte-Carlo error of a sample quantile,
+    se = sqrt(q (1 - q) / M) / density."""
+    from oracle.fit import sample_fixed_effect
+    from oracle.summary import fixed_effect_summary
+    names = list(readme["fixed_quartiles"])
+    tab = fixed_effect_summary(sample_fixed_effect(covid_fit, names).T)
+    for j, nm in enumerate(names):
+        g, sd = readme["fixed_quartiles"][nm], readme["fixed"][nm]["sd"]
+        se_q = np.sqrt(0.25 * 0.75 / readme["M"]) / (0.3178 / sd)
+        se_m = np.sqrt(0.25 / readme["M"]) / (0.3989 / sd)
+        assert abs(tab["1st Qu."][j] - g["q1"]) < 6 * se_q * np.sqrt(2), nm
+        assert abs(tab["3rd Qu."][j] - g["q3"]) < 6 * se_q * np.sqrt(2), nm
+        assert abs(tab["Median"][j] - g["median"]) < 6 * se_m * np.sqrt(2), nm
