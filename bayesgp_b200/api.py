@@ -48,6 +48,16 @@ class AGHQ:
             self.marginals.append({"theta": th, "logmargpost": lm, "w": ww})
         self._modes = None
         self._Hs = None
+        fb, it, t_opt, t_grid = C.c_int(), C.c_int64(), C.c_double(), C.c_double()
+        check(self._lib.bgp_fit_get_diagnostics(self._h, C.byref(fb), C.byref(it), C.byref(t_opt), C.byref(t_grid)))
+        # hessian_fallback > 0: the Richardson Hessian needed larger steps than numDeriv's default (opt-in retry;
+        # the reference would have stopped in chol())
+        self.optresults["hessian_fallback"] = fb.value
+        self.diagnostics = {"hessian_fallback": fb.value, "grid_newton_iters": it.value, "opt_ms": t_opt.value,
+                            "grid_ms": t_grid.value}
+        owner = np.empty(self.K, dtype=np.int32)
+        check(self._lib.bgp_fit_node_owner(self._h, owner.ctypes.data_as(_lib.c_int32_p)))
+        self.node_owner = owner
 
     @property
     def lognormconst(self):
@@ -110,7 +120,10 @@ def sample_marginal(quad: AGHQ, M: int, Z=None, node_idx=None, seed: int = 0):
         idx = np.empty(M, dtype=np.int32)
         check(lib.bgp_sample_draw(quad._h, M, int(seed), dptr(samps), idx.ctypes.data_as(_lib.c_int32_p)))
     theta = quad.normalized_posterior["nodesandweights"]["theta"][idx]
-    return {"samps": samps, "theta": theta, "node": idx}
+    # "resident": the same p x M matrix is still on the device behind `quad` (predict reads it in place) until the
+    # next sample_marginal call on that object replaces it
+    quad._resident_token = token = object()
+    return {"samps": samps, "theta": theta, "node": idx, "resident": (quad, token)}
 
 
 class FitResult:
@@ -133,12 +146,26 @@ class FitResult:
 
 
 def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]] = None, family="Gaussian", size=None,
-                    control_family=None, control_fixed=None, device=0, shard=None):
+                    control_family=None, control_fixed=None, device=0, shard=None, node_group=None):
     """get_result_by_method up to MakeADFun (R/02_model_fit.R:1-183,249-282): returns (ff, index maps).
     ``shard = (rank, world, nccl_unique_id)``: y / x / fixed are this rank's rows of an observation-sharded
-    problem (terms must then carry the GLOBAL knots and initial_location)."""
+    problem; the terms must then carry the GLOBAL knots / initial_location (IWP) or region / initial_location (sGP):
+    defaults taken from the local rows would give every rank a different basis.
+    ``node_group = (rank, world, nccl_unique_id)``: ranks holding the same rows split quadrature nodes, sample blocks
+    and prediction rows (bgp_model_set_node_group)."""
     if family not in FAMILY_CODES:
         raise ValueError("family %r is outside the B200 hot path (Gaussian / Poisson / Binomial / none)" % family)
+    if shard is not None and shard[1] > 1:
+        for t in terms:
+            if t.kind == "IWP" and (t.knots is None or t.initial_location is None):
+                raise ValueError("observation-sharded model: IWP term %r needs explicit global knots and "
+                                 "initial_location" % t.name)
+            if t.kind == "sGP" and (t.region is None or t.initial_location is None):
+                raise ValueError("observation-sharded model: sGP term %r needs an explicit global region and "
+                                 "initial_location" % t.name)
+            if t.kind == "IID":
+                raise ValueError("observation-sharded model: IID term %r needs the global level set; build its "
+                                 "design with add_random" % t.name)
     fixed = fixed or {}
     control_fixed = dict(control_fixed or {})
     control_family = control_family or {"u": 1.0, "alpha": 0.5}
@@ -169,6 +196,8 @@ def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]]
             ff.set_noise_prior(control_family.get("u", 1.0), control_family.get("alpha", 0.5))
         if shard is not None:
             ff.set_shard(*shard)
+        if node_group is not None:
+            ff.set_node_group(*node_group)
         ff.finalize()
     except Exception:
         ff.close()
@@ -192,12 +221,12 @@ def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]]
 
 def model_fit(y, terms: List[Term], fixed=None, method="aghq", family="Gaussian", control_family=None,
               control_fixed=None, aghq_k=4, size=None, M=3000, device=0, Z=None, node_idx=None, seed=0,
-              optresults=None) -> FitResult:
+              optresults=None, shard=None, node_group=None) -> FitResult:
     """model_fit(formula, data, method = "aghq", family, ..., aghq_k = 4, M = 3000)."""
     if method != "aghq":
         raise ValueError("only method = 'aghq' is on the B200 hot path (nlminb / MCMC stay in R)")
     ff, terms, rand_idx, bnd_idx, fix_idx = build_objective(y, terms, fixed, family, size, control_family,
-                                                            control_fixed, device)
+                                                            control_fixed, device, shard, node_group)
     if ff.S == 0:
         ff.close()
         raise ValueError("For model with no hyper-parameter, the method cannot be aghq or MCMC.")
@@ -265,6 +294,33 @@ def compute_post_fun_sGP(samps, global_samps=None, k=None, refined_x=None, a=Non
     return out
 
 
+def _predict_resident(object: FitResult, term, variable, refined_x, degree, include_intercept, level):
+    """compute_post_fun_IWP / compute_post_fun_sGP + extract_mean_interval_given_samps on the device-resident
+    samples (bgp_fit_predict_*): same rows of samps$samps as the host path selects (R/03_post_fit.R:65-76)."""
+    lib = _lib.load()
+    x = fvec(refined_x)
+    G = len(x)
+    mean, lo, hi = np.empty(G), np.empty(G), np.empty(G)
+    r0 = int(object.random_samp_indexes[variable][0])
+    bidx = object.boundary_samp_indexes.get(variable)
+    g0 = int(bidx[0]) if bidx is not None and len(bidx) else -1
+    i0 = int(object.fixed_samp_indexes["intercept"]) if include_intercept else -1
+    h = object.mod._h
+    if term.kind == "IWP":
+        if term.order <= degree:
+            print("Error: The degree of derivative to compute is not defined. Should consider higher order smoothing "
+                  "model or lower order of the derivative degree.")
+            return None
+        kn = fvec(term.knots)
+        check(lib.bgp_fit_predict_iwp(h, r0, g0, i0, dptr(kn), len(kn), int(term.order), int(degree), dptr(x), G,
+                                      float(level), dptr(mean), dptr(lo), dptr(hi)))
+    else:
+        reg = fvec(term.region)
+        check(lib.bgp_fit_predict_sgp(h, r0, g0, i0, float(term.a), int(term.k), int(term.m), dptr(reg),
+                                      int(term.boundary), dptr(x), G, float(level), dptr(mean), dptr(lo), dptr(hi)))
+    return {"x": x, "plower": lo, "pupper": hi, "mean": mean}
+
+
 def predict(object: FitResult, newdata=None, variable=None, degree=0, include_intercept=True, only_samples=False,
             level=0.95):
     """predict.FitResult(object, newdata, variable, degree, include.intercept, only.samples)."""
@@ -283,6 +339,15 @@ def predict(object: FitResult, newdata=None, variable=None, degree=0, include_in
         refined_x = np.sort(np.asarray(newdata, dtype=np.float64) - term.initial_location)
     intercept = samps[object.fixed_samp_indexes["intercept"], :] if include_intercept else None
     dev = object.ff.device
+    quad, token = object.samps.get("resident") or (None, None)
+    if (not only_samples and quad is not None and quad is object.mod and quad._h and term.kind in ("IWP", "sGP")
+            and getattr(quad, "_resident_token", None) is token):
+        # the samples are still on the device behind the fit: no p x M host copy, grid rows split over the node group
+        f = _predict_resident(object, term, variable, refined_x, degree, include_intercept, level)
+        if f is None:
+            return None
+        f["x"] = f["x"] + term.initial_location
+        return f
     if term.kind == "IWP":
         f = compute_post_fun_IWP(coefsamps, global_samps, term.knots, refined_x, term.order, degree, intercept, level,
                                  only_samples, dev)

@@ -180,7 +180,13 @@ struct bgp_model {
   int rank = 0, world = 1;
   int64_t n_total = 0;
   bgp::Comm* comm = nullptr;
-  double* red_buf = nullptr;    // packed [H | g | scalars] for the allreduce
+  double* red_buf = nullptr;    // [g_lik | ll | sumsq | flag | max d eta] for the all-reduce after a likelihood pass
+  double* hpack = nullptr;      // packed lower triangle of the likelihood Hessian for its all-reduce
+  // node group (bgp_model_set_node_group): ranks that hold the same rows and split quadrature nodes, sample blocks
+  // and prediction rows between them; independent of the observation shards (a 2-D layout is allowed)
+  int node_rank = 0, node_world = 1;
+  bgp::Comm* node_comm = nullptr;
+  bool hessian_retry = false;   // Richardson retry with larger steps when the theta Hessian is not PD (fit.cu)
   // ---- timing ----------------------------------------------------------------------------------
   cudaEvent_t ev[8] = {nullptr};
   double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0;
@@ -199,8 +205,15 @@ struct bgp_fit {
   std::vector<double> nodes;           // K x S column-major
   std::vector<double> weights, logpost, logpost_norm;
   double lognormconst = 0.0;
-  std::vector<double> modes;           // p x K
-  std::vector<double> Hs;              // p x p x K
+  // Per-node modes and Hessians (modesandhessians) stay on the device, internal column order, on the node-group
+  // rank that evaluated the node: sampling reads them in place; bgp_fit_get_modes rotates and gathers on request.
+  std::vector<int> owner;              // K: node-group rank holding node j
+  std::vector<int> slot;               // K: slot of node j in modes_dev / Hs_dev on its owner, -1 elsewhere
+  int n_local = 0;
+  double* modes_dev = nullptr;         // n_local x lda
+  double* Hs_dev = nullptr;            // n_local x (p x ldh)
+  int64_t grid_newton_iters = 0;       // inner Newton iterations spent on the quadrature grids (this rank)
+  double grid_ms = 0.0, opt_ms = 0.0;  // wall clock of the grid phase / the BFGS + Richardson phase
   std::vector<std::vector<double>> marg_theta, marg_lmp, marg_w;
   // device residents for sampling / prediction (sample.cu)
   double* samps_dev = nullptr;         // p x M column-major
@@ -248,11 +261,24 @@ inline int ext2int(const bgp_model* m, int e) { return e < m->p - m->nD ? e + m-
 int copy_vec_in(bgp_model* m, const double* host_ext, double* dev_int);     // pads dev_int to lda with zeros
 int copy_vec_out(bgp_model* m, const double* dev_int, double* host_ext);
 int copy_H_out(bgp_model* m, double* host_ext);                             // from m->H (p x ldh) to p x p
+int rot_vec_dev(bgp_model* m, const double* dev_int, double* dev_ext);      // p doubles, external order, on the device
+int rot_H_dev(bgp_model* m, const double* H_int, double* dev_ext, int lde); // p x ldh internal -> p x lde external
 int launch_sgp_block(const double* x_dev, int64_t n, double x0, double a, int k, int m, double lo, double hi, double* dstB,
                      double* dstX, cudaStream_t st);
 // newton.cu
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
+// where a batch of evaluations leaves its modes / Hessians: caller arrays in the external order (modes p x K,
+// Hs p x p x K) and / or device arrays in the internal order (modes K x lda, Hs K x (p x ldh); slot dev_slot[j])
+struct BatchSink {
+  double* modes_host = nullptr;
+  double* Hs_host = nullptr;
+  double* modes_dev = nullptr;
+  double* Hs_dev = nullptr;
+  const int* dev_slot = nullptr;
+};
+int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char* mine, double* values,
+                  const BatchSink& sink, int* iters_total, int* first_failed);
 // grad.cu: d/dtheta of the Laplace objective at the mode left on the device by laplace_inner
 int laplace_gradient(bgp_model* m, const double* theta, double* grad_host);
 void grad_plan_destroy(bgp_model* m);
@@ -272,5 +298,18 @@ int comm_unique_id(void* id128);
 int comm_create(bgp_model* m, const void* id128);
 void comm_destroy(bgp_model* m);
 int comm_allreduce_sum(bgp_model* m, double* buf, size_t count);
+int comm_open(Comm** out, int rank, int world, const void* id128);
+void comm_close(Comm** c);
+int node_allreduce_sum(bgp_model* m, double* buf, size_t count);
+// owner of piece j of K when K pieces are dealt to `world` ranks in contiguous, balanced runs
+inline int piece_owner(int64_t j, int64_t K, int world) {
+  const int64_t base = K / world, rem = K % world, cut = rem * (base + 1);
+  return (int)(j < cut ? j / (base + 1) : rem + (j - cut) / (base > 0 ? base : 1));
+}
+inline void piece_bounds(int64_t K, int rank, int world, int64_t* lo, int64_t* hi) {
+  const int64_t base = K / world, rem = K % world;
+  *lo = rank * base + (rank < rem ? rank : rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+}
 
 }  // namespace bgp

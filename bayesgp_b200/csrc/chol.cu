@@ -4,7 +4,7 @@
 // Hessian and the 1/2 logdet H term of the Laplace approximation (TMB::MakeADFun(random = "W"),
 // call site /root/reference/R/02_model_fit.R:276-284).
 //
-// One thread-block cluster (8 CTAs x 512 threads) owns one problem; H stays in global memory
+// One thread-block cluster (8 CTAs x 256 threads) owns one problem; H stays in global memory
 // (L2-resident: <= 8 MB).  Right-looking blocked algorithm, panel width NB, two cluster barriers per panel:
 //   1. every CTA factors the NB x NB diagonal block itself (one warp, rows in registers, shuffles —
 //      no CTA barrier inside the 32 dependent steps);

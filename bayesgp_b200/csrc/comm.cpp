@@ -72,7 +72,7 @@ int comm_unique_id(void* id128) {
   return BGP_OK;
 }
 
-int comm_create(bgp_model* m, const void* id128) {
+int comm_open(Comm** out, int rank, int world, const void* id128) {
   NcclApi* api = nccl_api();
   if (!api) {
     set_error("libnccl.so.2 could not be loaded");
@@ -80,38 +80,57 @@ int comm_create(bgp_model* m, const void* id128) {
   }
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
-  m->comm = new Comm();
-  ncclResult_t r = api->CommInitRank(&m->comm->comm, m->world, id, m->rank);
+  Comm* c = new Comm();
+  ncclResult_t r = api->CommInitRank(&c->comm, world, id, rank);
   if (r != ncclSuccess) {
     set_error("ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
-    delete m->comm;
-    m->comm = nullptr;
+    delete c;
     return BGP_ERR_NCCL;
   }
+  *out = c;
   return BGP_OK;
 }
 
-void comm_destroy(bgp_model* m) {
-  if (!m->comm) return;
+void comm_close(Comm** c) {
+  if (!c || !*c) return;
   NcclApi* api = nccl_api();
-  if (api && m->comm->comm) api->CommDestroy(m->comm->comm);
-  delete m->comm;
-  m->comm = nullptr;
+  if (api && (*c)->comm) api->CommDestroy((*c)->comm);
+  delete *c;
+  *c = nullptr;
 }
 
-int comm_allreduce_sum(bgp_model* m, double* buf, size_t count) {
-  if (m->world <= 1) return BGP_OK;
+int comm_sum(Comm* c, double* buf, size_t count, cudaStream_t st) {
   NcclApi* api = nccl_api();
-  if (!api || !m->comm) {
-    set_error("sharded model without a communicator");
+  if (!api || !c) {
+    set_error("collective on a model without a communicator");
     return BGP_ERR_NCCL;
   }
-  ncclResult_t r = api->AllReduce(buf, buf, count, ncclFloat64, ncclSum, m->comm->comm, m->stream);
+  ncclResult_t r = api->AllReduce(buf, buf, count, ncclFloat64, ncclSum, c->comm, st);
   if (r != ncclSuccess) {
     set_error("ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
     return BGP_ERR_NCCL;
   }
   return BGP_OK;
+}
+
+int comm_create(bgp_model* m, const void* id128) { return comm_open(&m->comm, m->rank, m->world, id128); }
+
+void comm_destroy(bgp_model* m) {
+  comm_close(&m->comm);
+  comm_close(&m->node_comm);
+}
+
+int comm_allreduce_sum(bgp_model* m, double* buf, size_t count) {
+  if (m->world <= 1) return BGP_OK;
+  return comm_sum(m->comm, buf, count, m->stream);
+}
+
+// Node group: ranks holding replicas of the same rows split quadrature nodes, sample blocks and prediction rows.
+// Every piece has exactly one owner and the other ranks contribute zeros, so a SUM all-reduce assembles the whole
+// bit-exactly (x + 0 = x) whatever the reduction order.
+int node_allreduce_sum(bgp_model* m, double* buf, size_t count) {
+  if (m->node_world <= 1) return BGP_OK;
+  return comm_sum(m->node_comm, buf, count, m->stream);
 }
 
 }  // namespace bgp

@@ -6,6 +6,7 @@
 //   normalize_logpost -> mvQuad "GHe" product grid rescaled by chol(H^-1)          (A.4)
 //   marginals ("reuse"), per-node modes and Hessians                               (A.5)
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <limits>
 
@@ -387,9 +388,13 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   f->k = k;
   FF ff{m};
   auto fail = [&](int code) {
+    fit_release_device(f);
     delete f;
     return code;
   };
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_opt0 = now();
+  cudaEventRecord(m->ev[0], m->stream);     // device time of the whole call -> bgp_model_last_timing(total_ms)
   f->mode.assign(S, 0.0);
   if (mode_in) {
     f->mode.assign(mode_in, mode_in + S);
@@ -404,9 +409,6 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   } else {
     int st = richardson_jacobian(ff, f->mode, f->hessian);
     if (st != BGP_OK) return fail(st);
-    // numDeriv's default step (d = 1e-4) differentiates a gradient that carries ~cond(H) * eps * |L| of rounding
-    // noise; at large n the result can come out indefinite, where aghq would stop with a chol() error.  Retry with
-    // 10x / 100x larger steps (less noise amplification), recorded in hessian_fallback.
     auto is_pd = [&](const std::vector<double>& H) {
       std::vector<double> C;
       if (!invert_general(H, S, C)) return false;
@@ -424,13 +426,20 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
       fprintf(stderr, "\n");
     };
     dump("richardson d=1e-4");
-    for (double d = 1e-3; !is_pd(f->hessian) && d <= 1.001e-2; d *= 10.0) {
-      st = richardson_jacobian(ff, f->mode, f->hessian, d);
-      if (st != BGP_OK) return fail(st);
-      ++f->hessian_fallback;
-      dump("richardson retry");
-    }
+    // numDeriv's default step (d = 1e-4) differentiates a gradient that carries ~cond(H) * eps * |L| of rounding
+    // noise; at large n the result can come out indefinite, where aghq stops with a chol() error — and so does
+    // this library (rescaled_grid below) unless the caller opted into the retry with 10x / 100x larger steps
+    // (bgp_model_set_hessian_retry); the number of retries is reported by bgp_fit_get_diagnostics.
+    if (m->hessian_retry)
+      for (double d = 1e-3; !is_pd(f->hessian) && d <= 1.001e-2; d *= 10.0) {
+        st = richardson_jacobian(ff, f->mode, f->hessian, d);
+        if (st != BGP_OK) return fail(st);
+        ++f->hessian_fallback;
+        dump("richardson retry");
+      }
   }
+  f->opt_ms = now() - t_opt0;
+  const double t_grid0 = now();
   std::vector<int> ord(S);
   for (int i = 0; i < S; ++i) ord[i] = i;
   double L00 = 1.0;
@@ -439,21 +448,71 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   const int K = (int)f->weights.size();
   f->K = K;
   f->logpost.assign(K, 0.0);
-  f->modes.assign((size_t)p * K, 0.0);
-  f->Hs.assign((size_t)p * p * K, 0.0);
-  std::vector<double> th(S);
+  // Node shards: the K nodes of a grid are dealt to the ranks of the node group in contiguous runs of
+  // the expand.grid order (neighbours along the first coordinate share a rank: good warm starts).  Each rank keeps
+  // the modes / Hessians of its nodes on its device; only the K values are exchanged.
+  const int nw = m->node_world, nr = m->node_rank;
+  f->owner.resize(K);
+  f->slot.assign(K, -1);
+  std::vector<unsigned char> mine(K, 0);
+  for (int j = 0; j < K; ++j) {
+    f->owner[j] = piece_owner(j, K, nw);
+    if (f->owner[j] == nr) {
+      mine[j] = 1;
+      f->slot[j] = f->n_local++;
+    }
+  }
+  if (f->n_local > 0) {
+    if (cudaMalloc(&f->modes_dev, (size_t)f->n_local * m->lda * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&f->Hs_dev, (size_t)f->n_local * p * m->ldh * sizeof(double)) != cudaSuccess) {
+      set_error("out of device memory for %d per-node Hessians (%d x %d)", f->n_local, p, p);
+      return fail(BGP_ERR_CUDA);
+    }
+  }
+  double* vals_dev = nullptr;
+  if (nw > 1 && cudaMalloc(&vals_dev, (size_t)K * sizeof(double)) != cudaSuccess) {
+    set_error("cudaMalloc failed");
+    return fail(BGP_ERR_CUDA);
+  }
+  struct Free {
+    double* p;
+    ~Free() { if (p) cudaFree(p); }
+  } free_vals{vals_dev};
+  std::vector<double> th((size_t)S * K), vals(K);
+  // one grid: this rank's nodes through the batch path (centre-out order, nothing but scalars crosses PCIe), then
+  // the values of all ranks.  aghq stops when a node's log posterior is not finite; so does this (every rank sees
+  // the NaN through the all-reduce and returns the same error).
   auto eval_grid = [&](const std::vector<double>& nodes, std::vector<double>& lp, bool keep) -> int {
+    for (int j = 0; j < K; ++j)
+      for (int a = 0; a < S; ++a) th[(size_t)j * S + a] = nodes[(size_t)a * K + j];
+    std::fill(vals.begin(), vals.end(), 0.0);
+    BatchSink sink;
+    if (keep) {
+      sink.modes_dev = f->modes_dev;
+      sink.Hs_dev = f->Hs_dev;
+      sink.dev_slot = f->slot.data();
+    }
+    int iters = 0, bad = -1;
+    int rc = laplace_batch(m, K, th.data(), nw > 1 ? mine.data() : nullptr, vals.data(), sink, &iters, &bad);
+    if (rc == BGP_ERR_CUDA || rc == BGP_ERR_NCCL) return rc;
+    std::string local_msg = rc != BGP_OK ? g_last_error : std::string();
+    f->grid_newton_iters += iters;
+    ff.n_fn += K;
+    if (nw > 1) {
+      BGP_CUDA(cudaMemcpyAsync(vals_dev, vals.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+      BGP_TRY(node_allreduce_sum(m, vals_dev, (size_t)K));
+      BGP_CUDA(cudaMemcpyAsync(vals.data(), vals_dev, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    BGP_CUDA(cudaStreamSynchronize(m->stream));
     for (int j = 0; j < K; ++j) {
-      for (int a = 0; a < S; ++a) th[a] = nodes[(size_t)a * K + j];
-      double v;
-      BGP_TRY(ff.fn(th.data(), &v));
-      lp[j] = -v;
-      if (keep && std::isfinite(v)) {
-        // mode_j = last.par[random], H_j = spHess(last.par, random = TRUE)   (A.5)
-        BGP_TRY(copy_vec_out(m, m->Wmode, &f->modes[(size_t)j * p]));
-        BGP_TRY(copy_H_out(m, &f->Hs[(size_t)j * p * p]));
-        BGP_CUDA(cudaStreamSynchronize(m->stream));
+      if (!std::isfinite(vals[j])) {
+        std::string at;
+        for (int a = 0; a < S; ++a) at += (a ? ", " : "") + std::to_string(th[(size_t)j * S + a]);
+        set_error("log posterior is not finite at quadrature node %d (theta = %s)%s%s", j, at.c_str(),
+                  local_msg.empty() ? "" : ": ", local_msg.c_str());
+        return rc != BGP_OK ? rc : BGP_ERR_NONFINITE;
       }
+      lp[j] = -vals[j];
     }
     return BGP_OK;
   };
@@ -504,10 +563,57 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
       f->marg_lmp[j][q] = logsumexp(t) - std::log(f->marg_w[j][q]);
     }
   }
+  cudaEventRecord(m->ev[1], m->stream);
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess) {
+    set_error("CUDA error at the end of the fit");
+    return fail(BGP_ERR_CUDA);
+  }
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+    m->t_total = ms;
+  }
+  f->grid_ms = now() - t_grid0;
   f->fn_count = ff.n_fn;
   f->gr_count = ff.n_gr;
   *out = f;
   return BGP_OK;
+}
+
+// modesandhessians in the caller's layout (external order): every node is rotated on the device of its owner,
+// gathered over the node group (zeros from the other ranks) and copied out, a few nodes at a time
+static int gather_modes(const bgp_fit* f, double* modes, double* Hs) {
+  bgp_model* m = f->model;
+  const int p = f->p, K = f->K;
+  const size_t per = (Hs ? (size_t)p * p : 0) + (size_t)p;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, ((size_t)256 << 20) / (per * sizeof(double))));
+  double* stage = nullptr;
+  BGP_CUDA(cudaMalloc(&stage, (size_t)chunk * per * sizeof(double)));
+  std::vector<double> host;
+  int rc = [&]() -> int {
+    for (int j0 = 0; j0 < K; j0 += chunk) {
+      const int nj = std::min(chunk, K - j0);
+      if (m->node_world > 1) BGP_CUDA(cudaMemsetAsync(stage, 0, (size_t)nj * per * sizeof(double), m->stream));
+      for (int j = j0; j < j0 + nj; ++j) {
+        if (f->slot[j] < 0) continue;
+        double* dst = stage + (size_t)(j - j0) * per;
+        BGP_TRY(rot_vec_dev(m, f->modes_dev + (size_t)f->slot[j] * m->lda, dst));
+        if (Hs) BGP_TRY(rot_H_dev(m, f->Hs_dev + (size_t)f->slot[j] * p * m->ldh, dst + p, p));
+      }
+      BGP_TRY(node_allreduce_sum(m, stage, (size_t)nj * per));
+      host.resize((size_t)nj * per);
+      BGP_CUDA(cudaMemcpyAsync(host.data(), stage, (size_t)nj * per * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+      BGP_CUDA(cudaStreamSynchronize(m->stream));
+      for (int j = j0; j < j0 + nj; ++j) {
+        const double* src = host.data() + (size_t)(j - j0) * per;
+        if (modes) std::copy(src, src + p, modes + (size_t)j * p);
+        if (Hs) std::copy(src + p, src + p + (size_t)p * p, Hs + (size_t)j * p * p);
+      }
+    }
+    return BGP_OK;
+  }();
+  cudaFree(stage);
+  return rc;
 }
 
 }  // namespace bgp
@@ -571,9 +677,25 @@ int bgp_fit_get_grid(const bgp_fit* f, double* nodes, double* weights, double* l
 }
 
 int bgp_fit_get_modes(const bgp_fit* f, double* modes, double* Hs) {
+  if (!f || !f->model) return BGP_ERR_ARG;
+  if (!modes && !Hs) return BGP_OK;
+  BGP_CUDA(cudaSetDevice(f->model->device));
+  return gather_modes(f, modes, Hs);
+}
+
+int bgp_fit_get_diagnostics(const bgp_fit* f, int* hessian_fallback, int64_t* grid_newton_iters, double* opt_ms,
+                            double* grid_ms) {
   if (!f) return BGP_ERR_ARG;
-  if (modes) std::copy(f->modes.begin(), f->modes.end(), modes);
-  if (Hs) std::copy(f->Hs.begin(), f->Hs.end(), Hs);
+  if (hessian_fallback) *hessian_fallback = f->hessian_fallback;
+  if (grid_newton_iters) *grid_newton_iters = f->grid_newton_iters;
+  if (opt_ms) *opt_ms = f->opt_ms;
+  if (grid_ms) *grid_ms = f->grid_ms;
+  return BGP_OK;
+}
+
+int bgp_fit_node_owner(const bgp_fit* f, int32_t* owner) {
+  if (!f || !owner) return BGP_ERR_ARG;
+  for (int j = 0; j < f->K; ++j) owner[j] = f->owner[j];
   return BGP_OK;
 }
 

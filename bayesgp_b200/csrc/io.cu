@@ -21,12 +21,12 @@ __global__ void rot_out_kernel(const double* __restrict__ src, int p, int nD, do
   ext[e] = src[e < nU ? e + nD : e - nU];
 }
 
-__global__ void rot_H_kernel(const double* __restrict__ H, int p, int nD, int ldh, double* __restrict__ ext) {
+__global__ void rot_H_kernel(const double* __restrict__ H, int p, int nD, int ldh, double* __restrict__ ext, int lde) {
   const int er = blockIdx.x * blockDim.x + threadIdx.x, ec = blockIdx.y;
   if (er >= p) return;
   const int nU = p - nD;
   const int ir = er < nU ? er + nD : er - nU, ic = ec < nU ? ec + nD : ec - nU;
-  ext[(size_t)ec * p + er] = H[(size_t)ic * ldh + ir];
+  ext[(size_t)ec * lde + er] = H[(size_t)ic * ldh + ir];
 }
 
 int copy_vec_in(bgp_model* m, const double* host_ext, double* dev_int) {
@@ -47,10 +47,26 @@ int copy_vec_out(bgp_model* m, const double* dev_int, double* host_ext) {
 
 int copy_H_out(bgp_model* m, double* host_ext) {
   dim3 grid((m->p + 255) / 256, m->p);
-  rot_H_kernel<<<grid, 256, 0, m->stream>>>(m->H, m->p, m->nD, m->ldh, m->xbuf);
+  rot_H_kernel<<<grid, 256, 0, m->stream>>>(m->H, m->p, m->nD, m->ldh, m->xbuf, m->p);
   count_launch();
   BGP_CUDA(cudaGetLastError());
   BGP_CUDA(cudaMemcpyAsync(host_ext, m->xbuf, (size_t)m->p * m->p * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  return BGP_OK;
+}
+
+// device-to-device rotations into the external order (fit getters / node-group gathers)
+int rot_vec_dev(bgp_model* m, const double* dev_int, double* dev_ext) {
+  rot_out_kernel<<<(m->p + 255) / 256, 256, 0, m->stream>>>(dev_int, m->p, m->nD, dev_ext);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
+int rot_H_dev(bgp_model* m, const double* H_int, double* dev_ext, int lde) {
+  dim3 grid((m->p + 255) / 256, m->p);
+  rot_H_kernel<<<grid, 256, 0, m->stream>>>(H_int, m->p, m->nD, m->ldh, dev_ext, lde);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
   return BGP_OK;
 }
 

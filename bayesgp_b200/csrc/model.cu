@@ -296,8 +296,16 @@ int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, co
 int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm, const double* region,
                       const double* P, double logPdet, double u, double alpha, double boundary_prec, double boundary_mean) {
   BGP_CHECK_BUILDING(m);
-  if (!x || !region || !P || k < 5 || nharm < 1 || !(region[1] > region[0])) {
-    set_error("bgp_model_add_sgp: bad arguments (k must be >= 5, m >= 1, region increasing)");
+  if (k < 3) {      // R/02_model_fit.R:511-514
+    set_error("Error: parameter <k> in the random effect part should be >= 3.");
+    return BGP_ERR_ARG;
+  }
+  if (k < 4) {      // R accepts k = 3, then fda::create.bspline.basis(nbasis = 3, norder = 4) stops (R/01_utility.R:179-183)
+    set_error("sGP with k = 3: fda::create.bspline.basis needs nbasis >= norder = 4");
+    return BGP_ERR_ARG;
+  }
+  if (!x || !region || !P || nharm < 1 || !(region[1] > region[0])) {
+    set_error("bgp_model_add_sgp: bad arguments (m >= 1, region increasing)");
     return BGP_ERR_ARG;
   }
   if ((int)m->rnd.size() >= 16) {
@@ -348,6 +356,25 @@ int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_uniq
   m->rank = rank;
   m->world = world;
   if (world > 1) BGP_TRY(comm_create(m, nccl_unique_id));
+  return BGP_OK;
+}
+
+int bgp_model_set_node_group(bgp_model* m, int rank, int world, const void* nccl_unique_id) {
+  if (!m || world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_unique_id)) {
+    set_error("bgp_model_set_node_group: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  BGP_CUDA(cudaSetDevice(m->device));
+  comm_close(&m->node_comm);
+  m->node_rank = rank;
+  m->node_world = world;
+  if (world > 1) BGP_TRY(comm_open(&m->node_comm, rank, world, nccl_unique_id));
+  return BGP_OK;
+}
+
+int bgp_model_set_hessian_retry(bgp_model* m, int allow) {
+  if (!m) return BGP_ERR_ARG;
+  m->hessian_retry = allow != 0;
   return BGP_OK;
 }
 
@@ -490,7 +517,8 @@ void bgp_model_destroy(bgp_model* m) {
   for (auto& rb : m->rnd)
     if (rb.P_dev) cudaFree(rb.P_dev);
   for (double* ptr : {m->A, m->y, m->size, m->eta, m->wobs, m->c3, m->qfix, m->mu0, m->W, m->Wtrial, m->Wmode, m->g,
-                      m->step, m->Tan, m->xbuf, m->H, m->L, m->Ldinv, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf})
+                      m->step, m->Tan, m->xbuf, m->H, m->L, m->Ldinv, m->theta_dev, m->part_g, m->part_s, m->part_H, m->red_buf,
+                      m->hpack})
     if (ptr) cudaFree(ptr);
   for (auto& h : m->hist) {
     if (h.W) cudaFree(h.W);

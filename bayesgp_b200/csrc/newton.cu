@@ -313,10 +313,16 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     gmax = sc.gmax;
     ++iters;
     if (gmax < m->grad_tol && full_step && m->allow_reuse && std::isfinite(sc.logdet)) {
-      // Converged by a full Newton step from the point where H was factored.  |logdet H(w1) - logdet H(w0)| <=
-      // p * delta (delta = max |d eta|; sharded models carry the SUM over ranks of the local maxima, an upper
-      // bound every rank sees identically; Gaussian: H does not depend on W at all), so when that is far inside
-      // the tolerances the factor of the last iteration serves as the factor at the mode.
+      // Converged by a full Newton step from the point w0 where H was factored.  With delta = max_i |eta_i(w1) -
+      // eta_i(w0)| the observation weights obey w_i(w1) = w_i(w0) e^{e_i}, |e_i| <= delta (Poisson: log w = eta;
+      // Binomial: d log w / d eta = 1 - 2 pi in (-1, 1); Gaussian: w constant), hence in the Loewner order
+      //     e^{-delta} H(w0)  <=  H(w1)  <=  e^{delta} H(w0)          (Q >= 0 only helps)
+      // and EXACTLY (no linearisation)  |logdet H(w1) - logdet H(w0)| <= p * delta,
+      //                                 ||H(w1) - H(w0)||_2 <= (e^{delta} - 1) ||H(w0)||_2.
+      // Sharded models carry the SUM over ranks of the local maxima, an upper bound every rank sees identically.
+      // When p * delta / 2 is far inside the 1e-8 tolerance of the value (and delta <= 1e-7 far inside the 1e-6
+      // tolerance of the Hessian) the factor of the last iteration serves as the factor at the mode; the H left
+      // on the device — what the caller receives as spHess — is then H(w0), within (e^{delta} - 1) of H(w1).
       const double val = f + 0.5 * sc.logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
       const bool tiny = m->family == BGP_FAMILY_GAUSSIAN ||
                         (deta_full <= m->reuse_eta_tol && 0.5 * m->p * deta_full <= m->reuse_rel_tol * std::fabs(val));
@@ -379,6 +385,128 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   m->n_reuse += reused ? 1 : 0;
   *value = f + 0.5 * logdet - 0.5 * (double)m->p * std::log(2.0 * M_PI);
   return BGP_OK;
+}
+
+// K Laplace evaluations (theta: S x K, node j at theta + j*S) of which this call runs those with mine[j] != 0
+// (NULL: all).  Evaluation order (results go back to slot j): start next to what is already known — the nearest
+// history entry, or the node closest to the centroid when the history is empty (the warm start is the mode at the
+// grid centre in aghq's flow) — then always the node nearest to an evaluated one, so every inner solve starts from a
+// close, usually collinear, pair of neighbours.  Modes / Hessians leave either through two pinned slots (host sink:
+// the device -> pinned copy is asynchronous, the pinned -> caller copy runs while the next evaluation's kernels are
+// in flight) or by device-to-device copies (device sink: nothing crosses PCIe).  Nodes that fail get NaN and the
+// worst status is returned after all nodes were tried; values of nodes that are not mine are left untouched.
+int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char* mine, double* values,
+                  const BatchSink& sink, int* iters_total, int* first_failed) {
+  int total = 0, worst = BGP_OK;
+  if (first_failed) *first_failed = -1;
+  // the deferred copies point into the caller's arrays: none may outlive this call, whichever way it returns
+  struct HookGuard {
+    bgp_model* m;
+    ~HookGuard() { m->host_hook = nullptr; }
+  } hook_guard{m};
+  m->host_hook = nullptr;
+  const int S = m->S;
+  std::vector<int> order;
+  {
+    std::vector<char> done((size_t)K, 0);
+    int todo = 0;
+    for (int j = 0; j < K; ++j) {
+      if (mine && !mine[j]) done[j] = 1;
+      else ++todo;
+    }
+    std::vector<double> known;                          // thetas with a mode on record
+    for (const auto& h : m->hist)
+      if (h.stamp && (int)h.theta.size() == S) known.insert(known.end(), h.theta.begin(), h.theta.end());
+    if (known.empty()) {
+      std::vector<double> c((size_t)S, 0.0);
+      for (int j = 0; j < K; ++j)
+        if (!done[j])
+          for (int k = 0; k < S; ++k) c[k] += theta[(size_t)j * S + k] / todo;
+      known = c;
+    }
+    // distance of every open node to the nearest known theta, updated as nodes are taken (O(K^2 S) in all)
+    std::vector<double> dist((size_t)K, INFINITY);
+    auto relax = [&](const double* t) {
+      for (int j = 0; j < K; ++j) {
+        if (done[j]) continue;
+        double d = 0.0;
+        for (int k = 0; k < S; ++k) {
+          const double u = theta[(size_t)j * S + k] - t[k];
+          d += u * u;
+        }
+        dist[j] = std::min(dist[j], d);
+      }
+    };
+    for (size_t e = 0; e + S <= known.size(); e += S) relax(&known[e]);
+    for (int it = 0; it < todo; ++it) {
+      int best = -1;
+      for (int j = 0; j < K; ++j)
+        if (!done[j] && (best < 0 || dist[j] < dist[best])) best = j;
+      done[best] = 1;
+      order.push_back(best);
+      relax(theta + (size_t)best * S);
+    }
+  }
+  const size_t pp = (size_t)m->p * m->p;
+  for (size_t oi = 0; oi < order.size(); ++oi) {
+    const int j = order[oi];
+    int iters = 0;
+    double v = NAN;
+    int st = laplace_inner(m, theta + (size_t)j * m->S, &v, &iters);
+    total += iters;
+    values[j] = st == BGP_OK ? v : NAN;
+    if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
+    if (st != BGP_OK) {
+      if (worst == BGP_OK && first_failed) *first_failed = j;
+      worst = st;
+      continue;
+    }
+    if (sink.modes_dev || sink.Hs_dev) {
+      const size_t slot = sink.dev_slot ? (size_t)sink.dev_slot[j] : (size_t)j;
+      if (sink.modes_dev)
+        BGP_CUDA(cudaMemcpyAsync(sink.modes_dev + slot * m->lda, m->Wmode, (size_t)m->lda * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, m->stream));
+      if (sink.Hs_dev)
+        BGP_CUDA(cudaMemcpyAsync(sink.Hs_dev + slot * (size_t)m->p * m->ldh, m->H, (size_t)m->p * m->ldh * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, m->stream));
+    }
+    if (sink.modes_host || sink.Hs_host) {
+      const size_t need = pp + (size_t)m->p;
+      if (m->pin_out_elems < need) {
+        for (int i = 0; i < 2; ++i) {
+          if (m->pin_out[i]) cudaFreeHost(m->pin_out[i]);
+          m->pin_out[i] = nullptr;
+          BGP_CUDA(cudaMallocHost(&m->pin_out[i], need * sizeof(double)));
+          if (!m->pin_ev[i]) BGP_CUDA(cudaEventCreateWithFlags(&m->pin_ev[i], cudaEventDisableTiming));
+        }
+        m->pin_out_elems = need;
+      }
+      if (m->host_hook) {                   // the slot's previous tenant (two evaluations ago at the latest)
+        m->host_hook();
+        m->host_hook = nullptr;
+      }
+      const int slot = (int)(oi & 1);
+      double* pin = m->pin_out[slot];
+      if (sink.modes_host) BGP_TRY(copy_vec_out(m, m->Wmode, pin + pp));
+      if (sink.Hs_host) BGP_TRY(copy_H_out(m, pin));
+      BGP_CUDA(cudaEventRecord(m->pin_ev[slot], m->stream));
+      double* mode_dst = sink.modes_host ? sink.modes_host + (size_t)j * m->p : nullptr;
+      double* H_dst = sink.Hs_host ? sink.Hs_host + (size_t)j * pp : nullptr;
+      cudaEvent_t ev = m->pin_ev[slot];
+      const size_t pn = (size_t)m->p;
+      m->host_hook = [pin, pp, pn, mode_dst, H_dst, ev]() {
+        cudaEventSynchronize(ev);
+        if (mode_dst) memcpy(mode_dst, pin + pp, pn * sizeof(double));
+        if (H_dst) memcpy(H_dst, pin, pp * sizeof(double));
+      };
+    }
+  }
+  if (m->host_hook) {
+    m->host_hook();
+    m->host_hook = nullptr;
+  }
+  if (iters_total) *iters_total = total;
+  return worst;
 }
 
 }  // namespace bgp
@@ -474,110 +602,17 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
     set_error("bgp_laplace_eval_batch: bad arguments");
     return BGP_ERR_ARG;
   }
-  int total = 0, worst = BGP_OK;
-  // the deferred copies point into the caller's arrays: none may outlive this call, whichever way it returns
-  struct HookGuard {
-    bgp_model* m;
-    ~HookGuard() { m->host_hook = nullptr; }
-  } hook_guard{m};
-  m->host_hook = nullptr;
+  BatchSink sink;
+  sink.modes_host = modes;
+  sink.Hs_host = Hs;
   cudaEventRecord(m->ev[0], m->stream);
-  // Evaluation order (results go back to the caller's slots): start next to what is already known — the
-  // nearest history entry, or the node closest to the centroid when the history is empty (the warm start is
-  // the mode at the grid centre in aghq's flow) — then always the node nearest to an evaluated one, so every
-  // inner solve starts from a close, usually collinear, pair of neighbours.
-  const int S = m->S;
-  std::vector<int> order;
-  {
-    std::vector<char> done((size_t)K, 0);
-    std::vector<double> known;                          // thetas with a mode on record
-    for (const auto& h : m->hist)
-      if (h.stamp && (int)h.theta.size() == S) known.insert(known.end(), h.theta.begin(), h.theta.end());
-    if (known.empty()) {
-      std::vector<double> c((size_t)S, 0.0);
-      for (int j = 0; j < K; ++j)
-        for (int k = 0; k < S; ++k) c[k] += theta[(size_t)j * S + k] / K;
-      known = c;
-    }
-    for (int it = 0; it < K; ++it) {
-      int best = -1;
-      double bd = 0.0;
-      for (int j = 0; j < K; ++j) {
-        if (done[j]) continue;
-        double dj = INFINITY;
-        for (size_t e = 0; e + S <= known.size(); e += S) {
-          double d = 0.0;
-          for (int k = 0; k < S; ++k) {
-            const double t = theta[(size_t)j * S + k] - known[e + k];
-            d += t * t;
-          }
-          dj = std::min(dj, d);
-        }
-        if (best < 0 || dj < bd) {
-          best = j;
-          bd = dj;
-        }
-      }
-      done[best] = 1;
-      order.push_back(best);
-      known.insert(known.end(), theta + (size_t)best * S, theta + (size_t)best * S + S);
-    }
-  }
-  for (int oi = 0; oi < K; ++oi) {
-    const int j = order[oi];
-    int iters = 0;
-    double v = NAN;
-    int st = laplace_inner(m, theta + (size_t)j * m->S, &v, &iters);
-    total += iters;
-    values[j] = st == BGP_OK ? v : NAN;
-    if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
-    if (st != BGP_OK) {
-      worst = st;
-      continue;
-    }
-    if (modes || Hs) {
-      // device -> pinned slot now (asynchronous); pinned slot -> caller's arrays while the next evaluation runs
-      const size_t pp = (size_t)m->p * m->p, need = pp + (size_t)m->p;
-      if (m->pin_out_elems < need) {
-        for (int i = 0; i < 2; ++i) {
-          if (m->pin_out[i]) cudaFreeHost(m->pin_out[i]);
-          m->pin_out[i] = nullptr;
-          BGP_CUDA(cudaMallocHost(&m->pin_out[i], need * sizeof(double)));
-          if (!m->pin_ev[i]) BGP_CUDA(cudaEventCreateWithFlags(&m->pin_ev[i], cudaEventDisableTiming));
-        }
-        m->pin_out_elems = need;
-      }
-      if (m->host_hook) {                   // the slot's previous tenant (two evaluations ago at the latest)
-        m->host_hook();
-        m->host_hook = nullptr;
-      }
-      const int slot = oi & 1;
-      double* pin = m->pin_out[slot];
-      if (modes) BGP_TRY(copy_vec_out(m, m->Wmode, pin + pp));
-      if (Hs) BGP_TRY(copy_H_out(m, pin));
-      BGP_CUDA(cudaEventRecord(m->pin_ev[slot], m->stream));
-      double* mode_dst = modes ? modes + (size_t)j * m->p : nullptr;
-      double* H_dst = Hs ? Hs + (size_t)j * pp : nullptr;
-      cudaEvent_t ev = m->pin_ev[slot];
-      const size_t pn = (size_t)m->p;
-      m->host_hook = [pin, pp, pn, mode_dst, H_dst, ev]() {
-        cudaEventSynchronize(ev);
-        if (mode_dst) memcpy(mode_dst, pin + pp, pn * sizeof(double));
-        if (H_dst) memcpy(H_dst, pin, pp * sizeof(double));
-      };
-    }
-  }
-  if (m->host_hook) {
-    m->host_hook();
-    m->host_hook = nullptr;
-  }
+  int st = laplace_batch(m, K, theta, nullptr, values, sink, newton_iters_total, nullptr);
   cudaEventRecord(m->ev[1], m->stream);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
   m->t_total = ms;
-  if (newton_iters_total) *newton_iters_total = total;
-  return worst;
+  return st;
 }
 
 int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,

@@ -111,11 +111,12 @@ __global__ void sgp_design_kernel(const SgpDesignArgs a) {
 
 // ---- coefficient matrix C[s][c] (M x ld, K-major) from R-layout sample blocks --------------------------
 struct CoefArgs {
-  const double* icpt;     // M or NULL
-  const double* glob;     // nglob x M column-major or NULL
+  const double* icpt;     // M (stride icpt_ld) or NULL
+  const double* glob;     // nglob x M column-major (column pitch glob_ld) or NULL
   int nglob;
-  const double* coef;     // ncoef x M column-major
+  const double* coef;     // ncoef x M column-major (column pitch coef_ld)
   int ncoef;
+  int64_t icpt_ld, glob_ld, coef_ld;
   int skip;               // rows of rbind(icpt, glob) dropped from the top (= degree for IWP, 0 for sGP)
   int nX;                 // rows of rbind(icpt, glob) kept
   int64_t M;
@@ -130,10 +131,10 @@ __global__ void build_coef_kernel(const CoefArgs a) {
     double v = 0.0;
     if (c < a.nX) {
       const int r = c + a.skip;          // row of rbind(intercept_samps, global_samps)
-      if (r == 0) v = a.icpt ? a.icpt[s] : 0.0;
-      else v = (a.glob && r - 1 < a.nglob) ? a.glob[(size_t)s * a.nglob + (r - 1)] : 0.0;
+      if (r == 0) v = a.icpt ? a.icpt[(size_t)s * a.icpt_ld] : 0.0;
+      else v = (a.glob && r - 1 < a.nglob) ? a.glob[(size_t)s * a.glob_ld + (r - 1)] : 0.0;
     } else if (c < a.nX + a.ncoef) {
-      v = a.coef[(size_t)s * a.ncoef + (c - a.nX)];
+      v = a.coef[(size_t)s * a.coef_ld + (c - a.nX)];
     }
     row[c] = v;
   }
@@ -1058,8 +1059,9 @@ static void split_knots(const double* knots, int nknots, std::vector<double>& kn
 }
 
 // upload R-layout sample blocks and assemble the K-major coefficient matrix
+// inputs_on_device: the three blocks are rows of a device-resident p x M sample matrix (column pitch resident_ld)
 static int build_coef(const double* coef, int ncoef, const double* glob, int nglob, const double* icpt, int64_t M, int skip,
-                      int nX, int ldk, cudaStream_t st, DevBuf& Cb, bool inputs_on_device) {
+                      int nX, int ldk, cudaStream_t st, DevBuf& Cb, bool inputs_on_device, int64_t resident_ld = 0) {
   DevBuf cb, gb, ib;
   const double *cd = coef, *gd = glob, *id = icpt;
   if (!inputs_on_device) {
@@ -1082,10 +1084,13 @@ static int build_coef(const double* coef, int ncoef, const double* glob, int ngl
   BGP_TRY(Cb.alloc((size_t)M * ldk * sizeof(double)));
   CoefArgs a;
   a.icpt = id;
-  a.glob = gd;
+  a.glob = (gd && nglob > 0) ? gd : nullptr;
   a.nglob = nglob;
   a.coef = cd;
   a.ncoef = ncoef;
+  a.icpt_ld = inputs_on_device ? resident_ld : 1;
+  a.glob_ld = inputs_on_device ? resident_ld : nglob;
+  a.coef_ld = inputs_on_device ? resident_ld : ncoef;
   a.skip = skip;
   a.nX = nX;
   a.M = M;
@@ -1148,8 +1153,8 @@ int bgp_predict_iwp(const double* coef, const double* global, const double* icpt
 int bgp_predict_sgp(const double* coef, const double* global, const double* icpt, int64_t M, double a, int k, int m,
                     const double* region, int boundary, const double* x, int64_t G, double level, int device,
                     double* mean, double* plower, double* pupper, double* samples) {
-  if (!coef || !region || !x || M <= 0 || G <= 0 || k < 5 || m < 1) {
-    set_error("bgp_predict_sgp: bad arguments (k must be >= 5)");
+  if (!coef || !region || !x || M <= 0 || G <= 0 || k < 4 || m < 1) {
+    set_error("bgp_predict_sgp: bad arguments (k must be >= 4: cubic B-splines)");
     return BGP_ERR_ARG;
   }
   if (!(level > 0.0 && level < 1.0)) {
@@ -1184,6 +1189,105 @@ int bgp_predict_sgp(const double* coef, const double* global, const double* icpt
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   return rc;
+}
+
+// predict from the samples bgp_sample* left on the device; grid rows split over the node group:
+// every rank summarises its block of x (all M sample columns are resident on every rank), the three G-vectors are
+// assembled by the group's SUM all-reduce (one owner per row, zeros elsewhere)
+static int fit_predict(bgp_fit* f, const DesignSpec& ds, int coef_row0, int ncoef, int glob_row0, int nglob, int icpt_row,
+                       int skip, int nX, const double* x, int64_t G, double level, double* mean, double* plower,
+                       double* pupper) {
+  bgp_model* m = f->model;
+  const int p = f->p;
+  const int64_t M = f->samps_M;
+  if (!f->samps_dev || M <= 0) {
+    set_error("no resident samples: call bgp_sample / bgp_sample_draw on this fit first");
+    return BGP_ERR_STATE;
+  }
+  if (coef_row0 < 0 || coef_row0 + ncoef > p || (nglob > 0 && (glob_row0 < 0 || glob_row0 + nglob > p)) || icpt_row >= p) {
+    set_error("bgp_fit_predict: coefficient rows outside the latent vector (p = %d)", p);
+    return BGP_ERR_ARG;
+  }
+  BGP_CUDA(cudaSetDevice(m->device));
+  const int ldk = round_up(ds.ncols, 16);
+  DevBuf Cb;
+  BGP_TRY(build_coef(f->samps_dev + coef_row0, ncoef, nglob > 0 ? f->samps_dev + glob_row0 : nullptr, nglob,
+                     icpt_row >= 0 ? f->samps_dev + icpt_row : nullptr, M, skip, nX, ldk, m->stream, Cb, true, p));
+  int64_t lo = 0, hi = G;
+  piece_bounds(G, m->node_rank, m->node_world, &lo, &hi);
+  const int64_t Gl = hi - lo;
+  std::vector<double> out((size_t)3 * G, 0.0);
+  if (Gl > 0)
+    BGP_TRY(predict_core(ds, Cb.as<double>(), ldk, M, x + lo, Gl, level, m->stream, out.data() + lo, out.data() + G + lo,
+                         out.data() + 2 * G + lo, nullptr));
+  if (m->node_world > 1) {
+    DevBuf ob;
+    BGP_TRY(ob.alloc((size_t)3 * G * sizeof(double)));
+    BGP_CUDA(cudaMemcpyAsync(ob.p, out.data(), (size_t)3 * G * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    BGP_TRY(node_allreduce_sum(m, ob.as<double>(), (size_t)3 * G));
+    BGP_CUDA(cudaMemcpyAsync(out.data(), ob.p, (size_t)3 * G * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    BGP_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  if (mean) std::copy(out.begin(), out.begin() + G, mean);
+  if (plower) std::copy(out.begin() + G, out.begin() + 2 * G, plower);
+  if (pupper) std::copy(out.begin() + 2 * G, out.end(), pupper);
+  return BGP_OK;
+}
+
+int bgp_fit_predict_iwp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row, const double* knots, int nknots, int order,
+                        int degree, const double* x, int64_t G, double level, double* mean, double* plower,
+                        double* pupper) {
+  if (!f || !f->model || !knots || !x || G <= 0 || nknots < 2 || order < 1 || order > 8 || degree < 0) {
+    set_error("bgp_fit_predict_iwp: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  if (order <= degree) {   // R/03_post_fit.R:201-203
+    set_error("Error: The degree of derivative to compute is not defined. Should consider higher order smoothing "
+              "model or lower order of the derivative degree.");
+    return BGP_ERR_ARG;
+  }
+  if (!(level > 0.0 && level < 1.0)) {
+    set_error("bgp_fit_predict_iwp: level must be in (0, 1)");
+    return BGP_ERR_ARG;
+  }
+  DesignSpec ds;
+  ds.iwp = true;
+  ds.order = order;
+  ds.degree = degree;
+  split_knots(knots, nknots, ds.kneg, ds.kpos);
+  const int nB = (ds.kneg.empty() ? 0 : (int)ds.kneg.size() - 1) + (ds.kpos.empty() ? 0 : (int)ds.kpos.size() - 1);
+  const int nX = order - degree;
+  ds.ncols = nX + nB;
+  return fit_predict(f, ds, coef_row0, nB, global_row0, global_row0 >= 0 ? order - 1 : 0, icpt_row, degree, nX, x, G, level,
+                     mean, plower, pupper);
+}
+
+int bgp_fit_predict_sgp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row, double a, int k, int m,
+                        const double* region, int boundary, const double* x, int64_t G, double level, double* mean,
+                        double* plower, double* pupper) {
+  if (!f || !f->model || !region || !x || G <= 0 || k < 4 || m < 1) {
+    set_error("bgp_fit_predict_sgp: bad arguments (k must be >= 4: cubic B-splines)");
+    return BGP_ERR_ARG;
+  }
+  if (!(level > 0.0 && level < 1.0)) {
+    set_error("bgp_fit_predict_sgp: level must be in (0, 1)");
+    return BGP_ERR_ARG;
+  }
+  DesignSpec ds;
+  ds.iwp = false;
+  ds.a = a;
+  ds.k = k;
+  ds.m = m;
+  ds.boundary = boundary ? 1 : 0;
+  ds.lo = std::min(region[0], region[1]);
+  ds.hi = std::max(region[0], region[1]);
+  ds.x0 = x[0];
+  for (int64_t i = 1; i < G; ++i) ds.x0 = std::min(ds.x0, x[i]);   // initial_location = NULL => min(refined_x)
+  const int nb = boundary ? k - 2 : k;
+  const int nX = 1 + 2 * m;
+  ds.ncols = nX + 3 * nb * m;
+  return fit_predict(f, ds, coef_row0, 3 * nb * m, global_row0, global_row0 >= 0 ? 2 * m : 0, icpt_row, 0, nX, x, G, level,
+                     mean, plower, pupper);
 }
 
 int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms) {

@@ -61,10 +61,19 @@ __global__ void normal_z_kernel(uint64_t seed, int p, int64_t M, const int32_t* 
   }
 }
 
+// first node whose Hessian failed to factor: flag[0] = node + 1, flag[1] = pivot index (doubles: the flag travels
+// through the node group's SUM all-reduce)
+__global__ void note_chol_info_kernel(const EvalScalars* __restrict__ sc, int node, double* __restrict__ flag) {
+  if (sc->chol_info != 0 && flag[0] == 0.0) {
+    flag[0] = (double)(node + 1);
+    flag[1] = (double)sc->chol_info;
+  }
+}
+
 void fit_release_device(bgp_fit* f) {
   if (!f) return;
   if (f->model) cudaSetDevice(f->model->device);
-  for (double** p : {&f->samps_dev, &f->Linv_dev, &f->LinvT_dev, &f->mode_dev})
+  for (double** p : {&f->samps_dev, &f->Linv_dev, &f->LinvT_dev, &f->mode_dev, &f->modes_dev, &f->Hs_dev})
     if (*p) {
       cudaFree(*p);
       *p = nullptr;
@@ -104,7 +113,7 @@ static int sample_core(bgp_fit* f, int64_t M, const double* Z_host, uint64_t see
     BGP_CUDA(cudaMemset(f->Linv_dev, 0, (size_t)p * ldl * sizeof(double)));
     BGP_CUDA(cudaMemset(f->LinvT_dev, 0, (size_t)p * ldl * sizeof(double)));
   }
-  double *Zg = nullptr, *Zraw = nullptr;
+  double *Zg = nullptr, *Zraw = nullptr, *flag_dev = nullptr;
   int32_t* perm_dev = nullptr;
   int st = [&]() -> int {
     BGP_CUDA(cudaMalloc(&Zg, (size_t)M * ldl * sizeof(double)));
@@ -119,28 +128,47 @@ static int sample_core(bgp_fit* f, int64_t M, const double* Z_host, uint64_t see
     }
     count_launch();
     BGP_CUDA(cudaGetLastError());
+    BGP_CUDA(cudaMalloc(&flag_dev, 2 * sizeof(double)));
+    BGP_CUDA(cudaMemsetAsync(flag_dev, 0, 2 * sizeof(double), m->stream));
+    const bool sharded = m->node_world > 1;
+    // node shards: every rank draws the samples of the nodes it holds into its columns of a zeroed p x M matrix;
+    // the SUM over the node group assembles the whole (one owner per column, zeros elsewhere => bit-exact)
+    if (sharded) BGP_CUDA(cudaMemsetAsync(f->samps_dev, 0, (size_t)p * M * sizeof(double), m->stream));
     for (int j = 0; j < K; ++j) {
-      if (count[j] == 0) continue;
-      // R_j = chol(forceSymmetric(H_j)): the lower factor of the symmetric H_j, transposed
-      BGP_CUDA(cudaMemcpy2DAsync(m->H, (size_t)m->ldh * sizeof(double), &f->Hs[(size_t)j * p * p],
-                                 (size_t)p * sizeof(double), (size_t)p * sizeof(double), p, cudaMemcpyHostToDevice,
-                                 m->stream));
-      BGP_CUDA(cudaMemcpyAsync(f->mode_dev, &f->modes[(size_t)j * p], (size_t)p * sizeof(double),
-                               cudaMemcpyHostToDevice, m->stream));
+      if (count[j] == 0 || f->slot[j] < 0) continue;
+      // R_j = chol(forceSymmetric(H_j)): the lower factor of the symmetric H_j, transposed.  H_j and the mode are
+      // where the grid evaluation left them on this device; the factor must be that of H in the W order of
+      // src/BayesGP.cpp:76-127 (the same z gives a different W under any other ordering), so both are rotated
+      BGP_TRY(rot_H_dev(m, f->Hs_dev + (size_t)f->slot[j] * p * m->ldh, m->H, m->ldh));
+      BGP_TRY(rot_vec_dev(m, f->modes_dev + (size_t)f->slot[j] * m->lda, f->mode_dev));
       BGP_TRY(launch_chol_solve(m, false));
+      note_chol_info_kernel<<<1, 1, 0, m->stream>>>(m->sc_dev, j, flag_dev);
+      count_launch();
       BGP_TRY(launch_trtri(m, f->Linv_dev, ldl, f->LinvT_dev));
       BGP_TRY(launch_kgemm(f->LinvT_dev, p, ldl, Zg + (size_t)offset[j] * ldl, count[j], ldl, p, f->mode_dev,
                            f->samps_dev, p, true, perm_dev + offset[j], m->stream));
     }
-    BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
+    if (sharded) {
+      BGP_TRY(node_allreduce_sum(m, f->samps_dev, (size_t)p * M));
+      BGP_TRY(node_allreduce_sum(m, flag_dev, 2));
+    }
+    double flag[2] = {0.0, 0.0};
+    BGP_CUDA(cudaMemcpyAsync(flag, flag_dev, sizeof(flag), cudaMemcpyDeviceToHost, m->stream));
     if (samps_host)
       BGP_CUDA(cudaMemcpyAsync(samps_host, f->samps_dev, (size_t)p * M * sizeof(double), cudaMemcpyDeviceToHost,
                                m->stream));
     BGP_CUDA(cudaStreamSynchronize(m->stream));
+    if (flag[0] != 0.0) {
+      // aghq::sample_marginal stops in chol() here; garbage samples must not leave with BGP_OK
+      set_error("Hessian of quadrature node %d is not positive definite (pivot %d): cannot sample", (int)flag[0] - 1,
+                (int)flag[1]);
+      return BGP_ERR_NOT_PD;
+    }
     return BGP_OK;
   }();
   if (Zg) cudaFree(Zg);
   if (Zraw) cudaFree(Zraw);
+  if (flag_dev) cudaFree(flag_dev);
   if (perm_dev) cudaFree(perm_dev);
   return st;
 }

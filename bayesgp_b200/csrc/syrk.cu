@@ -8,12 +8,13 @@
 //   * FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — tcgen05 has no FP64 kind; the larger f64 mma
 //     shapes lower to the same instruction).  Measured issue rate: one DMMA per 16.1 clk per SM sub-partition
 //     = 37.0 TFLOP/s at 1965 MHz (scripts/ubench/dmma_bench.cu).
-//   * Persistent, warp-specialised CTAs (2 per SM): one producer warp + 8 consumer warps.  A CTA tile is
-//     128 rows x 64 columns of H; consumer warp w owns a 16 x 64 strip (one 16-column box of the M panel
-//     against the four boxes of the N panel), 32 accumulator doubles per thread.  The diag(w) scaling is
-//     applied to the strip's two A fragments only (2 DMUL per 16 DMMA — a DMUL costs ~4.7 clk of the same pipe).
+//   * Persistent, warp-specialised CTAs (3 per SM): one producer warp + 4 consumer warps.  A CTA tile is
+//     up to 4 row boxes x one N panel (64 x 64 of H); consumer warp w owns column box w of the panel and runs over
+//     the tile's row boxes (a 64 x 16 strip, 32 accumulator doubles per thread).  The diag(w) scaling is
+//     applied to the warp's own column-box fragments only (2 DMUL per 16 DMMA — a DMUL costs ~4.7 clk of the
+//     same pipe).
 //   * Operands are TMA-staged: A is observation-major, so a TMA box of {16 columns, 16 observations} lands as
-//     16 lines of 128 B with the hardware 128B swizzle; a stage is 8 + 4 boxes + 16 weights.  The producer
+//     16 lines of 128 B with the hardware 128B swizzle; a stage is 4 + 4 boxes + 16 weights.  The producer
 //     warp runs a 4-stage mbarrier ring ahead of the consumers (full / empty barriers, no CTA-wide barrier).
 //     Fragment loads are LDS.128 with a column permutation chosen so the swizzled lines are read
 //     conflict-free; the permutation is undone in the epilogue.
@@ -703,9 +704,37 @@ int launch_add_q(bgp_model* m, const double* theta) {
   return BGP_OK;
 }
 
+// lower triangle of H, column by column: element (r, c), r >= c, at c p - c (c - 1) / 2 + (r - c)
+__global__ void pack_lower_kernel(const double* __restrict__ H, int p, int ldh, double* __restrict__ out) {
+  const int c = blockIdx.x;
+  double* dst = out + ((size_t)c * p - (size_t)c * (c - 1) / 2);
+  for (int r = c + threadIdx.x; r < p; r += blockDim.x) dst[r - c] = H[(size_t)c * ldh + r];
+}
+__global__ void unpack_lower_kernel(const double* __restrict__ in, int p, int ldh, double* __restrict__ H) {
+  const int c = blockIdx.x;
+  const double* src = in + ((size_t)c * p - (size_t)c * (c - 1) / 2);
+  for (int r = c + threadIdx.x; r < p; r += blockDim.x) {
+    const double v = src[r - c];
+    H[(size_t)c * ldh + r] = v;
+    H[(size_t)r * ldh + c] = v;
+  }
+}
+
 int launch_hessian(bgp_model* m, const double* theta) {
   BGP_TRY(launch_syrk(m));
-  if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->H, (size_t)m->ldh * m->p));
+  if (m->world > 1) {
+    // observation shards: the likelihood Hessians of the ranks are summed over NVLink; only the packed lower
+    // triangle (p (p + 1) / 2 doubles) travels, both triangles are rewritten from the sum so that every rank holds
+    // the same symmetric matrix bit for bit
+    const size_t np = (size_t)m->p * (m->p + 1) / 2;
+    if (!m->hpack) BGP_CUDA(cudaMalloc(&m->hpack, np * sizeof(double)));
+    pack_lower_kernel<<<m->p, 128, 0, m->stream>>>(m->H, m->p, m->ldh, m->hpack);
+    count_launch();
+    BGP_TRY(comm_allreduce_sum(m, m->hpack, np));
+    unpack_lower_kernel<<<m->p, 128, 0, m->stream>>>(m->hpack, m->p, m->ldh, m->H);
+    count_launch();
+    BGP_CUDA(cudaGetLastError());
+  }
   return launch_add_q(m, theta);
 }
 

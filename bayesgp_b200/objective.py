@@ -68,6 +68,7 @@ class LaplaceObjective:
         self.n_fn = 0
         self.n_gr = 0
         self.newton_iters = 0
+        self.node_rank, self.node_world = 0, 1
         if data is not None:
             y, family, size = data.y, data.family, data.size
         fam = FAMILY_CODES[family] if isinstance(family, str) else int(family)
@@ -133,6 +134,15 @@ class LaplaceObjective:
     def set_shard(self, rank: int, world: int, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         check(self._lib.bgp_model_set_shard(self._h, rank, world, buf))
+
+    def set_node_group(self, rank: int, world: int, unique_id: bytes):
+        """Join a node group: replicas that split quadrature nodes, sample blocks and prediction rows."""
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self._lib.bgp_model_set_node_group(self._h, rank, world, buf))
+        self.node_rank, self.node_world = rank, world
+
+    def set_hessian_retry(self, allow=True):
+        check(self._lib.bgp_model_set_hessian_retry(self._h, int(allow)))
 
     def finalize(self):
         check(self._lib.bgp_model_finalize(self._h))

@@ -63,6 +63,8 @@ def prepare_term(t: Term) -> Term:
             t.k = 30
         if t.k < 3:
             raise ValueError("Error: parameter <k> in the random effect part should be >= 3.")
+        if t.k < 4:         # accepted by R/02_model_fit.R:511-514, refused by fda inside Compute_B_sB (R/01_utility.R:179-183)
+            raise ValueError("sGP with k = 3: fda::create.bspline.basis needs nbasis >= norder = 4")
         if t.a < 0:
             raise ValueError("Error: Parameter <a> in the random effect part should be positive.")
         if t.initial_location is None:

@@ -8,11 +8,13 @@ aghq::normalize_logpost does through ff$fn (/root/reference/R/02_model_fit.R:276
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n ROWS]
 
-N > 1 is launched by torchrun (one process per GPU); every rank holds a replica of the data and
-evaluates its own 15 nodes (node-sharded, no data-path collective) => weak scaling.
+N > 1 is launched by torchrun (one process per GPU): ONE 15-node grid per step is split over the
+ranks (node shards on replicated rows, NCCL all-reduce of the values) => strong scaling; the same
+grid with the observations sharded (all-reduce of g and H per Newton iteration) and N independent
+replicas are reported as extra keys, together with sharded-vs-single-GPU errors.
 `value` is timed on the device with CUDA events on the library's stream (inputs resident in HBM);
-`e2e` is the wall clock of the same step through the C ABI with host buffers (theta / warm start
-in, values + modes + Hessians out).  The roofline is for the dominant kernel (the DMMA Hessian).
+`e2e` is the wall clock of the same step through the C ABI with host buffers (warm start in;
+values, modes and Hessians out).  The roofline is for the dominant kernel (the DMMA Hessian).
 """
 from __future__ import annotations
 
@@ -23,6 +25,13 @@ import subprocess
 import sys
 import threading
 import time
+
+# The CPU legs (cpu_baseline, --impl reference) use every host core whatever the launcher exported: torchrun sets
+# OMP_NUM_THREADS=1 for its workers, which would shrink the reference arm 3-4x at N > 1.  Must precede numpy.
+HOST_THREADS = os.cpu_count() or 1
+if int(os.environ.get("RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(HOST_THREADS)
 
 import numpy as np
 
@@ -130,13 +139,26 @@ def fp64_peak_tflops(device):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def build_b200(x, y, device):
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") == "blas"] or [1])
+    except Exception:
+        return None
+
+
+def build_b200(x, y, device, x0=None, knots=None, shard=None, node_group=None):
     from bayesgp_b200.objective import LaplaceObjective
     from bayesgp_b200.workloads import iwp_knots
-    x0, knots = iwp_knots(x, P_KNOTS)
+    if knots is None:
+        x0, knots = iwp_knots(x, P_KNOTS)
     ff = LaplaceObjective(y=y, family="Poisson", device=device)
     ff.add_iwp(x, x0, knots, ORDER)                 # device-side B / X / P from the covariate
     ff.add_fixed(np.ones(len(y)))                   # intercept (R/02_model_fit.R:572-578)
+    if shard is not None:
+        ff.set_shard(*shard)
+    if node_group is not None:
+        ff.set_node_group(*node_group)
     ff.finalize()
     return ff
 
@@ -150,6 +172,34 @@ def node_grid(ff):
     return mode, sd, thetas, ff.env.last_par.copy()
 
 
+def timed_steps(step, steps, dist, sampler=None):
+    """EXACTLY `steps` steps between barrier + synchronize on both sides; device ms and wall s are summed per rank
+    and the maximum over ranks is returned."""
+    import ctypes as C
+    if dist:
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+    if sampler:
+        sampler.mark_start()
+    t_region = time.perf_counter()
+    dev_ms = wall_s = 0.0
+    extra = []
+    for _ in range(steps):
+        out = step()
+        dev_ms += out["dev_ms"]
+        wall_s += out["wall_s"]
+        extra.append(out)
+    if dist:
+        import torch
+        torch.cuda.synchronize()
+        t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
+        dev_ms, wall_s = float(t[0]), float(t[1])
+        dist.barrier()
+    return dev_ms, wall_s, time.perf_counter() - t_region, extra
+
+
 def run_b200(args):
     rank, world, local = _rank_world()
     dist = None
@@ -158,67 +208,134 @@ def run_b200(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import bayesgp_b200 as bg
     from bayesgp_b200 import _lib
-    from bayesgp_b200.workloads import c3_data
+    from bayesgp_b200.distributed import broadcast_unique_id, nccl_unique_id, shard_bounds
+    from bayesgp_b200.workloads import c3_data, iwp_knots
     lib = _lib.load()
     x, y = c3_data(args.n)
+    x0, knots = iwp_knots(x, P_KNOTS)
     t0 = time.time()
-    ff = build_b200(x, y, local)
+    # every rank holds a replica of the rows; the ranks form one node group (quadrature nodes are split inside
+    # bgp_aghq_fit*); at N = 1 the group is trivial and the same code path runs
+    group = (rank, world, broadcast_unique_id(nccl_unique_id, rank)) if world > 1 else None
+    ff = build_b200(x, y, local, x0, knots, node_group=group)
     t_build = time.time() - t0
     mode, sd, thetas, w_mode = node_grid(ff)
     p, n = ff.p, ff.n
+    opt = {"mode": np.array([mode]), "hessian": np.array([[1.0 / (sd * sd)]])}
 
-    def step():
+    # ---- the step: ONE 15-node grid through the product's own entry point (aghq::normalize_logpost inside
+    # marginal_laplace_tmb with the optimisation results given), split over the node group.  Every step starts
+    # from the mode at the grid centre only (set_start clears the warm-start history).
+    def step_grid(want_host=True):
         ff.set_start(w_mode)                                          # H2D: p doubles
         t0 = time.perf_counter()
-        vals, modes, Hs, iters = ff.fn_batch(thetas, want_modes=True, want_hess=True)   # D2H: values, modes, Hessians
+        mod = bg.marginal_laplace_tmb(ff, K_NODES, None, optresults=opt)
+        ms = ff.last_timing()["total_ms"]
+        iters = mod.diagnostics["grid_newton_iters"]
+        res = {"lognormconst": mod.lognormconst,
+               "logpost": mod.normalized_posterior["nodesandweights"]["logpost"].copy()}
+        if want_host:
+            mh = mod.modesandhessians                                 # D2H: all modes + Hessians (gathered)
+            res["modes"] = mh["mode"]
+            res["Hs"] = mh["H"]
         wall = time.perf_counter() - t0
-        return vals, iters, wall, ff.last_timing()["total_ms"]
+        mod.close()
+        return {"dev_ms": ms, "wall_s": wall, "iters": iters, "res": res}
 
-    for _ in range(max(3, args.warmup)):
-        vals, iters, _, _ = step()
-    tm0 = ff.last_timing()
-    cnt0 = ff.counters()
+    # the batch entry point on one rank's replica (the round-1 headline; also the single-GPU reference values)
+    def step_batch():
+        ff.set_start(w_mode)
+        t0 = time.perf_counter()
+        vals, modes, Hs, iters = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+        wall = time.perf_counter() - t0
+        return {"dev_ms": ff.last_timing()["total_ms"], "wall_s": wall, "iters": iters,
+                "res": {"logpost": -vals, "modes": modes, "Hs": Hs}}
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        out_b = step_batch()
+    single = out_b["res"]                   # single-GPU values of the same grid (every rank: identical replicas)
+    for _ in range(W):
+        step_grid()
+    tm0, cnt0 = ff.last_timing(), ff.counters()
     launches0 = lib.bgp_kernel_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)                       # nvidia-smi is up and streaming before the region starts
-    if dist:
-        dist.barrier()
-    dev_ms, wall_s, iters_tot = 0.0, 0.0, 0
-    if sampler:
-        sampler.mark_start()
-    t_region = time.perf_counter()
-    for _ in range(args.steps):
-        vals, iters, wall, ms = step()
-        dev_ms += ms
-        wall_s += wall
-        iters_tot += iters
+    # device-timed value: results stay on the device (values reduced over the group); e2e: the same step with all
+    # modes and Hessians gathered to the host, by wall clock
+    dev_ms, _, region_s, ex = timed_steps(lambda: step_grid(False), args.steps, dist, sampler)
+    clocks = sampler.stop() if sampler else None
+    tm1, cnt1 = ff.last_timing(), ff.counters()
+    launches = lib.bgp_kernel_launch_count() - launches0
+    iters_rank = sum(e["iters"] for e in ex)
+    _, wall_s, _, ex2 = timed_steps(lambda: step_grid(True), args.steps, dist)
+    grid_res = ex2[-1]["res"]
+    evals = K_NODES * args.steps
+    value = evals / (dev_ms * 1e-3)
+    e2e = evals / wall_s
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, np.max(np.abs(b))))
+    shard_parity = {"what": "node-sharded grid (this run) vs the same grid on one GPU (bgp_laplace_eval_batch on a replica)",
+                    "max_rel_logpost": rel(grid_res["logpost"], single["logpost"]),
+                    "max_rel_mode": rel(grid_res["modes"], single["modes"]),
+                    "max_rel_hessian": rel(grid_res["Hs"], single["Hs"])}
+    iters_all = iters_rank
     if dist:
         import torch
-        t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
-        dev_ms, wall_s = float(t[0]), float(t[1])
-        dist.barrier()
-    region_s = time.perf_counter() - t_region
-    clocks = sampler.stop() if sampler else None
-    tm1 = ff.last_timing()
-    cnt1 = ff.counters()
-    launches = lib.bgp_kernel_launch_count() - launches0
+        t = torch.tensor([float(iters_rank)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        iters_all = float(t[0])
+
+    extra = {}
+    if world > 1:
+        # ---- second number: the same grid with the OBSERVATIONS sharded (each rank holds n / N rows, every rank
+        # evaluates all 15 nodes, NCCL all-reduce of [g | scalars] and the likelihood Hessian per Newton iteration)
+        lo, hi = shard_bounds(n, rank, world)
+        ffs = build_b200(x[lo:hi], y[lo:hi], local, x0, knots,
+                         shard=(rank, world, broadcast_unique_id(nccl_unique_id, rank)))
+
+        def step_obs():
+            ffs.set_start(w_mode)
+            t0 = time.perf_counter()
+            vals, modes, Hs, iters = ffs.fn_batch(thetas, want_modes=True, want_hess=True)
+            return {"dev_ms": ffs.last_timing()["total_ms"], "wall_s": time.perf_counter() - t0, "iters": iters,
+                    "res": {"logpost": -vals, "modes": modes, "Hs": Hs}}
+
+        for _ in range(W):
+            step_obs()
+        tmo0 = ffs.last_timing()
+        o_ms, o_wall, _, exo = timed_steps(step_obs, args.steps, dist)
+        tmo1 = ffs.last_timing()
+        ores = exo[-1]["res"]
+        nh = max(1, tmo1["hess_launches"] - tmo0["hess_launches"])
+        extra["obs_sharded"] = {
+            "value": evals / (o_ms * 1e-3), "e2e": evals / o_wall, "unit": "evals/s", "rows_per_rank": hi - lo,
+            "collective": "per Newton iteration: ncclAllReduce of [g_lik | ll | sumsq | flag] (%d doubles) and of the "
+                          "packed lower triangle of the likelihood Hessian (%d doubles)" % (ffs.p + 4, ffs.p * (ffs.p + 1) // 2),
+            "hess_ms_per_launch_incl_allreduce": (tmo1["hess_ms"] - tmo0["hess_ms"]) / nh,
+            "newton_iters_per_eval": sum(e["iters"] for e in exo) / evals,
+            "parity_vs_single_gpu": {"max_rel_logpost": rel(ores["logpost"], single["logpost"]),
+                                     "max_rel_mode": rel(ores["modes"], single["modes"]),
+                                     "max_rel_hessian": rel(ores["Hs"], single["Hs"])}}
+        ffs.close()
+        # ---- third: N independent replicas, each evaluating its own 15 nodes (round 1's "weak" number)
+        r_ms, r_wall, _, _ = timed_steps(step_batch, args.steps, dist)
+        extra["replicas"] = {"value": evals * world / (r_ms * 1e-3), "unit": "evals/s", "scaling": "weak",
+                             "note": "every rank evaluates the whole grid on its replica, no collective"}
     if rank != 0:
         ff.close()
         if dist:
             dist.destroy_process_group()
         return
-    evals = K_NODES * args.steps * world
-    value = evals / (dev_ms * 1e-3)
-    e2e = evals / wall_s
     n_hess = tm1["hess_launches"] - tm0["hess_launches"]
     n_lik = tm1["lik_launches"] - tm0["lik_launches"]
     hess_ms = (tm1["hess_ms"] - tm0["hess_ms"]) / max(1, n_hess)
     lik_ms = (tm1["lik_ms"] - tm0["lik_ms"]) / max(1, n_lik)
     chol_ms = (tm1["chol_ms"] - tm0["chol_ms"]) / max(1, tm1["chol_launches"] - tm0["chol_launches"])
+    my_evals = max(1, cnt1["laplace_evals"] - cnt0["laplace_evals"])
     peaks, peak_src = measured_peaks()
     try:
         fp64_peak = fp64_peak_tflops(local)
@@ -235,22 +352,32 @@ def run_b200(args):
     lik_gbs = lik_bytes / (lik_ms * 1e-3) / 1e9
     line = {
         "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300",
-        "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d), 1-D AGHQ 15 nodes per step "
-                               "per GPU, warm-started inner Newton to max|g|<1e-8 + log-det" % (n, p),
-                   "nodes_per_step": K_NODES, "newton_iters_per_eval": iters_tot / (K_NODES * args.steps),
-                   "hessians_per_eval": n_hess / (K_NODES * args.steps),
-                   "logdet_from_last_newton_factor": "%d of %d evaluations (certified |d logdet| <= p max|d eta| <= 2e-10 |L|; "
-                                                     "bgp_model_set_factor_reuse, DESIGN.md section 5)"
-                                                     % (cnt1["factor_reuses"] - cnt0["factor_reuses"],
-                                                        cnt1["laplace_evals"] - cnt0["laplace_evals"]),
+        "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d): ONE 1-D AGHQ grid of 15 nodes per "
+                               "step through bgp_aghq_fit_at (aghq::normalize_logpost), nodes split over the %d GPU(s) of "
+                               "the node group; warm-started inner Newton to max|g|<1e-8 + log-det" % (n, p, world),
+                   "nodes_per_step": K_NODES, "newton_iters_per_eval": iters_all / evals,
+                   "hessians_per_eval_rank0": n_hess / my_evals,
+                   "logdet_from_last_newton_factor": "%d of %d evaluations on rank 0 (certified |d logdet| <= p max|d eta| <= "
+                                                     "2e-10 |L|; bgp_model_set_factor_reuse, DESIGN.md section 5)"
+                                                     % (cnt1["factor_reuses"] - cnt0["factor_reuses"], my_evals),
                    "theta_mode": mode, "theta_sd": sd, "l2_flush": "inputs (2.4 GB design matrix) exceed the 126 MB L2",
-                   "parallelism": "node-sharded replicas x%d" % world, "model_build_s": t_build},
-        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + K_NODES),
-                "d2h_bytes_per_step": 8 * K_NODES * (1 + p + p * p)},
+                   "parallelism": "node shards x%d (replicated rows), NCCL all-reduce of the 15 values" % world
+                                  if world > 1 else "single GPU",
+                   "model_build_s": t_build},
+        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + 2),
+                "d2h_bytes_per_step": 8 * K_NODES * (3 + p + p * p),
+                "what": "set_start (H2D) + bgp_aghq_fit_at + bgp_fit_get_* incl. all modes and Hessians gathered to the "
+                        "host, wall clock, max over ranks"},
         "gpu_launches": int(launches),
+        "parity_note": "oracle pinned on the README printout only (DESIGN.md section 3): 'parity' keys compare this run "
+                       "with that oracle / with the single-GPU path, not with a run of R/TMB/aghq",
+        "sharded_vs_single_gpu": shard_parity,
+        "batch_entry_point": {"value": K_NODES / (out_b["dev_ms"] * 1e-3), "e2e": K_NODES / out_b["wall_s"],
+                              "unit": "evals/s", "what": "bgp_laplace_eval_batch on one replica, modes + Hessians to "
+                                                         "the host (round-1 headline), last warm-up step"},
         "roofline": {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": achieved,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if fp64_peak else None,
                      "traffic": SYRK_DRAM_TRAFFIC_BYTES if n == 1_000_000 else None, "traffic_unit": "bytes",
@@ -269,14 +396,65 @@ def run_b200(args):
         "clocks": clocks,
         "wall_s_timed_region": region_s,
     }
+    line.update(extra)
+    if world == 1 and not args.no_fit:
+        line["fit"] = fit_leg(ff)
+    if world == 1 and not args.no_grad:
+        line["gradient"] = gradient_leg(ff, mode, fp64_peak)
     if world == 1 and not args.no_predict:
         line["predict"] = predict_leg(local, fp64_peak)
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(x, y, thetas, w_mode, budget_s=args.cpu_budget)
+        cb, par = cpu_baseline(x, y, thetas, w_mode, single, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = cb
+        line["parity"] = par
     print(json.dumps(line), flush=True)
     ff.close()
     if dist:
         dist.destroy_process_group()
+
+
+def fit_leg(ff):
+    """What model_fit() costs at C3 on the same device-resident model: aghq::marginal_laplace_tmb from theta = 0
+    (BFGS by vmmin, Richardson Hessian of ff$gr, the 15-node grid, marginals), wall clock, with the evaluation counts
+    and the in-situ rate of the grid phase (to be compared with the headline)."""
+    import bayesgp_b200 as bg
+    ff.set_start(None)
+    fn0, it0 = ff.counters()["laplace_evals"], ff.counters()["newton_iters"]
+    t0 = time.perf_counter()
+    mod = bg.marginal_laplace_tmb(ff, K_NODES, np.zeros(ff.S))
+    wall = time.perf_counter() - t0
+    d, c = mod.diagnostics, ff.counters()
+    out = {"what": "marginal_laplace_tmb(ff, k=15, theta0=0) on the resident C3 model: BFGS + Richardson + grid + marginals",
+           "wall_s": wall, "opt_s": d["opt_ms"] * 1e-3, "grid_s": d["grid_ms"] * 1e-3,
+           "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"],
+           "laplace_evals": c["laplace_evals"] - fn0, "newton_iters": c["newton_iters"] - it0,
+           "theta_mode": float(mod.optresults["mode"][0]), "theta_hessian": float(mod.optresults["hessian"][0, 0]),
+           "convergence": mod.optresults["convergence"], "hessian_fallback": d["hessian_fallback"],
+           "lognormconst": mod.lognormconst,
+           "grid_evals_per_s_in_situ": K_NODES / (d["grid_ms"] * 1e-3),
+           "grid_newton_iters_per_eval": d["grid_newton_iters"] / K_NODES}
+    mod.close()
+    return out
+
+
+def gradient_leg(ff, mode, fp64_peak, reps=8):
+    """ff$gr at C3: Laplace value + its theta-gradient (leverage pass q_i = a_i^T H^-1 a_i, traces, implicit term)
+    against ff$fn alone at the same thetas."""
+    ths = [np.array([mode + 0.01 * (i + 1)]) for i in range(reps)]
+    ff.set_start(None)
+    ff.fn(np.array([mode]))
+    t0 = time.perf_counter()
+    for th in ths:
+        ff.fn(th)
+    t_fn = (time.perf_counter() - t0) / reps
+    ff.set_start(None)
+    ff.fn(np.array([mode]))
+    t0 = time.perf_counter()
+    for th in ths:
+        ff.gr(th)
+    t_gr = (time.perf_counter() - t0) / reps
+    return {"fn_ms": t_fn * 1e3, "gr_ms": t_gr * 1e3, "gr_over_fn": t_gr / t_fn,
+            "what": "wall clock per call through the C ABI, %d thetas stepping away from the mode; gr includes fn" % reps}
 
 
 def predict_leg(device, fp64_peak, G=100_000, M=10_000):
@@ -325,26 +503,39 @@ def oracle_model(x, y):
     return model, OracleFF(model)
 
 
-def cpu_baseline(x, y, thetas, w_mode, budget_s=20.0):
+def cpu_baseline(x, y, thetas, w_mode, gpu, budget_s=20.0):
     """Oracle port timed on the host cores on a bounded sample: the first nodes of the same grid at
-    the same n, p (numpy / OpenBLAS, all threads), until >= 3 evaluations and >= budget seconds."""
+    the same n, p (numpy / OpenBLAS, all threads), until >= 3 evaluations and >= budget seconds.  The values and
+    modes it computes are the full-size parity check of the GPU results of the same nodes (north_star: log marginal
+    likelihood 1e-8 relative, mode 1e-6)."""
     t0 = time.time()
     model, off = oracle_model(x, y)
     t_build = time.time() - t0
     off.last_par = w_mode.copy()
     done, t0 = 0, time.time()
-    for th in thetas:
-        off.fn(th)
+    rv = rm = rh = 0.0
+    for j, th in enumerate(thetas):
+        v = off.fn(th)
         done += 1
+        rv = max(rv, abs(-v - gpu["logpost"][j]) / abs(v))
+        rm = max(rm, float(np.max(np.abs(off.last_par - gpu["modes"][j])) / np.max(np.abs(off.last_par))))
+        H = off.sp_hess()
+        rh = max(rh, float(np.max(np.abs(H - gpu["Hs"][j])) / np.max(np.abs(H))))
         if done >= 3 and time.time() - t0 >= budget_s:
             break
         if time.time() - t0 >= 3 * budget_s:
             break
     dt = time.time() - t0
-    return {"value": done / dt, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "first %d of %d nodes, same n=%d p=%d, warm start from the mode; numpy/OpenBLAS FP64 "
-                      "(oracle/laplace.py), design build %.1f s untimed" % (done, len(thetas), model.n, model.p, t_build),
-            "newton_iters_per_eval": off.newton_iters / max(1, done)}
+    cb = {"value": done / dt, "unit": "evals/s", "cores": HOST_THREADS, "blas_threads": blas_threads(), "kind": "port",
+          "sample": "first %d of %d nodes, same n=%d p=%d, warm start from the mode; dense numpy/OpenBLAS FP64 port "
+                    "(oracle/laplace.py; not sparse-aware as TMB would be), design build %.1f s untimed"
+                    % (done, len(thetas), model.n, model.p, t_build),
+          "newton_iters_per_eval": off.newton_iters / max(1, done)}
+    par = {"what": "GPU (bgp_laplace_eval_batch, full size) vs the oracle port on the same nodes",
+           "nodes": done, "max_rel_value": rv, "max_rel_mode": rm, "max_rel_hessian": rh,
+           "tolerance": {"value": 1e-8, "mode": 1e-6, "hessian": 1e-6},
+           "ok": bool(rv <= 1e-8 and rm <= 1e-6 and rh <= 1e-6), "pin": "readme-pinned oracle"}
+    return cb, par
 
 
 def run_reference(args):
@@ -378,12 +569,15 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300", "value": v, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 synthetic Poisson n=%d, IWP3 k=300 + intercept (p=%d), 1-D AGHQ 15-node grid; "
                                "each step = %d node evaluations (bounded sample)" % (model.n, model.p, nodes_per_step),
                    "newton_iters_per_eval": (off.newton_iters - it0) / evals},
-        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d node evaluations per step at full n, numpy/OpenBLAS FP64" % nodes_per_step},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": HOST_THREADS, "blas_threads": blas_threads(),
+                         "kind": "port",
+                         "sample": "%d node evaluations per step at full n, dense numpy/OpenBLAS FP64 port "
+                                   "(not sparse-aware)" % nodes_per_step},
+        "threads": blas_threads(),
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -398,6 +592,8 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-predict", action="store_true", help="skip the predict GFLOP/s leg")
+    ap.add_argument("--no-fit", action="store_true", help="skip the model_fit() leg")
+    ap.add_argument("--no-grad", action="store_true", help="skip the ff$gr leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-nodes", type=int, default=1)
     args = ap.parse_args()

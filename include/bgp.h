@@ -84,6 +84,14 @@ int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, do
  * bgp_nccl_unique_id on rank 0 and broadcast by the launcher). Must precede finalize. */
 int bgp_nccl_unique_id(void* id128);
 int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_unique_id);
+/* node group: the `world` processes of this communicator hold the SAME rows (replicas, or the same observation
+ * shard) and split between them the quadrature nodes of bgp_aghq_fit's grids (the K node evaluations of
+ * aghq::normalize_logpost, R/02_model_fit.R:284, contiguous runs of the expand.grid order), the per-node sample
+ * blocks of bgp_sample* (aghq::sample_marginal, :687-689) and the grid rows of bgp_fit_predict_*
+ * (R/03_post_fit.R:235,287-296).  BFGS and the Richardson Hessian run replicated (identical on every rank).
+ * Independent of bgp_model_set_shard (both may be set: a 2-D layout); may be called before or after finalize.
+ * With a node group every rank must make the same fit / sample / predict / bgp_fit_get_modes calls. */
+int bgp_model_set_node_group(bgp_model* m, int rank, int world, const void* nccl_unique_id);
 int bgp_model_finalize(bgp_model* m);
 void bgp_model_destroy(bgp_model* m);
 
@@ -123,11 +131,17 @@ int bgp_model_set_newton(bgp_model* m, double grad_tol, double step_tol, int max
  * marginals ("reuse"), per-node modes and Hessians.
  * ---------------------------------------------------------------------------------------- */
 int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
+/* When numDeriv's Richardson Hessian of ff$gr (d = 1e-4) is not positive definite aghq stops in chol(); so does
+ * bgp_aghq_fit (BGP_ERR_NOT_PD).  allow = 1 opts into a retry with d = 1e-3 and 1e-2 (not in the reference); the
+ * number of retries a fit needed is reported by bgp_fit_get_diagnostics. */
+int bgp_model_set_hessian_retry(bgp_model* m, int allow);
 /* same, but with the optimisation results supplied (aghq's `optresults` argument) */
 int bgp_aghq_fit_at(bgp_model* m, int k, const double* mode, const double* hessian /* S x S */, bgp_fit** out);
 void bgp_fit_destroy(bgp_fit* f);
 int bgp_fit_dims(const bgp_fit* f, int* S, int* K, int* p, int* k);
-/* getters mirror mod$optresults / mod$normalized_posterior / mod$modesandhessians / mod$marginals */
+/* getters mirror mod$optresults / mod$normalized_posterior / mod$modesandhessians / mod$marginals.  The per-node
+ * modes and Hessians live on the device(s) that evaluated them; bgp_fit_get_modes rotates them into the W order and
+ * copies them out (a collective call when the model has a node group). */
 int bgp_fit_get_opt(const bgp_fit* f, double* mode /* S */, double* hessian /* S*S */, int* convergence,
                     int* fn_count, int* gr_count);
 int bgp_fit_get_grid(const bgp_fit* f, double* nodes /* K x S col-major */, double* weights /* K */,
@@ -135,6 +149,12 @@ int bgp_fit_get_grid(const bgp_fit* f, double* nodes /* K x S col-major */, doub
 int bgp_fit_get_modes(const bgp_fit* f, double* modes /* p x K */, double* Hs /* p x p x K, may be NULL */);
 int bgp_fit_get_marginal(const bgp_fit* f, int j, double* theta /* k */, double* logmargpost /* k */,
                          double* w /* k */);
+/* how the fit went: Richardson retries used (0 = numDeriv's default step, as the reference), inner Newton iterations
+ * spent on the quadrature grids by this rank, wall clock (ms) of the BFGS + Richardson phase and of the grid phase */
+int bgp_fit_get_diagnostics(const bgp_fit* f, int* hessian_fallback, int64_t* grid_newton_iters, double* opt_ms,
+                            double* grid_ms);
+/* node-group rank that evaluated (and holds the mode / Hessian of) each of the K nodes */
+int bgp_fit_node_owner(const bgp_fit* f, int32_t* owner /* K */);
 
 /* ------------------------------------------------------------------------------------------
  * aghq::sample_marginal(mod, M)  (R/02_model_fit.R:687-689) with the random inputs explicit:
@@ -162,6 +182,17 @@ int bgp_predict_iwp(const double* coef, const double* global, const double* icpt
 int bgp_predict_sgp(const double* coef, const double* global, const double* icpt, int64_t M, double a, int k, int m,
                     const double* region /* 2 */, int boundary, const double* x, int64_t G, double level, int device,
                     double* mean, double* plower, double* pupper, double* samples);
+/* The same two evaluations from the samples bgp_sample / bgp_sample_draw left on the device (no host copy of the
+ * p x M matrix): coef_row0 / global_row0 / icpt_row are the first 0-based rows of the term's spline block, its
+ * boundary block and the intercept in samps$samps (random_samp_indexes / boundary_samp_indexes /
+ * fixed_samp_indexes$intercept, R/02_model_fit.R:627-675; -1 = block absent / not included).  With a node group the
+ * rows of x are split over the ranks and the three G-vectors are returned whole on every rank. */
+int bgp_fit_predict_iwp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row, const double* knots, int nknots, int order,
+                        int degree, const double* x, int64_t G, double level, double* mean, double* plower,
+                        double* pupper);
+int bgp_fit_predict_sgp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row, double a, int k, int m,
+                        const double* region /* 2 */, int boundary, const double* x, int64_t G, double level, double* mean,
+                        double* plower, double* pupper);
 /* device time (CUDA events on the call's stream, ms) of the last bgp_predict_* call on this thread: the FP64
  * tensor-pipe GEMM strips, the per-row quantile selection, and the whole device sequence */
 int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms);
@@ -175,11 +206,14 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
 /* counters since creation: Laplace evaluations, accepted Newton iterations, evaluations whose log-determinant
  * came from the factor of the last Newton iteration (certified: |d logdet| <= p * max|d eta|, see below) */
 int bgp_model_counters(const bgp_model* m, int64_t* laplace_evals, int64_t* newton_iters, int64_t* factor_reuses);
-/* When the inner Newton converges by a full step that moved the linear predictor by delta = max |d eta| with
+/* When the inner Newton converges by a full step w0 -> w1 that moved the linear predictor by delta = max |d eta| with
  * delta <= eta_tol (default 1e-7) and p * delta / 2 <= rel_tol * |value| (default 1e-10), the factor of that
- * last iteration is used for 1/2 logdet H instead of a new Hessian + Cholesky at the mode (TMB recomputes;
- * the certified difference is 100x inside the 1e-8 tolerance).  allow = 0 restores the recomputation.
- * Gradients always use the factor at the mode. */
+ * last iteration is used for 1/2 logdet H instead of a new Hessian + Cholesky at the mode (TMB recomputes).
+ * Exact bounds (newton.cu): e^-delta H(w0) <= H(w1) <= e^delta H(w0), so |d logdet| <= p delta (100x inside the 1e-8
+ * tolerance of the value) and the H returned by bgp_laplace_eval* / kept by bgp_aghq_fit* — then H(w0), not H(w1) —
+ * is within (e^delta - 1) <= 1e-7 relative (2-norm) of ff$env$spHess at the mode, 10x inside the 1e-6 tolerance.
+ * allow = 0 restores the recomputation.  Gradients always re-form H and its factor at the mode, so a call that
+ * asks for grad AND H returns H(w1). */
 int bgp_model_set_factor_reuse(bgp_model* m, int allow, double eta_tol, double rel_tol);
 /* flops of one Hessian launch H = A^T diag(w) A: dense (n p (p+1)) and the structurally non-zero part the
  * kernel executes after skipping empty {64-observation x 16-column} cells (roofline reporting) */
