@@ -4,9 +4,11 @@ The reference has no distributed path; SURVEY.md section 8e defines the three sh
   * observation shards  — rank g holds rows [lo, hi) of the data; every Newton iteration all-reduces
     [g_lik | ll | sumsq | flag] (p + 4 doubles) and the p x p likelihood Hessian (NCCL, on the
     library's stream); prior / Cholesky / step run replicated, so ranks stay bit-identical;
-  * node shards         — each rank evaluates a slice of the quadrature nodes on a full replica
-    (no data-path collective; results all-gathered at the end);
-  * grid-row shards     — predict rows are split across ranks (no collective).
+  * node shards         — the ranks of a node group (bgp_model_set_node_group) hold the same rows and each
+    evaluates a contiguous run of the quadrature nodes inside bgp_aghq_fit*; the K values are all-reduced, modes
+    and Hessians stay on the device that produced them; bgp_sample* draws each node's block on its owner and
+    all-reduces the p x M matrix (one owner per column, zeros elsewhere);
+  * grid-row shards     — bgp_fit_predict_* splits the rows of x_new over the node group the same way.
 """
 from __future__ import annotations
 
@@ -21,9 +23,12 @@ def shard_bounds(n: int, rank: int, world: int):
 
 
 def node_slice(K: int, rank: int, world: int):
-    """Quadrature nodes owned by `rank` (round-robin keeps neighbouring thetas — and therefore good
-    warm starts — on one rank when K >> world is false, and balances otherwise)."""
-    return list(range(rank, int(K), int(world)))
+    """Quadrature nodes (or sample blocks / prediction rows) owned by node-group rank `rank`: the same contiguous,
+    balanced runs of the expand.grid order as the library deals them (piece_bounds in csrc/bgp_internal.h;
+    neighbours along the first coordinate share a rank, which keeps the warm starts close).  The owners a fit
+    actually used are reported by ``AGHQ.node_owner`` (bgp_fit_node_owner)."""
+    lo, hi = shard_bounds(K, rank, world)
+    return list(range(lo, hi))
 
 
 def broadcast_unique_id(make_id, rank: int, group=None) -> bytes:
