@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     syrk_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ wobs, double* __restrict__ part,
                 const SkTile* __restrict__ tiles, const uint32_t* __restrict__ entries, const int2* __restrict__ units,
                 int nunits, int* __restrict__ counter, const unsigned long long* __restrict__ occ,
-                unsigned long long* __restrict__ dbg) {
+                unsigned long long* __restrict__ dbg, int rot_units) {
   extern __shared__ uint8_t smem_raw[];
   if (dbg && threadIdx.x == 0) {
     unsigned long long t0;
@@ -304,8 +304,13 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
       cur_unit = unit;
       const SkTile* tp = tiles + meta.y;
       const int j4 = 4 * tp->J;
-      smask_w = tp->wrows[warp];
-      wc = tp->wcol[warp];
+      // Column boxes are dealt to the warps with a per-unit rotation.  After the zero-pattern sort the occupied
+      // column boxes of a chunk are a prefix, so box 0 of a panel carries ~31 % of a tile's DMMAs and box 3 ~20 %
+      // (C3); warp w of every CTA sits on SM sub-partition w, each with its own FP64 tensor pipe, so a fixed
+      // box -> warp map keeps one pipe saturated while another idles a third of the time.
+      const int wi = (warp + (rot_units ? unit : 0)) & 3;
+      smask_w = tp->wrows[wi];
+      wc = tp->wcol[wi];
 #pragma unroll
       for (int sr = 0; sr < 4; ++sr) {
         const int r = tp->rows[sr];
@@ -620,10 +625,12 @@ void syrk_plan_destroy(bgp_model* m) {
 // H_lik = A^T diag(w) A (both triangles); Q is added by launch_add_q after the optional allreduce
 int launch_syrk(bgp_model* m) {
   SyrkPlan* pl = (SyrkPlan*)m->syrk_plan;
+  static const bool sk_rotate = getenv("BGP_SK_NOROT") == nullptr;     // env: diagnostics (fixed box -> warp map)
   BGP_CUDA(cudaMemsetAsync(pl->counter_dev, 0, sizeof(int), m->stream));
   syrk_kernel<<<pl->G, SK_THREADS, SK_SMEM, m->stream>>>(pl->tmA, m->wobs, m->part_H, pl->tiles_dev, pl->entries_dev,
                                                         pl->units_dev, pl->nunits, pl->counter_dev,
-                                                        (const unsigned long long*)m->occ_dev, pl->dbg_dev);
+                                                        (const unsigned long long*)m->occ_dev, pl->dbg_dev,
+                                                        sk_rotate ? 1 : 0);
   count_launch();
   if (pl->dbg_dev && pl->dbg_left > 0) {
     --pl->dbg_left;
