@@ -78,6 +78,7 @@ SIGNATURES = {
     "bgp_model_set_node_group": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bgp_model_set_hessian_retry": (C.c_int, [C.c_void_p, C.c_int]),
     "bgp_fit_get_diagnostics": (C.c_int, [C.c_void_p, c_int_p, c_int64_p, c_double_p, c_double_p]),
+    "bgp_fit_host_arrays": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]),
     "bgp_fit_node_owner": (C.c_int, [C.c_void_p, c_int32_p]),
     "bgp_fit_predict_iwp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, C.c_int,
                                       c_double_p, C.c_int64, C.c_double, c_double_p, c_double_p, c_double_p]),

@@ -81,6 +81,15 @@ class AGHQ:
             self._modes, self._Hs = modes, Hs
         return {"theta": self.normalized_posterior["nodesandweights"]["theta"], "mode": self._modes, "H": self._Hs}
 
+    def modesandhessians_view(self):
+        """Zero-copy views of the fit's own page-locked host arrays (bgp_fit_host_arrays): valid until ``close()``.
+        ``modesandhessians`` returns owned copies instead."""
+        pm, pH = _lib.c_double_p(), _lib.c_double_p()
+        check(self._lib.bgp_fit_host_arrays(self._h, C.byref(pm), C.byref(pH)))
+        modes = np.ctypeslib.as_array(pm, shape=(self.K, self.p))
+        Hs = np.ctypeslib.as_array(pH, shape=(self.K, self.p, self.p))
+        return {"theta": self.normalized_posterior["nodesandweights"]["theta"], "mode": modes, "H": Hs}
+
     def close(self):
         if self._h:
             self._lib.bgp_fit_destroy(self._h)
@@ -123,7 +132,7 @@ def sample_marginal(quad: AGHQ, M: int, Z=None, node_idx=None, seed: int = 0):
     # "resident": the same p x M matrix is still on the device behind `quad` (predict reads it in place) until the
     # next sample_marginal call on that object replaces it
     quad._resident_token = token = object()
-    return {"samps": samps, "theta": theta, "node": idx, "resident": (quad, token)}
+    return {"samps": samps, "theta": theta, "node": idx, "resident": (quad, token, samps)}
 
 
 class FitResult:
@@ -339,9 +348,9 @@ def predict(object: FitResult, newdata=None, variable=None, degree=0, include_in
         refined_x = np.sort(np.asarray(newdata, dtype=np.float64) - term.initial_location)
     intercept = samps[object.fixed_samp_indexes["intercept"], :] if include_intercept else None
     dev = object.ff.device
-    quad, token = object.samps.get("resident") or (None, None)
+    quad, token, arr = object.samps.get("resident") or (None, None, None)
     if (not only_samples and quad is not None and quad is object.mod and quad._h and term.kind in ("IWP", "sGP")
-            and getattr(quad, "_resident_token", None) is token):
+            and getattr(quad, "_resident_token", None) is token and object.samps["samps"] is arr):
         # the samples are still on the device behind the fit: no p x M host copy, grid rows split over the node group
         f = _predict_resident(object, term, variable, refined_x, degree, include_intercept, level)
         if f is None:

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -187,6 +188,11 @@ struct bgp_model {
   int node_rank = 0, node_world = 1;
   bgp::Comm* node_comm = nullptr;
   bool hessian_retry = false;   // Richardson retry with larger steps when the theta Hessian is not PD (fit.cu)
+  // blocks lent to fits (per-node Hessians on the device, their pinned host mirror) come back here when the fit is
+  // destroyed: a fit per quadrature grid must not pay a cudaMalloc / cudaHostAlloc / cudaFree each time
+  struct PoolBlock { size_t bytes; void* ptr; };
+  std::vector<PoolBlock> dev_pool, pin_pool;
+  std::shared_ptr<int> alive = std::make_shared<int>(1);   // fits outliving the model see 0 here
   // ---- timing ----------------------------------------------------------------------------------
   cudaEvent_t ev[8] = {nullptr};
   double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0;
@@ -212,6 +218,12 @@ struct bgp_fit {
   int n_local = 0;
   double* modes_dev = nullptr;         // n_local x lda
   double* Hs_dev = nullptr;            // n_local x (p x ldh)
+  size_t modes_dev_bytes = 0, Hs_dev_bytes = 0, mirror_bytes = 0;
+  // pinned host mirror in the caller's layout (external order): modes p x K, then Hs p x p x K.  Filled while the
+  // grid is being evaluated (asynchronous copies behind each node); nodes of other node-group ranks on request.
+  double* mirror = nullptr;
+  std::vector<unsigned char> mirrored;  // K
+  std::shared_ptr<int> model_alive;
   int64_t grid_newton_iters = 0;       // inner Newton iterations spent on the quadrature grids (this rank)
   double grid_ms = 0.0, opt_ms = 0.0;  // wall clock of the grid phase / the BFGS + Richardson phase
   std::vector<std::vector<double>> marg_theta, marg_lmp, marg_w;
@@ -265,6 +277,9 @@ int rot_vec_dev(bgp_model* m, const double* dev_int, double* dev_ext);      // p
 int rot_H_dev(bgp_model* m, const double* H_int, double* dev_ext, int lde); // p x ldh internal -> p x lde external
 int launch_sgp_block(const double* x_dev, int64_t n, double x0, double a, int k, int m, double lo, double hi, double* dstB,
                      double* dstX, cudaStream_t st);
+// model.cu: size-keyed free lists of device / pinned blocks (see bgp_model::dev_pool)
+void* pool_take(bgp_model* m, bool pinned, size_t bytes, size_t* got_bytes);
+void pool_give(bgp_model* m, bool pinned, void* ptr, size_t bytes);
 // newton.cu
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
@@ -273,6 +288,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);
 struct BatchSink {
   double* modes_host = nullptr;
   double* Hs_host = nullptr;
+  bool host_pinned = false;       // the host arrays are page-locked: copy straight into them, no staging slots
   double* modes_dev = nullptr;
   double* Hs_dev = nullptr;
   const int* dev_slot = nullptr;

@@ -462,12 +462,20 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
       f->slot[j] = f->n_local++;
     }
   }
+  f->model_alive = m->alive;
   if (f->n_local > 0) {
-    if (cudaMalloc(&f->modes_dev, (size_t)f->n_local * m->lda * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&f->Hs_dev, (size_t)f->n_local * p * m->ldh * sizeof(double)) != cudaSuccess) {
-      set_error("out of device memory for %d per-node Hessians (%d x %d)", f->n_local, p, p);
-      return fail(BGP_ERR_CUDA);
-    }
+    f->modes_dev = (double*)pool_take(m, false, (size_t)f->n_local * m->lda * sizeof(double), &f->modes_dev_bytes);
+    f->Hs_dev = (double*)pool_take(m, false, (size_t)f->n_local * p * m->ldh * sizeof(double), &f->Hs_dev_bytes);
+    if (!f->modes_dev || !f->Hs_dev) return fail(BGP_ERR_CUDA);
+  }
+  // host mirror of modesandhessians (external order), page-locked: each node's mode / Hessian follows its
+  // evaluation out over PCIe while the next node is being evaluated.  Skipped when it would not fit comfortably
+  // in host memory (then bgp_fit_get_modes rotates and copies on request).
+  const size_t mirror_need = ((size_t)K * p + (size_t)K * p * p) * sizeof(double);
+  if (mirror_need <= ((size_t)2 << 30)) {
+    f->mirror = (double*)pool_take(m, true, mirror_need, &f->mirror_bytes);
+    if (!f->mirror) return fail(BGP_ERR_CUDA);
+    f->mirrored.assign(K, 0);
   }
   double* vals_dev = nullptr;
   if (nw > 1 && cudaMalloc(&vals_dev, (size_t)K * sizeof(double)) != cudaSuccess) {
@@ -491,6 +499,12 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
       sink.modes_dev = f->modes_dev;
       sink.Hs_dev = f->Hs_dev;
       sink.dev_slot = f->slot.data();
+      if (f->mirror) {
+        sink.modes_host = f->mirror;
+        sink.Hs_host = f->mirror + (size_t)K * p;
+        sink.host_pinned = true;
+        for (int j = 0; j < K; ++j) f->mirrored[j] = (nw > 1 ? mine[j] : 1);
+      }
     }
     int iters = 0, bad = -1;
     int rc = laplace_batch(m, K, th.data(), nw > 1 ? mine.data() : nullptr, vals.data(), sink, &iters, &bad);
@@ -580,39 +594,71 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   return BGP_OK;
 }
 
-// modesandhessians in the caller's layout (external order): every node is rotated on the device of its owner,
-// gathered over the node group (zeros from the other ranks) and copied out, a few nodes at a time
-static int gather_modes(const bgp_fit* f, double* modes, double* Hs) {
+// modesandhessians in the caller's layout (external order).  Nodes evaluated by this rank are already in the pinned
+// mirror; nodes held by other ranks of the node group are rotated on their owner's device, gathered over the group
+// (zeros from everyone else) and copied in, a few nodes at a time.  Without a mirror everything takes that route.
+static int complete_mirror(const bgp_fit* f, double* modes, double* Hs) {
   bgp_model* m = f->model;
   const int p = f->p, K = f->K;
-  const size_t per = (Hs ? (size_t)p * p : 0) + (size_t)p;
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, ((size_t)256 << 20) / (per * sizeof(double))));
-  double* stage = nullptr;
-  BGP_CUDA(cudaMalloc(&stage, (size_t)chunk * per * sizeof(double)));
+  const size_t pp = (size_t)p * p;
+  double* dst_modes = f->mirror ? f->mirror : modes;
+  double* dst_Hs = f->mirror ? f->mirror + (size_t)K * p : Hs;
+  std::vector<int> todo;
+  for (int j = 0; j < K; ++j)
+    if (!f->mirror || !f->mirrored[j]) todo.push_back(j);
+  // every rank of a node group walks the same list (its own nodes are "mirrored", the others' are not, so the
+  // lists differ): the collective is therefore over ALL nodes that are missing on ANY rank = all K when sharded
+  if (m->node_world > 1) {
+    todo.clear();
+    for (int j = 0; j < K; ++j) todo.push_back(j);
+  }
+  if (todo.empty()) return BGP_OK;
+  const bool want_H = f->mirror || Hs;
+  const size_t per = (want_H ? pp : 0) + (size_t)p;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(todo.size(), ((size_t)256 << 20) / (per * sizeof(double))));
+  size_t stage_bytes = 0;
+  double* stage = (double*)pool_take(m, false, (size_t)chunk * per * sizeof(double), &stage_bytes);
+  if (!stage) return BGP_ERR_CUDA;
   std::vector<double> host;
   int rc = [&]() -> int {
-    for (int j0 = 0; j0 < K; j0 += chunk) {
-      const int nj = std::min(chunk, K - j0);
+    for (size_t t0 = 0; t0 < todo.size(); t0 += chunk) {
+      const int nj = (int)std::min<size_t>(chunk, todo.size() - t0);
       if (m->node_world > 1) BGP_CUDA(cudaMemsetAsync(stage, 0, (size_t)nj * per * sizeof(double), m->stream));
-      for (int j = j0; j < j0 + nj; ++j) {
+      for (int q = 0; q < nj; ++q) {
+        const int j = todo[t0 + q];
         if (f->slot[j] < 0) continue;
-        double* dst = stage + (size_t)(j - j0) * per;
+        double* dst = stage + (size_t)q * per;
         BGP_TRY(rot_vec_dev(m, f->modes_dev + (size_t)f->slot[j] * m->lda, dst));
-        if (Hs) BGP_TRY(rot_H_dev(m, f->Hs_dev + (size_t)f->slot[j] * p * m->ldh, dst + p, p));
+        if (want_H) BGP_TRY(rot_H_dev(m, f->Hs_dev + (size_t)f->slot[j] * p * m->ldh, dst + p, p));
       }
       BGP_TRY(node_allreduce_sum(m, stage, (size_t)nj * per));
-      host.resize((size_t)nj * per);
-      BGP_CUDA(cudaMemcpyAsync(host.data(), stage, (size_t)nj * per * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-      BGP_CUDA(cudaStreamSynchronize(m->stream));
-      for (int j = j0; j < j0 + nj; ++j) {
-        const double* src = host.data() + (size_t)(j - j0) * per;
-        if (modes) std::copy(src, src + p, modes + (size_t)j * p);
-        if (Hs) std::copy(src + p, src + p + (size_t)p * p, Hs + (size_t)j * p * p);
+      if (f->mirror) {
+        for (int q = 0; q < nj; ++q) {
+          const int j = todo[t0 + q];
+          if (f->mirrored[j]) continue;
+          BGP_CUDA(cudaMemcpyAsync(dst_modes + (size_t)j * p, stage + (size_t)q * per, (size_t)p * sizeof(double),
+                                   cudaMemcpyDeviceToHost, m->stream));
+          BGP_CUDA(cudaMemcpyAsync(dst_Hs + (size_t)j * pp, stage + (size_t)q * per + p, pp * sizeof(double),
+                                   cudaMemcpyDeviceToHost, m->stream));
+        }
+        BGP_CUDA(cudaStreamSynchronize(m->stream));
+      } else {
+        host.resize((size_t)nj * per);
+        BGP_CUDA(cudaMemcpyAsync(host.data(), stage, (size_t)nj * per * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        BGP_CUDA(cudaStreamSynchronize(m->stream));
+        for (int q = 0; q < nj; ++q) {
+          const int j = todo[t0 + q];
+          const double* src = host.data() + (size_t)q * per;
+          if (dst_modes) std::copy(src, src + p, dst_modes + (size_t)j * p);
+          if (dst_Hs) std::copy(src + p, src + p + pp, dst_Hs + (size_t)j * pp);
+        }
       }
     }
     return BGP_OK;
   }();
-  cudaFree(stage);
+  pool_give(m, false, stage, stage_bytes);
+  if (rc == BGP_OK && f->mirror)
+    for (int j = 0; j < K; ++j) const_cast<bgp_fit*>(f)->mirrored[j] = 1;
   return rc;
 }
 
@@ -680,7 +726,26 @@ int bgp_fit_get_modes(const bgp_fit* f, double* modes, double* Hs) {
   if (!f || !f->model) return BGP_ERR_ARG;
   if (!modes && !Hs) return BGP_OK;
   BGP_CUDA(cudaSetDevice(f->model->device));
-  return gather_modes(f, modes, Hs);
+  BGP_TRY(complete_mirror(f, modes, Hs));
+  if (f->mirror) {
+    const size_t nm = (size_t)f->K * f->p;
+    if (modes) memcpy(modes, f->mirror, nm * sizeof(double));
+    if (Hs) memcpy(Hs, f->mirror + nm, nm * f->p * sizeof(double));
+  }
+  return BGP_OK;
+}
+
+int bgp_fit_host_arrays(const bgp_fit* f, const double** modes, const double** Hs) {
+  if (!f || !f->model) return BGP_ERR_ARG;
+  if (!f->mirror) {
+    set_error("this fit keeps no host mirror of its modes / Hessians (more than 2 GiB): use bgp_fit_get_modes");
+    return BGP_ERR_STATE;
+  }
+  BGP_CUDA(cudaSetDevice(f->model->device));
+  BGP_TRY(complete_mirror(f, nullptr, nullptr));
+  if (modes) *modes = f->mirror;
+  if (Hs) *Hs = f->mirror + (size_t)f->K * f->p;
+  return BGP_OK;
 }
 
 int bgp_fit_get_diagnostics(const bgp_fit* f, int* hessian_fallback, int64_t* grid_newton_iters, double* opt_ms,

@@ -35,6 +35,47 @@ __global__ void transpose_in_kernel(const double* __restrict__ src, int64_t n, i
   }
 }
 
+void* pool_take(bgp_model* m, bool pinned, size_t bytes, size_t* got_bytes) {
+  auto& pool = pinned ? m->pin_pool : m->dev_pool;
+  int best = -1;
+  for (int i = 0; i < (int)pool.size(); ++i)
+    if (pool[i].bytes >= bytes && (best < 0 || pool[i].bytes < pool[best].bytes)) best = i;
+  if (best >= 0 && pool[best].bytes <= 2 * bytes + (1u << 20)) {
+    void* p = pool[best].ptr;
+    *got_bytes = pool[best].bytes;
+    pool.erase(pool.begin() + best);
+    return p;
+  }
+  void* p = nullptr;
+  const cudaError_t e = pinned ? cudaHostAlloc(&p, bytes, cudaHostAllocDefault) : cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s of %zu bytes failed: %s", pinned ? "cudaHostAlloc" : "cudaMalloc", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  *got_bytes = bytes;
+  return p;
+}
+
+void pool_give(bgp_model* m, bool pinned, void* ptr, size_t bytes) {
+  if (!ptr) return;
+  auto& pool = pinned ? m->pin_pool : m->dev_pool;
+  if (pool.size() >= 8) {                     // bounded: drop the smallest block
+    int small = 0;
+    for (int i = 1; i < (int)pool.size(); ++i)
+      if (pool[i].bytes < pool[small].bytes) small = i;
+    if (pool[small].bytes < bytes) {
+      if (pinned) cudaFreeHost(pool[small].ptr);
+      else cudaFree(pool[small].ptr);
+      pool[small] = {bytes, ptr};
+    } else {
+      if (pinned) cudaFreeHost(ptr);
+      else cudaFree(ptr);
+    }
+    return;
+  }
+  pool.push_back({bytes, ptr});
+}
+
 static int stage_block(bgp_model* m, std::vector<bgp_model::Staged>& dst, int ncol, const double* host) {
   bgp_model::Staged s;
   s.ncol = ncol;
@@ -524,6 +565,9 @@ void bgp_model_destroy(bgp_model* m) {
     if (h.W) cudaFree(h.W);
     if (h.T) cudaFree(h.T);
   }
+  *m->alive = 0;
+  for (auto& b : m->dev_pool) cudaFree(b.ptr);
+  for (auto& b : m->pin_pool) cudaFreeHost(b.ptr);
   if (m->occ_dev) cudaFree(m->occ_dev);
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);

@@ -470,7 +470,12 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
         BGP_CUDA(cudaMemcpyAsync(sink.Hs_dev + slot * (size_t)m->p * m->ldh, m->H, (size_t)m->p * m->ldh * sizeof(double),
                                  cudaMemcpyDeviceToDevice, m->stream));
     }
-    if (sink.modes_host || sink.Hs_host) {
+    if ((sink.modes_host || sink.Hs_host) && sink.host_pinned) {
+      // page-locked destination: rotate on the device, copy straight into slot j (asynchronous; the staging
+      // buffer is reused by the next node in stream order)
+      if (sink.modes_host) BGP_TRY(copy_vec_out(m, m->Wmode, sink.modes_host + (size_t)j * m->p));
+      if (sink.Hs_host) BGP_TRY(copy_H_out(m, sink.Hs_host + (size_t)j * pp));
+    } else if (sink.modes_host || sink.Hs_host) {
       const size_t need = pp + (size_t)m->p;
       if (m->pin_out_elems < need) {
         for (int i = 0; i < 2; ++i) {

@@ -72,12 +72,24 @@ __global__ void note_chol_info_kernel(const EvalScalars* __restrict__ sc, int no
 
 void fit_release_device(bgp_fit* f) {
   if (!f) return;
-  if (f->model) cudaSetDevice(f->model->device);
-  for (double** p : {&f->samps_dev, &f->Linv_dev, &f->LinvT_dev, &f->mode_dev, &f->modes_dev, &f->Hs_dev})
+  // a fit may outlive its model (garbage-collected host objects): then the pools are gone and the blocks are freed here
+  const bool model_ok = f->model && f->model_alive && *f->model_alive;
+  if (model_ok) cudaSetDevice(f->model->device);
+  for (double** p : {&f->samps_dev, &f->Linv_dev, &f->LinvT_dev, &f->mode_dev})
     if (*p) {
       cudaFree(*p);
       *p = nullptr;
     }
+  if (model_ok) {
+    pool_give(f->model, false, f->modes_dev, f->modes_dev_bytes);
+    pool_give(f->model, false, f->Hs_dev, f->Hs_dev_bytes);
+    pool_give(f->model, true, f->mirror, f->mirror_bytes);
+  } else {
+    if (f->modes_dev) cudaFree(f->modes_dev);
+    if (f->Hs_dev) cudaFree(f->Hs_dev);
+    if (f->mirror) cudaFreeHost(f->mirror);
+  }
+  f->modes_dev = f->Hs_dev = f->mirror = nullptr;
 }
 
 static int sample_core(bgp_fit* f, int64_t M, const double* Z_host, uint64_t seed, const int32_t* node_idx,

@@ -149,6 +149,10 @@ int bgp_fit_get_grid(const bgp_fit* f, double* nodes /* K x S col-major */, doub
 int bgp_fit_get_modes(const bgp_fit* f, double* modes /* p x K */, double* Hs /* p x p x K, may be NULL */);
 int bgp_fit_get_marginal(const bgp_fit* f, int j, double* theta /* k */, double* logmargpost /* k */,
                          double* w /* k */);
+/* the same arrays without a copy: pointers into the fit's own page-locked host mirror (modes p x K, Hs p x p x K, W
+ * order), valid until bgp_fit_destroy; filled while the grid was being evaluated (collective when the model has a
+ * node group: the other ranks' nodes are gathered on the first call) */
+int bgp_fit_host_arrays(const bgp_fit* f, const double** modes, const double** Hs);
 /* how the fit went: Richardson retries used (0 = numDeriv's default step, as the reference), inner Newton iterations
  * spent on the quadrature grids by this rank, wall clock (ms) of the BFGS + Richardson phase and of the grid phase */
 int bgp_fit_get_diagnostics(const bgp_fit* f, int* hessian_fallback, int64_t* grid_newton_iters, double* opt_ms,
