@@ -54,8 +54,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libbgp build failed")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl"]
+    # link under a temporary name and rename: a snapshot / loader never sees a half-written library
+    tmp = OUT + ".tmp%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-ldl"]
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return OUT

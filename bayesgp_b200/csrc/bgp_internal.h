@@ -175,7 +175,9 @@ struct bgp_model {
   // p * delta / 2 <= reuse_rel_tol * |value|  (|logdet H(w1) - logdet H(w0)| <= p * delta).
   bool allow_reuse = true;
   double reuse_eta_tol = 1e-7, reuse_rel_tol = 1e-10;
-  bool factor_is_exact = true;   // H / L in memory were formed at the mode itself
+  bool factor_is_exact = true;   // H in memory was formed at the mode itself (and L is its factor unless L_is_reversed)
+  bool obs_at_mode = false;      // eta / wobs / c3 / sc_dev on the device belong to the last mode (Wmode)
+  bool L_is_reversed = false;    // the gradient left the factor of H in reversed order in L (grad.cu)
   int64_t n_evals = 0, n_newton = 0, n_reuse = 0;
   // ---- sharding ------------------------------------------------------------------------------
   int rank = 0, world = 1;

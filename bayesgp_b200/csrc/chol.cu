@@ -510,6 +510,7 @@ static void fill_tangent_args(bgp_model* m, const double* theta, const double* W
 
 // L <- chol(H) (H is left untouched), logdet, optionally step = -H^-1 g
 int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan, const double* W_tan) {
+  m->L_is_reversed = false;
   BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   CholArgs a;
   a.L = m->L;

@@ -6,11 +6,12 @@
 //   dL/dtheta_k = df/dtheta_k + 1/2 tr(Hi dH/dtheta_k) - 1/2 v^T Hi c_k,
 //   v = A^T (c3 * q),  q_i = a_i^T Hi a_i (leverages),  c_k = d2f / dW dtheta_k.
 // Device work:
-//   1. L^-1 by block forward substitution (32x32 blocks, one CTA per block column);
-//   2. leverages q_i = || L^-1 a_i ||^2 : a TRMM-shaped FP64 DMMA kernel (n p^2 flops), TMA-staged
-//      operands (both K-major, 128B swizzle), Y tiles never leave registers, fused row norms;
-//   3. v = A^T (c3 * q) with the streaming kernel of lik.cu.
-// The p-sized algebra that remains (traces, two triangular products) runs on the host.
+//   1. H = U U^T (Cholesky in reversed order, chol.cu), V = U^-1 by block forward substitution (32x32 blocks,
+//      one CTA per block column) — upper triangular, so structural zeros of a_i cut BOTH loops of V a_i;
+//   2. leverages q_i = || V a_i ||^2 : a TRMM-shaped FP64 DMMA kernel, TMA-staged operands (both K-major, 128B
+//      swizzle), Y tiles never leave registers, fused row norms, empty {chunk x column box} cells skipped;
+//   3. v = A^T (c3 * q) with the streaming kernel of lik.cu;
+//   4. the p-sized algebra (V v, V^T V v, diag H^-1, block traces) in one CTA.  S doubles go back to the host.
 #include <algorithm>
 
 #include "bgp_internal.h"
@@ -105,57 +106,71 @@ __global__ void __launch_bounds__(256) trtri_offdiag_kernel(const double* __rest
 }
 
 // ---- 2. leverages -----------------------------------------------------------------------------------
-constexpr int LV_TM = 128;    // observations per CTA
-constexpr int LV_TN = 64;     // rows of L^-1 per pass
-constexpr int LV_KB = 16;     // contraction slice per stage (one 128-byte line)
+// q_i = a_i^T H^-1 a_i = || V a_i ||^2 with V = U^-1 UPPER triangular, H = U U^T (the Cholesky factor of H taken
+// in reversed order).  With an upper factor y = V a reads y_k = sum_{c >= k} V[k][c] a_c, so a row whose non-zeros
+// end at column m (after the zero-pattern sort the occupied column boxes of a chunk are a prefix) costs m^2 / 2
+// instead of the p^2 / 2 of the lower factor: both the contraction slices c and the output rows k beyond the last
+// occupied box are skipped, box by box, from the same occupancy words the Hessian kernel uses.
+constexpr int LV_TM = 128;    // observations per CTA (two 64-observation chunks of the occupancy map)
+constexpr int LV_TN = 64;     // rows of V per pass
+constexpr int LV_KB = 16;     // contraction slice per stage (one 128-byte line, one column box)
 constexpr int LV_STAGES = 3;
 constexpr int LV_THREADS = 256;
 constexpr int LV_A_BYTES = LV_TM * 128;
 constexpr int LV_B_BYTES = LV_TN * 128;
 constexpr int LV_STAGE_BYTES = LV_A_BYTES + LV_B_BYTES;
-constexpr int LV_SMEM = LV_STAGES * LV_STAGE_BYTES + 64 + 1024 + 2 * LV_TM * 8;
+constexpr int LV_MAXLIST = 16 * 64 / 2 + 64;     // (row block, slice) pairs on or above the diagonal, p <= 1024
+constexpr int LV_SMEM = LV_STAGES * LV_STAGE_BYTES + 64 + 1024 + 2 * LV_TM * 8 + LV_MAXLIST * 4;
 
 __global__ void __launch_bounds__(LV_THREADS, 2)
-    leverage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmL,
-                    const double* __restrict__ c3, double* __restrict__ z, int64_t n, int p, int ldl) {
+    leverage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmV,
+                    const double* __restrict__ c3, const unsigned long long* __restrict__ occ, int64_t nchunks,
+                    double* __restrict__ z, int64_t n, int p, int ldl) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + LV_STAGES * LV_STAGE_BYTES;
-  double* sQ = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)) + LV_STAGES * LV_STAGE_BYTES + 64);
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw)) + LV_STAGES * LV_STAGE_BYTES + 64;
+  double* sQ = reinterpret_cast<double*>(gen);
+  // work list: entry = row block << 16 | slice << 1 | last-of-block
+  uint32_t* list = reinterpret_cast<uint32_t*>(gen + 2 * LV_TM * 8);
+  __shared__ int s_total;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int fj = lane >> 2, fk = lane & 3;
   const int obs0 = blockIdx.x * LV_TM;
   const int NT = (p + LV_TN - 1) / LV_TN;
+  const int nslices = ldl / LV_KB;
 
   if (tid == 0) {
     for (int s = 0; s < LV_STAGES; ++s) mbar_init(bar_base + 8 * s, 1);
     mbar_fence_init();
+    const int64_t c0 = 2 * (int64_t)blockIdx.x;
+    unsigned long long o = c0 < nchunks ? occ[c0] : 0ull;
+    if (c0 + 1 < nchunks) o |= occ[c0 + 1];
+    int cnt = 0;
+    for (int nb = 0; nb < NT; ++nb) {
+      int first = cnt;
+      for (int ks = 4 * nb; ks < nslices; ++ks)
+        if ((o >> ks) & 1ull) list[cnt++] = ((uint32_t)nb << 16) | ((uint32_t)ks << 1);
+      if (cnt > first) list[cnt - 1] |= 1u;
+    }
+    s_total = cnt;
   }
   __syncthreads();
+  const int total = s_total;
 
-  auto ksteps = [&](int nb) {
-    const int kmax = min(ldl, (nb + 1) * LV_TN);
-    return (kmax + LV_KB - 1) / LV_KB;
-  };
-  int total = 0;
-  for (int nb = 0; nb < NT; ++nb) total += ksteps(nb);
-
-  // producer state (thread 0 only)
-  int p_nb = 0, p_ks = 0, p_it = 0;
+  int p_it = 0;
   auto issue = [&]() {
     const int s = p_it % LV_STAGES;
     const uint32_t bar = bar_base + 8 * s;
     const uint32_t sa = base + s * LV_STAGE_BYTES;
+    const uint32_t e = list[p_it];
+    const int nb = (int)(e >> 16), ks = (int)((e >> 1) & 0x7fffu);
     mbar_expect_tx(bar, LV_STAGE_BYTES);
-    tma_load_2d(sa, &tmA, p_ks * LV_KB, obs0, bar);
-    tma_load_2d(sa + LV_A_BYTES, &tmL, p_ks * LV_KB, p_nb * LV_TN, bar);
+    tma_load_2d(sa, &tmA, ks * LV_KB, obs0, bar);
+    tma_load_2d(sa + LV_A_BYTES, &tmV, ks * LV_KB, nb * LV_TN, bar);
     ++p_it;
-    if (++p_ks == ksteps(p_nb)) {
-      p_ks = 0;
-      ++p_nb;
-    }
   };
   if (tid == 0)
     for (int i = 0; i < LV_STAGES - 1 && p_it < total; ++i) issue();
@@ -180,7 +195,6 @@ __global__ void __launch_bounds__(LV_THREADS, 2)
     b_sw[f] = rb & 7;
   }
 
-  int c_nb = 0, c_ks = 0;
   for (int it = 0; it < total; ++it) {
     __syncthreads();
     if (tid == 0 && p_it < total) issue();
@@ -202,8 +216,8 @@ __global__ void __launch_bounds__(LV_THREADS, 2)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
-    if (++c_ks == ksteps(c_nb)) {
-      // this 128 x 64 slab of Y = A L^-T is complete: fold its squares into the row norms
+    if (list[it] & 1u) {
+      // this 128 x 64 slab of Y = A V^T is complete: fold its squares into the row norms
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -212,8 +226,6 @@ __global__ void __launch_bounds__(LV_THREADS, 2)
           qacc[mi] = fma(acc[mi][ni][1], acc[mi][ni][1], qacc[mi]);
           acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         }
-      c_ks = 0;
-      ++c_nb;
     }
   }
   // rows are shared by the 4 lanes of a quad and by the two N-halves (wn)
@@ -237,6 +249,152 @@ __global__ void __launch_bounds__(LV_THREADS, 2)
   }
 }
 
+// H in reversed index order (both triangles): Hr[i][j] = H[p-1-i][p-1-j]
+__global__ void reverse_sym_kernel(const double* __restrict__ H, int p, int ldh, double* __restrict__ Hr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i < p) Hr[(size_t)j * ldh + i] = H[(size_t)(p - 1 - j) * ldh + (p - 1 - i)];
+}
+
+// V = U^-1 (row-major p x ldl, upper) from the inverse of the reversed factor (row-major lower):
+// V[k][c] = Linv_r[p-1-k][p-1-c]
+__global__ void unreverse_tri_kernel(const double* __restrict__ Lr, int p, int ldl, double* __restrict__ V) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (c < ldl) V[(size_t)k * ldl + c] = (c >= k && c < p) ? Lr[(size_t)(p - 1 - k) * ldl + (p - 1 - c)] : 0.0;
+}
+
+// ---- 3. the p-sized algebra, one CTA ------------------------------------------------------------------
+struct GradSmallArgs {
+  const double* V;          // p x ldl row-major upper, H^-1 = V^T V
+  int p, ldl, lda, S, J, gaussian;
+  const double* v;          // A^T (c3 * q) (lda) or NULL
+  const double* W;          // mode (lda)
+  const double* qfix;       // theta-independent diagonal of Q
+  const EvalScalars* sc;    // sumsq at the mode
+  double n_total;
+  struct {
+    int off, d, diag;
+    const double* P;
+    double etheta, theta, phi;
+  } rnd[16];
+  double noise_theta, noise_phi;
+  double* scratch;          // 4 * lda doubles
+  double* grad;             // S
+};
+
+// t1 = V v: one warp per row k, lanes over the columns c >= k
+__global__ void __launch_bounds__(256) grad_vv_kernel(const double* __restrict__ V, int p, int ldl, const double* __restrict__ v,
+                                                      double* __restrict__ t1) {
+  const int lane = threadIdx.x & 31, k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= p) return;
+  double s = 0.0;
+  if (v)
+    for (int c = k + lane; c < p; c += 32) s = fma(V[(size_t)k * ldl + c], v[c], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) t1[k] = s;
+}
+
+// Hiv = V^T t1 and diag(H^-1) = column square norms of V: a CTA owns 32 columns, its 8 warps split the rows
+// k <= c (row r goes to warp r % 8), partial sums combined in warp order
+__global__ void __launch_bounds__(256) grad_vt_kernel(const double* __restrict__ V, int p, int ldl, const double* __restrict__ t1,
+                                                      double* __restrict__ Hiv, double* __restrict__ dHi) {
+  __shared__ double sm[2][8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int kmax = min(p, blockIdx.x * 32 + 32);
+  double s = 0.0, d = 0.0;
+  if (c < p)
+    for (int k = warp; k < kmax; k += 8) {
+      const double x = V[(size_t)k * ldl + c];          // zero below the diagonal (k > c)
+      s = fma(x, t1[k], s);
+      d = fma(x, x, d);
+    }
+  sm[0][warp][lane] = s;
+  sm[1][warp][lane] = d;
+  __syncthreads();
+  if (warp == 0 && c < p) {
+    double ts = 0.0, td = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      ts += sm[0][w][lane];
+      td += sm[1][w][lane];
+    }
+    Hiv[c] = ts;
+    dHi[c] = td;
+  }
+}
+
+__global__ void __launch_bounds__(1024) grad_small_kernel(const GradSmallArgs a) {
+  __shared__ double s_red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  double* Hiv = a.scratch + a.lda;        // V^T (V v), from grad_vt_kernel
+  double* dHi = a.scratch + 2 * a.lda;    // diag(H^-1)
+  double* PU = a.scratch + 3 * a.lda;     // P_k U_k per block entry
+  auto block_sum = [&](double x) -> double {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += s_red[w];       // fixed order
+    return t;
+  };
+  double trHiQ = 0.0;
+  for (int b = 0; b < a.J; ++b) {
+    const int off = a.rnd[b].off, d = a.rnd[b].d;
+    const double* P = a.rnd[b].P;
+    double upu = 0.0, hpu = 0.0, tr = 0.0;
+    if (a.rnd[b].diag) {
+      for (int c = tid; c < d; c += blockDim.x) {
+        const double pu = P[c] * a.W[off + c];
+        upu = fma(a.W[off + c], pu, upu);
+        hpu = fma(Hiv[off + c], pu, hpu);
+        tr = fma(P[c], dHi[off + c], tr);
+      }
+    } else {
+      for (int c = tid; c < d; c += blockDim.x) {
+        double s = 0.0;
+        for (int e = 0; e < d; ++e) s = fma(P[(size_t)e * d + c], a.W[off + e], s);
+        PU[c] = s;
+        upu = fma(a.W[off + c], s, upu);
+        hpu = fma(Hiv[off + c], s, hpu);
+      }
+      // tr(H^-1_bb P) = sum_k x_k^T P x_k, x_k = V[k][block] (zero left of the diagonal): one row per warp
+      for (int k = warp; k < off + d && k < a.p; k += nw) {
+        const double* x = a.V + (size_t)k * a.ldl + off;
+        const int c_lo = k > off ? k - off : 0;
+        double s = 0.0;
+        for (int c = c_lo + lane; c < d; c += 32) {
+          double t = 0.0;
+          for (int e = c_lo; e < d; ++e) t = fma(P[(size_t)e * d + c], x[e], t);
+          s = fma(x[c], t, s);
+        }
+        tr += s;
+      }
+    }
+    upu = block_sum(upu);
+    hpu = block_sum(hpu);
+    tr = block_sum(tr);
+    const double ek = a.rnd[b].etheta;
+    if (tid == 0) {
+      const double dfdth = 0.5 * ek * upu - 0.5 * d - 0.5 * a.rnd[b].phi * exp(-0.5 * a.rnd[b].theta) + 0.5;
+      a.grad[b] = dfdth + 0.5 * ek * tr - 0.5 * ek * hpu;
+    }
+    trHiQ += ek * tr;
+  }
+  if (a.gaussian) {
+    double t = 0.0;
+    for (int c = tid; c < a.p; c += blockDim.x) t = fma(a.qfix[c], dHi[c], t);
+    t = block_sum(t);
+    if (tid == 0) {
+      const double tau = exp(a.noise_theta);
+      const double dfdth = -0.5 * a.n_total + 0.5 * tau * a.sc->sumsq - 0.5 * a.noise_phi * exp(-0.5 * a.noise_theta) + 0.5;
+      a.grad[a.S - 1] = dfdth + 0.5 * ((double)a.p - (trHiQ + t));
+    }
+  }
+}
+
 int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT) {
   const int p = m->p, nb = (p + 31) / 32;
   trtri_diag_kernel<<<nb, 32, 0, m->stream>>>(m->L, p, m->ldh, Linv, ldl, LinvT);
@@ -250,8 +408,11 @@ int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT) {
 }
 
 struct GradPlan {
-  CUtensorMap tmA, tmL;
-  std::vector<double> hLinv, hv, hw;
+  CUtensorMap tmA, tmV;
+  double* Hrev = nullptr;      // p x ldh: H in reversed index order
+  double* V = nullptr;         // p x ldl row-major upper: U^-1
+  double* scratch = nullptr;   // 4 lda + S doubles
+  double* grad_host = nullptr; // pinned, S doubles + chol info
 };
 
 static int grad_plan_get(bgp_model* m, GradPlan** out) {
@@ -261,27 +422,37 @@ static int grad_plan_get(bgp_model* m, GradPlan** out) {
   }
   GradPlan* gp = new GradPlan();
   m->ldl = round_up(m->p, 16);
+  const size_t zb = (size_t)(round_up64(m->n, 64) + 64) * sizeof(double);
   BGP_CUDA(cudaMalloc(&m->Linv, (size_t)m->p * m->ldl * sizeof(double)));
   BGP_CUDA(cudaMemset(m->Linv, 0, (size_t)m->p * m->ldl * sizeof(double)));
-  BGP_CUDA(cudaMalloc(&m->zobs, (size_t)(round_up64(m->n, 64) + 64) * sizeof(double)));
-  BGP_CUDA(cudaMemset(m->zobs, 0, (size_t)(round_up64(m->n, 64) + 64) * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&gp->V, (size_t)round_up(m->p, 64) * m->ldl * sizeof(double)));
+  BGP_CUDA(cudaMemset(gp->V, 0, (size_t)round_up(m->p, 64) * m->ldl * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&gp->Hrev, (size_t)m->p * m->ldh * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&gp->scratch, ((size_t)4 * m->lda + 32) * sizeof(double)));
+  BGP_CUDA(cudaMallocHost(&gp->grad_host, 32 * sizeof(double)));
+  BGP_CUDA(cudaMalloc(&m->zobs, zb));
+  BGP_CUDA(cudaMemset(m->zobs, 0, zb));
   if (make_tensormap_f64(&gp->tmA, m->A, (uint64_t)m->lda, (uint64_t)m->n, (uint64_t)m->lda, 16, LV_TM) != 0 ||
-      make_tensormap_f64(&gp->tmL, m->Linv, (uint64_t)m->ldl, (uint64_t)m->p, (uint64_t)m->ldl, 16, LV_TN) != 0) {
+      make_tensormap_f64(&gp->tmV, gp->V, (uint64_t)m->ldl, (uint64_t)m->p, (uint64_t)m->ldl, 16, LV_TN) != 0) {
     delete gp;
     set_error("cuTensorMapEncodeTiled failed for the leverage kernel");
     return BGP_ERR_CUDA;
   }
   BGP_CUDA(cudaFuncSetAttribute(leverage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LV_SMEM));
-  gp->hLinv.resize((size_t)m->p * m->ldl);
-  gp->hv.resize(m->lda);
-  gp->hw.resize(m->lda);
   m->grad_plan = gp;
   *out = gp;
   return BGP_OK;
 }
 
 void grad_plan_destroy(bgp_model* m) {
-  if (m->grad_plan) delete (GradPlan*)m->grad_plan;
+  if (m->grad_plan) {
+    GradPlan* gp = (GradPlan*)m->grad_plan;
+    if (gp->Hrev) cudaFree(gp->Hrev);
+    if (gp->V) cudaFree(gp->V);
+    if (gp->scratch) cudaFree(gp->scratch);
+    if (gp->grad_host) cudaFreeHost(gp->grad_host);
+    delete gp;
+  }
   m->grad_plan = nullptr;
   if (m->Linv) cudaFree(m->Linv);
   if (m->zobs) cudaFree(m->zobs);
@@ -306,123 +477,113 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   }
 }
 
+// Everything stays on the device; S doubles come back.  Sequence: (likelihood pass at the mode unless the inner
+// solve just left one there) -> (Hessian at the mode unless it is in memory) -> reversed-order Cholesky ->
+// triangular inverse -> V -> leverages -> A^T (c3 q) -> the p-sized algebra in one CTA.
 int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   GradPlan* gp = nullptr;
   BGP_TRY(grad_plan_get(m, &gp));
   const int p = m->p, ldl = m->ldl;
   const bool gaussian = m->family == BGP_FAMILY_GAUSSIAN;
   const bool has_c3 = m->family == BGP_FAMILY_POISSON || m->family == BGP_FAMILY_BINOMIAL;
-  // exact per-observation quantities at the mode (also fixes sumsq for the Gaussian noise theta)
-  BGP_TRY(eval_fg_async(m, m->Wmode, theta, true));
+  if (p > 1024) {
+    set_error("laplace gradient: p = %d exceeds the leverage kernel's work list (1024)", p);
+    return BGP_ERR_ARG;
+  }
+  // exact per-observation quantities at the mode (w, c3; sumsq for the Gaussian noise theta)
+  if (!m->obs_at_mode) {
+    BGP_TRY(eval_fg_async(m, m->Wmode, theta, true));
+    m->obs_at_mode = true;
+  }
   if (!m->factor_is_exact) {
-    // the inner solve kept the factor of its last Newton iteration (newton.cu); the gradient differentiates
-    // through H^-1, so it gets the factor at the mode itself
+    // the inner solve kept the Hessian of its last Newton iteration (newton.cu); the gradient differentiates
+    // through H^-1, so it gets the Hessian at the mode itself
+    phase_mark(m, PH_HESS);
     BGP_TRY(launch_hessian(m, theta));
-    BGP_TRY(launch_chol_solve(m, false));
+    m->n_hess++;
     m->factor_is_exact = true;
   }
-  // 1. L^-1
+  // H = U U^T: Cholesky of H in reversed order (the factor left in m->L is that of the reversed matrix from here on)
+  phase_mark(m, PH_CHOL);
+  {
+    dim3 grid((p + 255) / 256, p);
+    reverse_sym_kernel<<<grid, 256, 0, m->stream>>>(m->H, p, m->ldh, gp->Hrev);
+    count_launch();
+    double* keep = m->H;
+    m->H = gp->Hrev;
+    const int st = launch_chol_solve(m, false);
+    m->H = keep;
+    m->n_chol++;
+    BGP_TRY(st);
+    m->L_is_reversed = true;
+  }
   BGP_TRY(launch_trtri(m, m->Linv, ldl, nullptr));
-  // 2./3. leverage term v = A^T (c3 * q)
-  std::fill(gp->hv.begin(), gp->hv.end(), 0.0);
+  {
+    dim3 grid((ldl + 255) / 256, p);
+    unreverse_tri_kernel<<<grid, 256, 0, m->stream>>>(m->Linv, p, ldl, gp->V);
+    count_launch();
+  }
+  phase_mark(m, PH_OTHER);
+  const double* v_dev = nullptr;
   if (has_c3) {
-    leverage_kernel<<<(unsigned)((m->n + LV_TM - 1) / LV_TM), LV_THREADS, LV_SMEM, m->stream>>>(gp->tmA, gp->tmL, m->c3,
-                                                                                                 m->zobs, m->n, p, ldl);
+    leverage_kernel<<<(unsigned)((m->n + LV_TM - 1) / LV_TM), LV_THREADS, LV_SMEM, m->stream>>>(
+        gp->tmA, gp->tmV, m->c3, (const unsigned long long*)m->occ_dev, m->nchunks, m->zobs, m->n, p, ldl);
     count_launch();
     BGP_CUDA(cudaGetLastError());
     BGP_TRY(launch_lik(m, m->Wmode, false, 1.0, m->zobs));
     reduce_partials_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->lik_blocks, m->lda, m->red_buf);
     count_launch();
     if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda));
-    BGP_CUDA(cudaMemcpyAsync(gp->hv.data(), m->red_buf, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    v_dev = m->red_buf;
   }
-  BGP_CUDA(cudaMemcpyAsync(gp->hLinv.data(), m->Linv, (size_t)p * ldl * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  BGP_CUDA(cudaMemcpyAsync(gp->hw.data(), m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  GradSmallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.V = gp->V;
+  a.p = p;
+  a.ldl = ldl;
+  a.lda = m->lda;
+  a.S = m->S;
+  a.J = m->J;
+  a.gaussian = gaussian ? 1 : 0;
+  a.v = v_dev;
+  a.W = m->Wmode;
+  a.qfix = m->qfix;
+  a.sc = m->sc_dev;
+  a.n_total = (double)m->n_total;
+  for (int k = 0; k < m->J; ++k) {
+    const RandomBlock& rb = m->rnd[k];
+    a.rnd[k].off = rb.off;
+    a.rnd[k].d = rb.d;
+    a.rnd[k].diag = rb.diag ? 1 : 0;
+    a.rnd[k].P = rb.P_dev;
+    a.rnd[k].etheta = std::exp(theta[k]);
+    a.rnd[k].theta = theta[k];
+    a.rnd[k].phi = -std::log(rb.alpha) / rb.u;
+  }
+  if (gaussian) {
+    a.noise_theta = theta[m->S - 1];
+    a.noise_phi = -std::log(m->theta_alpha[m->S - 1]) / m->theta_u[m->S - 1];
+  }
+  a.scratch = gp->scratch;
+  a.grad = gp->scratch + 4 * m->lda;
+  grad_vv_kernel<<<(p + 7) / 8, 256, 0, m->stream>>>(gp->V, p, ldl, v_dev, a.scratch);
+  grad_vt_kernel<<<(p + 31) / 32, 256, 0, m->stream>>>(gp->V, p, ldl, a.scratch, a.scratch + m->lda, a.scratch + 2 * m->lda);
+  count_launch(2);
+  grad_small_kernel<<<1, 1024, 0, m->stream>>>(a);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  BGP_CUDA(cudaMemcpyAsync(gp->grad_host, a.grad, (size_t)m->S * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
   phase_mark(m, PH_OTHER);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   phase_harvest(m);
-  const double sumsq = m->sc_host->sumsq;
-  const double* Li = gp->hLinv.data();
-  const double* w = gp->hw.data();
-  // Hi v = L^-T (L^-1 v)
-  std::vector<double> t1(p, 0.0), Hiv(p, 0.0);
-  if (has_c3) {
-    for (int i = 0; i < p; ++i) {
-      double s = 0.0;
-      for (int a = 0; a <= i; ++a) s += Li[(size_t)i * ldl + a] * gp->hv[a];
-      t1[i] = s;
-    }
-    for (int i = 0; i < p; ++i) {
-      const double ti = t1[i];
-      for (int a = 0; a <= i; ++a) Hiv[a] += Li[(size_t)i * ldl + a] * ti;
-    }
+  if (m->sc_host->chol_info != 0) {
+    // H was positive definite in the natural order; a failure of the reversed factorisation is a rounding accident
+    // on a numerically singular H: NaN gradient, as TMB answers when its factorisation fails
+    for (int k = 0; k < m->S; ++k) grad[k] = NAN;
+    return BGP_OK;
   }
-  double trHiQ = 0.0;
-  for (int k = 0; k < m->J; ++k) {
-    const RandomBlock& rb = m->rnd[k];
-    const int off = rb.off, d = rb.d;
-    const double* P = rb.P_host.data();
-    const double ek = std::exp(theta[k]);
-    std::vector<double> PU(d, 0.0);
-    double tr = 0.0;
-    if (rb.diag) {
-      for (int c = 0; c < d; ++c) PU[c] = P[c] * w[off + c];
-      for (int c = 0; c < d; ++c) {
-        double s = 0.0;
-        for (int i = off + c; i < p; ++i) {
-          const double v = Li[(size_t)i * ldl + off + c];
-          s += v * v;
-        }
-        tr += P[c] * s;
-      }
-    } else {
-      for (int c = 0; c < d; ++c) {
-        double s = 0.0;
-        for (int b = 0; b < d; ++b) s += P[(size_t)b * d + c] * w[off + b];
-        PU[c] = s;
-      }
-      std::vector<double> tmp(d);
-      for (int i = off; i < p; ++i) {
-        const double* mi = Li + (size_t)i * ldl + off;
-        const int dd = std::min(d, i - off + 1);     // L^-1 is lower triangular
-        for (int c = 0; c < dd; ++c) {
-          double s = 0.0;
-          for (int b = 0; b < dd; ++b) s += P[(size_t)b * d + c] * mi[b];
-          tmp[c] = s;
-        }
-        double s = 0.0;
-        for (int c = 0; c < dd; ++c) s += mi[c] * tmp[c];
-        tr += s;
-      }
-    }
-    double upu = 0.0, hpu = 0.0;
-    for (int c = 0; c < d; ++c) {
-      upu += w[off + c] * PU[c];
-      hpu += Hiv[off + c] * PU[c];
-    }
-    const double phi = -std::log(rb.alpha) / rb.u;
-    const double dfdth = 0.5 * ek * upu - 0.5 * d - 0.5 * phi * std::exp(-0.5 * theta[k]) + 0.5;
-    grad[k] = dfdth + 0.5 * ek * tr - 0.5 * ek * hpu;
-    trHiQ += ek * tr;
-  }
-  if (gaussian) {
-    const int k = m->S - 1;
-    const double tau = std::exp(theta[k]);
-    const std::vector<double>& qfix = m->qfix_host;
-    for (int c = 0; c < p; ++c) {
-      if (qfix[c] == 0.0) continue;
-      double s = 0.0;
-      for (int i = c; i < p; ++i) {
-        const double v = Li[(size_t)i * ldl + c];
-        s += v * v;
-      }
-      trHiQ += qfix[c] * s;
-    }
-    const double phi = -std::log(m->theta_alpha[k]) / m->theta_u[k];
-    const double dfdth = -0.5 * (double)m->n_total + 0.5 * tau * sumsq - 0.5 * phi * std::exp(-0.5 * theta[k]) + 0.5;
-    grad[k] = dfdth + 0.5 * ((double)p - trHiQ);
-  }
+  for (int k = 0; k < m->S; ++k) grad[k] = gp->grad_host[k];
   return BGP_OK;
 }
 

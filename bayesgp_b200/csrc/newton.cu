@@ -91,6 +91,7 @@ static int read_scalars2(bgp_model* m, EvalScalars* start, EvalScalars* out) {
 // f, g (device), gmax at W_dev; leaves eta / wobs (/ c3) of that point on the device
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3) {
   const double tau = tau_of(m, theta);
+  m->obs_at_mode = false;                 // callers that evaluate at the mode set it again
   phase_mark(m, PH_LIK);
   BGP_TRY(launch_lik(m, W_dev, want_c3, tau));
   m->n_lik++;
@@ -101,6 +102,10 @@ int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool w
 
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_out) {
   EvalScalars sc;
+  // c3 = d w / d eta rides along with every pass (one more 8-byte store per observation): a gradient call at this
+  // theta then finds w, c3 and the scalars of the mode on the device and needs no pass of its own
+  const bool c3w = m->family == BGP_FAMILY_POISSON || m->family == BGP_FAMILY_BINOMIAL;
+  bool pass_at_W = false;                 // the last likelihood pass was evaluated at m->W
   const int threads = 256, blocks = (m->lda + threads - 1) / threads;
   // start from the previous mode (TMB last.par.best), moved along the tangent d w_hat / d theta when the
   // step in theta is moderate; fall back to the plain warm start, then to W = 0, if that point is non-finite
@@ -185,7 +190,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   if (!predicted)
     BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
-  BGP_TRY(eval_fg_async(m, m->W, theta, false));
+  BGP_TRY(eval_fg_async(m, m->W, theta, c3w));
+  pass_at_W = true;
   // Speculation: a start predicted from a different theta is practically never converged or non-finite, so the
   // first Newton iteration is enqueued behind it at once and the starting point's scalars are read together with
   // the iteration's (one host round trip less; a wrong guess costs one likelihood pass or is redone below).
@@ -199,12 +205,14 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   if (sc.nonfinite && predicted) {
     BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
-    BGP_TRY(eval_fg_async(m, m->W, theta, false));
+    BGP_TRY(eval_fg_async(m, m->W, theta, c3w));
+    pass_at_W = true;
     BGP_TRY(read_scalars(m, &sc));
   }
   if (sc.nonfinite) {
     BGP_CUDA(cudaMemsetAsync(m->W, 0, (size_t)m->lda * sizeof(double), m->stream));
-    BGP_TRY(eval_fg_async(m, m->W, theta, false));
+    BGP_TRY(eval_fg_async(m, m->W, theta, c3w));
+    pass_at_W = true;
     BGP_TRY(read_scalars(m, &sc));
     if (sc.nonfinite) {
       set_error("objective is not finite at the starting point");
@@ -235,7 +243,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     count_launch();
     // the Cholesky scalars must be captured before the trial evaluation overwrites f / gmax:
     // they live in different fields of EvalScalars, so one read after the trial eval suffices.
-    BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
+    BGP_TRY(eval_fg_async(m, m->Wtrial, theta, c3w));
+    pass_at_W = false;
     if (spec_now) {
       EvalScalars sc0;
       BGP_TRY(read_scalars2(m, &sc0, &sc));
@@ -243,11 +252,13 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       if (sc0.nonfinite) {
         // the predicted start was not finite: what was enqueued behind it is void; redo from the plain warm start
         BGP_CUDA(cudaMemcpyAsync(m->W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
-        BGP_TRY(eval_fg_async(m, m->W, theta, false));
+        BGP_TRY(eval_fg_async(m, m->W, theta, c3w));
+        pass_at_W = true;
         BGP_TRY(read_scalars(m, &sc));
         if (sc.nonfinite) {
           BGP_CUDA(cudaMemsetAsync(m->W, 0, (size_t)m->lda * sizeof(double), m->stream));
-          BGP_TRY(eval_fg_async(m, m->W, theta, false));
+          BGP_TRY(eval_fg_async(m, m->W, theta, c3w));
+          pass_at_W = true;
           BGP_TRY(read_scalars(m, &sc));
           if (sc.nonfinite) {
             set_error("objective is not finite at the starting point");
@@ -304,11 +315,13 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
       full_step = false;
       axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, t, m->p, m->lda, m->Wtrial);
       count_launch();
-      BGP_TRY(eval_fg_async(m, m->Wtrial, theta, false));
+      BGP_TRY(eval_fg_async(m, m->Wtrial, theta, c3w));
+      pass_at_W = false;
       BGP_TRY(read_scalars(m, &sc));
     }
     if (!accepted) break;
     std::swap(m->W, m->Wtrial);
+    pass_at_W = true;
     f = sc.f;
     gmax = sc.gmax;
     ++iters;
@@ -380,6 +393,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     BGP_CUDA(cudaMemcpyAsync(h.T, m->Tan, (size_t)m->S * m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   }
   m->factor_is_exact = !reused;
+  m->obs_at_mode = pass_at_W;
   ++m->n_evals;
   m->n_newton += iters;
   m->n_reuse += reused ? 1 : 0;
