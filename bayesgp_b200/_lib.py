@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbgp.so")
+# BGP_LIB_PATH: diagnostics only (A/B runs of two builds of the same library)
+LIB_PATH = os.environ.get("BGP_LIB_PATH") or os.path.join(_HERE, "libbgp.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -84,6 +85,9 @@ SIGNATURES = {
                                       c_double_p, C.c_int64, C.c_double, c_double_p, c_double_p, c_double_p]),
     "bgp_fit_predict_sgp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p,
                                       C.c_int, c_double_p, C.c_int64, C.c_double, c_double_p, c_double_p, c_double_p]),
+    "bgp_sgp_precision": (C.c_int, [C.c_double, C.c_int, C.c_int, c_double_p, C.c_double, C.c_int, c_double_p, c_double_p]),
+    "bgp_model_add_sgp_auto": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int, c_double_p,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "bgp_model_last_timing": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int64_p,
                                         c_int64_p, c_int64_p]),
 }

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, dptr, fmat, fvec
 from .objective import FAMILY_CODES, LaplaceObjective
-from .terms import Term, iid_design, prepare_term, sgp_design, sgp_precision
+from .terms import Term, iid_design, prepare_term
 
 
 class AGHQ:
@@ -188,10 +188,9 @@ def build_objective(y, terms: List[Term], fixed: Optional[Dict[str, np.ndarray]]
                 # random + boundary block generated on the device (blocks keep the order of the calls)
                 ff.add_iwp(t.x, t.initial_location, t.knots, t.order, t.u, t.alpha, t.boundary_prec, t.boundary_mean)
             elif t.kind == "sGP":
-                # design on the device from the covariate; the (d x d) precision Compute_Q_sB stays on the host
-                P = sgp_precision(t)
-                ff.add_sgp(t.x, t.initial_location, t.a, t.k, t.m, [float(t.region.min()), float(t.region.max())], P,
-                           float(np.linalg.slogdet(P)[1]), t.u, t.alpha, t.boundary_prec, t.boundary_mean)
+                # design AND precision (Compute_Q_sB) on the device from the covariate / the term's parameters
+                ff.add_sgp_auto(t.x, t.initial_location, t.a, t.k, t.m, [float(t.region.min()), float(t.region.max())],
+                                t.accuracy, t.u, t.alpha, t.boundary_prec, t.boundary_mean)
             else:
                 B, Pd = iid_design(t)
                 ff.add_random(B, Pd, 0.0, t.u, t.alpha)

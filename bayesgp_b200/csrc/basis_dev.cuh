@@ -66,4 +66,66 @@ __device__ __forceinline__ void bspline4(double x, double lo, double hi, int nbr
   v[3] = N[3];
 }
 
+// The same splines with their first and second derivatives (fda::eval.basis(x, basis, Lfdobj = 1 | 2)):
+//   B'_{i,4}  = 3 [ B_{i,3} / (t_{i+3} - t_i) - B_{i+1,3} / (t_{i+4} - t_{i+1}) ]
+//   B''_{i,4} = 3 [ B'_{i,3} / (t_{i+3} - t_i) - B'_{i+1,3} / (t_{i+4} - t_{i+1}) ],  B'_{i,3} likewise from order 2.
+// Terms whose knot difference is zero belong to splines that vanish identically and are dropped.
+__device__ __forceinline__ void bspline4_d(double x, double lo, double hi, int nbreaks, int& first, double v[4],
+                                           double d1[4], double d2[4]) {
+  const int nint = nbreaks - 1;
+  const double h = (hi - lo) / nint;
+  int iv = (int)floor((x - lo) / h);
+  if (iv < 0) iv = 0;
+  if (iv > nint - 1) iv = nint - 1;
+  auto knot = [&](int idx) {
+    int b = idx - 3;
+    if (b < 0) b = 0;
+    if (b > nint) b = nint;
+    return b == nint ? hi : lo + h * b;
+  };
+  const int mu = iv + 3;
+  double N[4] = {1.0, 0.0, 0.0, 0.0};
+  double N2[2] = {0.0, 0.0}, N3[3] = {0.0, 0.0, 0.0};
+  double dl[4], dr[4];
+  for (int j = 1; j <= 3; ++j) {
+    dr[j] = knot(mu + j) - x;
+    dl[j] = x - knot(mu + 1 - j);
+    double saved = 0.0;
+    for (int r = 0; r < j; ++r) {
+      const double term = N[r] / (dr[r + 1] + dl[j - r]);
+      N[r] = saved + dr[r + 1] * term;
+      saved = dl[j - r] * term;
+    }
+    N[j] = saved;
+    if (j == 1) {
+      N2[0] = N[0];
+      N2[1] = N[1];
+    } else if (j == 2) {
+      N3[0] = N[0];
+      N3[1] = N[1];
+      N3[2] = N[2];
+    }
+  }
+  // order-o spline number q (of the o non-zero ones at x) is B_{mu-o+1+q, o}
+  auto inv = [&](int a, int b) {
+    const double d = knot(b) - knot(a);
+    return d > 0.0 ? 1.0 / d : 0.0;
+  };
+  double dN3[3];     // first derivatives of the three order-3 splines
+  for (int q = 0; q < 3; ++q) {
+    const int i = mu - 2 + q;
+    const double t1 = q >= 1 ? N2[q - 1] * inv(i, i + 2) : 0.0;
+    const double t2 = q <= 1 ? N2[q] * inv(i + 1, i + 3) : 0.0;
+    dN3[q] = 2.0 * (t1 - t2);
+  }
+  for (int q = 0; q < 4; ++q) {
+    const int i = mu - 3 + q;
+    const double w1 = inv(i, i + 3), w2 = inv(i + 1, i + 4);
+    d1[q] = 3.0 * ((q >= 1 ? N3[q - 1] * w1 : 0.0) - (q <= 2 ? N3[q] * w2 : 0.0));
+    d2[q] = 3.0 * ((q >= 1 ? dN3[q - 1] * w1 : 0.0) - (q <= 2 ? dN3[q] * w2 : 0.0));
+    v[q] = N[q];
+  }
+  first = iv;
+}
+
 }  // namespace bgp

@@ -282,6 +282,8 @@ int launch_sgp_block(const double* x_dev, int64_t n, double x0, double a, int k,
 // model.cu: size-keyed free lists of device / pinned blocks (see bgp_model::dev_pool)
 void* pool_take(bgp_model* m, bool pinned, size_t bytes, size_t* got_bytes);
 void pool_give(bgp_model* m, bool pinned, void* ptr, size_t bytes);
+// basis.cu: Compute_Q_sB per harmonic into the block-diagonal d x d precision (column-major, device)
+int launch_sgp_precision(double a, int k, int m, double lo, double hi, double accuracy, double* P_dev, cudaStream_t st);
 // newton.cu
 int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool want_c3);
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters);

@@ -386,6 +386,71 @@ int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, do
   return BGP_OK;
 }
 
+// determinant(P)$modulus (R/02_model_fit.R:66): log |det P| by LU with partial pivoting, P d x d column-major
+static double log_abs_det(std::vector<double> A, int d) {
+  double s = 0.0;
+  for (int c = 0; c < d; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < d; ++r)
+      if (std::fabs(A[(size_t)c * d + r]) > std::fabs(A[(size_t)c * d + piv])) piv = r;
+    const double pv = A[(size_t)c * d + piv];
+    if (pv == 0.0) return -INFINITY;
+    if (piv != c)
+      for (int j = c; j < d; ++j) std::swap(A[(size_t)j * d + c], A[(size_t)j * d + piv]);
+    s += std::log(std::fabs(pv));
+    for (int r = c + 1; r < d; ++r) A[(size_t)c * d + r] /= pv;
+    for (int j = c + 1; j < d; ++j) {
+      const double f = A[(size_t)j * d + c];
+      if (f == 0.0) continue;
+      double* col = &A[(size_t)j * d];
+      const double* l = &A[(size_t)c * d];
+      for (int r = c + 1; r < d; ++r) col[r] -= l[r] * f;
+    }
+  }
+  return s;
+}
+
+int bgp_sgp_precision(double a, int k, int nharm, const double* region, double accuracy, int device, double* P,
+                      double* logPdet) {
+  if (k < 4 || nharm < 1 || !region || !(region[1] > region[0]) || !(accuracy > 0.0) || !P) {
+    set_error("bgp_sgp_precision: bad arguments (k >= 4, m >= 1, region increasing, accuracy > 0)");
+    return BGP_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_error("no CUDA device %d available: libbgp has no CPU fallback", device);
+    return BGP_ERR_CUDA;
+  }
+  BGP_CUDA(cudaSetDevice(device));
+  const int d = 3 * (k - 2) * nharm;
+  double* P_dev = nullptr;
+  BGP_CUDA(cudaMalloc(&P_dev, (size_t)d * d * sizeof(double)));
+  int rc = launch_sgp_precision(a, k, nharm, region[0], region[1], accuracy, P_dev, 0);
+  if (rc == BGP_OK && cudaMemcpy(P, P_dev, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("cudaMemcpy of the sGP precision failed");
+    rc = BGP_ERR_CUDA;
+  }
+  cudaFree(P_dev);
+  if (rc == BGP_OK && logPdet) *logPdet = log_abs_det(std::vector<double>(P, P + (size_t)d * d), d);
+  return rc;
+}
+
+int bgp_model_add_sgp_auto(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm,
+                           const double* region, double accuracy, double u, double alpha, double boundary_prec,
+                           double boundary_mean) {
+  BGP_CHECK_BUILDING(m);
+  if (k < 4 || nharm < 1 || !region) {
+    set_error("bgp_model_add_sgp_auto: bad arguments");
+    return BGP_ERR_ARG;
+  }
+  const int d = 3 * (k - 2) * nharm;
+  std::vector<double> P((size_t)d * d);
+  double logPdet = 0.0;
+  BGP_TRY(bgp_sgp_precision(a, k, nharm, region, accuracy, m->device, P.data(), &logPdet));
+  return bgp_model_add_sgp(m, x, initial_location, a, k, nharm, region, P.data(), logPdet, u, alpha, boundary_prec,
+                           boundary_mean);
+}
+
 int bgp_nccl_unique_id(void* id128) { return comm_unique_id(id128); }
 
 int bgp_model_set_shard(bgp_model* m, int rank, int world, const void* nccl_unique_id) {

@@ -127,6 +127,15 @@ class LaplaceObjective:
                                           dptr(Pm), float(logPdet), float(u), float(alpha), float(boundary_prec),
                                           float(boundary_mean)))
 
+    def add_sgp_auto(self, x, initial_location, a, k, m, region, accuracy=0.01, u=1.0, alpha=0.5, boundary_prec=0.01,
+                     boundary_mean=0.0):
+        """sGP term entirely on the device: design from the covariate, precision by Compute_Q_sB (bgp_sgp_precision)."""
+        x = fvec(x)
+        reg = fvec(np.asarray(region, dtype=np.float64)[:2])
+        check(self._lib.bgp_model_add_sgp_auto(self._h, dptr(x), float(initial_location), float(a), int(k), int(m),
+                                               dptr(reg), float(accuracy), float(u), float(alpha), float(boundary_prec),
+                                               float(boundary_mean)))
+
     def set_noise_prior(self, u=1.0, alpha=0.5):
         check(self._lib.bgp_model_set_noise_prior(self._h, float(u), float(alpha)))
 

@@ -85,107 +85,8 @@ def prepare_term(t: Term) -> Term:
 
 
 # ---- dense blocks for the terms that are not generated on the device ------------------------------------
-def _bspline_all(x, lo, hi, k, deriv=0):
-    """Cubic B-spline basis of fda::create.bspline.basis(c(lo, hi), nbasis = k, norder = 4) and its
-    derivatives, vectorised Cox-de Boor on the clamped knot vector; (len(x), k)."""
-    norder = 4
-    breaks = np.linspace(lo, hi, k - norder + 2)
-    t = np.concatenate([np.full(norder - 1, lo), breaks, np.full(norder - 1, hi)])
-    nt = len(t)
-    x = np.asarray(x, dtype=np.float64)
-    B = np.zeros((len(x), nt - 1))
-    last = np.max(np.nonzero(t[1:] > t[:-1])[0])
-    for j in range(nt - 1):
-        if t[j + 1] > t[j]:
-            B[:, j] = (x >= t[j]) & ((x < t[j + 1]) | ((j == last) & (x <= t[j + 1])))
-    for m in range(2, norder - deriv + 1):
-        Bn = np.zeros((len(x), nt - m))
-        for j in range(nt - m):
-            d1, d2 = t[j + m - 1] - t[j], t[j + m] - t[j + 1]
-            if d1 > 0:
-                Bn[:, j] += (x - t[j]) / d1 * B[:, j]
-            if d2 > 0:
-                Bn[:, j] += (t[j + m] - x) / d2 * B[:, j + 1]
-        B = Bn
-    for m in range(norder - deriv + 1, norder + 1):
-        Bn = np.zeros((len(x), nt - m))
-        for j in range(nt - m):
-            d1, d2 = t[j + m - 1] - t[j], t[j + m] - t[j + 1]
-            if d1 > 0:
-                Bn[:, j] += (m - 1) / d1 * B[:, j]
-            if d2 > 0:
-                Bn[:, j] -= (m - 1) / d2 * B[:, j + 1]
-        B = Bn
-    return B * ((x >= lo) & (x <= hi))[:, None]
-
-
-def sgp_design(t: Term):
-    """B = cbind over harmonics of [B cos, B sin, B]; X = cbind(cos, sin) (R/01_utility.R:177-195,224-239,301-312).
-    Fit-time B always drops the first two B-splines (boundary = TRUE is hard-wired there, A.8)."""
-    xi = np.asarray(t.x, dtype=np.float64) - t.initial_location
-    lo, hi = float(t.region.min()), float(t.region.max())
-    Bm = _bspline_all(xi, lo, hi, t.k)[:, 2:]
-    Bs, Xs = [], []
-    for i in range(1, t.m + 1):
-        c, s = np.cos(i * t.a * xi)[:, None], np.sin(i * t.a * xi)[:, None]
-        Bs += [Bm * c, Bm * s, Bm]
-        Xs += [c, s]
-    return np.concatenate(Bs, axis=1), np.concatenate(Xs, axis=1)
-
-
-def sgp_precision(t: Term):
-    """Compute_Q_sB per harmonic, block-diagonal (R/01_utility.R:67-174,255-272)."""
-    lo, hi = float(t.region.min()), float(t.region.max())
-    nx = int(np.floor((hi - lo) / t.accuracy + 1e-10)) + 1
-    x = lo + t.accuracy * np.arange(nx)
-    B0 = _bspline_all(x, lo, hi, t.k, 0)[:, 2:]
-    B1 = _bspline_all(x, lo, hi, t.k, 1)[:, 2:]
-    B2 = _bspline_all(x, lo, hi, t.k, 2)[:, 2:]
-    wI = np.diff(np.concatenate([[0.0], x]))[:, None]
-    blocks = []
-    for i in range(1, t.m + 1):
-        a = i * t.a
-        c, s = np.cos(a * x)[:, None], np.sin(a * x)[:, None]
-        Bc, B1c, B2c, Bs, B1s, B2s = B0 * c, B1 * c, B2 * c, B0 * s, B1 * s, B2 * s
-
-        def ip(U, V):
-            return U.T @ (wI * V)
-
-        def ss(Mx):
-            return Mx + Mx.T
-
-        T00, T10, T11, T20, T21, T22 = ip(Bc, Bc), ip(B1c, Bc), ip(B1c, B1c), ip(B2c, Bc), ip(B2c, B1c), ip(B2c, B2c)
-        L00, L10, L11, L20, L21, L22 = ip(Bs, Bs), ip(B1s, Bs), ip(B1s, B1s), ip(B2s, Bs), ip(B2s, B1s), ip(B2s, B2s)
-        I00, I10, I11, I20, I21, I22 = ip(Bs, Bc), ip(B1s, Bc), ip(B1s, B1c), ip(B2s, Bc), ip(B2s, B1c), ip(B2s, B2c)
-        BB, B2B2, BB2 = ip(B0, B0), ip(B2, B2), ip(B0, B2)
-        BS, BC, BS1, BC1, BS2, BC2 = ip(B0, Bs), ip(B0, Bc), ip(B0, B1s), ip(B0, B1c), ip(B0, B2s), ip(B0, B2c)
-        B2S, B2C, B2S1, B2C1, B2S2, B2C2 = ip(B2, Bs), ip(B2, Bc), ip(B2, B1s), ip(B2, B1c), ip(B2, B2s), ip(B2, B2c)
-        Gm = np.block([[T00, I00.T, BC.T], [I00, L00, BS.T], [BC, BS, BB]])
-        C11 = T22 - 2 * a * ss(I21) - a ** 2 * ss(T20) + 2 * a ** 3 * ss(I10) + 4 * a ** 2 * L11 + a ** 4 * T00
-        C22 = L22 + 2 * a * ss(I21) - a ** 2 * ss(L20) - 2 * a ** 3 * ss(I10) + 4 * a ** 2 * T11 + a ** 4 * L00
-        C12 = (I22 + 2 * a * T21 - a ** 2 * ss(I20) - 2 * a * L21.T - 4 * a ** 2 * I11 + 2 * a ** 3 * L10
-               - 2 * a ** 3 * T10.T + a ** 4 * I00)
-        C13 = B2C2.T - 2 * a * B2S1.T - a ** 2 * B2C.T
-        C23 = B2S2.T + 2 * a * B2C1.T - a ** 2 * B2S.T
-        Cm = np.block([[C11, C12, C13], [C12.T, C22, C23], [C13.T, C23.T, B2B2]])
-        M11 = T20.T - 2 * a * I10.T - a ** 2 * T00
-        M12 = I20.T + 2 * a * T10.T - a ** 2 * I00
-        M21 = I20.T - 2 * a * L10.T - a ** 2 * I00
-        M22 = L20.T + 2 * a * I10.T - a ** 2 * L00
-        M31 = BC2 - 2 * a * BS1 - a ** 2 * BC
-        M32 = BS2 + 2 * a * BC1 - a ** 2 * BS
-        Mm = np.block([[M11, M12, B2C.T], [M21, M22, B2S.T], [M31, M32, BB2]])
-        Q = a ** 4 * Gm + Cm + a ** 2 * ss(Mm)
-        blocks.append(np.triu(Q) + np.triu(Q, 1).T)
-    n = sum(b.shape[0] for b in blocks)
-    P = np.zeros((n, n))
-    o = 0
-    for b in blocks:
-        P[o:o + len(b), o:o + len(b)] = b
-        o += len(b)
-    return P
-
-
+# (IWP and sGP designs, the IWP precision and the sGP precision Compute_Q_sB are all built on the device:
+#  bgp_model_add_iwp / bgp_model_add_sgp_auto / bgp_sgp_precision, csrc/basis.cu)
 def iid_design(t: Term):
     lev, inv = np.unique(np.asarray(t.x), return_inverse=True)
     B = np.zeros((len(inv), len(lev)))

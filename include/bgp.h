@@ -79,6 +79,17 @@ int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, co
 int bgp_model_add_sgp(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm,
                       const double* region /* 2 */, const double* P, double logPdet, double u, double alpha,
                       double boundary_prec, double boundary_mean);
+/* Compute_Q_sB on the device (/root/reference/R/01_utility.R:67-174,255-272): the sGP precision, block diagonal over
+ * the harmonics i = 1..m (frequency i a), d = 3 (k - 2) m, from the cubic B-spline basis on `region` minus its first
+ * two functions and its first / second derivatives on the grid seq(region[0], region[1], by = accuracy) with weights
+ * diff(c(0, x)): one FP64 tensor-pipe Gram product of the nine function families, then the reference's block
+ * formulas.  P is d x d column-major; logPdet = determinant(P)$modulus (R/02_model_fit.R:66), may be NULL. */
+int bgp_sgp_precision(double a, int k, int nharm, const double* region /* 2 */, double accuracy, int device, double* P,
+                      double* logPdet);
+/* bgp_model_add_sgp with P and logPdet computed by bgp_sgp_precision on the model's device */
+int bgp_model_add_sgp_auto(bgp_model* m, const double* x, double initial_location, double a, int k, int nharm,
+                           const double* region /* 2 */, double accuracy, double u, double alpha, double boundary_prec,
+                           double boundary_mean);
 /* observation sharding: this process holds rows [row0, row0 + n) of a global problem of n_total rows and
  * joins an NCCL communicator of `world` ranks (nccl_unique_id: the 128-byte ncclUniqueId produced by
  * bgp_nccl_unique_id on rank 0 and broadcast by the launcher). Must precede finalize. */

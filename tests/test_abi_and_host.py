@@ -63,11 +63,9 @@ def test_term_setup_matches_oracle_constructors():
     x = rng.uniform(-0.3, 1.2, 400)
     t = pt.prepare_term(pt.Term("sGP", "x", x, a=2 * np.pi * 3, k=9, m=2, region=np.array([0.0, 1.5])))
     o = build_term(OTerm("sGP", "x", x, a=2 * np.pi * 3, k=9, m=2, region=np.array([0.0, 1.5])))
-    B, X = pt.sgp_design(t)
-    assert np.allclose(B, o.B, rtol=1e-12, atol=1e-13) and np.allclose(X, o.X, rtol=1e-14)
-    P = pt.sgp_precision(t)
-    assert np.allclose(P, o.P, rtol=1e-10, atol=1e-10 * np.abs(o.P).max())
-    assert t.n_basis == o.B.shape[1] and t.n_boundary == o.X.shape[1]
+    # design and precision of an sGP term are built on the device (tests/test_gpu_edge.py compares them with the
+    # oracle's constructors); the host only sizes the blocks
+    assert t.n_basis == o.B.shape[1] == o.P.shape[0] and t.n_boundary == o.X.shape[1]
     ti = pt.prepare_term(pt.Term("IWP", "x", x, order=3, k=11))
     oi = build_term(OTerm("IWP", "x", x, order=3, k=11))
     assert np.allclose(ti.knots, oi.knots) and ti.initial_location == oi.initial_location

@@ -80,6 +80,26 @@ def test_iid_term_and_default_binomial_size():
     _compare(model, [np.array([0.0, 0.0]), np.array([1.0, 2.0])])
 
 
+@pytest.mark.parametrize("a,k,m,region,acc", [(2 * np.pi * 3, 9, 2, (0.0, 1.5), 0.01), (2 * np.pi * 5, 20, 1, (0.0, 1.0), 0.01),
+                                              (1.7, 4, 1, (0.2, 2.0), 0.05), (2 * np.pi, 31, 3, (-0.5, 0.75), 0.002)])
+def test_sgp_precision_on_the_device_matches_compute_q_sb(a, k, m, region, acc):
+    """Compute_Q_sB (R/01_utility.R:67-174) on the device — one Gram GEMM of the nine basis families + the block
+    formulas — against the oracle's restatement, and determinant(P)$modulus against numpy's slogdet."""
+    import ctypes as C
+    from bayesgp_b200 import _lib
+    from oracle import basis as ob
+    lib = _lib.load()
+    d = 3 * (k - 2) * m
+    P = np.empty((d, d), order="F")
+    reg = np.array(region, dtype=np.float64)
+    ld = C.c_double()
+    _lib.check(lib.bgp_sgp_precision(a, k, m, _lib.dptr(reg), acc, 0, _lib.dptr(P), C.byref(ld)))
+    want = ob.compute_P_sGP(a, k, m, reg, acc)
+    assert np.array_equal(P, P.T)
+    assert relerr(P, want) < 1e-11
+    assert abs(ld.value - np.linalg.slogdet(want)[1]) <= 1e-6 * max(1.0, abs(ld.value))
+
+
 def test_predict_derivatives_match_oracle():
     """f, f', f'' from the same samples (degree < order, R/03_post_fit.R:201-203 rejects the rest)."""
     import bayesgp_b200 as bg
