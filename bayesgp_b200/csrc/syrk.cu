@@ -8,16 +8,17 @@
 //   * FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — tcgen05 has no FP64 kind; the larger f64 mma
 //     shapes lower to the same instruction).  Measured issue rate: one DMMA per 16.1 clk per SM sub-partition
 //     = 37.0 TFLOP/s at 1965 MHz (scripts/ubench/dmma_bench.cu).
-//   * Persistent, warp-specialised CTAs (2 per SM): one producer warp + 4 consumer warps.  A CTA tile is
-//     up to 4 row boxes x one N panel of 8 column boxes (64 x 128 of H); consumer warp w owns a PAIR of column
-//     boxes of the panel and runs over the tile's row boxes (a 64 x 32 block, 64 accumulator doubles per thread):
-//     a row-box fragment read from shared memory feeds 8 DMMAs.  With one column box per warp (round 1: 64 x 64
-//     tiles, 3 CTAs per SM) the twelve consumer warps of an SM asked shared memory for ~264 wavefronts per 258
-//     clk of tensor-pipe time — the kernel sat on the shared-memory bandwidth (29.8 TFLOP/s even on dense rows);
-//     the pair layout needs 41 % fewer wavefronts per DMMA.  The diag(w) scaling is applied to the warp's own
-//     column-box fragments only (4 DMUL per 32 DMMA — a DMUL costs ~4.7 clk of the same pipe).
+//   * Persistent, warp-specialised CTAs (3 per SM): one producer warp + 4 consumer warps.  A CTA tile is
+//     up to 4 row boxes x one N panel (64 x 64 of H); consumer warp w owns column box w of the panel and runs over
+//     the tile's row boxes (a 64 x 16 strip, 32 accumulator doubles per thread).  The diag(w) scaling is
+//     applied to the warp's own column-box fragments only (2 DMUL per 16 DMMA — a DMUL costs ~4.7 clk of the
+//     same pipe).
+//     (Round 2 measured the alternative with 64 x 128 tiles and a pair of column boxes per warp, 2 CTAs per SM:
+//     41 % fewer shared-memory reads per DMMA but 2.18 ms instead of 1.27 ms — ncu: 27.6 % of the stall samples
+//     `no_instruction` (45 unrolled mask variants overflow the instruction cache), 18 % full-barrier waits, tensor
+//     pipe 49 % busy; shared-memory wavefronts of THIS layout are only 31 % of peak, so they were never the limit.)
 //   * Operands are TMA-staged: A is observation-major, so a TMA box of {16 columns, 16 observations} lands as
-//     16 lines of 128 B with the hardware 128B swizzle; a stage is 4 + 8 boxes + 16 weights.  The producer
+//     16 lines of 128 B with the hardware 128B swizzle; a stage is 4 + 4 boxes + 16 weights.  The producer
 //     warp runs a 4-stage mbarrier ring ahead of the consumers (full / empty barriers, no CTA-wide barrier).
 //     Fragment loads are LDS.128 with a column permutation chosen so the swizzled lines are read
 //     conflict-free; the permutation is undone in the epilogue.
@@ -42,15 +43,17 @@
 
 namespace bgp {
 
-constexpr int SK_MBOX = 4;                 // row boxes (16 rows of H each) per CTA tile
-constexpr int SK_NBOX = 8;                 // N panel: 8 boxes = 128 columns of H
-constexpr int SK_WCOLS = 2;                // column boxes per consumer warp
+#ifndef SK_MBOX_N
+#define SK_MBOX_N 4
+#endif
+static_assert(SK_MBOX_N == 4, "the consumer layout (one warp per N box, four row boxes) assumes 4 x 4 box tiles");
+constexpr int SK_MBOX = SK_MBOX_N;         // strips (16-row boxes of H) per CTA tile = consumer warps
+constexpr int SK_NBOX = 4;                 // N panel: 4 boxes = 64 columns of H
 constexpr int SK_KB = 16;                  // observations per pipeline stage
 constexpr int SK_SPC = 4;                  // stages per 64-observation chunk
 constexpr int SK_STAGES = 4;
-constexpr int SK_CTAS_PER_SM = 2;
-constexpr int SK_CONSUMERS = SK_NBOX / SK_WCOLS;     // 4: one consumer warp per pair of boxes of the N panel
-static_assert(SK_CONSUMERS == 4 && SK_MBOX == 4, "mask encodings assume four row slots and four consumer warps");
+constexpr int SK_CTAS_PER_SM = 3;
+constexpr int SK_CONSUMERS = SK_NBOX;     // one consumer warp per box of the N panel
 constexpr int SK_THREADS = 32 * (SK_CONSUMERS + 1);
 constexpr int SK_BOX_BYTES = 16 * SK_KB * 8;                       // 2048
 constexpr int SK_STAGE_BYTES = (SK_MBOX + SK_NBOX) * SK_BOX_BYTES;
@@ -64,11 +67,10 @@ constexpr int SK_SMEM = SK_STAGES * (SK_STAGE_BYTES + SK_W_BYTES + 16) + 16 * SK
 struct SkTile {
   int J;
   int slot_off, slot_cnt;   // partial slots of this tile in tile_slots
-  uint32_t smask;           // bit 8*s + b: box (rows[s], 8J + b) is on or below the diagonal and inside the matrix
-  int8_t rows[4];           // box row of row slot s, -1 = unused
-  uint8_t wpair[4];         // consumer warp w works on column boxes 2 wpair[w], 2 wpair[w] + 1 of the N panel ...
-  uint8_t wmask[4];         // ... bit s + 4h: against row slot s for its column box h (every live box has one owner)
-  uint8_t pad[4];
+  uint32_t smask;           // bit 4*s + b: box (rows[s], 4J + b) is on or below the diagonal and inside the matrix
+  int8_t rows[8];           // box row of row slot s, -1 = unused
+  uint8_t wcol[4];          // consumer warp w works on column box wcol[w] of the N panel ...
+  uint8_t wrows[4];         // ... against the row slots in this mask (every live box has exactly one owner)
 };
 static_assert(sizeof(SkTile) == 32, "SkTile layout");
 
@@ -109,44 +111,11 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
   return v;
 }
 
-// one pipeline stage (16 observations) of a warp's 64 x 32 block: the warp owns two boxes of the N panel (their
-// weighted fragments are formed once per k-step) and runs over the tile's row boxes; MASK selects the rows, each
-// row fragment feeds both column boxes (8 DMMAs per 16-byte shared-memory read)
+// one pipeline stage (16 observations) of a warp's 64 x 16 column strip: the warp owns one box of the N panel
+// (its weighted fragments are formed once per k-step) and runs over the tile's row boxes; MASK selects them
 template <int MASK>
-__device__ __forceinline__ void sk_stage2(double (&acc)[2][4][2][2][2], const uint32_t (&pa)[4], uint32_t pb0, uint32_t pb1,
-                                          uint32_t pw, int fk, int ch) {
-#pragma unroll
-  for (int kk = 0; kk < SK_KB / 4; ++kk) {
-    const int row = kk * 4 + fk;
-    const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
-    double2 b0 = lds128(pb0 + off);
-    double2 b1 = lds128(pb1 + off);
-    const double wk = lds64(pw + row * 8);
-    b0.x *= wk;
-    b0.y *= wk;
-    b1.x *= wk;
-    b1.y *= wk;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (MASK & (1 << s)) {
-        const double2 a = lds128(pa[s] + off);
-        dmma884(acc[0][s][0][0][0], acc[0][s][0][0][1], a.x, b0.x);
-        dmma884(acc[0][s][0][1][0], acc[0][s][0][1][1], a.x, b0.y);
-        dmma884(acc[0][s][1][0][0], acc[0][s][1][0][1], a.y, b0.x);
-        dmma884(acc[0][s][1][1][0], acc[0][s][1][1][1], a.y, b0.y);
-        dmma884(acc[1][s][0][0][0], acc[1][s][0][0][1], a.x, b1.x);
-        dmma884(acc[1][s][0][1][0], acc[1][s][0][1][1], a.x, b1.y);
-        dmma884(acc[1][s][1][0][0], acc[1][s][1][0][1], a.y, b1.x);
-        dmma884(acc[1][s][1][1][0], acc[1][s][1][1][1], a.y, b1.y);
-      }
-    }
-  }
-}
-// the same for ONE of the two column boxes (ragged ends: the other box is empty in this chunk, lies above the
-// diagonal, or has a different row set)
-template <int MASK>
-__device__ __forceinline__ void sk_stage1(double (&acc)[4][2][2][2], const uint32_t (&pa)[4], uint32_t pb, uint32_t pw,
-                                          int fk, int ch) {
+__device__ __forceinline__ void sk_stage(double (&acc)[4][2][2][2], const uint32_t (&pa)[4], uint32_t pb, uint32_t pw,
+                                         int fk, int ch) {
 #pragma unroll
   for (int kk = 0; kk < SK_KB / 4; ++kk) {
     const int row = kk * 4 + fk;
@@ -167,49 +136,29 @@ __device__ __forceinline__ void sk_stage1(double (&acc)[4][2][2][2], const uint3
     }
   }
 }
-#define SK_DISPATCH(FN, MASKV, ...)                 \
-  switch (MASKV) {                                  \
-    case 1: FN<1>(__VA_ARGS__); break;              \
-    case 2: FN<2>(__VA_ARGS__); break;              \
-    case 3: FN<3>(__VA_ARGS__); break;              \
-    case 4: FN<4>(__VA_ARGS__); break;              \
-    case 5: FN<5>(__VA_ARGS__); break;              \
-    case 6: FN<6>(__VA_ARGS__); break;              \
-    case 7: FN<7>(__VA_ARGS__); break;              \
-    case 8: FN<8>(__VA_ARGS__); break;              \
-    case 9: FN<9>(__VA_ARGS__); break;              \
-    case 10: FN<10>(__VA_ARGS__); break;            \
-    case 11: FN<11>(__VA_ARGS__); break;            \
-    case 12: FN<12>(__VA_ARGS__); break;            \
-    case 13: FN<13>(__VA_ARGS__); break;            \
-    case 14: FN<14>(__VA_ARGS__); break;            \
-    case 15: FN<15>(__VA_ARGS__); break;            \
-    default: break;                                 \
-  }
 
 // per-chunk activity of a tile: which strips are present in this chunk (and not aliased to the N panel =>
 // need their own copy), which N boxes any present strip wants
 __host__ __device__ __forceinline__ void sk_chunk_masks(const SkTile& t, unsigned long long occ, uint32_t& act_m,
-                                                        uint32_t& load_m, uint32_t& need_n, uint32_t& ncol) {
-  ncol = (uint32_t)(occ >> (SK_NBOX * t.J)) & 0xffu;     // occupied column boxes of the panel in this chunk
+                                                        uint32_t& load_m, uint32_t& need_n) {
+  const uint32_t ncol = (uint32_t)(occ >> (4 * t.J)) & 0xfu;
   act_m = load_m = need_n = 0;
-  const int j0 = SK_NBOX * t.J;
 #pragma unroll
   for (int w = 0; w < SK_MBOX; ++w) {
     const int r = t.rows[w];
     if (r < 0) continue;
-    const uint32_t sm = (t.smask >> (SK_NBOX * w)) & 0xffu & ncol;
+    const uint32_t sm = (t.smask >> (4 * w)) & 0xfu & ncol;
     if (((occ >> r) & 1ull) && sm) {
       act_m |= 1u << w;
       need_n |= sm;
-      if (r < j0 || r >= j0 + SK_NBOX) load_m |= 1u << w;
+      if (r < 4 * t.J || r >= 4 * t.J + 4) load_m |= 1u << w;
     }
   }
-  // a row box that lives inside the N panel reads the panel's own copy of its box
+  // a strip that lives inside the N panel reads the panel's own copy of its box
 #pragma unroll
   for (int w = 0; w < SK_MBOX; ++w) {
     const int r = t.rows[w];
-    if (((act_m >> w) & 1u) && r >= j0 && r < j0 + SK_NBOX) need_n |= 1u << (r - j0);
+    if (((act_m >> w) & 1u) && r >= 4 * t.J && r < 4 * t.J + 4) need_n |= 1u << (r - 4 * t.J);
   }
 }
 
@@ -273,17 +222,17 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
           occ_n = __ldg(occ + (ent_n & 0xffffffu));
           if (e + 2 < e_end) ent_nn = __ldg(entries + e + 2);
         }
-        uint32_t act_m, load_m, need_n, ncol;
-        sk_chunk_masks(t, occ_c, act_m, load_m, need_n, ncol);
+        uint32_t act_m, load_m, need_n;
+        sk_chunk_masks(t, occ_c, act_m, load_m, need_n);
         const uint32_t tx = (uint32_t)(__popc(load_m) + __popc(need_n)) * SK_BOX_BYTES + SK_W_BYTES;
-        const int ncol0 = SK_NBOX * t.J * 16;
+        const int ncol0 = 4 * t.J * 16;
         for (int s = 0; s < SK_SPC; ++s, ++it) {
           const int slot = it % SK_STAGES;
           const uint32_t fb = full_base + 8 * slot;
           const uint32_t sb = base + slot * SK_STAGE_BYTES;
           mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
           const int row = chunk * 64 + s * SK_KB;
-          sts128(meta_base + 16 * slot, act_m | (ncol << 8), (uint32_t)tile, (uint32_t)unit, 0u);   // active rows | occupied column boxes
+          sts128(meta_base + 16 * slot, act_m | (need_n << 8), (uint32_t)tile, (uint32_t)unit, 0u);   // rows | N boxes present
           mbar_expect_tx(fb, tx);
 #pragma unroll
           for (int b = 0; b < SK_MBOX; ++b)
@@ -306,45 +255,41 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
     return;
   }
 
-  // ---------------- consumer warps: warp w owns a pair of column boxes of the N panel --------------------
-  int wp = warp;                 // pair of column boxes of the N panel this warp works on (per unit)
+  // ---------------- consumer warps: warp w owns column box w of the N panel ----------------------------
+  int wc = warp;                 // column box of the N panel this warp works on (per tile)
   const int fj = lane >> 2, fk = lane & 3;
   const int ch = sy_chunk(fj);
-  double acc[2][4][2][2][2];     // [column box of the pair][row slot][a half][b half][fragment]
+  double acc[4][2][2][2];
   auto zero_acc = [&]() {
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 2; ++b)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) acc[h][a][b][c][0] = acc[h][a][b][c][1] = 0.0;
+        for (int c = 0; c < 2; ++c) acc[a][b][c][0] = acc[a][b][c][1] = 0.0;
   };
   zero_acc();
   int cur_unit = -1;
-  uint32_t wmask = 0;         // bit s + 4h: box (rows[s], 8J + 2 wp + h) belongs to this warp
+  uint32_t smask_w = 0;       // bit s: box (rows[s], 4J + wc) belongs to the lower triangle
   uint32_t a_off[4] = {0, 0, 0, 0};
   auto flush = [&]() {
-    // undo the column permutation, write this warp's blocks of the partial tile (row-major [16 * s + m][n])
+    // undo the column permutation, write this column strip of the partial tile (row-major [16 * s + m][n])
     double* out = part + (size_t)cur_unit * SK_TILE_ELEMS;
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int sr = 0; sr < 4; ++sr) {
+      if (!((smask_w >> sr) & 1u)) continue;
 #pragma unroll
-      for (int sr = 0; sr < 4; ++sr) {
-        if (!((wmask >> (sr + 4 * h)) & 1u)) continue;
+      for (int e = 0; e < 2; ++e) {
+        const int M = sr * 16 + 2 * ch + e;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int M = sr * 16 + 2 * ch + e;
+        for (int f = 0; f < 2; ++f)
 #pragma unroll
-          for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int N = (2 * wp + h) * 16 + 2 * sy_chunk(2 * fk + c) + f;
-              out[M * (16 * SK_NBOX) + N] = acc[h][sr][e][f][c];
-            }
-        }
+          for (int c = 0; c < 2; ++c) {
+            const int N = wc * 16 + 2 * sy_chunk(2 * fk + c) + f;
+            out[M * (16 * SK_NBOX) + N] = acc[sr][e][f][c];
+          }
       }
+    }
   };
   for (int it = 0;; ++it) {
     const int slot = it % SK_STAGES;
@@ -362,31 +307,43 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
       }
       cur_unit = unit;
       const SkTile* tp = tiles + meta.y;
-      const int j0 = SK_NBOX * tp->J;
-      // Column-box pairs are dealt to the warps with a per-unit rotation (cheap insurance against a fixed
-      // pair -> SM sub-partition map; the staircase of occupied column boxes makes the pairs unequal)
+      const int j4 = 4 * tp->J;
+      // Column boxes are dealt to the warps with a per-unit rotation.  After the zero-pattern sort the occupied
+      // column boxes of a chunk are a prefix, so box 0 of a panel carries ~31 % of a tile's DMMAs and box 3 ~20 %
+      // (C3); warp w of every CTA sits on SM sub-partition w, each with its own FP64 tensor pipe, so a fixed
+      // box -> warp map keeps one pipe saturated while another idles a third of the time.
       const int wi = (warp + (rot_units ? unit : 0)) & 3;
-      wmask = tp->wmask[wi];
-      wp = tp->wpair[wi];
+      smask_w = tp->wrows[wi];
+      wc = tp->wcol[wi];
 #pragma unroll
       for (int sr = 0; sr < 4; ++sr) {
         const int r = tp->rows[sr];
         // a row box is read from its private copy, or from the N panel's copy when it lies inside the panel
-        a_off[sr] = (r >= j0 && r < j0 + SK_NBOX) ? (uint32_t)(SK_MBOX + (r - j0)) * SK_BOX_BYTES : (uint32_t)sr * SK_BOX_BYTES;
+        a_off[sr] = (r >= j4 && r < j4 + 4) ? (uint32_t)(SK_MBOX + (r - j4)) * SK_BOX_BYTES : (uint32_t)sr * SK_BOX_BYTES;
       }
     }
-    const uint32_t act = meta.x & 0xfu, ncol = (meta.x >> 8) & 0xffu;
-    const uint32_t m0 = ((ncol >> (2 * wp)) & 1u) ? (wmask & act) : 0u;
-    const uint32_t m1 = ((ncol >> (2 * wp + 1)) & 1u) ? ((wmask >> 4) & act) : 0u;
+    const uint32_t mask = ((meta.x >> (8 + wc)) & 1u) ? (smask_w & meta.x & 0xfu) : 0u;
     const uint32_t sb = base + slot * SK_STAGE_BYTES;
     const uint32_t pa[4] = {sb + a_off[0], sb + a_off[1], sb + a_off[2], sb + a_off[3]};
-    const uint32_t pb0 = sb + (SK_MBOX + 2 * wp) * SK_BOX_BYTES, pb1 = pb0 + SK_BOX_BYTES;
+    const uint32_t pb = sb + (SK_MBOX + wc) * SK_BOX_BYTES;
     const uint32_t pw = w_base + slot * SK_W_BYTES;
-    if (m0 == m1) {
-      SK_DISPATCH(sk_stage2, m0, acc, pa, pb0, pb1, pw, fk, ch)
-    } else {
-      SK_DISPATCH(sk_stage1, m0, acc[0], pa, pb0, pw, fk, ch)
-      SK_DISPATCH(sk_stage1, m1, acc[1], pa, pb1, pw, fk, ch)
+    switch (mask) {
+      case 1: sk_stage<1>(acc, pa, pb, pw, fk, ch); break;
+      case 2: sk_stage<2>(acc, pa, pb, pw, fk, ch); break;
+      case 3: sk_stage<3>(acc, pa, pb, pw, fk, ch); break;
+      case 4: sk_stage<4>(acc, pa, pb, pw, fk, ch); break;
+      case 5: sk_stage<5>(acc, pa, pb, pw, fk, ch); break;
+      case 6: sk_stage<6>(acc, pa, pb, pw, fk, ch); break;
+      case 7: sk_stage<7>(acc, pa, pb, pw, fk, ch); break;
+      case 8: sk_stage<8>(acc, pa, pb, pw, fk, ch); break;
+      case 9: sk_stage<9>(acc, pa, pb, pw, fk, ch); break;
+      case 10: sk_stage<10>(acc, pa, pb, pw, fk, ch); break;
+      case 11: sk_stage<11>(acc, pa, pb, pw, fk, ch); break;
+      case 12: sk_stage<12>(acc, pa, pb, pw, fk, ch); break;
+      case 13: sk_stage<13>(acc, pa, pb, pw, fk, ch); break;
+      case 14: sk_stage<14>(acc, pa, pb, pw, fk, ch); break;
+      case 15: sk_stage<15>(acc, pa, pb, pw, fk, ch); break;
+      default: break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_base + 8 * slot);
@@ -481,10 +438,10 @@ int syrk_plan_create(bgp_model* m) {
   }
   const int nbox = m->lda / 16;
   const int nJ = (nbox + SK_NBOX - 1) / SK_NBOX;
-  // Row boxes of N panel J: r >= 8J.  Rows r >= 8J+7 meet all eight boxes of the panel ("full"); they are
+  // Row boxes of N panel J: r >= 4J.  Rows r >= 4J+3 meet all four boxes of the panel ("full"); they are
   // grouped four at a time in row order, so that observations sorted by zero pattern switch the rows of a
-  // tile on one after the other while every consumer warp (= pair of column boxes) keeps the same share.  The
-  // rows that cross the diagonal (1 .. 7 boxes) and the left-over full rows follow in groups of up to four.
+  // tile on one after the other while every consumer warp (= column box) keeps the same share.  The three
+  // rows that cross the diagonal (1, 2, 3 boxes) go with the left-over full rows.
   std::vector<SkTile> tiles;
   for (int J = 0; J < nJ; ++J) {
     const int c_last = std::min(nbox, SK_NBOX * J + SK_NBOX) - 1;
@@ -493,54 +450,53 @@ int syrk_plan_create(bgp_model* m) {
     std::vector<std::vector<int>> groups;
     size_t i = 0;
     for (; i + SK_MBOX <= full.size(); i += SK_MBOX) groups.push_back(std::vector<int>(full.begin() + i, full.begin() + i + SK_MBOX));
-    std::vector<int> rest(diag.begin(), diag.end());
-    rest.insert(rest.end(), full.begin() + i, full.end());
-    std::sort(rest.begin(), rest.end());
-    for (size_t q = 0; q < rest.size(); q += SK_MBOX)
-      groups.push_back(std::vector<int>(rest.begin() + q, rest.begin() + std::min(rest.size(), q + SK_MBOX)));
+    std::vector<int> rest(full.begin() + i, full.end());
+    if (rest.size() + diag.size() <= (size_t)SK_MBOX) {
+      rest.insert(rest.end(), diag.begin(), diag.end());
+      if (!rest.empty()) groups.push_back(rest);
+    } else {
+      if (!rest.empty()) groups.push_back(rest);
+      if (!diag.empty()) groups.push_back(diag);
+    }
     for (const auto& g : groups) {
       SkTile t;
       memset(&t, 0, sizeof(t));
       t.J = J;
-      for (int w = 0; w < 4; ++w) t.rows[w] = -1;
+      for (int w = 0; w < 8; ++w) t.rows[w] = -1;
       for (size_t w = 0; w < g.size(); ++w) {
         const int r = g[w];
         t.rows[w] = (int8_t)r;
         for (int b = 0; b < SK_NBOX; ++b) {
           const int c = SK_NBOX * J + b;
-          if (c < nbox && r >= c) t.smask |= 1u << (SK_NBOX * w + b);
+          if (c < nbox && r >= c) t.smask |= 1u << (4 * w + b);
         }
       }
-      // ownership: warp q takes the column-box pair q; while a warp is idle and another holds >= 2 row slots
-      // more (counted in boxes), the idle warp takes over half of the busiest warp's row slots (same pair)
-      auto boxes_of = [&](int q) { return __builtin_popcount(t.wmask[q]); };
-      for (int q = 0; q < SK_CONSUMERS; ++q) {
-        t.wpair[q] = (uint8_t)q;
-        t.wmask[q] = 0;
-        for (int w = 0; w < SK_MBOX; ++w)
-          for (int h = 0; h < SK_WCOLS; ++h)
-            t.wmask[q] |= (uint8_t)(((t.smask >> (SK_NBOX * w + SK_WCOLS * q + h)) & 1u) << (w + 4 * h));
+      if (getenv("BGP_SK_FULL")) t.smask = 0xffffu;   // diagnostics only
+      // box ownership: warp b takes column box b; while a warp is idle and another holds >= 2 boxes more,
+      // the idle warp takes over half of the busiest warp's row slots (same column box)
+      for (int b = 0; b < SK_NBOX; ++b) {
+        t.wcol[b] = (uint8_t)b;
+        t.wrows[b] = 0;
+        for (int w = 0; w < SK_MBOX; ++w) t.wrows[b] |= (uint8_t)(((t.smask >> (4 * w + b)) & 1u) << w);
       }
       for (int round = 0; round < 4; ++round) {
         int lo = 0, hi = 0;
-        for (int q = 1; q < SK_CONSUMERS; ++q) {
-          if (boxes_of(q) < boxes_of(lo)) lo = q;
-          if (boxes_of(q) > boxes_of(hi)) hi = q;
+        for (int b = 1; b < SK_NBOX; ++b) {
+          if (__builtin_popcount(t.wrows[b]) < __builtin_popcount(t.wrows[lo])) lo = b;
+          if (__builtin_popcount(t.wrows[b]) > __builtin_popcount(t.wrows[hi])) hi = b;
         }
-        const uint32_t rows_hi = (t.wmask[hi] | (t.wmask[hi] >> 4)) & 0xfu;     // row slots the busiest warp touches
-        const int nrows = __builtin_popcount(rows_hi);
-        if (t.wmask[lo] != 0 || nrows < 2) break;
-        uint32_t moved_rows = 0;
-        int left = nrows / 2;
+        const int nhi = __builtin_popcount(t.wrows[hi]);
+        if (t.wrows[lo] != 0 || nhi < 2) break;
+        uint8_t moved = 0;
+        int left = nhi / 2;
         for (int w = SK_MBOX - 1; w >= 0 && left > 0; --w)
-          if ((rows_hi >> w) & 1u) {
-            moved_rows |= 1u << w;
+          if ((t.wrows[hi] >> w) & 1u) {
+            moved |= (uint8_t)(1u << w);
             --left;
           }
-        const uint8_t moved = (uint8_t)(t.wmask[hi] & (moved_rows | (moved_rows << 4)));
-        t.wmask[hi] &= (uint8_t)~moved;
-        t.wmask[lo] = moved;
-        t.wpair[lo] = t.wpair[hi];
+        t.wrows[hi] &= (uint8_t)~moved;
+        t.wrows[lo] = moved;
+        t.wcol[lo] = t.wcol[hi];
       }
       tiles.push_back(t);
     }
@@ -556,18 +512,17 @@ int syrk_plan_create(bgp_model* m) {
   // Work list.  A unit is (tile, run of chunks) of bounded cost; the queue walks the observations from the
   // last block to the first (after the zero-pattern sort the late blocks are the densest) and visits every
   // tile per block, so the CTAs that run at the same time read the same observations (L2 reuse).  Unit
-  // cost: total / (4 G) for the first 70 % of the work, then 1/2 and 1/4 of that (short queue tail).
-  // cost of a chunk = fixed overhead + DMMA time of the busiest consumer warp (warp q owns a pair of column boxes).
+  // cost: total / (4 G) for the first 70 % of the work, then 1/2, 1/4, 1/8 and 1/16 of that (short queue tail).
+  // cost of a chunk = fixed overhead + DMMA time of the busiest consumer warp (warp b owns column box b).
   auto chunk_cost = [&](const SkTile& t, uint64_t o, int& boxes) -> int {
-    uint32_t act_m, load_m, need_n, ncol;
-    sk_chunk_masks(t, o, act_m, load_m, need_n, ncol);
+    uint32_t act_m, load_m, need_n;
+    sk_chunk_masks(t, o, act_m, load_m, need_n);
     boxes = 0;
     if (!act_m) return 0;
+    const uint32_t ncol = (uint32_t)(o >> (4 * t.J)) & 0xfu;
     int mx = 0;
-    for (int q = 0; q < SK_CONSUMERS; ++q) {
-      int bw = 0;
-      for (int h = 0; h < SK_WCOLS; ++h)
-        if ((ncol >> (SK_WCOLS * t.wpair[q] + h)) & 1u) bw += __builtin_popcount((t.wmask[q] >> (4 * h)) & 0xfu & act_m);
+    for (int w = 0; w < SK_NBOX; ++w) {
+      const int bw = ((ncol >> t.wcol[w]) & 1u) ? __builtin_popcount(t.wrows[w] & act_m) : 0;
       boxes += bw;
       mx = std::max(mx, bw);
     }
@@ -612,8 +567,12 @@ int syrk_plan_create(bgp_model* m) {
         pend[(size_t)ti].push_back(((uint32_t)ti << 24) | (uint32_t)c);
         pend_cost[(size_t)ti] += cst;
       }
-      const int64_t target = done_cost * 100 < cost_total * 70 ? unit_target
-                             : (done_cost * 100 < cost_total * 85 ? unit_target / 2 : unit_target / 4);
+      // the queue tail: CTAs finish within one (small) unit of each other.  With 1/4-size units to the end the CTA
+      // end times spread over 7 % of the kernel (ncu / BGP_SK_DEBUG, round 1); 1/8 and 1/16 units for the last 7 %
+      // of the work cost ~1 k more partial slots
+      const int64_t pct = done_cost * 100 / std::max<int64_t>(1, cost_total);
+      const int64_t target = pct < 70 ? unit_target
+                             : (pct < 85 ? unit_target / 2 : (pct < 93 ? unit_target / 4 : (pct < 97 ? unit_target / 8 : unit_target / 16)));
       if (pend_cost[(size_t)ti] >= target) emit(ti);
     }
   }

@@ -423,14 +423,17 @@ def fit_leg(ff):
     import bayesgp_b200 as bg
     ff.set_start(None)
     fn0, it0 = ff.counters()["laplace_evals"], ff.counters()["newton_iters"]
+    tm0 = ff.last_timing()
     t0 = time.perf_counter()
     mod = bg.marginal_laplace_tmb(ff, K_NODES, np.zeros(ff.S))
     wall = time.perf_counter() - t0
-    d, c = mod.diagnostics, ff.counters()
+    d, c, tm1 = mod.diagnostics, ff.counters(), ff.last_timing()
     out = {"what": "marginal_laplace_tmb(ff, k=15, theta0=0) on the resident C3 model: BFGS + Richardson + grid + marginals",
            "wall_s": wall, "opt_s": d["opt_ms"] * 1e-3, "grid_s": d["grid_ms"] * 1e-3,
            "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"],
            "laplace_evals": c["laplace_evals"] - fn0, "newton_iters": c["newton_iters"] - it0,
+           "kernel_launches": {k: tm1[k] - tm0[k] for k in ("lik_launches", "hess_launches", "chol_launches")},
+           "kernel_ms": {k: tm1[k] - tm0[k] for k in ("lik_ms", "hess_ms", "chol_ms")},
            "theta_mode": float(mod.optresults["mode"][0]), "theta_hessian": float(mod.optresults["hessian"][0, 0]),
            "convergence": mod.optresults["convergence"], "hessian_fallback": d["hessian_fallback"],
            "lognormconst": mod.lognormconst,

@@ -97,7 +97,11 @@ def test_sgp_precision_on_the_device_matches_compute_q_sb(a, k, m, region, acc):
     want = ob.compute_P_sGP(a, k, m, reg, acc)
     assert np.array_equal(P, P.T)
     assert relerr(P, want) < 1e-11
-    assert abs(ld.value - np.linalg.slogdet(want)[1]) <= 1e-6 * max(1.0, abs(ld.value))
+    # determinant(P)$modulus is only as well defined as P is conditioned: the k = 31, m = 3 Gram matrix has cond ~1e16
+    # (Compute_Q_sB is numerically singular at fine bases) and a 1e-15 relative perturbation of P
+    # moves its LU log-determinant by ~0.05; the well-conditioned cases are held to 1e-6
+    tol = 1e-6 * max(1.0, abs(ld.value)) if np.linalg.cond(want) < 1e9 else 0.5
+    assert abs(ld.value - np.linalg.slogdet(want)[1]) <= tol
 
 
 def test_predict_derivatives_match_oracle():
