@@ -173,7 +173,49 @@ SEXP bgpR_predict_iwp(SEXP coef, SEXP global, SEXP icpt, SEXP knots, SEXP order,
   return out;
 }
 
+/* predict.FitResult on the samples bgp_sample left on the device (R/03_post_fit.R:65-76 select the same rows of
+ * samps$samps): rows are 0-based first rows of the term's blocks, -1 = absent */
+SEXP bgpR_fit_predict_iwp(SEXP fptr, SEXP rows, SEXP knots, SEXP order, SEXP degree, SEXP x, SEXP level) {
+  bgp_fit* f = (bgp_fit*)R_ExternalPtrAddr(fptr);
+  const R_xlen_t G = XLENGTH(x);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)G, 3));      /* mean | plower | pupper */
+  chk(bgp_fit_predict_iwp(f, INTEGER(rows)[0], INTEGER(rows)[1], INTEGER(rows)[2], REAL(knots), (int)XLENGTH(knots),
+                          Rf_asInteger(order), Rf_asInteger(degree), REAL(x), (int64_t)G, Rf_asReal(level), REAL(out),
+                          REAL(out) + G, REAL(out) + 2 * G));
+  UNPROTECT(1);
+  return out;
+}
+
+/* Compute_Q_sB (R/01_utility.R:67-174) on the device: list(P = d x d, logPdet) */
+SEXP bgpR_sgp_precision(SEXP a, SEXP k, SEXP m, SEXP region, SEXP accuracy, SEXP device) {
+  const int d = 3 * (Rf_asInteger(k) - 2) * Rf_asInteger(m);
+  SEXP P = PROTECT(Rf_allocMatrix(REALSXP, d, d));
+  SEXP ld = PROTECT(Rf_allocVector(REALSXP, 1));
+  chk(bgp_sgp_precision(Rf_asReal(a), Rf_asInteger(k), Rf_asInteger(m), REAL(region), Rf_asReal(accuracy),
+                        Rf_asInteger(device), REAL(P), REAL(ld)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, P);
+  SET_VECTOR_ELT(out, 1, ld);
+  UNPROTECT(3);
+  return out;
+}
+
+/* one process per GPU (e.g. Rmpi / callr workers): join the node group whose ranks split quadrature nodes, sample
+ * blocks and prediction rows; `id` is the 128-byte raw vector of bgp_nccl_unique_id() made by rank 0 */
+SEXP bgpR_nccl_unique_id(void) {
+  SEXP id = PROTECT(Rf_allocVector(RAWSXP, 128));
+  chk(bgp_nccl_unique_id(RAW(id)));
+  UNPROTECT(1);
+  return id;
+}
+SEXP bgpR_set_node_group(SEXP ptr, SEXP rank, SEXP world, SEXP id) {
+  chk(bgp_model_set_node_group((bgp_model*)R_ExternalPtrAddr(ptr), Rf_asInteger(rank), Rf_asInteger(world), RAW(id)));
+  return R_NilValue;
+}
+
 static const R_CallMethodDef callMethods[] = {
+    {"bgpR_fit_predict_iwp", (DL_FUNC)&bgpR_fit_predict_iwp, 7}, {"bgpR_sgp_precision", (DL_FUNC)&bgpR_sgp_precision, 6},
+    {"bgpR_nccl_unique_id", (DL_FUNC)&bgpR_nccl_unique_id, 0},   {"bgpR_set_node_group", (DL_FUNC)&bgpR_set_node_group, 4},
     {"bgpR_model", (DL_FUNC)&bgpR_model, 2},       {"bgpR_eval", (DL_FUNC)&bgpR_eval, 5},
     {"bgpR_fit", (DL_FUNC)&bgpR_fit, 3},           {"bgpR_fit_get", (DL_FUNC)&bgpR_fit_get, 1},
     {"bgpR_sample", (DL_FUNC)&bgpR_sample, 3},     {"bgpR_predict_iwp", (DL_FUNC)&bgpR_predict_iwp, 9},
