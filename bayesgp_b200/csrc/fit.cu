@@ -33,7 +33,15 @@ struct FF {
       return BGP_OK;
     }
     int iters = 0;
+    const int64_t h0 = m->n_hess, l0 = m->n_lik;
     int st = laplace_inner(m, theta, value, &iters);
+    static const bool dbg = getenv("BGP_FIT_DEBUG") != nullptr;     // env: diagnostics
+    if (dbg) {
+      fprintf(stderr, "[fit] ff(");
+      for (int i = 0; i < S; ++i) fprintf(stderr, "%s%.6f", i ? ", " : "", theta[i]);
+      fprintf(stderr, ") = %.10g  status %d  newton %d  hessians %lld  passes %lld\n", *value, st, iters,
+              (long long)(m->n_hess - h0), (long long)(m->n_lik - l0));
+    }
     if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
     if (st != BGP_OK) {
       *value = NAN;          // inner failure => NaN, the optimiser backtracks (R_FINITE test)

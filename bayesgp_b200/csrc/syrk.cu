@@ -557,7 +557,24 @@ int syrk_plan_create(bgp_model* m) {
     pend_cost[(size_t)ti] = 0;
   };
   const int64_t nblk = (m->nchunks + blk - 1) / blk;
-  for (int64_t bk = nblk - 1; bk >= 0; --bk) {
+  // Walk order of the observation blocks.  After the zero-pattern sort the late blocks are the densest, the early
+  // ones touch a few column boxes only: their stages carry so little work that the 4-stage ring cannot cover the
+  // TMA latency (full-barrier waits; dense rows run 8 % faster per executed flop).  Walking dense -> sparse left all
+  // of that latency-bound work for the end of the queue, when nothing else shares the SM (measured: CTA end times
+  // spread over 7 % of the kernel whatever the unit size).  Alternating blocks from both ends keeps sparse and
+  // dense units resident together (3 CTAs per SM), so one CTA's waits are the others' tensor-pipe time, and ends
+  // the queue in the middle of the range.  BGP_SK_WALK=0 restores dense -> sparse (diagnostics).
+  std::vector<int64_t> walk;
+  {
+    const char* e = getenv("BGP_SK_WALK");
+    const bool interleave = !(e && e[0] == '0');
+    int64_t lo = 0, hi = nblk - 1;
+    while (lo <= hi) {
+      walk.push_back(hi--);
+      if (interleave && lo <= hi) walk.push_back(lo++);
+    }
+  }
+  for (int64_t bk : walk) {
     const int64_t c0 = bk * blk, c1 = std::min<int64_t>(m->nchunks, c0 + blk);
     for (int ti = 0; ti < pl->ntiles; ++ti) {
       for (int64_t c = c0; c < c1; ++c) {
