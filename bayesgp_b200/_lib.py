@@ -51,6 +51,8 @@ SIGNATURES = {
     "bgp_laplace_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     "bgp_laplace_eval_batch": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     "bgp_model_set_start": (C.c_int, [C.c_void_p, c_double_p]),
+    "bgp_model_get_tangent": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "bgp_model_set_start_at": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "bgp_model_set_newton": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "bgp_aghq_fit": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_void_p)]),
     "bgp_aghq_fit_at": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),

@@ -224,11 +224,25 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   int iters = 0;
   bool converged = false, have_factor = false, reused = false;
   double logdet = NAN;
+  // Stagnation: TMB's newton() runs to maxit = 100 and answers NaN when max|g| never reaches the tolerance (a theta
+  // far outside the posterior, e.g. exp(theta) = 1e-29: the gradient's rounding noise sits above 1e-8).  Twelve
+  // consecutive iterations that improve neither the best max|g| by 10 % nor f end the same way ~85 Hessians earlier.
+  double best_gmax = INFINITY, best_f = INFINITY;
+  int since_progress = 0;
   for (int it = 0; it < m->maxit; ++it) {
     const bool spec_now = spec && it == 0;
     if (!spec_now && gmax < m->grad_tol) {
       converged = true;
       break;
+    }
+    if (!spec_now) {
+      if (gmax < 0.9 * best_gmax || f < best_f - 1e-12 * std::fabs(best_f)) {
+        best_gmax = std::min(best_gmax, gmax);
+        best_f = std::min(best_f, f);
+        since_progress = 0;
+      } else if (++since_progress >= 12) {
+        break;                                   // not converged: NaN, as after maxit iterations
+      }
     }
     phase_mark(m, PH_HESS);
     BGP_TRY(launch_hessian(m, theta));
@@ -350,7 +364,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
   }
   *iters_out = iters;
   if (!converged) {
-    set_error("inner Newton did not converge in %d iterations (max|g| = %.3e)", m->maxit, gmax);
+    set_error("inner Newton did not converge (%d iterations, max|g| = %.3e)", iters, gmax);
     *value = NAN;
     return BGP_ERR_NO_CONVERGENCE;
   }
@@ -569,6 +583,42 @@ int bgp_model_set_start(bgp_model* m, const double* W) {
   if (W) BGP_TRY(copy_vec_in(m, W, m->Wmode));
   m->tan_valid = false;
   for (auto& h : m->hist) h.stamp = 0;
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  return BGP_OK;
+}
+
+int bgp_model_get_tangent(bgp_model* m, double* theta, double* T) {
+  BGP_CHECK_READY(m);
+  if (!m->tan_valid || (int)m->theta_last.size() != m->S) {
+    set_error("bgp_model_get_tangent: no Laplace evaluation on record (or the predictor is switched off)");
+    return BGP_ERR_STATE;
+  }
+  if (theta) std::copy(m->theta_last.begin(), m->theta_last.end(), theta);
+  if (T)
+    for (int k = 0; k < m->S; ++k) BGP_TRY(copy_vec_out(m, m->Tan + (size_t)k * m->lda, T + (size_t)k * m->p));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  return BGP_OK;
+}
+
+int bgp_model_set_start_at(bgp_model* m, const double* theta, const double* W, const double* T) {
+  BGP_CHECK_READY(m);
+  if (!theta || !W) {
+    set_error("bgp_model_set_start_at: NULL theta / W");
+    return BGP_ERR_ARG;
+  }
+  BGP_TRY(bgp_model_set_start(m, W));                    // clears the history, W becomes the warm start
+  if (!T || !m->use_predictor || m->S > 17) return BGP_OK;
+  auto& h = m->hist[0];
+  h.theta.assign(theta, theta + m->S);
+  h.stamp = ++m->hist_clock;
+  BGP_CUDA(cudaMemcpyAsync(h.W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  for (int k = 0; k < m->S; ++k) {
+    BGP_TRY(copy_vec_in(m, T + (size_t)k * m->p, h.T + (size_t)k * m->lda));
+    BGP_CUDA(cudaStreamSynchronize(m->stream));          // copy_vec_in stages through one buffer
+  }
+  BGP_CUDA(cudaMemcpyAsync(m->Tan, h.T, (size_t)m->S * m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  m->theta_last = h.theta;
+  m->tan_valid = true;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   return BGP_OK;
 }

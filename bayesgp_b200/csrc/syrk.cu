@@ -698,6 +698,35 @@ int launch_syrk(bgp_model* m) {
           ctot += (double)pl->unit_cost_dbg[(size_t)u];
         }
       }
+      // the end of the queue: the units that were started last, and when the CTAs that ran them finished
+      {
+        std::vector<std::pair<unsigned long long, int>> by_start;
+        for (int u = 0; u < pl->nunits; ++u) by_start.push_back({h[2 * pl->G + 2 * u], u});
+        std::sort(by_start.begin(), by_start.end());
+        fprintf(stderr, "[syrk] last units (start us, cost, tile, cta, cta end us):");
+        for (size_t i = by_start.size() > 24 ? by_start.size() - 24 : 0; i < by_start.size(); ++i) {
+          const int u = by_start[i].second;
+          const int g = (int)h[2 * pl->G + 2 * u + 1];
+          fprintf(stderr, " (%.0f, %lld, %d, %d, %.0f)", (double)(by_start[i].first - t0) * 1e-3,
+                  (long long)pl->unit_cost_dbg[(size_t)u], pl->unit_tile_dbg[(size_t)u], g, (double)(h[2 * g + 1] - t0) * 1e-3);
+        }
+        fprintf(stderr, "\n[syrk] unit cost quantiles: ");
+        std::vector<int64_t> uc(pl->unit_cost_dbg.begin(), pl->unit_cost_dbg.end());
+        std::sort(uc.begin(), uc.end());
+        for (double q : {0.0, 0.1, 0.5, 0.9, 1.0}) fprintf(stderr, " %lld", (long long)uc[(size_t)(q * (uc.size() - 1))]);
+        // the slowest CTAs: their units in order
+        std::vector<std::pair<double, int>> ends;
+        for (int g = 0; g < pl->G; ++g) ends.push_back({endt[g], g});
+        std::sort(ends.begin(), ends.end());
+        for (int k = 0; k < 3; ++k) {
+          const int g = ends[ends.size() - 1 - k].second;
+          fprintf(stderr, "\n[syrk] slow CTA %d (end %.0f us) units (start us, cost, tile):", g, endt[g]);
+          for (auto& pr : per_cta[(size_t)g])
+            fprintf(stderr, " (%.0f, %lld, %d)", (double)(pr.first - t0) * 1e-3, (long long)pl->unit_cost_dbg[(size_t)pr.second],
+                    pl->unit_tile_dbg[(size_t)pr.second]);
+        }
+        fprintf(stderr, "\n");
+      }
       fprintf(stderr, "[syrk] per tile: time share / cost share (ratio):");
       for (int t = 0; t < pl->ntiles; ++t)
         fprintf(stderr, " %d:%.3f/%.3f(%.2f)", t, tile_time[t] / ttot, tile_cost[t] / ctot,

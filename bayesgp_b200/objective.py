@@ -240,6 +240,19 @@ class LaplaceObjective:
     def set_start(self, W=None):
         check(self._lib.bgp_model_set_start(self._h, dptr(fvec(W)) if W is not None else None))
 
+    def get_tangent(self):
+        """(theta, T) of the most recent evaluation: T = d w_hat / d theta, p x S."""
+        th = np.empty(self.S)
+        T = np.empty((self.p, self.S), order="F")
+        check(self._lib.bgp_model_get_tangent(self._h, dptr(th), dptr(T)))
+        return th, T
+
+    def set_start_at(self, theta, W, T=None):
+        """Restore the state an optimiser leaves at its last evaluation (mode + tangent there)."""
+        th = fvec(np.atleast_1d(theta))
+        Tm = None if T is None else fmat(np.asarray(T, dtype=np.float64).reshape(self.p, self.S))
+        check(self._lib.bgp_model_set_start_at(self._h, dptr(th), dptr(fvec(W)), dptr(Tm)))
+
     def set_newton(self, grad_tol=1e-8, step_tol=1e-8, maxit=100):
         check(self._lib.bgp_model_set_newton(self._h, grad_tol, step_tol, maxit))
 

@@ -169,7 +169,8 @@ def node_grid(ff):
     mode, sd = locate_mode_1d(ff.fn, -25.0, 10.0, iters=32)
     thetas = (mode + sd * gh_nodes(K_NODES))[:, None]
     ff.fn(np.array([mode]))
-    return mode, sd, thetas, ff.env.last_par.copy()
+    _, T = ff.get_tangent()
+    return mode, sd, thetas, ff.env.last_par.copy(), T
 
 
 def timed_steps(step, steps, dist, sampler=None):
@@ -221,15 +222,17 @@ def run_b200(args):
     group = (rank, world, broadcast_unique_id(nccl_unique_id, rank)) if world > 1 else None
     ff = build_b200(x, y, local, x0, knots, node_group=group)
     t_build = time.time() - t0
-    mode, sd, thetas, w_mode = node_grid(ff)
+    mode, sd, thetas, w_mode, t_mode = node_grid(ff)
     p, n = ff.p, ff.n
     opt = {"mode": np.array([mode]), "hessian": np.array([[1.0 / (sd * sd)]])}
 
     # ---- the step: ONE 15-node grid through the product's own entry point (aghq::normalize_logpost inside
     # marginal_laplace_tmb with the optimisation results given), split over the node group.  Every step starts
-    # from the mode at the grid centre only (set_start clears the warm-start history).
+    # from what the optimisation phase leaves behind at the grid centre and nothing else: theta_mode, the mode
+    # there and its tangent d w_hat / d theta (set_start_at clears the warm-start history, then records that one
+    # entry) — the state bgp_aghq_fit's own grid phase starts from on every rank.
     def step_grid(want_host=True, keep=False):
-        ff.set_start(w_mode)                                          # H2D: p doubles
+        ff.set_start_at(np.array([mode]), w_mode, t_mode)             # H2D: 2 p + 1 doubles
         t0 = time.perf_counter()
         mod = bg.marginal_laplace_tmb(ff, K_NODES, None, optresults=opt)
         ms = ff.last_timing()["total_ms"]
@@ -370,9 +373,9 @@ def run_b200(args):
                    "parallelism": "node shards x%d (replicated rows), NCCL all-reduce of the 15 values" % world
                                   if world > 1 else "single GPU",
                    "model_build_s": t_build},
-        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (p + 2),
+        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": 8 * (2 * p + 3),
                 "d2h_bytes_per_step": 8 * K_NODES * (3 + p + p * p),
-                "what": "set_start (H2D) + bgp_aghq_fit_at + bgp_fit_get_* incl. all modes and Hessians gathered to the "
+                "what": "set_start_at (H2D) + bgp_aghq_fit_at + bgp_fit_get_* incl. all modes and Hessians gathered to the "
                         "host, wall clock, max over ranks"},
         "gpu_launches": int(launches),
         "parity_note": "oracle pinned on the README printout only (DESIGN.md section 3): 'parity' keys compare this run "

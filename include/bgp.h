@@ -133,6 +133,14 @@ int bgp_laplace_eval_batch(bgp_model* m, int K, const double* theta, double* val
                            int* newton_iters_total);
 /* reset / set the warm start (tmbparams W = 0, R/02_model_fit.R:249-252) */
 int bgp_model_set_start(bgp_model* m, const double* W /* NULL => zeros */);
+/* The state an optimiser leaves behind at its last evaluation: theta, the mode there (ff$env$last.par) and the
+ * tangent d w_hat / d theta (p x S column-major; -H^-1 d2f/dW dtheta, a by-product of the last factorisation, which
+ * the warm-start predictor of the next evaluations uses).  bgp_model_get_tangent reads (theta, T) of the most recent
+ * evaluation; bgp_model_set_start_at restores such a state (history cleared, then this single entry; T may be NULL:
+ * plain warm start as bgp_model_set_start).  bgp_aghq_fit does this implicitly: its grid phase starts from what
+ * BFGS / Richardson left. */
+int bgp_model_get_tangent(bgp_model* m, double* theta /* S, may be NULL */, double* T /* p x S, may be NULL */);
+int bgp_model_set_start_at(bgp_model* m, const double* theta, const double* W, const double* T);
 /* inner solver controls (TMB newton(): tol = grad.tol = step.tol = 1e-8, maxit = 100) */
 int bgp_model_set_newton(bgp_model* m, double grad_tol, double step_tol, int maxit);
 
