@@ -307,7 +307,10 @@ void grad_plan_destroy(bgp_model* m);
 //   out_col_major: out[n' * ldc + m] with n' = col_perm ? col_perm[n] : n ; else out[m * ldc + n]
 int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64_t N, int64_t ldb, int K,
                  const double* bias, double* out, int64_t ldc, bool out_col_major, const int32_t* col_perm,
-                 cudaStream_t st);
+                 cudaStream_t st, const unsigned long long* a_occ = nullptr);
+//   a_occ: optional map from launch_kgemm_occ (one word per 128-row tile of A, bit s = k-slice s not all zero, K <= 1024):
+//   empty slices are neither copied nor multiplied
+int launch_kgemm_occ(const double* A, int64_t M, int64_t lda, int K, unsigned long long* occ, cudaStream_t st);
 // grad.cu: L^-1 (row-major, lower) and optionally its transpose (row-major, upper) from m->L
 int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT);
 // sample.cu

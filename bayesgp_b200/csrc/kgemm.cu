@@ -30,6 +30,7 @@ struct KgemmArgs {
   int64_t ldc;
   int out_col_major;
   const int32_t* col_perm;
+  const unsigned long long* a_occ;   // per 128-row tile of A: bit s set iff k-slice s (16 wide) of the tile is not all zero
 };
 
 __global__ void __launch_bounds__(KG_THREADS, 2)
@@ -44,19 +45,34 @@ __global__ void __launch_bounds__(KG_THREADS, 2)
   const int wm = warp >> 1, wn = warp & 1;
   const int fj = lane >> 2, fk = lane & 3;
   const int64_t m0 = (int64_t)blockIdx.x * KG_TM, n0 = (int64_t)blockIdx.y * KG_TN;
-  const int niter = (a.K + KG_KB - 1) / KG_KB;
-
+  const int nslices = (a.K + KG_KB - 1) / KG_KB;
+  // k-slices of this row tile that carry anything: structural zeros of A (a prediction design B(x_new) is ~50 %
+  // zeros in prefix / band form, R/01_utility.R:346-364) are neither copied nor multiplied
+  __shared__ unsigned char s_list[64];
+  __shared__ int s_niter;
   if (tid == 0) {
     for (int s = 0; s < KG_STAGES; ++s) mbar_init(bar_base + 8 * s, 1);
     mbar_fence_init();
+    int cnt = 0;
+    if (a.a_occ) {
+      const unsigned long long o = a.a_occ[blockIdx.x];
+      for (int sl = 0; sl < nslices; ++sl)
+        if ((o >> sl) & 1ull) s_list[cnt++] = (unsigned char)sl;
+    } else {
+      cnt = nslices;
+    }
+    s_niter = cnt;
   }
   __syncthreads();
+  const int niter = s_niter;
+  const bool listed = a.a_occ != nullptr;
   auto issue = [&](int it) {
     const int s = it % KG_STAGES;
     const uint32_t bar = bar_base + 8 * s, sa = base + s * KG_STAGE_BYTES;
+    const int sl = listed ? (int)s_list[it] : it;
     mbar_expect_tx(bar, KG_STAGE_BYTES);
-    tma_load_2d(sa, &tmA, it * KG_KB, (int)m0, bar);
-    tma_load_2d(sa + KG_A_BYTES, &tmB, it * KG_KB, (int)n0, bar);
+    tma_load_2d(sa, &tmA, sl * KG_KB, (int)m0, bar);
+    tma_load_2d(sa + KG_A_BYTES, &tmB, sl * KG_KB, (int)n0, bar);
   };
   if (tid == 0)
     for (int it = 0; it < KG_STAGES - 1 && it < niter; ++it) issue(it);
@@ -133,9 +149,43 @@ __global__ void __launch_bounds__(KG_THREADS, 2)
   }
 }
 
+// per 128-row tile: OR over the rows of (row has a non-zero in k-slice s) << s
+__global__ void __launch_bounds__(256) kgemm_occ_kernel(const double* __restrict__ A, int64_t M, int64_t lda, int K,
+                                                        unsigned long long* __restrict__ occ) {
+  __shared__ unsigned long long sm[8];
+  const int64_t m0 = (int64_t)blockIdx.x * KG_TM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long o = 0ull;
+  for (int r = warp; r < KG_TM && m0 + r < M; r += 8) {
+    const double* row = A + (size_t)(m0 + r) * lda;
+    for (int c = lane; c < K; c += 32)
+      if (row[c] != 0.0) o |= 1ull << (c / KG_KB);
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) o |= __shfl_xor_sync(0xffffffffu, o, sft);
+  if (lane == 0) sm[warp] = o;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0ull;
+    for (int w = 0; w < 8; ++w) t |= sm[w];
+    occ[blockIdx.x] = t;
+  }
+}
+
+int launch_kgemm_occ(const double* A, int64_t M, int64_t lda, int K, unsigned long long* occ, cudaStream_t st) {
+  if (K > 64 * KG_KB) {
+    set_error("kgemm occupancy map: K = %d exceeds 1024", K);
+    return BGP_ERR_ARG;
+  }
+  kgemm_occ_kernel<<<(unsigned)((M + KG_TM - 1) / KG_TM), 256, 0, st>>>(A, M, lda, K, occ);
+  count_launch();
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
 int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64_t N, int64_t ldb, int K,
                  const double* bias, double* out, int64_t ldc, bool out_col_major, const int32_t* col_perm,
-                 cudaStream_t st) {
+                 cudaStream_t st, const unsigned long long* a_occ) {
   if (M <= 0 || N <= 0) return BGP_OK;
   if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     set_error("kgemm: operands must be 16-byte aligned with an even row pitch");
@@ -158,6 +208,7 @@ int launch_kgemm(const double* A, int64_t M, int64_t lda, const double* B, int64
   a.ldc = ldc;
   a.out_col_major = out_col_major ? 1 : 0;
   a.col_perm = col_perm;
+  a.a_occ = a_occ;
   dim3 grid((unsigned)((M + KG_TM - 1) / KG_TM), (unsigned)((N + KG_TN - 1) / KG_TN));
   kgemm_kernel<<<grid, KG_THREADS, KG_SMEM, st>>>(tmA, tmB, a);
   count_launch();

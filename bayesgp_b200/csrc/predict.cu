@@ -739,6 +739,17 @@ static ScratchPool g_scratch;
 
 // device time of the last predict call on this thread (CUDA events on its stream): GEMM, select, whole call
 static thread_local double g_pred_ms[3] = {0.0, 0.0, 0.0};
+static thread_local double g_pred_slices[2] = {0.0, 0.0};     // executed / total {128-row x 16-column} design slices
+
+// cnt[0] += popcount of the tile words, cnt[1] += tiles * slices
+__global__ void occ_count_kernel(const unsigned long long* __restrict__ occ, int ntiles, int nslices, double* __restrict__ cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0;
+    for (int t = 0; t < ntiles; ++t) a += (double)__popcll(occ[t]);
+    cnt[0] += a;
+    cnt[1] += (double)ntiles * nslices;
+  }
+}
 
 struct DevBuf {
   void* p = nullptr;
@@ -942,6 +953,15 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     cudaEventRecord(e, st);
     evs.push_back(e);
   };
+  static const bool occ_env = getenv("BGP_PREDICT_DENSE") == nullptr;     // env: diagnostics (multiply the zeros too)
+  const bool use_occ = occ_env && ds.ncols <= 1024;
+  DevBuf occb, occ_cnt;
+  if (use_occ) {
+    BGP_TRY(occb.alloc((size_t)((strip + 127) / 128) * sizeof(unsigned long long)));
+    BGP_TRY(occ_cnt.alloc(2 * sizeof(double)));
+    BGP_CUDA(cudaMemsetAsync(occ_cnt.p, 0, 2 * sizeof(double), st));
+  }
+  g_pred_slices[0] = g_pred_slices[1] = 0.0;
   mark();                                             // evs[0]: start
   for (int64_t g0 = 0; g0 < G; g0 += strip) {
     const int64_t rows = std::min(strip, G - g0);
@@ -977,13 +997,22 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     }
     count_launch();
     BGP_CUDA(cudaGetLastError());
+    // which 16-column slices of each 128-row tile of the design carry anything: x_new is sorted, so an O-spline
+    // block is a staircase and a cubic-B-spline block a band — about half of the slices are structurally empty
+    const unsigned long long* occ = nullptr;
+    if (use_occ) {
+      BGP_TRY(launch_kgemm_occ(Db.as<double>(), rows, ldk, ds.ncols, occb.as<unsigned long long>(), st));
+      occ = occb.as<unsigned long long>();
+      occ_count_kernel<<<1, 32, 0, st>>>(occ, (int)((rows + 127) / 128), (ds.ncols + 15) / 16, occ_cnt.as<double>());
+      count_launch();
+    }
     mark();                                           // per strip: [gemm start, gemm end, select end]
     BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Fb.as<double>(), ldF, false,
-                         nullptr, st));
+                         nullptr, st, occ));
     mark();
     if (samples)   // G x M column-major copy for only.samples = TRUE
       BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
-                           true, nullptr, st));
+                           true, nullptr, st, occ));
     sa.g0 = g0;
     sa.dbg = nullptr;
     if (sel_debug && g0 == 0) {
@@ -1013,6 +1042,7 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     }
     mark();
   }
+  if (use_occ) BGP_CUDA(cudaMemcpyAsync(g_pred_slices, occ_cnt.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (mean) BGP_CUDA(cudaMemcpyAsync(mean, o_mean, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (plower) BGP_CUDA(cudaMemcpyAsync(plower, o_lo, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (pupper) BGP_CUDA(cudaMemcpyAsync(pupper, o_hi, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1288,6 +1318,12 @@ int bgp_fit_predict_sgp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row
   ds.ncols = nX + 3 * nb * m;
   return fit_predict(f, ds, coef_row0, 3 * nb * m, global_row0, global_row0 >= 0 ? 2 * m : 0, icpt_row, 0, nX, x, G, level,
                      mean, plower, pupper);
+}
+
+int bgp_predict_last_occupancy(double* executed_slices, double* total_slices) {
+  if (executed_slices) *executed_slices = g_pred_slices[0];
+  if (total_slices) *total_slices = g_pred_slices[1];
+  return BGP_OK;
 }
 
 int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms) {

@@ -219,6 +219,10 @@ int bgp_fit_predict_sgp(bgp_fit* f, int coef_row0, int global_row0, int icpt_row
 /* device time (CUDA events on the call's stream, ms) of the last bgp_predict_* call on this thread: the FP64
  * tensor-pipe GEMM strips, the per-row quantile selection, and the whole device sequence */
 int bgp_predict_last_timing(double* gemm_ms, double* select_ms, double* total_ms);
+/* {128-row x 16-column} slices of the prediction design the GEMM of the last bgp_predict_* call executed, and how many
+ * there are: the structurally empty ones (x_new is sorted: an O-spline block is a staircase, a B-spline block a
+ * band) are neither copied nor multiplied.  Both zero when the map was not used (more than 1024 design columns). */
+int bgp_predict_last_occupancy(double* executed_slices, double* total_slices);
 /* basis evaluators on the device (R/01_utility.R:378-401, :413-419, :198-208): out is G x ncol col-major */
 int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, int64_t G, int device, double* out);
 

@@ -4,7 +4,10 @@
        numerically singular beyond k ~ 30 at this frequency — cond(H) 2e13 at k=40, not positive definite in
        FP64 at k>=60, measured — so the columns are moved to the IWP term)
    c5: Poisson  n = 1e7, three IWP3 k = 334 terms + intercept (p = 1006), 3-D AGHQ 5^3, M = 1e5, G = 1e5
-   Under torchrun the observations are sharded over the ranks (NCCL all-reduce of g and H per Newton iteration).
+   Under torchrun:  c4 — every rank holds all rows and the ranks form ONE NODE GROUP ("7^2 nodes sharded across 8
+   GPUs": grid nodes, sample blocks and prediction rows are split inside the library, BFGS / Richardson replicated);
+   c5 — 2-D layout: `BGP_NODE_RANKS` (default 2) node-group ranks x world / that many observation shards (NCCL
+   all-reduce of g and the packed H per Newton iteration inside each observation group).
    usage: run_config.py c4|c5 [n] [aghq_k] [M] [G]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
@@ -46,36 +49,74 @@ else:
     mk = lambda sl: [bg.Term("IWP", "x%d" % (i + 1), xs[i][sl], order=3, knots=np.linspace(0, xs[i].max() - xs[i].min(), 334),
                              initial_location=float(xs[i].min())) for i in range(3)]
     family = "Poisson"
-lo, hi = shard_bounds(n, rank, world)
+# layout: node-group ranks (same rows) x observation shards
+nnode = 1
+if world > 1:
+    nnode = world if cfg == "c4" else int(os.environ.get("BGP_NODE_RANKS", "2"))
+    nnode = max(1, min(world, nnode))
+    while world % nnode:
+        nnode -= 1
+nshard = world // nnode
+srank, nrank = rank // nnode, rank % nnode            # ranks (s * nnode + r) hold observation shard s
+
+
+def group_id(members, root):
+    """ncclUniqueId made by `root`, shared with `members` (a torch.distributed subgroup carries the 128 bytes)."""
+    import torch
+    g = dist.new_group(members)
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == root:
+        buf.copy_(torch.tensor(list(nccl_unique_id()), dtype=torch.uint8))
+    if rank in members:
+        dist.broadcast(buf, src=root, group=g)
+    return bytes(buf.cpu().tolist())
+
+
+shard = node_group = None
+if world > 1:
+    # every rank takes part in every new_group call (torch.distributed requirement)
+    ids_obs = [group_id([s * nnode + r for s in range(nshard)], r) for r in range(nnode)]
+    ids_node = [group_id([s * nnode + r for r in range(nnode)], s * nnode) for s in range(nshard)]
+    if nshard > 1:
+        shard = (srank, nshard, ids_obs[nrank])
+    if nnode > 1:
+        node_group = (nrank, nnode, ids_node[srank])
+lo, hi = shard_bounds(n, srank, nshard)
 sl = slice(lo, hi)
-shard = (rank, world, broadcast_unique_id(nccl_unique_id, rank)) if world > 1 else None
 t0 = time.time()
 ff, terms, rand_idx, bnd_idx, fix_idx = api.build_objective(y[sl], mk(sl), {}, family, None if size is None else size[sl],
-                                                            device=local, shard=shard)
+                                                            device=local, shard=shard, node_group=node_group)
+if cfg == "c5":
+    ff.set_hessian_retry(True)        # n = 1e7: numDeriv's default step can land on rounding noise (DESIGN.md section 3)
 t_build = time.time() - t0
 hf = ff.hessian_flops()
 t0 = time.time()
 mod = api.marginal_laplace_tmb(ff, k, np.zeros(ff.S))
 t_fit = time.time() - t0
-out = {"config": cfg, "n": n, "p": ff.p, "S": ff.S, "K": mod.K, "gpus": world, "build_s": t_build, "fit_s": t_fit,
+out = {"config": cfg, "n": n, "p": ff.p, "S": ff.S, "K": mod.K, "gpus": world, "observation_shards": nshard,
+       "node_group_ranks": nnode, "build_s": t_build, "fit_s": t_fit, "opt_s": mod.diagnostics["opt_ms"] * 1e-3,
+       "grid_s": mod.diagnostics["grid_ms"] * 1e-3, "hessian_fallback": mod.diagnostics["hessian_fallback"],
        "data_s": t0 - t_all - t_build, "hessian_structural_fraction": hf["structural"] / hf["dense"],
        "theta_mode": mod.optresults["mode"].tolist(), "convergence": mod.optresults["convergence"],
        "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"], "lognormconst": mod.lognormconst,
        "laplace_evals": ff.n_fn, "gradient_evals": ff.n_gr, "newton_iters": ff.newton_iters}
-if rank == 0:
+# sampling and predict are collective over the node group (every rank draws the sample blocks of its nodes and
+# summarises its block of prediction rows); with observation shards every shard group repeats them (replicated)
+t0 = time.time()
+samps = api.sample_marginal(mod, M, seed=1)
+out["sample_s"] = time.time() - t0
+res = api.FitResult(terms, mod, ff, bnd_idx, rand_idx, fix_idx, family)
+res.samps = samps
+out["predict_s"] = {}
+for t in terms:
+    xg = np.linspace(cols[t.name].min(), cols[t.name].max(), G)
     t0 = time.time()
-    samps = api.sample_marginal(mod, M, seed=1)
-    out["sample_s"] = time.time() - t0
-    res = api.FitResult(terms, mod, ff, bnd_idx, rand_idx, fix_idx, family)
-    res.samps = samps
-    out["predict_s"] = {}
-    for t in terms:
-        xg = np.linspace(cols[t.name].min(), cols[t.name].max(), G)
-        t0 = time.time()
-        pr = api.predict(res, newdata={t.name: xg}, variable=t.name, degree=0)
-        out["predict_s"][t.name] = time.time() - t0
-        out.setdefault("predict_mean_range", {})[t.name] = [float(np.min(pr["mean"])), float(np.max(pr["mean"]))]
-    out["total_s"] = time.time() - t_all
+    pr = api.predict(res, newdata={t.name: xg}, variable=t.name, degree=0)
+    out["predict_s"][t.name] = time.time() - t0
+    out.setdefault("predict_mean_range", {})[t.name] = [float(np.min(pr["mean"])), float(np.max(pr["mean"]))]
+out["total_s"] = time.time() - t_all
+out["node_owner_counts"] = np.bincount(mod.node_owner, minlength=nnode).tolist()
+if rank == 0:
     print("RUN_CONFIG " + json.dumps(out), flush=True)
 if dist:
     dist.barrier()
