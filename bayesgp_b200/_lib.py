@@ -75,6 +75,7 @@ SIGNATURES = {
     "bgp_model_lik_bytes": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "bgp_predict_last_occupancy": (C.c_int, [c_double_p, c_double_p]),
     "bgp_predict_last_timing": (C.c_int, [c_double_p, c_double_p, c_double_p]),
+    "bgp_model_gradient_timing": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_double_p, c_double_p]),
     "bgp_model_counters": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
     "bgp_model_set_factor_reuse": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "bgp_model_add_sgp": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p,

@@ -197,8 +197,9 @@ struct bgp_model {
   std::shared_ptr<int> alive = std::make_shared<int>(1);   // fits outliving the model see 0 here
   // ---- timing ----------------------------------------------------------------------------------
   cudaEvent_t ev[8] = {nullptr};
-  double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0;
-  int64_t n_lik = 0, n_hess = 0, n_chol = 0;
+  double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0, t_lev = 0;
+  int64_t n_lik = 0, n_hess = 0, n_chol = 0, n_lev = 0;
+  double lev_flops = 0.0;          // executed flops of one leverage launch (structurally non-zero slices, grad.cu)
   // per-phase device timing: marks are (event, phase starting here); harvested after each sync
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> marks;
@@ -238,7 +239,7 @@ struct bgp_fit {
 };
 
 namespace bgp {
-enum { PH_OTHER = 0, PH_LIK = 1, PH_HESS = 2, PH_CHOL = 3 };
+enum { PH_OTHER = 0, PH_LIK = 1, PH_HESS = 2, PH_CHOL = 3, PH_LEV = 4 };
 void phase_mark(bgp_model* m, int phase);
 void phase_harvest(bgp_model* m);   // call only right after a stream synchronize
 }  // namespace bgp

@@ -35,6 +35,7 @@ void phase_harvest(bgp_model* m) {
       case PH_LIK: m->t_lik += ms; break;
       case PH_HESS: m->t_hess += ms; break;
       case PH_CHOL: m->t_chol += ms; break;
+      case PH_LEV: m->t_lev += ms; break;
       default: break;
     }
   }

@@ -439,6 +439,19 @@ static int grad_plan_get(bgp_model* m, GradPlan** out) {
     return BGP_ERR_CUDA;
   }
   BGP_CUDA(cudaFuncSetAttribute(leverage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LV_SMEM));
+  {
+    // executed work of one leverage launch: (row block, slice) pairs on or above the diagonal whose slice is
+    // occupied in the CTA's two chunks, 128 x 64 x 16 multiply-adds each
+    const int NT = (m->p + LV_TN - 1) / LV_TN, nslices = m->ldl / LV_KB;
+    double pairs = 0.0;
+    for (int64_t c = 0; c < m->nchunks; c += 2) {
+      unsigned long long o = m->occ_host[(size_t)c];
+      if (c + 1 < m->nchunks) o |= m->occ_host[(size_t)c + 1];
+      for (int nb = 0; nb < NT; ++nb)
+        for (int ks = 4 * nb; ks < nslices; ++ks) pairs += (double)((o >> ks) & 1ull);
+    }
+    m->lev_flops = pairs * 2.0 * LV_TM * LV_TN * LV_KB;
+  }
   m->grad_plan = gp;
   *out = gp;
   return BGP_OK;
@@ -526,15 +539,20 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   phase_mark(m, PH_OTHER);
   const double* v_dev = nullptr;
   if (has_c3) {
+    phase_mark(m, PH_LEV);
     leverage_kernel<<<(unsigned)((m->n + LV_TM - 1) / LV_TM), LV_THREADS, LV_SMEM, m->stream>>>(
         gp->tmA, gp->tmV, m->c3, (const unsigned long long*)m->occ_dev, m->nchunks, m->zobs, m->n, p, ldl);
     count_launch();
     BGP_CUDA(cudaGetLastError());
+    m->n_lev++;
+    phase_mark(m, PH_LIK);
+    m->n_lik++;
     BGP_TRY(launch_lik(m, m->Wmode, false, 1.0, m->zobs));
     reduce_partials_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->lik_blocks, m->lda, m->red_buf);
     count_launch();
     if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda));
     v_dev = m->red_buf;
+    phase_mark(m, PH_OTHER);
   }
   GradSmallArgs a;
   memset(&a, 0, sizeof(a));

@@ -697,6 +697,16 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
   return BGP_OK;
 }
 
+int bgp_model_gradient_timing(const bgp_model* m, double* leverage_ms, int64_t* leverage_launches, double* leverage_flops,
+                              double* dense_flops) {
+  if (!m) return BGP_ERR_ARG;
+  if (leverage_ms) *leverage_ms = m->t_lev;
+  if (leverage_launches) *leverage_launches = m->n_lev;
+  if (leverage_flops) *leverage_flops = m->lev_flops;
+  if (dense_flops) *dense_flops = (double)m->n * m->p * m->p;     // n p^2: the lower-triangular factor on dense rows
+  return BGP_OK;
+}
+
 int bgp_model_counters(const bgp_model* m, int64_t* laplace_evals, int64_t* newton_iters, int64_t* factor_reuses) {
   if (!m) return BGP_ERR_ARG;
   if (laplace_evals) *laplace_evals = m->n_evals;

@@ -269,6 +269,11 @@ class LaplaceObjective:
         check(self._lib.bgp_model_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"laplace_evals": a.value, "newton_iters": b.value, "factor_reuses": c.value}
 
+    def gradient_timing(self):
+        t, n, f, d = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        check(self._lib.bgp_model_gradient_timing(self._h, C.byref(t), C.byref(n), C.byref(f), C.byref(d)))
+        return {"leverage_ms": t.value, "leverage_launches": n.value, "leverage_flops": f.value, "dense_flops": d.value}
+
     def set_factor_reuse(self, allow=True, eta_tol=1e-7, rel_tol=1e-10):
         check(self._lib.bgp_model_set_factor_reuse(self._h, int(allow), float(eta_tol), float(rel_tol)))
 

@@ -230,6 +230,11 @@ int bgp_basis_iwp(const double* knots, int nknots, int order, const double* x, i
 int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, double* hess_ms, double* chol_ms,
                           int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches);
 
+/* the leverage kernel of ff$gr (q_i = a_i^T H^-1 a_i, grad.cu): cumulative device time (ms), launches, executed flops
+ * per launch (structurally non-zero {128 observations x 64 rows x 16 columns} blocks of the upper-triangular product)
+ * and the n p^2 flops of the dense lower-triangular formulation */
+int bgp_model_gradient_timing(const bgp_model* m, double* leverage_ms, int64_t* leverage_launches, double* leverage_flops,
+                              double* dense_flops);
 /* counters since creation: Laplace evaluations, accepted Newton iterations, evaluations whose log-determinant
  * came from the factor of the last Newton iteration (certified: |d logdet| <= p * max|d eta|, see below) */
 int bgp_model_counters(const bgp_model* m, int64_t* laplace_evals, int64_t* newton_iters, int64_t* factor_reuses);
