@@ -34,6 +34,7 @@ SIGNATURES = {
     "bgp_last_error": (C.c_char_p, []),
     "bgp_version": (C.c_int, []),
     "bgp_kernel_launch_count": (C.c_int64, []),
+    "bgp_profiler_range": (C.c_int, [C.c_int]),
     "bgp_model_new": (C.c_int, [C.c_int64, C.c_int, c_double_p, c_double_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bgp_model_add_random": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int, C.c_double, C.c_double,
                                        C.c_double]),

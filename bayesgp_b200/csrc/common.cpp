@@ -1,6 +1,8 @@
 // Error plumbing and process-wide counters for libbgp.
 #include <cstdarg>
 
+#include <cuda_profiler_api.h>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -49,5 +51,7 @@ extern "C" {
 const char* bgp_last_error(void) { return bgp::g_last_error.c_str(); }
 int bgp_version(void) { return 100; }
 int64_t bgp_kernel_launch_count(void) { return bgp::g_launch_count; }
+// capture window for `ncu --profile-from-start off` (diagnostics)
+int bgp_profiler_range(int start) { return (start ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? BGP_OK : BGP_ERR_CUDA; }
 
 }  // extern "C"

@@ -476,7 +476,7 @@ def gradient_leg(ff, mode, fp64_peak, reps=8):
                                         "empty {128 obs x 64 x 16} blocks skipped (round 1: 3.5 ms dense)"}}
 
 
-def predict_leg(device, fp64_peak, G=100_000, M=10_000):
+def predict_leg(device, fp64_peak, G=100_000, M=10_000, reps=3):
     """Second half of the BASELINE metric: predict GFLOP/s for the sample -> function evaluation
     (compute_post_fun_IWP + extract_mean_interval_given_samps, /root/reference/R/03_post_fit.R:200-241,287-296)
     at the C3 term shape (IWP3, k = 300: 299 spline + 2 boundary + intercept columns), M = 1e4 posterior samples,
@@ -491,9 +491,10 @@ def predict_leg(device, fp64_peak, G=100_000, M=10_000):
     icpt = rng.standard_normal(M)
     xg = np.linspace(0.0, 1.0, G)
     kw = dict(global_samps=glob, knots=knots, refined_x=xg, p=ORDER, degree=0, intercept_samps=icpt, device=device)
-    compute_post_fun_IWP(coef, **kw)                     # warm-up (allocations, attributes)
+    if reps > 1:
+        compute_post_fun_IWP(coef, **kw)                 # warm-up (allocations, attributes)
     best = 1e30
-    for _ in range(3):
+    for _ in range(reps):
         t0 = time.perf_counter()
         out = compute_post_fun_IWP(coef, **kw)
         best = min(best, time.perf_counter() - t0)

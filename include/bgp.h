@@ -45,6 +45,8 @@ const char* bgp_last_error(void);
 int bgp_version(void);
 /* number of CUDA kernels this library has launched in this process (bench `gpu_launches`) */
 int64_t bgp_kernel_launch_count(void);
+/* cudaProfilerStart / Stop: the capture window of `ncu --profile-from-start off` (scripts/ncu_r02.sh) */
+int bgp_profiler_range(int start);
 
 /* ------------------------------------------------------------------------------------------
  * Model construction — replaces the `tmbdat` list + TMB::MakeADFun(data, parameters,
