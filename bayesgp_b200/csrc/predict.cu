@@ -746,8 +746,8 @@ __global__ void occ_count_kernel(const unsigned long long* __restrict__ occ, int
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double a = 0.0;
     for (int t = 0; t < ntiles; ++t) a += (double)__popcll(occ[t]);
-    cnt[0] += a;
-    cnt[1] += (double)ntiles * nslices;
+    atomicAdd(&cnt[0], a);                      // two strips may be in flight on two streams
+    atomicAdd(&cnt[1], (double)ntiles * nslices);
   }
 }
 
@@ -807,7 +807,7 @@ struct DesignSpec {
 static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, int64_t M, const double* x_host,
                         int64_t G, double level, cudaStream_t st, double* mean, double* plower, double* pupper,
                         double* samples) {
-  DevBuf xb, knb, kpb, Db, Fb, ob, Sb;
+  DevBuf xb, knb, kpb, Db, Fb, Db2, Fb2, ob, Sb;
   BGP_TRY(xb.alloc((size_t)G * sizeof(double)));
   BGP_CUDA(cudaMemcpyAsync(xb.p, x_host, (size_t)G * sizeof(double), cudaMemcpyHostToDevice, st));
   if (ds.iwp) {
@@ -818,13 +818,20 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     if (!ds.kpos.empty())
       BGP_CUDA(cudaMemcpyAsync(kpb.p, ds.kpos.data(), ds.kpos.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  // strip height: keep the F strip around 96 MB (L2-sized), multiple of 128 rows
-  int64_t strip = (int64_t)(96.0e6 / (8.0 * (double)M));
+  // Two strips are in flight on two streams (the GEMM of one overlaps the quantile selection of the other: the
+  // selection is latency-bound, the GEMM tensor-pipe bound); strip height: both F strips together around 96 MB
+  // (L2-sized), multiple of 128 rows.  BGP_PREDICT_SERIAL=1: one strip at a time on one stream (per-kernel timing).
+  const bool overlap = getenv("BGP_PREDICT_SERIAL") == nullptr && getenv("BGP_SEL_DEBUG") == nullptr;   // env: diagnostics
+  int64_t strip = (int64_t)((overlap ? 48.0e6 : 96.0e6) / (8.0 * (double)M));
   strip = std::max<int64_t>(128, strip / 128 * 128);
   strip = std::min<int64_t>(strip, round_up64(G, 128));
   const int64_t ldF = round_up64(M, 2);
   BGP_TRY(Db.alloc((size_t)strip * ldk * sizeof(double)));
   BGP_TRY(Fb.alloc((size_t)strip * ldF * sizeof(double)));
+  if (overlap) {
+    BGP_TRY(Db2.alloc((size_t)strip * ldk * sizeof(double)));
+    BGP_TRY(Fb2.alloc((size_t)strip * ldF * sizeof(double)));
+  }
   BGP_TRY(ob.alloc((size_t)3 * G * sizeof(double)));
   double* o_mean = ob.as<double>();
   double* o_lo = o_mean + G;
@@ -914,13 +921,13 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   const size_t dyn_bytes = (in_smem ? key_bytes : 0) + std::max((size_t)sa.pc * slot_bytes, (size_t)RS_SLOT_AREA_MIN) +
                            fixed_bytes;
   DevBuf cntb;
-  BGP_TRY(cntb.alloc(sizeof(unsigned int)));
+  BGP_TRY(cntb.alloc(2 * sizeof(unsigned int)));
   sa.counter = cntb.as<unsigned int>();
   int n_sm = 0, cur_dev = 0;
   BGP_CUDA(cudaGetDevice(&cur_dev));
   BGP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev));
   // persistent CTAs: as many as are resident at once, rows handed out by the counter
-  auto launch_select = [&](unsigned rows) -> int {
+  auto launch_select = [&](unsigned rows, cudaStream_t st) -> int {
     sa.rows = rows;
     BGP_CUDA(cudaMemsetAsync(sa.counter, 0, sizeof(unsigned int), st));
 #define BGP_RS_LAUNCH(IS, T)                                                                                        \
@@ -947,24 +954,58 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
   DevBuf dbgb;
   const bool sel_debug = getenv("BGP_SEL_DEBUG") != nullptr;
   std::vector<cudaEvent_t> evs;
-  auto mark = [&]() {
+  auto mark_on = [&](cudaStream_t sx) {
     cudaEvent_t e;
     cudaEventCreate(&e);
-    cudaEventRecord(e, st);
+    cudaEventRecord(e, sx);
     evs.push_back(e);
   };
+  auto mark = [&]() { mark_on(st); };
+  // second stream: waits for the uploads on the first, joins it again after the last strip
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_join = nullptr;
+  if (overlap) {
+    BGP_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    BGP_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+    BGP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  struct StreamGuard {
+    cudaStream_t& s;
+    cudaEvent_t &a, &b;
+    ~StreamGuard() {
+      if (s) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+      }
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } stream_guard{st2, ev_up, ev_join};
   static const bool occ_env = getenv("BGP_PREDICT_DENSE") == nullptr;     // env: diagnostics (multiply the zeros too)
   const bool use_occ = occ_env && ds.ncols <= 1024;
   DevBuf occb, occ_cnt;
+  const size_t occ_words = (size_t)((strip + 127) / 128);
   if (use_occ) {
-    BGP_TRY(occb.alloc((size_t)((strip + 127) / 128) * sizeof(unsigned long long)));
+    BGP_TRY(occb.alloc(2 * occ_words * sizeof(unsigned long long)));
     BGP_TRY(occ_cnt.alloc(2 * sizeof(double)));
     BGP_CUDA(cudaMemsetAsync(occ_cnt.p, 0, 2 * sizeof(double), st));
   }
   g_pred_slices[0] = g_pred_slices[1] = 0.0;
   mark();                                             // evs[0]: start
-  for (int64_t g0 = 0; g0 < G; g0 += strip) {
+  if (overlap) {
+    BGP_CUDA(cudaEventRecord(ev_up, st));
+    BGP_CUDA(cudaStreamWaitEvent(st2, ev_up, 0));
+  }
+  cudaStream_t st_main = st;
+  int strip_no = 0;
+  for (int64_t g0 = 0; g0 < G; g0 += strip, ++strip_no) {
     const int64_t rows = std::min(strip, G - g0);
+    const int set = overlap ? (strip_no & 1) : 0;
+    cudaStream_t st = set ? st2 : st_main;            // everything of this strip goes to its own stream
+    DevBuf& Dset = set ? Db2 : Db;
+    DevBuf& Fset = set ? Fb2 : Fb;
+    sa.F = Fset.as<double>();
+    sa.counter = cntb.as<unsigned int>() + set;
     if (ds.iwp) {
       IwpDesignArgs a;
       a.x = xb.as<double>();
@@ -976,7 +1017,7 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
       a.npos = (int)ds.kpos.size();
       a.order = ds.order;
       a.degree = ds.degree;
-      a.D = Db.as<double>();
+      a.D = Dset.as<double>();
       a.ld = ldk;
       iwp_design_kernel<<<(unsigned)rows, 128, 0, st>>>(a);
     } else {
@@ -991,7 +1032,7 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
       a.boundary = ds.boundary;
       a.lo = ds.lo;
       a.hi = ds.hi;
-      a.D = Db.as<double>();
+      a.D = Dset.as<double>();
       a.ld = ldk;
       sgp_design_kernel<<<(unsigned)rows, 128, 0, st>>>(a);
     }
@@ -1001,17 +1042,18 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
     // block is a staircase and a cubic-B-spline block a band — about half of the slices are structurally empty
     const unsigned long long* occ = nullptr;
     if (use_occ) {
-      BGP_TRY(launch_kgemm_occ(Db.as<double>(), rows, ldk, ds.ncols, occb.as<unsigned long long>(), st));
-      occ = occb.as<unsigned long long>();
+      unsigned long long* occ_set = occb.as<unsigned long long>() + (size_t)set * occ_words;
+      BGP_TRY(launch_kgemm_occ(Dset.as<double>(), rows, ldk, ds.ncols, occ_set, st));
+      occ = occ_set;
       occ_count_kernel<<<1, 32, 0, st>>>(occ, (int)((rows + 127) / 128), (ds.ncols + 15) / 16, occ_cnt.as<double>());
       count_launch();
     }
-    mark();                                           // per strip: [gemm start, gemm end, select end]
-    BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Fb.as<double>(), ldF, false,
+    if (!overlap) mark();                             // per strip: [gemm start, gemm end, select end]
+    BGP_TRY(launch_kgemm(Dset.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Fset.as<double>(), ldF, false,
                          nullptr, st, occ));
-    mark();
+    if (!overlap) mark();
     if (samples)   // G x M column-major copy for only.samples = TRUE
-      BGP_TRY(launch_kgemm(Db.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
+      BGP_TRY(launch_kgemm(Dset.as<double>(), rows, ldk, Cmat_dev, M, ldk, ds.ncols, nullptr, Sb.as<double>() + g0, G,
                            true, nullptr, st, occ));
     sa.g0 = g0;
     sa.dbg = nullptr;
@@ -1020,7 +1062,7 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
       BGP_CUDA(cudaMemsetAsync(dbgb.p, 0, (size_t)rows * RS_DBG_POINTS * sizeof(long long), st));
       sa.dbg = dbgb.as<long long>();
     }
-    BGP_TRY(launch_select((unsigned)rows));
+    BGP_TRY(launch_select((unsigned)rows, st));
     if (sa.dbg) {
       std::vector<long long> h((size_t)rows * RS_DBG_POINTS);
       BGP_CUDA(cudaMemcpyAsync(h.data(), dbgb.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -1040,7 +1082,12 @@ static int predict_core(const DesignSpec& ds, const double* Cmat_dev, int ldk, i
               acc[3] / std::max<int64_t>(nfast, 1), acc[4] / std::max<int64_t>(nfast, 1),
               acc[5] / std::max<int64_t>(nfast, 1), (acc[6] + acc[7]) / std::max<int64_t>(nfast, 1));
     }
-    mark();
+    if (!overlap) mark();
+  }
+  if (overlap) {
+    BGP_CUDA(cudaEventRecord(ev_join, st2));
+    BGP_CUDA(cudaStreamWaitEvent(st_main, ev_join, 0));
+    mark();                                           // evs[1]: end of the strips
   }
   if (use_occ) BGP_CUDA(cudaMemcpyAsync(g_pred_slices, occ_cnt.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (mean) BGP_CUDA(cudaMemcpyAsync(mean, o_mean, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
