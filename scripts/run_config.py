@@ -115,6 +115,17 @@ for t in terms:
     out["predict_s"][t.name] = time.time() - t0
     out.setdefault("predict_mean_range", {})[t.name] = [float(np.min(pr["mean"])), float(np.max(pr["mean"]))]
 out["total_s"] = time.time() - t_all
+# per-kernel rooflines of this rank's share (CUDA events around the phases, cumulative over the whole fit; with
+# observation shards the Hessian phase includes the all-reduce of the packed triangle)
+tm, lb = ff.last_timing(), ff.lik_bytes()
+nh, nl, nc = max(1, tm["hess_launches"]), max(1, tm["lik_launches"]), max(1, tm["chol_launches"])
+out["kernels"] = {"hess_ms_per_launch": tm["hess_ms"] / nh, "hess_launches": tm["hess_launches"],
+                  "hess_executed_tflops": hf["structural"] / (tm["hess_ms"] / nh * 1e-3) / 1e12,
+                  "hess_dense_equivalent_tflops": hf["dense"] / (tm["hess_ms"] / nh * 1e-3) / 1e12,
+                  "lik_ms_per_launch": tm["lik_ms"] / nl, "lik_launches": tm["lik_launches"],
+                  "lik_gbs_on_moved_bytes": lb["structural"] / (tm["lik_ms"] / nl * 1e-3) / 1e9,
+                  "chol_ms_per_launch": tm["chol_ms"] / nc, "chol_launches": tm["chol_launches"],
+                  "rows_on_this_rank": int(hi - lo)}
 out["node_owner_counts"] = np.bincount(mod.node_owner, minlength=nnode).tolist()
 if rank == 0:
     print("RUN_CONFIG " + json.dumps(out), flush=True)
