@@ -246,6 +246,46 @@ def model_fit(y, terms: List[Term], fixed=None, method="aghq", family="Gaussian"
     return res
 
 
+def model_fit_loop(loop_values, fit_args, prior_func=None, parallel=False, group=None):
+    """model_fit_loop(loop_holder, loop_values, prior_func, parallel, ...)  (R/02_model_fit.R:725-778): one model_fit
+    per value of the looping variable, the log marginal likelihoods (``mod$normalized_posterior$lognormconst``) and the
+    posterior of the variable normalised by ``sfsmisc::integrate.xy``.
+
+    ``fit_args(value)`` returns the keyword arguments of ``model_fit`` for that value (the R version substitutes the
+    value for the ``LOOP`` placeholder inside the call).  ``parallel = TRUE`` in the reference is a PSOCK cluster of
+    whole-model workers; here it is one process per GPU under ``torch.distributed``: rank r fits the values
+    r, r + world, ... on its own device and the log marginal likelihoods are all-gathered (``group``: the process
+    group, default the world)."""
+    from .post_fit import integrate_xy
+    loop_values = np.asarray(loop_values, dtype=np.float64)
+    L = len(loop_values)
+    log_ml = np.zeros(L)
+    rank, world = 0, 1
+    if parallel:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    for i in range(rank, L, world):
+        kw = dict(fit_args(float(loop_values[i])))
+        kw.setdefault("M", 0)                    # only lognormconst is read (R/02_model_fit.R:751)
+        res = model_fit(**kw)
+        log_ml[i] = res.mod.lognormconst
+        res.close()
+    if parallel and world > 1:
+        import torch
+        import torch.distributed as dist
+        dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
+               else torch.device("cpu"))
+        t = torch.from_numpy(log_ml).to(dev)
+        dist.all_reduce(t, group=group)          # every value has one owner, the others contribute zeros
+        log_ml = t.cpu().numpy()
+    prior = np.ones(L) if prior_func is None else np.asarray(prior_func(loop_values), dtype=np.float64) * np.ones(L)
+    log_joint = log_ml + np.log(prior)
+    log_joint = log_joint - np.max(log_joint)
+    post = np.exp(log_joint)
+    post = post / integrate_xy(loop_values, post)
+    return {"var": loop_values, "post": post, "log_ml": log_ml}
+
+
 def sample_fixed_effect(model_fit_result: FitResult, variables):
     """R/03_post_fit.R:159-165."""
     samps = model_fit_result.samps["samps"]

@@ -55,6 +55,65 @@ def _natural_spline(x, y):
     return f
 
 
+def fmm_spline(x, y, n):
+    """stats::spline(x, y, n = n, method = "fmm"): the Forsythe-Malcolm-Moler cubic spline (end conditions from the
+    cubics through the first and the last four points) evaluated at seq(min(x), max(x), length.out = n)."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    m = len(x)
+    xo = x[0] + (x[-1] - x[0]) * np.arange(n) / (n - 1.0) if n > 1 else np.array([x[0]])
+    if m < 2:
+        raise ValueError("spline needs at least two points")
+    b, c, d = np.zeros(m), np.zeros(m), np.zeros(m)
+    if m < 3:
+        b[:] = (y[1] - y[0]) / (x[1] - x[0])
+    else:
+        d[0] = x[1] - x[0]
+        c[1] = (y[1] - y[0]) / d[0]
+        for i in range(1, m - 1):
+            d[i] = x[i + 1] - x[i]
+            b[i] = 2.0 * (d[i - 1] + d[i])
+            c[i + 1] = (y[i + 1] - y[i]) / d[i]
+            c[i] = c[i + 1] - c[i]
+        b[0], b[m - 1] = -d[0], -d[m - 2]
+        c[0] = c[m - 1] = 0.0
+        if m > 3:
+            c[0] = c[2] / (x[3] - x[1]) - c[1] / (x[2] - x[0])
+            c[m - 1] = c[m - 2] / (x[m - 1] - x[m - 3]) - c[m - 3] / (x[m - 2] - x[m - 4])
+            c[0] = c[0] * d[0] * d[0] / (x[3] - x[0])
+            c[m - 1] = -c[m - 1] * d[m - 2] * d[m - 2] / (x[m - 1] - x[m - 4])
+        for i in range(1, m):                       # Gaussian elimination
+            t = d[i - 1] / b[i - 1]
+            b[i] -= t * d[i - 1]
+            c[i] -= t * c[i - 1]
+        c[m - 1] /= b[m - 1]                        # back substitution
+        for i in range(m - 2, -1, -1):
+            c[i] = (c[i] - d[i] * c[i + 1]) / b[i]
+        b[m - 1] = (y[m - 1] - y[m - 2]) / d[m - 2] + d[m - 2] * (c[m - 2] + 2.0 * c[m - 1])
+        for i in range(m - 1):
+            b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i])
+            d[i] = (c[i + 1] - c[i]) / d[i]
+            c[i] = 3.0 * c[i]
+        c[m - 1] = 3.0 * c[m - 1]
+        d[m - 1] = d[m - 2]
+    i = np.clip(np.searchsorted(x, xo, side="right") - 1, 0, m - 1)
+    dx = xo - x[i]
+    return xo, y[i] + dx * (b[i] + dx * (c[i] + dx * d[i]))
+
+
+def integrate_xy(x, fx):
+    """sfsmisc::integrate.xy(x, fx) over the whole range with its defaults (use.spline = TRUE): the fmm spline on
+    max(1024, 3 n) points, then the trapezoid rule (/root/reference/R/02_model_fit.R:774)."""
+    x, fx = np.asarray(x, dtype=np.float64), np.asarray(fx, dtype=np.float64)
+    order = np.argsort(x, kind="stable")
+    x, fx = x[order], fx[order]
+    keep = np.concatenate([[True], np.diff(x) != 0])
+    x, fx = x[keep], fx[keep]
+    xs, ys = fmm_spline(x, fx, max(1024, 3 * len(x)))
+    if xs[-1] < x[-1]:
+        xs, ys = np.append(xs, x[-1]), np.append(ys, fx[-1])
+    return float(np.sum(np.diff(xs) * (ys[1:] + ys[:-1]) / 2.0))
+
+
 def compute_pdf_and_cdf(marginal, transformation: Optional[str] = None, ngrid: int = 1000):
     """aghq::compute_pdf_and_cdf(marginal, interpolation = 'spline').  ``transformation='sd'`` adds the columns for
     sigma = exp(-theta / 2) the way var_density asks for them (totheta = -2 log x)."""

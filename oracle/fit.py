@@ -239,3 +239,62 @@ def predict(fit: FitResult, variable, newx=None, degree=0, include_intercept=Tru
     lo, hi, mean = extract_mean_interval_given_samps(F)
     out.update(plower=lo, pupper=hi, mean=mean)
     return out
+
+
+# ----------------------------------------------------------------------------
+# model_fit_loop (R/02_model_fit.R:725-778)
+# ----------------------------------------------------------------------------
+def fmm_spline_eval(x, y, xo):
+    """stats::spline(method = "fmm") evaluated at xo.  The FMM end conditions make the third derivative of the spline at
+    each end equal to that of the cubic through the four nearest points: solved here as a dense linear system for the
+    second derivatives (independent of the tridiagonal recurrences the product uses)."""
+    x, y, xo = np.asarray(x, float), np.asarray(y, float), np.asarray(xo, float)
+    m = len(x)
+    if m < 3:
+        return y[0] + (y[-1] - y[0]) / (x[-1] - x[0]) * (xo - x[0])
+    h = np.diff(x)
+    # unknowns: second derivatives M_0..M_{m-1}
+    A = np.zeros((m, m))
+    r = np.zeros(m)
+    for i in range(1, m - 1):
+        A[i, i - 1], A[i, i], A[i, i + 1] = h[i - 1], 2.0 * (h[i - 1] + h[i]), h[i]
+        r[i] = 6.0 * ((y[i + 1] - y[i]) / h[i] - (y[i] - y[i - 1]) / h[i - 1])
+    if m > 3:
+        def third_derivative(xx, yy):          # of the cubic through four points = 6 * leading coefficient
+            return 6.0 * np.polyfit(xx - xx[0], yy, 3)[0]
+        A[0, 0], A[0, 1] = -1.0 / h[0], 1.0 / h[0]
+        r[0] = third_derivative(x[:4], y[:4])
+        A[m - 1, m - 2], A[m - 1, m - 1] = -1.0 / h[-1], 1.0 / h[-1]
+        r[m - 1] = third_derivative(x[-4:], y[-4:])
+    else:                                        # three points: the FMM conditions degenerate to M_0 = M_1 = M_2 ... (c[1] = c[n] = 0)
+        A[0, 0], A[0, 1] = -1.0 / h[0], 1.0 / h[0]
+        A[m - 1, m - 2], A[m - 1, m - 1] = -1.0 / h[-1], 1.0 / h[-1]
+    M = np.linalg.solve(A, r)
+    i = np.clip(np.searchsorted(x, xo, side="right") - 1, 0, m - 2)
+    a, b = xo - x[i], x[i + 1] - xo
+    return ((M[i] * b ** 3 + M[i + 1] * a ** 3) / (6.0 * h[i]) + (y[i] / h[i] - M[i] * h[i] / 6.0) * b
+            + (y[i + 1] / h[i] - M[i + 1] * h[i] / 6.0) * a)
+
+
+def integrate_xy(x, fx):
+    """sfsmisc::integrate.xy with its defaults: fmm spline on max(1024, 3 n) points + trapezoid."""
+    x, fx = np.asarray(x, float), np.asarray(fx, float)
+    o = np.argsort(x, kind="stable")
+    x, fx = x[o], fx[o]
+    n = max(1024, 3 * len(x))
+    xs = x[0] + (x[-1] - x[0]) * np.arange(n) / (n - 1.0)
+    ys = fmm_spline_eval(x, fx, xs)
+    if xs[-1] < x[-1]:
+        xs, ys = np.append(xs, x[-1]), np.append(ys, fx[-1])
+    return float(np.sum(np.diff(xs) * (ys[1:] + ys[:-1]) / 2.0))
+
+
+def model_fit_loop(loop_values, fit_args, prior_func=None):
+    """R/02_model_fit.R:725-778 (sequential branch): log_ml per loop value, posterior normalised by integrate.xy."""
+    loop_values = np.asarray(loop_values, float)
+    log_ml = np.array([model_fit(**dict(fit_args(float(v)), M=0)).mod.lognormconst for v in loop_values])
+    prior = np.ones(len(loop_values)) if prior_func is None else np.asarray(prior_func(loop_values), float) * np.ones(len(loop_values))
+    lj = log_ml + np.log(prior)
+    lj = lj - lj.max()
+    post = np.exp(lj)
+    return {"var": loop_values, "post": post / integrate_xy(loop_values, post), "log_ml": log_ml}

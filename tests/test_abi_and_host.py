@@ -150,3 +150,25 @@ def test_r_shim_binds_only_declared_entry_points_with_matching_arity():
     rglue = open(os.path.join(ROOT, "integration", "r", "bgp_shim.R")).read()
     for nm in set(re.findall(r'\.Call\("(bgpR_[a-z_]+)"', rglue)):
         assert nm in table, nm
+
+
+def test_fmm_spline_and_integrate_xy_match_the_oracle_restatement():
+    """model_fit_loop's normalisation (sfsmisc::integrate.xy = stats::spline(method = "fmm") on max(1024, 3 n) points +
+    trapezoid, R/02_model_fit.R:774): the product's tridiagonal recurrences against the oracle's dense solve of the
+    defining end conditions, plus two closed forms."""
+    from bayesgp_b200.post_fit import fmm_spline, integrate_xy
+    from oracle.fit import fmm_spline_eval, integrate_xy as o_integrate
+    rng = np.random.default_rng(3)
+    for m in (2, 3, 4, 7, 25):
+        x = np.sort(rng.uniform(-1.0, 4.0, m))
+        y = np.exp(-0.5 * (x - 1.5) ** 2) + 0.05 * rng.standard_normal(m)
+        xo, yo = fmm_spline(x, y, 301)
+        assert xo[0] == x[0] and abs(xo[-1] - x[-1]) < 1e-15
+        assert np.max(np.abs(yo - fmm_spline_eval(x, y, xo))) < 1e-12
+        assert abs(integrate_xy(x, y) - o_integrate(x, y)) < 1e-12
+    # a cubic is reproduced exactly by the fmm end conditions (four-point cubics at both ends)
+    x = np.linspace(0.0, 2.0, 9)
+    cubic = lambda t: 1.0 + 2.0 * t - 0.5 * t ** 2 + 0.25 * t ** 3
+    xo, yo = fmm_spline(x, cubic(x), 101)
+    assert np.max(np.abs(yo - cubic(xo))) < 1e-12
+    assert abs(integrate_xy(x, cubic(x)) - (2.0 + 4.0 - 0.5 * 8.0 / 3.0 + 0.25 * 16.0 / 4.0)) < 1e-5   # trapezoid on 1024 points

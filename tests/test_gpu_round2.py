@@ -129,3 +129,27 @@ def test_trivial_node_group_and_failing_nodes():
     finally:
         a.close()
         b.close()
+
+
+def test_model_fit_loop_matches_the_oracle():
+    """model_fit_loop (R/02_model_fit.R:725-778): one fit per value of the looped variable (here the period of an sGP
+    term, the package's own use case), log marginal likelihoods and the normalised posterior of the variable."""
+    import bayesgp_b200 as bg
+    from oracle import fit as ofit
+    rng = np.random.default_rng(41)
+    n = 1500
+    x = rng.uniform(0, 4, n)
+    y = rng.poisson(np.exp(0.3 + 0.8 * np.sin(2 * np.pi * x / 1.0))).astype(np.float64)
+    periods = np.array([0.8, 0.9, 1.0, 1.1, 1.25])
+    region = np.array([0.0, 4.0])
+
+    def args(T, Term):
+        return dict(y=y, terms=[Term("sGP", "x", x, a=2 * np.pi / T, k=8, m=1, region=region, initial_location=0.0)],
+                    fixed={}, family="Poisson", aghq_k=3)
+
+    prior = lambda v: np.exp(-0.5 * ((v - 1.0) / 0.5) ** 2)
+    got = bg.model_fit_loop(periods, lambda T: args(T, bg.Term), prior_func=prior)
+    want = ofit.model_fit_loop(periods, lambda T: args(T, ofit.Term), prior_func=prior)
+    assert np.max(np.abs(got["log_ml"] - want["log_ml"]) / np.abs(want["log_ml"])) < 2e-7     # own BFGS on both sides
+    assert relerr(got["post"], want["post"]) < 1e-4
+    assert int(np.argmax(got["post"])) == 2                                                  # the true period
