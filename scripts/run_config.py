@@ -99,7 +99,8 @@ out = {"config": cfg, "n": n, "p": ff.p, "S": ff.S, "K": mod.K, "gpus": world, "
        "data_s": t0 - t_all - t_build, "hessian_structural_fraction": hf["structural"] / hf["dense"],
        "theta_mode": mod.optresults["mode"].tolist(), "convergence": mod.optresults["convergence"],
        "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"], "lognormconst": mod.lognormconst,
-       "laplace_evals": ff.n_fn, "gradient_evals": ff.n_gr, "newton_iters": ff.newton_iters}
+       "laplace_evals": ff.counters()["laplace_evals"], "newton_iters": ff.counters()["newton_iters"],
+       "factor_reuses": ff.counters()["factor_reuses"]}
 # sampling and predict are collective over the node group (every rank draws the sample blocks of its nodes and
 # summarises its block of prediction rows); with observation shards every shard group repeats them (replicated)
 t0 = time.time()
