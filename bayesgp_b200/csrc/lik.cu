@@ -46,7 +46,6 @@ struct LikArgs {
   double* part_s;   // [gridDim.x][4] : ll, sumsq, nonfinite, max |eta - previous eta|
   const double* rvec;   // if set: skip the likelihood and accumulate A^T rvec only (leverage term)
   const unsigned long long* occ;
-  int interleave;       // walk a CTA's chunks alternately from both ends of its list
 };
 
 struct LikPlan {
@@ -283,7 +282,6 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lda = a.lda;
-  const bool interleave = a.interleave != 0;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_base + 8 * s, 1);
@@ -303,26 +301,18 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
   const int nchunks = (int)a.nchunks;
   const int my_chunks = first < nchunks ? (nchunks - first + step - 1) / step : 0;
   const int my_stages = my_chunks * SPC;
-  // Order in which a CTA walks its chunks.  After the zero-pattern sort the chunks run from sparse (few occupied
-  // column groups, few bytes per stage) to dense; taken in list order the ring holds little data while a CTA is in the
-  // sparse part (fewer bytes in flight than HBM latency x bandwidth needs) — alternating between the two ends of the
-  // list keeps dense stages in the ring all the way.  A fixed function of (CTA, k): the partial sums stay reproducible.
-  auto kth_chunk = [&](int k) -> int {
-    const int kk = interleave ? ((k & 1) ? my_chunks - 1 - (k >> 1) : (k >> 1)) : k;
-    return first + kk * step;
-  };
   if (warp == NCW) {
     if (lane != 0) return;
-    unsigned long long o_next = my_chunks > 0 ? __ldg(a.occ + kth_chunk(0)) : 0ull;
+    unsigned long long o_next = my_chunks > 0 ? __ldg(a.occ + first) : 0ull;
     uint32_t gm = 0;
     int slot = 0;
     uint32_t par = 1;                         // parity to wait for on the empty barrier of `slot`
     for (int it = 0; it < my_stages; ++it) {
-      const int chunk = kth_chunk(it / SPC);
+      const int chunk = first + (it / SPC) * step;
       const int64_t row = (int64_t)chunk * 64 + (it % SPC) * LK_KB;
       if ((it % SPC) == 0) {
         const unsigned long long o = o_next;
-        if ((it / SPC) + 1 < my_chunks) o_next = __ldg(a.occ + kth_chunk(it / SPC + 1));   // prefetch: consumed a chunk later
+        if ((it / SPC) + 1 < my_chunks) o_next = __ldg(a.occ + chunk + step);   // prefetch: consumed a chunk later
         gm = 0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
@@ -363,7 +353,7 @@ __global__ void __launch_bounds__(lk_threads(NJ, R), 1) lik_kernel(const __grid_
   uint32_t par = 0;                           // parity to wait for on the full barrier of `slot`
   for (int it = team; it < my_stages; it += R) {
     mbar_wait(full_base + 8 * slot, par);
-    const int64_t row = (int64_t)kth_chunk(it / SPC) * 64 + (it % SPC) * LK_KB + wrow;
+    const int64_t row = (int64_t)(first + (it / SPC) * step) * 64 + (it % SPC) * LK_KB + wrow;
     uint32_t gm;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gm) : "r"(meta_base + 8 * slot) : "memory");
     const uint32_t sb = base + slot * STAGE_BYTES;
@@ -488,8 +478,6 @@ int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, cons
   a.part_g = m->part_g;
   a.part_s = m->part_s;
   a.occ = (const unsigned long long*)m->occ_dev;
-  static const bool lik_walk = getenv("BGP_LIK_WALK") == nullptr || getenv("BGP_LIK_WALK")[0] != '0';   // env: diagnostics
-  a.interleave = lik_walk ? 1 : 0;
   const int nj = (m->lda + 63) / 64;
   switch (nj) {
     case 1: return launch_lik_t<1>(m, a);

@@ -205,51 +205,42 @@ __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
       }
       const int2 ur = units[unit];
       const int e_begin = ur.x, e_end = ur.y;
-      // All entries of a unit belong to one tile.  They are issued two at a time with their stages interleaved
-      // (stage s of entry e, stage s of entry e + 1, ...): the plan orders a unit's chunks dense, sparse, dense, ... so
-      // the ring always holds stages with enough work to cover the TMA latency of the sparse ones.  Entries and
-      // occupancy words of the next pair are fetched while this pair is being issued.
-      uint32_t ent_a = __ldg(entries + e_begin);
-      uint32_t ent_b = e_begin + 1 < e_end ? __ldg(entries + e_begin + 1) : 0u;
-      const int tile = (int)(ent_a >> 24);
-      const SkTile t = tiles[tile];
-      unsigned long long occ_a = __ldg(occ + (ent_a & 0xffffffu));
-      unsigned long long occ_b = e_begin + 1 < e_end ? __ldg(occ + (ent_b & 0xffffffu)) : 0ull;
-      const int ncol0 = 4 * t.J * 16;
-      for (int e = e_begin; e < e_end; e += 2) {
-        const int npair = e + 1 < e_end ? 2 : 1;
-        const int chunk2[2] = {(int)(ent_a & 0xffffffu), (int)(ent_b & 0xffffffu)};
-        uint32_t act2[2], load2[2], need2[2], tx2[2];
-        sk_chunk_masks(t, occ_a, act2[0], load2[0], need2[0]);
-        sk_chunk_masks(t, occ_b, act2[1], load2[1], need2[1]);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) tx2[q] = (uint32_t)(__popc(load2[q]) + __popc(need2[q])) * SK_BOX_BYTES + SK_W_BYTES;
-        if (e + 2 < e_end) {
-          ent_a = __ldg(entries + e + 2);
-          occ_a = __ldg(occ + (ent_a & 0xffffffu));
-          if (e + 3 < e_end) {
-            ent_b = __ldg(entries + e + 3);
-            occ_b = __ldg(occ + (ent_b & 0xffffffu));
-          }
+      // software prefetch: the entry two chunks ahead, its tile descriptor and occupancy word one chunk ahead
+      // (three dependent L2 round trips would otherwise sit in front of every chunk)
+      uint32_t ent_n = __ldg(entries + e_begin);
+      uint32_t ent_nn = e_begin + 1 < e_end ? __ldg(entries + e_begin + 1) : 0u;
+      SkTile t_n = tiles[ent_n >> 24];
+      unsigned long long occ_n = __ldg(occ + (ent_n & 0xffffffu));
+      for (int e = e_begin; e < e_end; ++e) {
+        const uint32_t ent = ent_n;
+        const int tile = (int)(ent >> 24), chunk = (int)(ent & 0xffffffu);
+        const SkTile t = t_n;
+        const unsigned long long occ_c = occ_n;
+        if (e + 1 < e_end) {
+          ent_n = ent_nn;
+          t_n = tiles[ent_n >> 24];
+          occ_n = __ldg(occ + (ent_n & 0xffffffu));
+          if (e + 2 < e_end) ent_nn = __ldg(entries + e + 2);
         }
-        for (int s = 0; s < SK_SPC; ++s) {
-          for (int q = 0; q < npair; ++q, ++it) {
-            const int slot = it % SK_STAGES;
-            const uint32_t fb = full_base + 8 * slot;
-            const uint32_t sb = base + slot * SK_STAGE_BYTES;
-            const uint32_t act_m = act2[q], load_m = load2[q], need_n = need2[q];
-            mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
-            const int row = chunk2[q] * 64 + s * SK_KB;
-            sts128(meta_base + 16 * slot, act_m | (need_n << 8), (uint32_t)tile, (uint32_t)unit, 0u);   // rows | N boxes present
-            mbar_expect_tx(fb, tx2[q]);
+        uint32_t act_m, load_m, need_n;
+        sk_chunk_masks(t, occ_c, act_m, load_m, need_n);
+        const uint32_t tx = (uint32_t)(__popc(load_m) + __popc(need_n)) * SK_BOX_BYTES + SK_W_BYTES;
+        const int ncol0 = 4 * t.J * 16;
+        for (int s = 0; s < SK_SPC; ++s, ++it) {
+          const int slot = it % SK_STAGES;
+          const uint32_t fb = full_base + 8 * slot;
+          const uint32_t sb = base + slot * SK_STAGE_BYTES;
+          mbar_wait(empty_base + 8 * slot, (uint32_t)(((it / SK_STAGES) & 1) ^ 1));
+          const int row = chunk * 64 + s * SK_KB;
+          sts128(meta_base + 16 * slot, act_m | (need_n << 8), (uint32_t)tile, (uint32_t)unit, 0u);   // rows | N boxes present
+          mbar_expect_tx(fb, tx);
 #pragma unroll
-            for (int bx = 0; bx < SK_MBOX; ++bx)
-              if ((load_m >> bx) & 1u) tma_load_2d(sb + bx * SK_BOX_BYTES, &tmA, 16 * t.rows[bx], row, fb);
+          for (int b = 0; b < SK_MBOX; ++b)
+            if ((load_m >> b) & 1u) tma_load_2d(sb + b * SK_BOX_BYTES, &tmA, 16 * t.rows[b], row, fb);
 #pragma unroll
-            for (int bx = 0; bx < SK_NBOX; ++bx)
-              if ((need_n >> bx) & 1u) tma_load_2d(sb + (SK_MBOX + bx) * SK_BOX_BYTES, &tmA, ncol0 + bx * 16, row, fb);
-            bulk_load_1d(w_base + slot * SK_W_BYTES, wobs + row, SK_W_BYTES, fb);
-          }
+          for (int b = 0; b < SK_NBOX; ++b)
+            if ((need_n >> b) & 1u) tma_load_2d(sb + (SK_MBOX + b) * SK_BOX_BYTES, &tmA, ncol0 + b * 16, row, fb);
+          bulk_load_1d(w_base + slot * SK_W_BYTES, wobs + row, SK_W_BYTES, fb);
         }
       }
       unit = unit_next;
@@ -555,26 +546,9 @@ int syrk_plan_create(bgp_model* m) {
   std::vector<std::vector<uint32_t>> pend((size_t)pl->ntiles);
   std::vector<int64_t> pend_cost((size_t)pl->ntiles, 0);
   int64_t done_cost = 0;
-  static const bool pair_order = getenv("BGP_SK_PAIR") == nullptr || getenv("BGP_SK_PAIR")[0] != '0';   // env: diagnostics
   auto emit = [&](int ti) {
     if (pend[(size_t)ti].empty()) return;
     const int e0 = (int)entries.size();
-    if (pair_order && pend[(size_t)ti].size() > 2) {
-      // dense, sparse, dense, sparse, ...: the kernel interleaves the stages of consecutive entries
-      auto& v = pend[(size_t)ti];
-      std::vector<std::pair<int, uint32_t>> byc;
-      for (uint32_t en : v) {
-        int boxes;
-        byc.push_back({chunk_cost(tiles[ti], m->occ_host[(size_t)(en & 0xffffffu)], boxes), en});
-      }
-      std::stable_sort(byc.begin(), byc.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
-      size_t lo = 0, hi = byc.size();
-      size_t k = 0;
-      while (lo < hi) {
-        v[k++] = byc[lo++].second;
-        if (lo < hi) v[k++] = byc[--hi].second;
-      }
-    }
     entries.insert(entries.end(), pend[(size_t)ti].begin(), pend[(size_t)ti].end());
     units.push_back(make_int2(e0, (int)entries.size()));
     unit_cost_fine.push_back(pend_cost[(size_t)ti]);
