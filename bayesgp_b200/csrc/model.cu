@@ -474,7 +474,17 @@ int bgp_model_set_node_group(bgp_model* m, int rank, int world, const void* nccl
   comm_close(&m->node_comm);
   m->node_rank = rank;
   m->node_world = world;
-  if (world > 1) BGP_TRY(comm_open(&m->node_comm, rank, world, nccl_unique_id));
+  if (world > 1) {
+    BGP_TRY(comm_open(&m->node_comm, rank, world, nccl_unique_id));
+    // NCCL sets its channels up on the first collective (about a second): pay for it here, not inside the first fit
+    double* tmp = nullptr;
+    BGP_CUDA(cudaMalloc(&tmp, 8 * sizeof(double)));
+    BGP_CUDA(cudaMemsetAsync(tmp, 0, 8 * sizeof(double), m->stream));
+    const int st = node_allreduce_sum(m, tmp, 8);
+    cudaStreamSynchronize(m->stream);
+    cudaFree(tmp);
+    BGP_TRY(st);
+  }
   return BGP_OK;
 }
 
