@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cmath>
 #include <memory>
 #include <cstdio>
@@ -45,8 +46,8 @@ struct Status {
     if (_s != BGP_OK) return _s;   \
   } while (0)
 
-extern int64_t g_launch_count;
-inline void count_launch(int64_t k = 1) { g_launch_count += k; }
+extern std::atomic<int64_t> g_launch_count;      // models may be driven from different host threads
+inline void count_launch(int64_t k = 1) { g_launch_count.fetch_add(k, std::memory_order_relaxed); }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -104,6 +105,12 @@ struct bgp_model {
   std::vector<Staged> st_rnd, st_bnd, st_fix;
   // ---- device state --------------------------------------------------------------------------
   cudaStream_t stream = nullptr;
+  // SM partition (green.cpp, BGP_GREEN_SMS): the big streaming / tensor kernels run on `stream` inside the large
+  // partition, the 8-CTA Cholesky cluster on `chol_stream` inside the small one, so the Cholesky of one model overlaps
+  // the Hessian or likelihood pass of another model driven from a second host thread
+  cudaStream_t chol_stream = nullptr;
+  cudaEvent_t chol_ev[2] = {nullptr, nullptr};
+  int sm_count = 0;             // SMs the persistent kernels size their grids for
   double* A = nullptr;          // n x lda row-major (observation-major)
   double* y = nullptr;
   double* size = nullptr;
@@ -317,6 +324,8 @@ int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT);
 // sample.cu
 void fit_release_device(bgp_fit* f);
 
+// green.cpp: SM partition of a device into {small, rest}; streams inside either part
+int green_streams(int device, int small_sms, cudaStream_t* big, cudaStream_t* small, int* big_sm_count);
 // comm.cpp
 int comm_unique_id(void* id128);
 int comm_create(bgp_model* m, const void* id128);

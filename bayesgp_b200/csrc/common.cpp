@@ -8,7 +8,7 @@
 namespace bgp {
 
 thread_local std::string g_last_error;
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -50,7 +50,7 @@ extern "C" {
 
 const char* bgp_last_error(void) { return bgp::g_last_error.c_str(); }
 int bgp_version(void) { return 100; }
-int64_t bgp_kernel_launch_count(void) { return bgp::g_launch_count; }
+int64_t bgp_kernel_launch_count(void) { return bgp::g_launch_count.load(); }
 // capture window for `ncu --profile-from-start off` (diagnostics)
 int bgp_profiler_range(int start) { return (start ? cudaProfilerStart() : cudaProfilerStop()) == cudaSuccess ? BGP_OK : BGP_ERR_CUDA; }
 
