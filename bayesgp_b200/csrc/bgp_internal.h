@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <atomic>
 #include <cmath>
 #include <memory>
 #include <cstdio>
