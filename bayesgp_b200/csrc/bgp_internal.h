@@ -8,7 +8,6 @@
 #include <stdint.h>
 
 #include <atomic>
-#include <atomic>
 #include <cmath>
 #include <memory>
 #include <cstdio>
@@ -106,12 +105,6 @@ struct bgp_model {
   std::vector<Staged> st_rnd, st_bnd, st_fix;
   // ---- device state --------------------------------------------------------------------------
   cudaStream_t stream = nullptr;
-  // SM partition (green.cpp, BGP_GREEN_SMS): the big streaming / tensor kernels run on `stream` inside the large
-  // partition, the 8-CTA Cholesky cluster on `chol_stream` inside the small one, so the Cholesky of one model overlaps
-  // the Hessian or likelihood pass of another model driven from a second host thread
-  cudaStream_t chol_stream = nullptr;
-  cudaEvent_t chol_ev[2] = {nullptr, nullptr};
-  int sm_count = 0;             // SMs the persistent kernels size their grids for
   double* A = nullptr;          // n x lda row-major (observation-major)
   double* y = nullptr;
   double* size = nullptr;
@@ -325,8 +318,6 @@ int launch_trtri(bgp_model* m, double* Linv, int ldl, double* LinvT);
 // sample.cu
 void fit_release_device(bgp_fit* f);
 
-// green.cpp: SM partition of a device into {small, rest}; streams inside either part
-int green_streams(int device, int small_sms, cudaStream_t* big, cudaStream_t* small, int* big_sm_count);
 // comm.cpp
 int comm_unique_id(void* id128);
 int comm_create(bgp_model* m, const void* id128);

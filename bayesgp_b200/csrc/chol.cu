@@ -511,24 +511,6 @@ static void fill_tangent_args(bgp_model* m, const double* theta, const double* W
 // L <- chol(H) (H is left untouched), logdet, optionally step = -H^-1 g
 int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan, const double* W_tan) {
   m->L_is_reversed = false;
-  // SM partition (green.cpp): the factorisation runs on the small partition's stream, ordered after / before the
-  // model's main stream by two events
-  struct StreamSwap {
-    bgp_model* m;
-    cudaStream_t main;
-    bool on;
-    ~StreamSwap() {
-      if (!on) return;
-      cudaEventRecord(m->chol_ev[1], m->stream);
-      m->stream = main;
-      cudaStreamWaitEvent(main, m->chol_ev[1], 0);
-    }
-  } swap{m, m->stream, m->chol_stream != nullptr};
-  if (swap.on) {
-    cudaEventRecord(m->chol_ev[0], m->stream);
-    cudaStreamWaitEvent(m->chol_stream, m->chol_ev[0], 0);
-    m->stream = m->chol_stream;
-  }
   BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   CholArgs a;
   a.L = m->L;

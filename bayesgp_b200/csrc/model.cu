@@ -144,14 +144,7 @@ int bgp_model_new(int64_t n, int family, const double* y, const double* size, in
   if (const char* e = getenv("BGP_NO_PREDICTOR")) m->use_predictor = !(e[0] == '1');   // diagnostics only
   if (const char* e = getenv("BGP_NO_HERMITE")) m->use_hermite = !(e[0] == '1');
   int st = [&]() -> int {
-    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
-    const char* gs = getenv("BGP_GREEN_SMS");      // env: SM partition for overlapping models (green.cpp)
-    if (gs && atoi(gs) > 0) {
-      BGP_TRY(green_streams(device, atoi(gs), &m->stream, &m->chol_stream, &m->sm_count));
-      for (int i = 0; i < 2; ++i) BGP_CUDA(cudaEventCreateWithFlags(&m->chol_ev[i], cudaEventDisableTiming));
-    } else {
-      BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    }
+    BGP_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     const size_t nb = (size_t)n * sizeof(double);
     const size_t nb_pad = (size_t)(round_up64(n, 64) + 64) * sizeof(double);   // bulk copies read whole 8-row stages
     BGP_CUDA(cudaMalloc(&m->y, nb_pad));
@@ -598,7 +591,8 @@ int bgp_model_finalize(bgp_model* m) {
     BGP_TRY(dalloc(&h.T, (size_t)std::max(1, m->S) * m->lda * sizeof(double)));
     BGP_TRY(dalloc(&h.W, vb));
   }
-  const int sms = m->sm_count;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   m->lik_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (n + 7) / 8));   // one persistent CTA per SM
   BGP_TRY(dalloc(&m->part_g, (size_t)m->lik_blocks * m->lda * sizeof(double)));
   BGP_TRY(dalloc(&m->part_s, (size_t)m->lik_blocks * 4 * sizeof(double)));
@@ -660,9 +654,6 @@ void bgp_model_destroy(bgp_model* m) {
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
-  if (m->chol_stream) cudaStreamDestroy(m->chol_stream);
-  for (int i = 0; i < 2; ++i)
-    if (m->chol_ev[i]) cudaEventDestroy(m->chol_ev[i]);
   delete m;
 }
 

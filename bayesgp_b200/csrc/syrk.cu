@@ -506,7 +506,9 @@ int syrk_plan_create(bgp_model* m) {
     set_error("Hessian tile count %d exceeds the work-list encoding", pl->ntiles);
     return BGP_ERR_ARG;
   }
-  pl->G = SK_CTAS_PER_SM * m->sm_count;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  pl->G = SK_CTAS_PER_SM * sms;
   // Work list.  A unit is (tile, run of chunks) of bounded cost; the queue walks the observations from the
   // last block to the first (after the zero-pattern sort the late blocks are the densest) and visits every
   // tile per block, so the CTAs that run at the same time read the same observations (L2 reuse).  Unit
