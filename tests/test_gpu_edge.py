@@ -104,6 +104,23 @@ def test_sgp_precision_on_the_device_matches_compute_q_sb(a, k, m, region, acc):
     assert abs(ld.value - np.linalg.slogdet(want)[1]) <= tol
 
 
+def test_gradient_with_a_wide_dense_precision_block():
+    """ff$gr with an sGP term of 84 columns (two harmonics of 42, dense block-diagonal P): the block quadratic forms and
+    traces of the one-CTA gradient algebra (grad.cu) against the oracle's closed form."""
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(15)
+    n = 6000
+    x = rng.uniform(0, 3, n)
+    z = rng.uniform(0, 1, n)
+    eta = 0.2 + 0.7 * np.sin(2 * np.pi * x) + 0.3 * np.sin(4 * np.pi * x) + np.cos(3 * z)
+    y = rng.poisson(np.exp(eta)).astype(np.float64)
+    terms = [Term("sGP", "x", x, a=2 * np.pi, k=16, m=2, region=np.array([0.0, 3.0]), initial_location=0.0),
+             Term("IWP", "z", z, order=2, k=15)]
+    model = build_model(y, terms, {}, family="Poisson")[0]
+    assert model.B[0].shape[1] == 84
+    _compare(model, [np.array([1.0, -2.0]), np.array([0.4, -1.2])])
+
+
 def test_predict_derivatives_match_oracle():
     """f, f', f'' from the same samples (degree < order, R/03_post_fit.R:201-203 rejects the rest)."""
     import bayesgp_b200 as bg

@@ -72,6 +72,19 @@ def test_three_terms_above_512_columns(k, family):
     compare_with_oracle(model, [np.array([-3.0, -3.5, -4.0]), np.array([-3.4, -3.2, -4.3])])
 
 
+def test_gaussian_above_512_columns():
+    """Gaussian family (noise theta last, sumsq path of the likelihood pass, c3 = 0) at p = 601, S = 4."""
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(77)
+    n, k = 20000, 199
+    xs = [rng.uniform(0, 1, n) for _ in range(3)]
+    eta = 0.5 + np.sin(2 * np.pi * xs[0]) + 0.4 * np.sin(3 * np.pi * xs[1]) + 0.6 * np.sin(2.5 * np.pi * xs[2] + 1.0)
+    y = eta + 0.3 * rng.standard_normal(n)
+    model = build_model(y, [Term("IWP", "x%d" % (i + 1), xs[i], order=3, k=k) for i in range(3)], {}, family="Gaussian")[0]
+    assert model.p == 601 and model.S == 4
+    compare_with_oracle(model, [np.array([-3.0, -3.5, -4.0, 2.0]), np.array([-3.4, -3.2, -4.3, 2.4])])
+
+
 def _fit_both(oargs, pargs, k, mode, hessian):
     """oracle and product AGHQ objects on the same grid centre / scale (aghq's `optresults` argument)."""
     import bayesgp_b200 as bg
