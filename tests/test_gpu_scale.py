@@ -171,3 +171,41 @@ def test_full_size_batch_equals_single_and_is_deterministic(c3_full):
         ff.set_factor_reuse(True)
     fd = (f[-2] - 8.0 * f[-1] + 8.0 * f[1] - f[2]) / (12.0 * eps)
     assert abs(g[0] - fd) <= 1e-5 * max(1.0, abs(fd)), (g, fd)
+
+
+def test_c4_full_size_value_mode_hessian_match_oracle():
+    """BASELINE C4 at its full size (Binomial, n = 1e6, IWP2 k = 440 + sGP k = 20, p = 497; the generator of
+    scripts/run_config.py): one Laplace evaluation against the oracle — value 1e-8, mode and Hessian 1e-6, gradient
+    2e-7 of its largest entry.  About a minute of host time for the dense NumPy side."""
+    import bayesgp_b200 as bg
+    from bayesgp_b200 import api
+    from oracle import fit as ofit
+    from oracle.laplace import LaplaceObjective as OFF
+    n = 1_000_000
+    rng = np.random.default_rng(20244)
+    x1, x2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    eta = -0.3 + np.sin(2 * np.pi * x1) + 0.6 * np.cos(2 * np.pi * 5 * x2)
+    size = 1.0 + rng.poisson(9, n)
+    y = rng.binomial(size.astype(int), 1 / (1 + np.exp(-eta))).astype(np.float64)
+    kn = np.linspace(0, x1.max() - x1.min(), 440)
+    mk = lambda T: [T("IWP", "x1", x1, order=2, knots=kn, initial_location=float(x1.min())),
+                    T("sGP", "x2", x2, a=2 * np.pi * 5, k=20, m=1, region=np.array([0.0, 1.0]), accuracy=0.01)]
+    ff = api.build_objective(y, mk(bg.Term), {}, "Binomial", size)[0]
+    try:
+        assert ff.p == 497 and ff.n == n
+        theta = np.array([-3.4, 3.7])                 # next to the posterior mode of this data set
+        got, g, w, H = ff._eval(theta, want_grad=True, want_hess=True)
+        model = ofit.build_model(y, mk(ofit.Term), {}, "Binomial", size)[0]
+        off = OFF(model)
+        # the dense host side starts NEXT to the device's mode (a cold start would cost it five more Newton iterations of
+        # ~5e11 flops each) and converges by its own test
+        off.last_par = w * (1.0 + 1e-3)
+        want = off.fn(theta)
+        assert off.newton_iters >= 1
+        assert abs(got - want) <= 1e-8 * abs(want), (got, want)
+        assert relerr(w, off.last_par) < 1e-6
+        assert relerr(H, off.sp_hess()) < 1e-6
+        gw = off.gr(theta)
+        assert np.max(np.abs(g - gw)) <= 2e-7 * max(1.0, np.max(np.abs(gw))), (g, gw)
+    finally:
+        ff.close()
