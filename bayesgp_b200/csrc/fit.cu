@@ -463,51 +463,11 @@ static int fit_core(bgp_model* m, int k, const double* theta0, const double* mod
   f->owner.resize(K);
   f->slot.assign(K, -1);
   std::vector<unsigned char> mine(K, 0);
-  {
-    // Contiguous runs of the expand.grid order, balanced by COST rather than by count: every node costs one Newton
-    // iteration, and the first node a rank evaluates (the one of its run nearest to the grid centre, where the
-    // optimiser left mode and tangent) costs one more beyond 2.5 standard deviations and two more beyond 3.8
-    // (measured on C3: 1 / 2 / 3 iterations).  Minimise the most expensive run (linear partition, O(K^2 world)).
-    std::vector<double> zg, wg;
-    gh_rule(k, zg, wg);
-    std::vector<double> zn((size_t)K, 0.0);
-    for (int j = 0; j < K; ++j) {
-      int r = j;
-      double s2 = 0.0;
-      for (int d = 0; d < S; ++d) {
-        s2 += zg[r % k] * zg[r % k];
-        r /= k;
-      }
-      zn[j] = std::sqrt(s2);
-    }
-    auto run_cost = [&](int a, int b) {          // nodes a .. b-1
-      double zmin = INFINITY;
-      for (int j = a; j < b; ++j) zmin = std::min(zmin, zn[j]);
-      return (double)(b - a) + (zmin <= 2.5 ? 0.0 : (zmin <= 3.8 ? 1.0 : 2.0));
-    };
-    const int R = std::min(nw, K);
-    std::vector<std::vector<double>> best((size_t)R + 1, std::vector<double>((size_t)K + 1, INFINITY));
-    std::vector<std::vector<int>> cut((size_t)R + 1, std::vector<int>((size_t)K + 1, 0));
-    best[0][0] = 0.0;
-    for (int r = 1; r <= R; ++r)
-      for (int b = r; b <= K; ++b)
-        for (int a = r - 1; a < b; ++a) {
-          if (!std::isfinite(best[r - 1][a])) continue;
-          const double c = std::max(best[r - 1][a], run_cost(a, b));
-          if (c < best[r][b]) {
-            best[r][b] = c;
-            cut[r][b] = a;
-          }
-        }
-    std::vector<int> bounds((size_t)R + 1, K);
-    for (int r = R, b = K; r >= 1; --r) {
-      bounds[r] = b;
-      b = cut[r][b];
-      bounds[r - 1] = b;
-    }
-    for (int r = 0; r < R; ++r)
-      for (int j = bounds[r]; j < bounds[r + 1]; ++j) f->owner[j] = r;
-  }
+  // Contiguous, count-balanced runs of the expand.grid order.  Measured on C3 (scripts/partition_probe.py,
+  // profiles/r02_partition_probe.txt): from the optimiser's end state the FIRST node of any run costs two Newton
+  // iterations (4.0 ms) wherever it lies — the first-order predictor is not accurate enough for one — and every
+  // further node ~2.2 ms, so runs of equal length are the best split; weighting far runs lighter made it worse.
+  for (int j = 0; j < K; ++j) f->owner[j] = piece_owner(j, K, nw);
   for (int j = 0; j < K; ++j)
     if (f->owner[j] == nr) {
       mine[j] = 1;

@@ -23,11 +23,10 @@ def shard_bounds(n: int, rank: int, world: int):
 
 
 def node_slice(K: int, rank: int, world: int):
-    """Contiguous, balanced runs of K pieces over the ranks of a node group — how the library deals prediction rows
-    (piece_bounds in csrc/bgp_internal.h).  Quadrature nodes are dealt in contiguous runs of the expand.grid order
-    too (neighbours along the first coordinate share a rank, which keeps the warm starts close), but balanced by
-    expected Newton iterations rather than by count (fit.cu); the owners a fit actually used are reported by
-    ``AGHQ.node_owner`` (bgp_fit_node_owner)."""
+    """Contiguous, balanced runs of K pieces over the ranks of a node group — how the library deals quadrature nodes
+    (runs of the expand.grid order: neighbours along the first coordinate share a rank, which keeps the warm starts
+    close) and prediction rows (piece_owner / piece_bounds in csrc/bgp_internal.h).  The owners a fit actually used
+    are reported by ``AGHQ.node_owner`` (bgp_fit_node_owner)."""
     lo, hi = shard_bounds(K, rank, world)
     return list(range(lo, hi))
 
