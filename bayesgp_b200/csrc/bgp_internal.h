@@ -160,6 +160,17 @@ struct bgp_model {
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   std::function<void()> host_hook;
   double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
+  // O-spline moment path (ospline.cu): a model whose only smoothing term is an IWP evaluates eta, g_lik and H_lik
+  // from per-knot-interval moments instead of the dense design
+  struct IwpTerm {
+    double* x_dev = nullptr;     // covariate in the caller's row order (kept until finalize)
+    double x0 = 0.0;
+    int order = 0;
+    std::vector<double> kneg, kpos;
+  };
+  std::vector<IwpTerm> iwp_terms;
+  void* osp_plan = nullptr;     // opaque (ospline.cu)
+  bool osp_on = false;          // the likelihood pass / Hessian go through the moment path
   void* syrk_plan = nullptr;    // opaque (syrk.cu)
   void* lik_plan = nullptr;     // opaque (lik.cu)
   // {64-observation chunk} x {16-column box} occupancy (rowsort.cu): bit b of occ[c] set iff chunk c has a
@@ -254,6 +265,12 @@ int launch_lik(bgp_model* m, const double* W_dev, bool want_c3, double tau, cons
 int lik_max_lda();
 int lik_plan_create(bgp_model* m);
 void lik_plan_destroy(bgp_model* m);
+// ospline.cu: the same two steps from knot-interval moments (models with one IWP term); the pass leaves
+// [g_lik | ll | sumsq | flag | max d eta] in red_buf, the Hessian step H_lik in m->H
+int osp_plan_create(bgp_model* m);
+void osp_plan_destroy(bgp_model* m);
+int osp_launch_lik(bgp_model* m, const double* W_dev, double tau);
+int osp_launch_hessian(bgp_model* m);
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
 double theta_constant(const bgp_model* m, const double* theta);

@@ -152,8 +152,10 @@ double theta_constant(const bgp_model* m, const double* theta) {
 }
 
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau) {
-  finish_reduce_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
-  count_launch();
+  if (!m->osp_on) {               // the O-spline pass leaves its sums in red_buf itself
+    finish_reduce_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
+    count_launch();
+  }
   if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda + 4));
   PriorArgs a;
   a.red = m->red_buf;

@@ -503,6 +503,34 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
     set_error("laplace gradient: p = %d exceeds the leverage kernel's work list (1024)", p);
     return BGP_ERR_ARG;
   }
+  // The leverages and A^T (c3 q) need the design rows: a model on the O-spline moment path (ospline.cu) takes the
+  // dense passes here (its Hessian, if one is needed, still comes from the moments of the mode's own pass).
+  struct DenseScope {
+    bgp_model* m;
+    bool was;
+    explicit DenseScope(bgp_model* mm) : m(mm), was(mm->osp_on) {
+      if (was) {
+        m->osp_on = false;
+        m->obs_at_mode = false;
+      }
+    }
+    ~DenseScope() {
+      if (was) {
+        m->osp_on = true;
+        m->obs_at_mode = false;      // the dense arrays, not the moments, hold the mode's quantities
+      }
+    }
+  } dense_scope(m);
+  if (dense_scope.was && !m->factor_is_exact) {
+    // Hessian at the mode from the moment path (one pass over 40-60 bytes per observation) before switching over
+    m->osp_on = true;
+    BGP_TRY(eval_fg_async(m, m->Wmode, theta, false));
+    phase_mark(m, PH_HESS);
+    BGP_TRY(launch_hessian(m, theta));
+    m->n_hess++;
+    m->factor_is_exact = true;
+    m->osp_on = false;
+  }
   // exact per-observation quantities at the mode (w, c3; sumsq for the Gaussian noise theta)
   if (!m->obs_at_mode) {
     BGP_TRY(eval_fg_async(m, m->Wmode, theta, true));

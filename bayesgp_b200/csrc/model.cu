@@ -313,7 +313,16 @@ int bgp_model_add_iwp(bgp_model* m, const double* x, double initial_location, co
   BGP_TRY(launch_iwp_block(m, x_dev, m->n, initial_location, kn_dev, (int)kneg.size(), kp_dev, (int)kpos.size(), order,
                            sB.dev, (int)m->n, sX.dev, (int)m->n, true, m->stream));
   BGP_CUDA(cudaStreamSynchronize(m->stream));
-  cudaFree(x_dev);
+  {
+    // the covariate stays until finalize: a model with this single term takes the O-spline moment path (ospline.cu)
+    bgp_model::IwpTerm it;
+    it.x_dev = x_dev;
+    it.x0 = initial_location;
+    it.order = order;
+    it.kneg = kneg;
+    it.kpos = kpos;
+    m->iwp_terms.push_back(it);
+  }
   if (kn_dev) cudaFree(kn_dev);
   if (kp_dev) cudaFree(kp_dev);
   m->st_rnd.push_back(sB);
@@ -488,6 +497,27 @@ int bgp_model_set_node_group(bgp_model* m, int rank, int world, const void* nccl
   return BGP_OK;
 }
 
+int bgp_model_set_ospline(bgp_model* m, int on) {
+  if (!m || !m->finalized) {
+    set_error("bgp_model_set_ospline: model is not finalized");
+    return BGP_ERR_STATE;
+  }
+  if (on && !m->osp_plan) {
+    set_error("bgp_model_set_ospline: the model is not eligible (one IWP term of order <= 4 built by bgp_model_add_iwp, at most 8 dense columns)");
+    return BGP_ERR_ARG;
+  }
+  m->osp_on = on != 0;
+  m->obs_at_mode = false;
+  return BGP_OK;
+}
+
+int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on) {
+  if (!m) return BGP_ERR_ARG;
+  if (eligible) *eligible = m->osp_plan ? 1 : 0;
+  if (on) *on = m->osp_on ? 1 : 0;
+  return BGP_OK;
+}
+
 int bgp_model_set_hessian_retry(bgp_model* m, int allow) {
   if (!m) return BGP_ERR_ARG;
   m->hessian_retry = allow != 0;
@@ -546,6 +576,12 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(place(m->st_fix));
   BGP_TRY(place(m->st_rnd));
   BGP_CUDA(cudaStreamSynchronize(m->stream));
+  BGP_TRY(osp_plan_create(m));     // reads the staged dense columns, y and size in the caller's row order
+  for (auto& it : m->iwp_terms)
+    if (it.x_dev) {
+      cudaFree(it.x_dev);
+      it.x_dev = nullptr;
+    }
   for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix}) {
     for (auto& s : *v)
       if (s.dev) cudaFree(s.dev);
@@ -626,6 +662,9 @@ void bgp_model_destroy(bgp_model* m) {
   syrk_plan_destroy(m);
   lik_plan_destroy(m);
   grad_plan_destroy(m);
+  osp_plan_destroy(m);
+  for (auto& it : m->iwp_terms)
+    if (it.x_dev) cudaFree(it.x_dev);
   comm_destroy(m);
   for (auto* v : {&m->st_rnd, &m->st_bnd, &m->st_fix})
     for (auto& s : *v)

@@ -153,6 +153,16 @@ class LaplaceObjective:
     def set_hessian_retry(self, allow=True):
         check(self._lib.bgp_model_set_hessian_retry(self._h, int(allow)))
 
+    def set_ospline(self, on=True):
+        """Select the O-spline moment path (eligible models: one IWP term) or the dense DMMA path (on=False)."""
+        check(self._lib.bgp_model_set_ospline(self._h, int(on)))
+
+    def ospline(self):
+        """(eligible, on) of the O-spline moment path."""
+        e, o = C.c_int(), C.c_int()
+        check(self._lib.bgp_model_get_ospline(self._h, C.byref(e), C.byref(o)))
+        return bool(e.value), bool(o.value)
+
     def finalize(self):
         check(self._lib.bgp_model_finalize(self._h))
         n, p, S = C.c_int64(), C.c_int(), C.c_int()

@@ -152,6 +152,13 @@ int bgp_model_set_newton(bgp_model* m, double grad_tol, double step_tol, int max
  * marginals ("reuse"), per-node modes and Hessians.
  * ---------------------------------------------------------------------------------------- */
 int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
+/* O-spline moment path.  A model whose only smoothing term is an IWP of order <= 4 built by bgp_model_add_iwp, with at
+ * most 8 dense (boundary + fixed) columns, evaluates eta, A^T r and A^T diag(w) A from per-knot-interval moments of one
+ * streaming pass over (x, y, size, dense columns) instead of the two passes over the dense design: to the right of its
+ * own knot interval every O-spline column (R/01_utility.R:346-364) is a polynomial of degree order-1.  Same results to
+ * rounding; on by default for eligible models.  on = 0 selects the dense (DMMA) path, e.g. for A/B measurements. */
+int bgp_model_set_ospline(bgp_model* m, int on);
+int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on);
 /* When numDeriv's Richardson Hessian of ff$gr (d = 1e-4) is not positive definite aghq stops in chol(); so does
  * bgp_aghq_fit (BGP_ERR_NOT_PD).  allow = 1 opts into a retry with d = 1e-3 and 1e-2 (not in the reference); the
  * number of retries a fit needed is reported by bgp_fit_get_diagnostics. */

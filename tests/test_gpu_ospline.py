@@ -1,0 +1,189 @@
+"""GPU parity of the O-spline moment path (csrc/ospline.cu): models with one IWP term evaluate eta, A^T r and
+A^T diag(w) A from knot-interval moments instead of the dense design.  Each case is compared three ways on the same
+inputs: against the NumPy oracle (dense restatement of src/BayesGP.cpp:133-252 on get_local_poly's design,
+R/01_utility.R:346-364), against the product's own dense DMMA path (bgp_model_set_ospline(m, 0)), and through the
+Laplace objective ff$fn / ff$gr / mode / Hessian at the north_star tolerances (1e-8 / 1e-6 relative).
+Edge cases: orders 1..4, knots on both sides of the reference location, observations beyond the last knot, exactly on
+knots and on the reference location, empty knot intervals, fixed effects up to the 8-column limit, the three families."""
+import numpy as np
+import pytest
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(order, family, n=6000, k=24, nfixed=0, two_sided=False, seed=1, gap=False, beyond=False):
+    from oracle.fit import Term
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, n)
+    if gap:
+        x = np.where((x > 0.4) & (x < 0.6), x * 0.4, x)            # several empty knot intervals
+    knots = None
+    x0 = None
+    if two_sided:
+        x0 = 0.37
+        knots = np.linspace(-0.37, 0.63, k)
+        knots = np.sort(np.append(knots, 0.0)) if not np.any(knots == 0.0) else knots
+    elif beyond:
+        x0 = 0.0
+        knots = np.linspace(0.0, 0.8, k)                           # observations in (0.8, 1] lie beyond the last knot
+    # observations exactly on knots / on the reference location
+    if knots is not None:
+        x[:5] = (knots[[0, 1, len(knots) // 2, -2, -1]] + x0)
+        x[5] = x0
+    fixed = {"z%d" % i: rng.standard_normal(n) for i in range(nfixed)}
+    eta = 0.3 + np.sin(2 * np.pi * x) + sum(0.2 * v for v in fixed.values())
+    size = None
+    if family == "Poisson":
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+    elif family == "Binomial":
+        size = 1.0 + rng.poisson(6, n)
+        y = rng.binomial(size.astype(int), 1 / (1 + np.exp(-eta))).astype(np.float64)
+    else:
+        y = eta + 0.4 * rng.standard_normal(n)
+
+    def terms():
+        return [Term("IWP", "x", x.copy(), order=order, k=k, knots=None if knots is None else knots.copy(),
+                     initial_location=x0)]
+    return y, terms, fixed, family, size
+
+
+def build_both(case):
+    from bayesgp_b200.api import build_objective
+    from oracle.fit import build_model
+    y, terms, fixed, family, size = case
+    model = build_model(y, terms(), fixed, family=family, size=size)[0]
+    ff = build_objective(y, terms(), fixed, family=family, size=size)[0]
+    return model, ff
+
+
+CASES = [
+    dict(order=3, family="Poisson"),
+    dict(order=1, family="Poisson", nfixed=1),
+    dict(order=2, family="Binomial", nfixed=2),
+    dict(order=4, family="Poisson", k=16),
+    dict(order=3, family="Gaussian", nfixed=1),
+    dict(order=3, family="Poisson", two_sided=True),
+    dict(order=2, family="Binomial", two_sided=True, nfixed=3),
+    dict(order=3, family="Poisson", beyond=True, gap=True),
+    dict(order=3, family="Poisson", nfixed=5),            # 2 + 1 + 5 = 8 dense columns: the limit
+    dict(order=4, family="Gaussian", nfixed=4, k=12),     # 3 + 1 + 4 = 8
+]
+
+
+@pytest.mark.parametrize("kw", CASES, ids=lambda kw: "-".join("%s%s" % (k[0], v) for k, v in kw.items()))
+def test_objective_against_oracle_and_dense_path(kw):
+    model, ff = build_both(make_case(seed=31 + len(str(kw)), **kw))
+    try:
+        assert ff.ospline() == (True, True)
+        assert ff.p == model.p
+        rng = np.random.default_rng(9)
+        S = model.S
+        for rep in range(2):
+            W = 0.05 * rng.standard_normal(model.p)
+            theta = np.array([-2.0 - rep] + ([0.7] if S == 2 else []))
+            o = model.objective(W, theta, "fgH")
+            ff.set_ospline(True)
+            f, g, H = ff.objective(W, theta, want_grad=True, want_hess=True)
+            assert abs(f - o["f"]) <= 1e-11 * abs(o["f"])
+            assert relerr(g, o["g"]) < 1e-10 and relerr(H, o["H"]) < 1e-10
+            assert np.array_equal(H, H.T)
+            ff.set_ospline(False)
+            fd, gd, Hd = ff.objective(W, theta, want_grad=True, want_hess=True)
+            assert abs(f - fd) <= 1e-13 * abs(fd)
+            assert relerr(g, gd) < 1e-12 and relerr(H, Hd) < 1e-12
+            # entry by entry, relative to the entry's own scale (the moment path has no cancellation to hide behind
+            # the matrix norm): sqrt(H_ii H_jj) bounds |H_ij| for the likelihood part
+            d = np.sqrt(np.abs(np.diag(Hd)))
+            assert np.max(np.abs(H - Hd) / np.outer(d, d)) < 1e-11
+    finally:
+        ff.close()
+
+
+@pytest.mark.parametrize("kw", [CASES[0], CASES[2], CASES[4], CASES[5], CASES[7]],
+                         ids=["pois3", "binom2", "gauss3", "two-sided", "beyond-gap"])
+def test_laplace_objective(kw):
+    from oracle.laplace import LaplaceObjective as OFF
+    model, ff = build_both(make_case(seed=77, **kw))
+    off = OFF(model)
+    try:
+        S = model.S
+        for th0 in (-1.0, -3.5):
+            th = np.array([th0] + ([0.5] if S == 2 else []))
+            want = off.fn(th)
+            ff.set_ospline(True)
+            got, _, w, Hm = ff._eval(th, want_hess=True)
+            assert abs(got - want) <= 1e-8 * abs(want), (th, got, want)
+            assert relerr(w, off.last_par) < 1e-6 and relerr(Hm, off.sp_hess()) < 1e-6
+            gw, gg = off.gr(th), ff.gr(th)                    # the gradient switches to the dense passes inside
+            assert np.max(np.abs(gw - gg)) <= 2e-7 * max(1.0, np.max(np.abs(gw))), (th, gw, gg)
+            assert ff.ospline() == (True, True)
+            ff.set_ospline(False)
+            ff.set_start(None)
+            gd = ff._eval(th, want_hess=True)
+            assert abs(got - gd[0]) <= 1e-10 * abs(want)
+            assert relerr(w, gd[2]) < 1e-7
+        # repeated evaluations are bit-identical (fixed reduction order)
+        ff.set_ospline(True)
+        ff.set_start(None)
+        a = ff._eval(th, want_hess=True)
+        ff.set_start(None)
+        b = ff._eval(th, want_hess=True)
+        assert a[0] == b[0] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    finally:
+        ff.close()
+
+
+def test_model_fit_matches_dense_path_and_oracle():
+    """model_fit() end to end on the moment path: log normalising constant, theta mode, modes and Hessians per node."""
+    from bayesgp_b200.api import build_objective, marginal_laplace_tmb
+    from oracle.fit import build_model
+    from oracle.laplace import LaplaceObjective as OFF
+    from oracle.aghq import marginal_laplace_tmb as oracle_mlt
+    case = make_case(order=3, family="Poisson", n=8000, k=30, nfixed=1, seed=5)
+    y, terms, fixed, family, size = case
+    model = build_model(y, terms(), fixed, family=family, size=size)[0]
+    want = oracle_mlt(OFF(model), 5, np.zeros(1))
+    res = {}
+    for on in (True, False):
+        ff = build_objective(y, terms(), fixed, family=family, size=size)[0]
+        try:
+            ff.set_ospline(on)
+            mod = marginal_laplace_tmb(ff, 5, np.zeros(1))
+            mh = mod.modesandhessians
+            res[on] = (mod.lognormconst, np.array(mod.optresults["mode"]), np.array(mh["mode"]), np.array(mh["H"]))
+            mod.close()
+        finally:
+            ff.close()
+    assert abs(res[True][0] - want.lognormconst) <= 1e-8 * abs(want.lognormconst)
+    assert abs(res[True][0] - res[False][0]) <= 1e-9 * abs(res[False][0])
+    assert relerr(res[True][1], np.array(want.mode)) < 1e-5
+    assert relerr(res[True][2], res[False][2]) < 1e-6 and relerr(res[True][3], res[False][3]) < 1e-6
+
+
+def test_eligibility():
+    """Two smoothing terms, order above 4, more than 8 dense columns, caller-supplied designs: dense path only."""
+    from bayesgp_b200 import BgpError, make_objective
+    from bayesgp_b200.api import build_objective
+    from helpers import synth_poisson, tmbdata_from_oracle
+    from oracle.fit import Term
+    rng = np.random.default_rng(3)
+    n = 2000
+    x1, x2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    y = rng.poisson(np.exp(0.2 + np.sin(3 * x1))).astype(np.float64)
+    for terms, fixed in (([Term("IWP", "a", x1, order=2, k=10), Term("IWP", "b", x2, order=2, k=10)], {}),
+                         ([Term("IWP", "a", x1, order=5, k=10)], {}),
+                         ([Term("IWP", "a", x1, order=3, k=10)], {"z%d" % i: rng.standard_normal(n) for i in range(6)})):
+        ff = build_objective(y, terms, fixed, family="Poisson")[0]
+        try:
+            assert ff.ospline() == (False, False)
+            with pytest.raises(BgpError):
+                ff.set_ospline(True)
+        finally:
+            ff.close()
+    ff = make_objective(tmbdata_from_oracle(synth_poisson(n=3000, k=12)[0]))
+    try:
+        assert ff.ospline() == (False, False)
+    finally:
+        ff.close()
