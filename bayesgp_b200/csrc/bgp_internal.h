@@ -159,6 +159,13 @@ struct bgp_model {
   size_t pin_out_elems = 0;
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   std::function<void()> host_hook;
+  // page-locked destinations: the rotated mode / Hessian of a node leave through two device staging buffers and a
+  // second stream, so the copy over PCIe never holds up the next evaluation's kernels
+  cudaStream_t out_stream = nullptr;
+  double* out_stage[2] = {nullptr, nullptr};     // [H (p x p, external order) | mode (p)]
+  cudaEvent_t out_ready[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  bool out_used[2] = {false, false};
+  unsigned out_count = 0;
   double ll_const = 0.0;        // theta- and W-independent part of the log-likelihood
   // O-spline moment path (ospline.cu): a model whose only smoothing term is an IWP evaluates eta, g_lik and H_lik
   // from per-knot-interval moments instead of the dense design
@@ -269,8 +276,8 @@ void lik_plan_destroy(bgp_model* m);
 // [g_lik | ll | sumsq | flag | max d eta] in red_buf, the Hessian step H_lik in m->H
 int osp_plan_create(bgp_model* m);
 void osp_plan_destroy(bgp_model* m);
-int osp_launch_lik(bgp_model* m, const double* W_dev, double tau);
-int osp_launch_hessian(bgp_model* m);
+int osp_launch_lik(bgp_model* m, const double* W_dev, double tau, const double* theta = nullptr);
+int osp_launch_hessian(bgp_model* m, const double* theta);
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
 double theta_constant(const bgp_model* m, const double* theta);

@@ -6,31 +6,9 @@
 // Two tiny kernels so that, when observations are sharded across GPUs, the packed buffer
 // [g_lik (lda) | ll | sumsq | nonfinite | -] can be all-reduced between them.
 #include "bgp_internal.h"
+#include "finish_dev.cuh"
 
 namespace bgp {
-
-constexpr int MAX_RND = 16;
-
-struct RndDev {
-  int off, d, diag;
-  const double* P;
-  double etheta;
-};
-
-struct PriorArgs {
-  const double* red;     // [lda + 4]
-  int lda, p;
-  const double* W;
-  const double* mu0;
-  const double* qfix;
-  double* g;
-  EvalScalars* sc;
-  double theta_const;    // lpT + 1/2 sum(d_j theta_j + logPdet_j) + likelihood constants
-  double tau;
-  int family;
-  int nrnd;
-  RndDev rnd[MAX_RND];
-};
 
 // grid = ceil(lda / 32) CTAs of 256 threads: CTA c owns 32 columns, its 8 warps split the partial blocks
 // (block b goes to warp b % 8), partial sums are combined in a fixed order => deterministic.
@@ -85,54 +63,7 @@ __global__ void __launch_bounds__(256) finish_reduce_kernel(const double* __rest
 __global__ void __launch_bounds__(1024) finish_prior_kernel(const PriorArgs a) {
   __shared__ double s_quad[1024];
   __shared__ double s_gmax[1024];
-  double quad = 0.0, gmax = 0.0;
-  for (int c = threadIdx.x; c < a.lda; c += blockDim.x) {
-    double gv = 0.0;
-    if (c < a.p) {
-      const double dW = a.W[c] - a.mu0[c];
-      double q = a.qfix[c] * dW;
-      for (int b = 0; b < a.nrnd; ++b) {
-        const RndDev& rb = a.rnd[b];
-        if (c >= rb.off && c < rb.off + rb.d) {
-          const int i = c - rb.off;
-          if (rb.diag) {
-            q = rb.etheta * rb.P[i] * dW;
-          } else {
-            double s = 0.0;
-            for (int k = 0; k < rb.d; ++k) s = fma(rb.P[(size_t)k * rb.d + i], a.W[rb.off + k], s);
-            q = rb.etheta * s;
-          }
-        }
-      }
-      gv = -a.red[c] + q;
-      quad = fma(dW, q, quad);
-      gmax = fmax(gmax, fabs(gv));
-      if (!isfinite(gv)) gmax = INFINITY;
-    }
-    a.g[c] = gv;
-  }
-  s_quad[threadIdx.x] = quad;
-  s_gmax[threadIdx.x] = gmax;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      s_quad[threadIdx.x] += s_quad[threadIdx.x + o];
-      s_gmax[threadIdx.x] = fmax(s_gmax[threadIdx.x], s_gmax[threadIdx.x + o]);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double ll_raw = a.red[a.lda + 0], sumsq = a.red[a.lda + 1], bad = a.red[a.lda + 2];
-    const double ll = a.family == BGP_FAMILY_GAUSSIAN ? -0.5 * a.tau * sumsq : ll_raw;
-    const double f = -(ll + a.theta_const - 0.5 * s_quad[0]);
-    a.sc->f = f;
-    a.sc->ll = ll;
-    a.sc->gmax = s_gmax[0];
-    a.sc->quad = s_quad[0];
-    a.sc->sumsq = sumsq;
-    a.sc->pad = a.red[a.lda + 3];
-    a.sc->nonfinite = (bad != 0.0 || !isfinite(f)) ? 1 : 0;
-  }
+  finish_prior_body<1024>(a, s_quad, s_gmax);
 }
 
 // host side -------------------------------------------------------------------------------------
@@ -151,13 +82,8 @@ double theta_constant(const bgp_model* m, const double* theta) {
   return c;
 }
 
-int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau) {
-  if (!m->osp_on) {               // the O-spline pass leaves its sums in red_buf itself
-    finish_reduce_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
-    count_launch();
-  }
-  if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda + 4));
-  PriorArgs a;
+void fill_prior_args(bgp_model* m, const double* W_dev, const double* theta, double tau, PriorArgs* out) {
+  PriorArgs& a = *out;
   a.red = m->red_buf;
   a.lda = m->lda;
   a.p = m->p;
@@ -177,6 +103,16 @@ int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double
     a.rnd[j].P = m->rnd[j].P_dev;
     a.rnd[j].etheta = std::exp(theta[j]);
   }
+}
+
+int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau) {
+  if (!m->osp_on) {               // the O-spline pass leaves its sums in red_buf itself
+    finish_reduce_kernel<<<(m->lda + 31) / 32, 256, 0, m->stream>>>(m->part_g, m->part_s, m->lik_blocks, m->lda, m->red_buf);
+    count_launch();
+  }
+  if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda + 4));
+  PriorArgs a;
+  fill_prior_args(m, W_dev, theta, tau, &a);
   finish_prior_kernel<<<1, 1024, 0, m->stream>>>(a);
   count_launch();
   BGP_CUDA(cudaGetLastError());

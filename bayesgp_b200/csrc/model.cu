@@ -686,6 +686,12 @@ void bgp_model_destroy(bgp_model* m) {
   if (m->sc_dev) cudaFree(m->sc_dev);
   if (m->sc_host) cudaFreeHost(m->sc_host);
   for (int i = 0; i < 2; ++i) {
+    if (m->out_stage[i]) cudaFree(m->out_stage[i]);
+    if (m->out_ready[i]) cudaEventDestroy(m->out_ready[i]);
+    if (m->out_done[i]) cudaEventDestroy(m->out_done[i]);
+  }
+  if (m->out_stream) cudaStreamDestroy(m->out_stream);
+  for (int i = 0; i < 2; ++i) {
     if (m->pin_out[i]) cudaFreeHost(m->pin_out[i]);
     if (m->pin_ev[i]) cudaEventDestroy(m->pin_ev[i]);
   }

@@ -93,11 +93,60 @@ int eval_fg_async(bgp_model* m, const double* W_dev, const double* theta, bool w
   const double tau = tau_of(m, theta);
   m->obs_at_mode = false;                 // callers that evaluate at the mode set it again
   phase_mark(m, PH_LIK);
+  if (m->osp_on) {
+    // moment path (ospline.cu): on a single device the prior completion rides in its last kernel
+    BGP_TRY(osp_launch_lik(m, W_dev, tau, m->world == 1 ? theta : nullptr));
+    m->n_lik++;
+    if (m->world > 1) BGP_TRY(launch_finish(m, W_dev, theta, tau));
+    phase_mark(m, PH_OTHER);
+    return BGP_OK;
+  }
   BGP_TRY(launch_lik(m, W_dev, want_c3, tau));
   m->n_lik++;
   BGP_TRY(launch_finish(m, W_dev, theta, tau));
   phase_mark(m, PH_OTHER);
   return BGP_OK;
+}
+
+__global__ void commit_mode_kernel(const double* __restrict__ W, const double* __restrict__ Tan, int lda, int S,
+                                   double* __restrict__ Wmode, double* __restrict__ hist_W, double* __restrict__ hist_T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < lda) {
+    const double v = W[i];
+    Wmode[i] = v;
+    if (hist_W) hist_W[i] = v;
+  } else if (i < lda * (1 + S)) {
+    hist_T[i - lda] = Tan[i - lda];
+  }
+}
+
+// One node's results into the fit's device slots (internal order) and, rotated to the external order of the ABI
+// (io.cu), into a staging buffer [H (p x p) | mode (p)] for the copy to the host: one launch.
+struct SinkArgs {
+  const double *Wmode, *H;
+  int p, nD, lda, ldh;
+  double *modes_slot, *Hs_slot, *stage;
+};
+__global__ void sink_node_kernel(const SinkArgs a) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  const int nU = a.p - a.nD;
+  if (c == a.p) {                                  // the extra row of CTAs: the mode
+    if (r < a.lda && a.modes_slot) a.modes_slot[r] = a.Wmode[r];
+    if (r < a.p && a.stage) a.stage[(size_t)a.p * a.p + r] = a.Wmode[r < nU ? r + a.nD : r - nU];
+    return;
+  }
+  if (r < a.ldh && a.Hs_slot) a.Hs_slot[(size_t)c * a.ldh + r] = a.H[(size_t)c * a.ldh + r];
+  if (r < a.p && a.stage) {
+    const int ir = r < nU ? r + a.nD : r - nU, ic = c < nU ? c + a.nD : c - nU;
+    a.stage[(size_t)c * a.p + r] = a.H[(size_t)ic * a.ldh + ir];
+  }
+}
+
+__global__ void sink_modes_kernel(const SinkArgs a) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nU = a.p - a.nD;
+  if (r < a.lda && a.modes_slot) a.modes_slot[r] = a.Wmode[r];
+  if (r < a.p && a.stage) a.stage[(size_t)a.p * a.p + r] = a.Wmode[r < nU ? r + a.nD : r - nU];
 }
 
 int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_out) {
@@ -385,7 +434,7 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     }
     logdet = sc.logdet;
   }
-  BGP_CUDA(cudaMemcpyAsync(m->Wmode, m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  double *hist_W = nullptr, *hist_T = nullptr;
   if (m->use_predictor && m->S <= 17) {
     // the tangent came out of the last Cholesky launch (idle cluster ranks) unless there are too many thetas
     if (m->S > CHOL_TANGENT_MAX_S) BGP_TRY(launch_tangent(m, theta));
@@ -403,9 +452,13 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     auto& h = m->hist[slot];
     h.theta = m->theta_last;
     h.stamp = ++m->hist_clock;
-    BGP_CUDA(cudaMemcpyAsync(h.W, m->Wmode, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
-    BGP_CUDA(cudaMemcpyAsync(h.T, m->Tan, (size_t)m->S * m->lda * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    hist_W = h.W;
+    hist_T = h.T;
   }
+  // the mode into Wmode and, with its tangent, into the history slot: one launch
+  commit_mode_kernel<<<(m->lda * (1 + (hist_T ? m->S : 0)) + 255) / 256, 256, 0, m->stream>>>(m->W, m->Tan, m->lda, hist_T ? m->S : 0,
+                                                                                            m->Wmode, hist_W, hist_T);
+  count_launch();
   m->factor_is_exact = !reused;
   m->obs_at_mode = pass_at_W;
   ++m->n_evals;
@@ -430,7 +483,10 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
   // the deferred copies point into the caller's arrays: none may outlive this call, whichever way it returns
   struct HookGuard {
     bgp_model* m;
-    ~HookGuard() { m->host_hook = nullptr; }
+    ~HookGuard() {
+      m->host_hook = nullptr;
+      if (m->out_stream) cudaStreamSynchronize(m->out_stream);   // copies into the caller's arrays: none in flight
+    }
   } hook_guard{m};
   m->host_hook = nullptr;
   const int S = m->S;
@@ -489,20 +545,60 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
       worst = st;
       continue;
     }
-    if (sink.modes_dev || sink.Hs_dev) {
+    const bool to_pinned = (sink.modes_host || sink.Hs_host) && sink.host_pinned;
+    if (sink.modes_dev || sink.Hs_dev || to_pinned) {
       const size_t slot = sink.dev_slot ? (size_t)sink.dev_slot[j] : (size_t)j;
-      if (sink.modes_dev)
-        BGP_CUDA(cudaMemcpyAsync(sink.modes_dev + slot * m->lda, m->Wmode, (size_t)m->lda * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, m->stream));
-      if (sink.Hs_dev)
-        BGP_CUDA(cudaMemcpyAsync(sink.Hs_dev + slot * (size_t)m->p * m->ldh, m->H, (size_t)m->p * m->ldh * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, m->stream));
+      SinkArgs sa;
+      sa.Wmode = m->Wmode;
+      sa.H = m->H;
+      sa.p = m->p;
+      sa.nD = m->nD;
+      sa.lda = m->lda;
+      sa.ldh = m->ldh;
+      sa.modes_slot = sink.modes_dev ? sink.modes_dev + slot * m->lda : nullptr;
+      sa.Hs_slot = sink.Hs_dev ? sink.Hs_dev + slot * (size_t)m->p * m->ldh : nullptr;
+      sa.stage = nullptr;
+      int b = 0;
+      if (to_pinned) {
+        // page-locked destination: rotate into one of two staging buffers here, copy to slot j on the output stream
+        if (!m->out_stream) {
+          BGP_CUDA(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+          for (int i = 0; i < 2; ++i) {
+            BGP_CUDA(cudaMalloc(&m->out_stage[i], (pp + (size_t)m->p) * sizeof(double)));
+            BGP_CUDA(cudaEventCreateWithFlags(&m->out_ready[i], cudaEventDisableTiming));
+            BGP_CUDA(cudaEventCreateWithFlags(&m->out_done[i], cudaEventDisableTiming));
+          }
+        }
+        b = (int)(m->out_count++ & 1u);
+        if (m->out_used[b]) BGP_CUDA(cudaStreamWaitEvent(m->stream, m->out_done[b], 0));   // its previous tenant has left
+        sa.stage = m->out_stage[b];
+      }
+      const bool want_H = sa.Hs_slot || (to_pinned && sink.Hs_host);
+      dim3 grid((std::max(m->lda, m->ldh) + 255) / 256, m->p + 1);
+      if (!want_H) {                               // modes only: just the extra row
+        sa.H = nullptr;
+        grid = dim3((m->lda + 255) / 256, 1);
+        sink_modes_kernel<<<grid, 256, 0, m->stream>>>(sa);
+      } else {
+        sink_node_kernel<<<grid, 256, 0, m->stream>>>(sa);
+      }
+      count_launch();
+      BGP_CUDA(cudaGetLastError());
+      if (to_pinned) {
+        BGP_CUDA(cudaEventRecord(m->out_ready[b], m->stream));
+        BGP_CUDA(cudaStreamWaitEvent(m->out_stream, m->out_ready[b], 0));
+        if (sink.modes_host)
+          BGP_CUDA(cudaMemcpyAsync(sink.modes_host + (size_t)j * m->p, m->out_stage[b] + pp, (size_t)m->p * sizeof(double),
+                                   cudaMemcpyDeviceToHost, m->out_stream));
+        if (sink.Hs_host)
+          BGP_CUDA(cudaMemcpyAsync(sink.Hs_host + (size_t)j * pp, m->out_stage[b], pp * sizeof(double), cudaMemcpyDeviceToHost,
+                                   m->out_stream));
+        BGP_CUDA(cudaEventRecord(m->out_done[b], m->out_stream));
+        m->out_used[b] = true;
+      }
     }
-    if ((sink.modes_host || sink.Hs_host) && sink.host_pinned) {
-      // page-locked destination: rotate on the device, copy straight into slot j (asynchronous; the staging
-      // buffer is reused by the next node in stream order)
-      if (sink.modes_host) BGP_TRY(copy_vec_out(m, m->Wmode, sink.modes_host + (size_t)j * m->p));
-      if (sink.Hs_host) BGP_TRY(copy_H_out(m, sink.Hs_host + (size_t)j * pp));
+    if (to_pinned) {
+      // nothing more: the copies are in flight on the output stream
     } else if (sink.modes_host || sink.Hs_host) {
       const size_t need = pp + (size_t)m->p;
       if (m->pin_out_elems < need) {
@@ -538,6 +634,7 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
     m->host_hook();
     m->host_hook = nullptr;
   }
+  if (m->out_stream) BGP_CUDA(cudaStreamSynchronize(m->out_stream));
   if (iters_total) *iters_total = total;
   return worst;
 }

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "bgp_internal.h"
+#include "finish_dev.cuh"
 #include "lik_terms.cuh"
 
 namespace bgp {
@@ -36,6 +37,7 @@ constexpr int OSP_MAXD = 8;      // dense (boundary + fixed) columns
 
 struct OspPlan {
   int P = 0, nD = 0, NDC = 0, NG = 0, NC = 0, NM = 0, NACC = 0, np = 0;
+  int pass_grid = 0;              // resident CTAs of the pass kernel
   int64_t n = 0;
   // observations in interval order
   double *u = nullptr, *y = nullptr, *size = nullptr, *D = nullptr, *eta = nullptr;
@@ -49,7 +51,8 @@ struct OspPlan {
   double *c_t0 = nullptr, *c_t1 = nullptr;
   int *c_gid = nullptr, *c_gend = nullptr, *c_side = nullptr;
   // per evaluation
-  double *C = nullptr, *slots = nullptr, *mom = nullptr, *glob = nullptr, *Hdb = nullptr, *G = nullptr;
+  int* done = nullptr;
+  double *slots = nullptr, *mom = nullptr, *glob = nullptr, *Hdb = nullptr, *G = nullptr;
 };
 
 // accumulator layout of a piece: [R (P+1) | V (2P+1) | X (NDC x (P+1)) | DD (NDC (NDC+1)/2) | gD (NDC) | ll sumsq bad | max]
@@ -150,42 +153,13 @@ __global__ void osp_count_kernel(const uint32_t* __restrict__ gid, int64_t n, in
 }
 
 // ---- per evaluation ----------------------------------------------------------------------------------------------
-// C[gid][m]: coefficients (in u) of the tails of the columns left of interval gid, weighted by W.  One warp per interval.
-template <int P>
-__global__ void __launch_bounds__(128) osp_coef_kernel(const double* __restrict__ W, int nD, int NG, const double* __restrict__ g_t0,
-                                                       const int* __restrict__ g_c0, const int* __restrict__ g_nt,
-                                                       const double* __restrict__ c_t0, const double* __restrict__ c_t1,
-                                                       double* __restrict__ C) {
-  const int lane = threadIdx.x & 31;
-  const int gid = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (gid >= NG) return;
-  const int c0 = g_c0[gid], J = g_nt[gid];
-  const double t0 = g_t0[gid];
-  double acc[P];
-#pragma unroll
-  for (int m = 0; m < P; ++m) acc[m] = 0.0;
-  for (int i = lane; i < J; i += 32) {
-    const int col = c0 + i;
-    double al[P];
-    osp_alpha<P>(c_t1[col] - c_t0[col], t0 - c_t1[col], al);
-    const double wv = W[nD + col];
-#pragma unroll
-    for (int m = 0; m < P; ++m) acc[m] = fma(wv, al[m], acc[m]);
-  }
-#pragma unroll
-  for (int m = 0; m < P; ++m) {
-    const double v = osp_warp_sum(acc[m]);
-    if (lane == 0) C[gid * OSP_MAXP + m] = v;
-  }
-}
-
 struct OspPassArgs {
   const double *u, *y, *size, *D;
   double* eta;
   const int64_t* piece_beg;
   const int* piece_gid;
-  const double* C;
-  const int* g_own;
+  const int *g_own, *g_c0, *g_nt;
+  const double *g_t0, *c_t0, *c_t1;
   const double* W;
   int nD, np, family;
   int64_t n;
@@ -195,17 +169,34 @@ struct OspPassArgs {
 
 // One warp per piece (a run of observations of one knot interval): eta, the likelihood terms and the moments.
 template <int P, int NDC>
-__global__ void __launch_bounds__(128) osp_pass_kernel(const OspPassArgs a) {
+__global__ void __launch_bounds__(128, NDC <= 4 ? 3 : 2) osp_pass_kernel(const OspPassArgs a) {
   constexpr int OV = osp_offV(P), OX = osp_offX(P), ODD = osp_offDD(P, NDC), OGD = osp_offgD(P, NDC), OS = osp_offS(P, NDC);
   constexpr int NACC = osp_NACC(P, NDC);
   const int lane = threadIdx.x & 31;
-  const int pc = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (pc >= a.np) return;
+  // resident warps stride over the pieces (similar lengths): no partial last wave
+  for (int pc = blockIdx.x * 4 + (threadIdx.x >> 5); pc < a.np; pc += gridDim.x * 4) {
   const int gid = a.piece_gid[pc];
   const int64_t j0 = a.piece_beg[pc], j1 = a.piece_beg[pc + 1];
+  // cf[m]: coefficients (in u) of the tails of the columns left of this interval, weighted by W — the same sums in
+  // the same order for every piece of the interval
   double cf[P];
 #pragma unroll
-  for (int m = 0; m < P; ++m) cf[m] = a.C[gid * OSP_MAXP + m];
+  for (int m = 0; m < P; ++m) cf[m] = 0.0;
+  {
+    const int c0 = a.g_c0[gid], J = a.g_nt[gid];
+    const double t0 = a.g_t0[gid];
+    for (int i = lane; i < J; i += 32) {
+      const int col = c0 + i;
+      const double t1 = a.c_t1[col];
+      double al[P];
+      osp_alpha<P>(t1 - a.c_t0[col], t0 - t1, al);
+      const double wv = a.W[a.nD + col];
+#pragma unroll
+      for (int m = 0; m < P; ++m) cf[m] = fma(wv, al[m], cf[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < P; ++m) cf[m] = osp_warp_sum(cf[m]);
+  }
   const int own = a.g_own[gid];
   const double wown = own >= 0 ? a.W[a.nD + own] * osp_ifact(P) : 0.0;
   double wd[NDC];
@@ -262,6 +253,7 @@ __global__ void __launch_bounds__(128) osp_pass_kernel(const OspPassArgs a) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   if (lane == 0) slot[NACC - 1] = dmax;
+  }
 }
 
 // Interval moments (one warp per interval, lanes over its pieces) and the global sums (one CTA per value).
@@ -274,6 +266,16 @@ __global__ void __launch_bounds__(128) osp_reduce_kernel(const double* __restric
     const int gid = blockIdx.x * 4 + warp;
     if (gid >= NG) return;
     const int pb = gid_pbeg[gid], pe = gid_pbeg[gid + 1];
+    if (pe - pb <= 64) {
+      // the usual case: lane m sums moment m over the interval's pieces in order (coalesced rows, no shuffles)
+      for (int m = lane; m < NM; m += 32) {
+        double v = 0.0;
+#pragma unroll 8
+        for (int pc = pb; pc < pe; ++pc) v += slots[(size_t)pc * NACC + m];
+        mom[(size_t)gid * NM + m] = v;
+      }
+      return;
+    }
     for (int m = 0; m < NM; ++m) {
       double v = 0.0;
       for (int pc = pb + lane; pc < pe; pc += 32) v += slots[(size_t)pc * NACC + m];
@@ -306,17 +308,20 @@ struct OspApplyArgs {
   const double *mom, *glob;
   double* red;      // [g_lik (lda) | ll | sumsq | bad | max d eta]
   double* Hdb;      // NDC x NC
+  int* done;        // CTA counter for the fused prior completion (self-resetting)
+  int fuse_prior;
+  double* G;        // NC x OSP_MAXP: G[k][q] = sum over the observations right of column k's interval of w c_k(z) (z - t_{k+1})^q
 };
 
-// g_lik of the spline columns and the {dense x spline} block of H: one warp per column, lanes over the intervals to
-// its right.  The last CTA moves the global sums into the reduction buffer finish.cu reads.
+// g_lik of the spline columns, the {dense x spline} block of H and the weighted suffix moments G the {spline x spline}
+// block is assembled from: one warp per column, lanes over the intervals to its right.  The last CTA moves the global
+// sums into the reduction buffer finish.cu reads.
 template <int P, int NDC>
-__global__ void __launch_bounds__(128) osp_apply_kernel(const OspApplyArgs a) {
-  constexpr int OX = osp_offX(P), ODD = osp_offDD(P, NDC) - osp_NM(P, NDC), OGD = osp_offgD(P, NDC) - osp_NM(P, NDC),
-                OS = osp_offS(P, NDC) - osp_NM(P, NDC);
+__device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
+  constexpr int OV = osp_offV(P), OX = osp_offX(P), OGD = osp_offgD(P, NDC) - osp_NM(P, NDC), OS = osp_offS(P, NDC) - osp_NM(P, NDC);
+  constexpr int NE = 2 * P - 1;
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == gridDim.x - 1) {
-    (void)ODD;
     for (int c = threadIdx.x; c < a.nD; c += 128) a.red[c] = a.glob[OGD + c];
     if (threadIdx.x < 4) a.red[a.lda + threadIdx.x] = a.glob[OS + threadIdx.x];
     return;
@@ -325,12 +330,15 @@ __global__ void __launch_bounds__(128) osp_apply_kernel(const OspApplyArgs a) {
   if (col >= a.NC) return;
   const int own = a.c_gid[col], gend = a.c_gend[col];
   const double t1 = a.c_t1[col], d = t1 - a.c_t0[col];
-  double acc[NDC + 1];
+  double acc[NDC + 1], S[NE];
 #pragma unroll
   for (int e = 0; e <= NDC; ++e) acc[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) S[e] = 0.0;
   for (int g = own + 1 + lane; g < gend; g += 32) {
+    const double s = a.g_t0[g] - t1;
     double al[P];
-    osp_alpha<P>(d, a.g_t0[g] - t1, al);
+    osp_alpha<P>(d, s, al);
     const double* mg = a.mom + (size_t)g * a.NM;
 #pragma unroll
     for (int m = 0; m < P; ++m) {
@@ -338,47 +346,17 @@ __global__ void __launch_bounds__(128) osp_apply_kernel(const OspApplyArgs a) {
 #pragma unroll
       for (int c = 0; c < NDC; ++c) acc[1 + c] = fma(al[m], mg[OX + c * (P + 1) + m], acc[1 + c]);
     }
-  }
-  const double* mo = a.mom + (size_t)own * a.NM;
-#pragma unroll
-  for (int e = 0; e <= NDC; ++e) {
-    const double v = osp_warp_sum(acc[e]);
-    if (lane == 0) {
-      if (e == 0) a.red[a.nD + col] = v + mo[P] * osp_ifact(P);
-      else if (e - 1 < a.nD) a.Hdb[(size_t)(e - 1) * a.NC + col] = v + mo[OX + (e - 1) * (P + 1) + P] * osp_ifact(P);
-    }
-  }
-}
-
-// G[k][q] = sum over the observations right of column k's interval of  w c_k(z) (z - t_{k+1})^q,  q < P
-template <int P>
-__global__ void __launch_bounds__(128) osp_suffix_kernel(int NC, int NM, const double* __restrict__ c_t0, const double* __restrict__ c_t1,
-                                                         const int* __restrict__ c_gid, const int* __restrict__ c_gend,
-                                                         const double* __restrict__ g_t0, const double* __restrict__ mom,
-                                                         double* __restrict__ G) {
-  constexpr int OV = osp_offV(P), NE = 2 * P - 1;
-  const int lane = threadIdx.x & 31;
-  const int col = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (col >= NC) return;
-  const int own = c_gid[col], gend = c_gend[col];
-  const double t1 = c_t1[col], d = t1 - c_t0[col];
-  double S[NE];
-#pragma unroll
-  for (int e = 0; e < NE; ++e) S[e] = 0.0;
-  for (int g = own + 1 + lane; g < gend; g += 32) {
-    const double s = g_t0[g] - t1;
-    const double* V = mom + (size_t)g * NM + OV;
+    // sum w (u + s)^e = sum_{m<=e} binom(e, m) s^{e-m} V_m
     double sp[NE];
     sp[0] = 1.0;
 #pragma unroll
     for (int e = 1; e < NE; ++e) sp[e] = sp[e - 1] * s;
-    // sum w (u + s)^e = sum_{m<=e} binom(e, m) s^{e-m} V_m
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       double binom = 1.0;
 #pragma unroll
       for (int m = 0; m <= e; ++m) {
-        S[e] = fma(binom * sp[e - m], V[m], S[e]);
+        S[e] = fma(binom * sp[e - m], mg[OV + m], S[e]);
         binom = binom * (double)(e - m) / (double)(m + 1);
       }
     }
@@ -399,8 +377,39 @@ __global__ void __launch_bounds__(128) osp_suffix_kernel(int NC, int NM, const d
         for (int q2 = 0; q2 < P; ++q2) gq = fma(dp[P - q2] * (osp_ifact(P - q2) * osp_ifact(q2)), S[q + q2], gq);
       }
     }
-    G[col * OSP_MAXP + lane] = gq;
+    a.G[col * OSP_MAXP + lane] = gq;
   }
+  const double* mo = a.mom + (size_t)own * a.NM;
+#pragma unroll
+  for (int e = 0; e <= NDC; ++e) {
+    const double v = osp_warp_sum(acc[e]);
+    if (lane == 0) {
+      if (e == 0) a.red[a.nD + col] = v + mo[P] * osp_ifact(P);
+      else if (e - 1 < a.nD) a.Hdb[(size_t)(e - 1) * a.NC + col] = v + mo[OX + (e - 1) * (P + 1) + P] * osp_ifact(P);
+    }
+  }
+}
+
+// fuse_prior (single-device models): the CTA that finishes last completes f, g and max|g| (finish_dev.cuh) — every
+// entry of the reduction buffer is in L2 by then (fence + ticket), and one CTA does the whole completion in a fixed
+// order, so the result does not depend on which CTA that is.
+template <int P, int NDC>
+__global__ void __launch_bounds__(128) osp_apply_kernel(const OspApplyArgs a, const PriorArgs pr) {
+  osp_apply_body<P, NDC>(a);
+  if (!a.fuse_prior) return;
+  __shared__ int s_last;
+  __shared__ double s_quad[128], s_gmax[128];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(a.done, 1);
+    s_last = t == (int)gridDim.x - 1;
+    if (s_last) *a.done = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  finish_prior_body<128>(pr, s_quad, s_gmax);
 }
 
 struct OspHArgs {
@@ -409,6 +418,10 @@ struct OspHArgs {
   const int *c_gid, *c_side;
   const double *mom, *glob, *Hdb, *G;
   double* H;
+  // Q(theta) on the diagonal (an IWP precision is diagonal): qfix on the dense columns, e^theta P_i on the spline
+  // columns; NULL when the likelihood part is all-reduced over observation shards first
+  const double *qfix, *Pdiag;
+  double etheta;
 };
 
 // H_lik, both triangles, internal column order (dense columns first): one thread per entry.
@@ -454,25 +467,21 @@ __global__ void __launch_bounds__(256) osp_hwrite_kernel(const OspHArgs a) {
       }
     }
   }
+  if (r == c && a.qfix) v += r < a.nD ? a.qfix[r] : a.etheta * a.Pdiag[r - a.nD];
   a.H[(size_t)c * a.ldh + r] = v;
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
-template <int P>
-static void coef_launch(bgp_model* m, OspPlan* pl, const double* W) {
-  osp_coef_kernel<P><<<(pl->NG + 3) / 4, 128, 0, m->stream>>>(W, pl->nD, pl->NG, pl->g_t0, pl->g_c0, pl->g_nt, pl->c_t0, pl->c_t1, pl->C);
-}
 template <int P, int NDC>
-static void pass_launch(bgp_model* m, OspPlan* pl, const OspPassArgs& pa, const OspApplyArgs& aa) {
-  osp_pass_kernel<P, NDC><<<(pl->np + 3) / 4, 128, 0, m->stream>>>(pa);
+static void pass_launch(bgp_model* m, OspPlan* pl, const OspPassArgs& pa, const OspApplyArgs& aa, const PriorArgs& pr) {
+  osp_pass_kernel<P, NDC><<<std::min((pl->np + 3) / 4, pl->pass_grid), 128, 0, m->stream>>>(pa);
   osp_reduce_kernel<<<(pl->NG + 3) / 4 + (pl->NACC - pl->NM), 128, 0, m->stream>>>(pl->slots, pl->NACC, pl->NM, pl->NG, pl->gid_pbeg,
                                                                                    pl->np, pl->mom, pl->glob);
-  osp_apply_kernel<P, NDC><<<(pl->NC + 3) / 4 + 1, 128, 0, m->stream>>>(aa);
+  osp_apply_kernel<P, NDC><<<(pl->NC + 3) / 4 + 1, 128, 0, m->stream>>>(aa, pr);
 }
 template <int P, int NDC>
 static void hess_launch(bgp_model* m, OspPlan* pl, const OspHArgs& ha) {
-  osp_suffix_kernel<P><<<(pl->NC + 3) / 4, 128, 0, m->stream>>>(pl->NC, pl->NM, pl->c_t0, pl->c_t1, pl->c_gid, pl->c_gend, pl->g_t0,
-                                                              pl->mom, pl->G);
+  (void)pl;
   dim3 grid((ha.p + 255) / 256, ha.p);
   osp_hwrite_kernel<P, NDC><<<grid, 256, 0, m->stream>>>(ha);
 }
@@ -493,14 +502,12 @@ static void hess_launch(bgp_model* m, OspPlan* pl, const OspHArgs& ha) {
     }                                                                           \
   } while (0)
 
-int osp_launch_lik(bgp_model* m, const double* W_dev, double tau) {
+// theta != NULL (single-device models): the prior completion of finish.cu runs inside the last kernel as well
+int osp_launch_lik(bgp_model* m, const double* W_dev, double tau, const double* theta) {
   OspPlan* pl = (OspPlan*)m->osp_plan;
-  switch (pl->P) {
-    case 1: coef_launch<1>(m, pl, W_dev); break;
-    case 2: coef_launch<2>(m, pl, W_dev); break;
-    case 3: coef_launch<3>(m, pl, W_dev); break;
-    default: coef_launch<4>(m, pl, W_dev); break;
-  }
+  PriorArgs pr;
+  memset(&pr, 0, sizeof(pr));
+  if (theta) fill_prior_args(m, W_dev, theta, tau, &pr);
   OspPassArgs pa;
   pa.u = pl->u;
   pa.y = pl->y;
@@ -509,8 +516,12 @@ int osp_launch_lik(bgp_model* m, const double* W_dev, double tau) {
   pa.eta = pl->eta;
   pa.piece_beg = pl->piece_beg;
   pa.piece_gid = pl->piece_gid;
-  pa.C = pl->C;
   pa.g_own = pl->g_own;
+  pa.g_c0 = pl->g_c0;
+  pa.g_nt = pl->g_nt;
+  pa.g_t0 = pl->g_t0;
+  pa.c_t0 = pl->c_t0;
+  pa.c_t1 = pl->c_t1;
   pa.W = W_dev;
   pa.nD = pl->nD;
   pa.np = pl->np;
@@ -532,15 +543,22 @@ int osp_launch_lik(bgp_model* m, const double* W_dev, double tau) {
   aa.glob = pl->glob;
   aa.red = m->red_buf;
   aa.Hdb = pl->Hdb;
-  OSP_DISPATCH(pass_launch, m, pl, pa, aa);
-  count_launch(4);
+  aa.G = pl->G;
+  aa.done = pl->done;
+  aa.fuse_prior = theta ? 1 : 0;
+  OSP_DISPATCH(pass_launch, m, pl, pa, aa, pr);
+  count_launch(3);
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
 }
 
-int osp_launch_hessian(bgp_model* m) {
+// theta != NULL: Q(theta) is added in the same kernel (single-device models)
+int osp_launch_hessian(bgp_model* m, const double* theta) {
   OspPlan* pl = (OspPlan*)m->osp_plan;
   OspHArgs ha;
+  ha.qfix = theta ? m->qfix : nullptr;
+  ha.Pdiag = m->rnd[0].P_dev;
+  ha.etheta = theta ? std::exp(theta[0]) : 0.0;
   ha.p = m->p;
   ha.ldh = m->ldh;
   ha.nD = pl->nD;
@@ -556,7 +574,7 @@ int osp_launch_hessian(bgp_model* m) {
   ha.G = pl->G;
   ha.H = m->H;
   OSP_DISPATCH(hess_launch, m, pl, ha);
-  count_launch(2);
+  count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;
 }
@@ -566,7 +584,7 @@ void osp_plan_destroy(bgp_model* m) {
   if (!pl) return;
   for (void* ptr : {(void*)pl->u, (void*)pl->y, (void*)pl->size, (void*)pl->D, (void*)pl->eta, (void*)pl->piece_beg,
                     (void*)pl->piece_gid, (void*)pl->gid_pbeg, (void*)pl->g_t0, (void*)pl->g_own, (void*)pl->g_c0, (void*)pl->g_nt,
-                    (void*)pl->c_t0, (void*)pl->c_t1, (void*)pl->c_gid, (void*)pl->c_gend, (void*)pl->c_side, (void*)pl->C,
+                    (void*)pl->c_t0, (void*)pl->c_t1, (void*)pl->c_gid, (void*)pl->c_gend, (void*)pl->c_side, (void*)pl->done,
                     (void*)pl->slots, (void*)pl->mom, (void*)pl->glob, (void*)pl->Hdb, (void*)pl->G})
     if (ptr) cudaFree(ptr);
   delete pl;
@@ -696,22 +714,31 @@ int osp_plan_create(bgp_model* m) {
     std::vector<int> cnt((size_t)pl->NG);
     BGP_CUDA(cudaMemcpyAsync(cnt.data(), cnt_dev, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     BGP_CUDA(cudaStreamSynchronize(m->stream));
-    // pieces: runs of at most PL observations of one interval; ~16 warps per SM worth of them on a large model
+    // pieces: every interval is cut into equal runs of at most PL observations; PL is the smallest length for which
+    // the pieces fit two rounds of the pass kernel's resident warps (no ragged last wave)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-    int64_t PL = (n / ((int64_t)sms * 16) + 31) / 32 * 32;
-    PL = std::max<int64_t>(128, std::min<int64_t>(2048, PL));
+    pl->pass_grid = sms * (pl->NDC <= 4 ? 3 : 2);
+    const int64_t target = (int64_t)pl->pass_grid * 4 * 2;
+    auto count_pieces = [&](int64_t len) {
+      int64_t c = 0;
+      for (int g = 0; g < pl->NG; ++g) c += (cnt[(size_t)g] + len - 1) / len;
+      return c;
+    };
+    int64_t PL = std::max<int64_t>(64, n / target);
+    while (PL < n && count_pieces(PL) > target) PL += std::max<int64_t>(1, PL / 32);
     if (const char* e = getenv("BGP_OSP_PIECE")) PL = std::max(32, atoi(e));
     std::vector<int64_t> piece_beg;
     std::vector<int> piece_gid, gid_pbeg((size_t)pl->NG + 1);
     int64_t off = 0;
     for (int g = 0; g < pl->NG; ++g) {
       gid_pbeg[(size_t)g] = (int)piece_gid.size();
-      for (int64_t b = 0; b < cnt[(size_t)g]; b += PL) {
-        piece_beg.push_back(off + b);
+      const int64_t c = cnt[(size_t)g], k = (c + PL - 1) / PL;
+      for (int64_t b = 0; b < k; ++b) {
+        piece_beg.push_back(off + c * b / k);
         piece_gid.push_back(g);
       }
-      off += cnt[(size_t)g];
+      off += c;
     }
     gid_pbeg[(size_t)pl->NG] = (int)piece_gid.size();
     piece_beg.push_back(off);
@@ -738,7 +765,8 @@ int osp_plan_create(bgp_model* m) {
       BGP_CUDA(cudaMemset(*ptr, 0, std::max<size_t>(1, count) * sizeof(double)));
       return BGP_OK;
     };
-    BGP_TRY(zalloc(&pl->C, (size_t)pl->NG * OSP_MAXP));
+    BGP_CUDA(cudaMalloc(&pl->done, sizeof(int)));
+    BGP_CUDA(cudaMemset(pl->done, 0, sizeof(int)));
     BGP_TRY(zalloc(&pl->slots, (size_t)std::max(1, pl->np) * pl->NACC));
     BGP_TRY(zalloc(&pl->mom, (size_t)pl->NG * pl->NM));
     BGP_TRY(zalloc(&pl->glob, (size_t)(pl->NACC - pl->NM)));

@@ -782,8 +782,13 @@ __global__ void unpack_lower_kernel(const double* __restrict__ in, int p, int ld
 }
 
 int launch_hessian(bgp_model* m, const double* theta) {
-  if (m->osp_on) BGP_TRY(osp_launch_hessian(m));
-  else BGP_TRY(launch_syrk(m));
+  if (m->osp_on) {
+    // moment path: H_lik and, on a single device, Q(theta) in one kernel
+    BGP_TRY(osp_launch_hessian(m, m->world > 1 ? nullptr : theta));
+    if (m->world == 1) return BGP_OK;
+  } else {
+    BGP_TRY(launch_syrk(m));
+  }
   if (m->world > 1) {
     // observation shards: the likelihood Hessians of the ranks are summed over NVLink; only the packed lower
     // triangle (p (p + 1) / 2 doubles) travels, both triangles are rewritten from the sum so that every rank holds
