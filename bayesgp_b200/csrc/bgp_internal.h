@@ -220,8 +220,8 @@ struct bgp_model {
   int64_t n_lik = 0, n_hess = 0, n_chol = 0, n_lev = 0;
   double lev_flops = 0.0;          // executed flops of one leverage launch (structurally non-zero slices, grad.cu)
   // per-phase device timing: marks are (event, phase starting here); harvested after each sync
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<int> marks;
+  std::vector<cudaEvent_t> ev_pool, sealed_pool;
+  std::vector<int> marks, sealed_marks;
 };
 
 struct bgp_fit {
@@ -260,7 +260,8 @@ struct bgp_fit {
 namespace bgp {
 enum { PH_OTHER = 0, PH_LIK = 1, PH_HESS = 2, PH_CHOL = 3, PH_LEV = 4 };
 void phase_mark(bgp_model* m, int phase);
-void phase_harvest(bgp_model* m);   // call only right after a stream synchronize
+void phase_harvest(bgp_model* m);   // call only right after a stream synchronize: seals the marks of the finished segment
+void phase_collect(bgp_model* m);   // elapsed times of the sealed segment into the timers (any time later)
 }  // namespace bgp
 
 namespace bgp {

@@ -19,6 +19,9 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
+// Phase timing without holding up the device: marks are event records in stream order; after a synchronize the list
+// is only SEALED (phase_harvest); the elapsed times of a sealed list are read later, while the device is busy with the
+// next segment (phase_collect: read_scalars before its synchronize, the timing getters).
 void phase_mark(bgp_model* m, int phase) {
   if (m->marks.size() >= m->ev_pool.size()) {
     cudaEvent_t e;
@@ -29,11 +32,11 @@ void phase_mark(bgp_model* m, int phase) {
   m->marks.push_back(phase);
 }
 
-void phase_harvest(bgp_model* m) {
-  for (size_t i = 0; i + 1 < m->marks.size(); ++i) {
+void phase_collect(bgp_model* m) {
+  for (size_t i = 0; i + 1 < m->sealed_marks.size(); ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, m->ev_pool[i], m->ev_pool[i + 1]) != cudaSuccess) continue;
-    switch (m->marks[i]) {
+    if (cudaEventElapsedTime(&ms, m->sealed_pool[i], m->sealed_pool[i + 1]) != cudaSuccess) continue;
+    switch (m->sealed_marks[i]) {
       case PH_LIK: m->t_lik += ms; break;
       case PH_HESS: m->t_hess += ms; break;
       case PH_CHOL: m->t_chol += ms; break;
@@ -41,7 +44,13 @@ void phase_harvest(bgp_model* m) {
       default: break;
     }
   }
-  m->marks.clear();
+  m->sealed_marks.clear();
+}
+
+void phase_harvest(bgp_model* m) {
+  if (!m->sealed_marks.empty()) phase_collect(m);
+  m->sealed_marks.swap(m->marks);       // marks is empty now
+  m->sealed_pool.swap(m->ev_pool);      // the other set of events serves the next segment
 }
 
 }  // namespace bgp

@@ -424,14 +424,16 @@ static int grad_plan_get(bgp_model* m, GradPlan** out) {
   m->ldl = round_up(m->p, 16);
   const size_t zb = (size_t)(round_up64(m->n, 64) + 64) * sizeof(double);
   BGP_CUDA(cudaMalloc(&m->Linv, (size_t)m->p * m->ldl * sizeof(double)));
-  BGP_CUDA(cudaMemset(m->Linv, 0, (size_t)m->p * m->ldl * sizeof(double)));
+  BGP_CUDA(cudaMemsetAsync(m->Linv, 0, (size_t)m->p * m->ldl * sizeof(double), m->stream));   // in stream order: the stream does not wait for the legacy default stream
   BGP_CUDA(cudaMalloc(&gp->V, (size_t)round_up(m->p, 64) * m->ldl * sizeof(double)));
-  BGP_CUDA(cudaMemset(gp->V, 0, (size_t)round_up(m->p, 64) * m->ldl * sizeof(double)));
+  BGP_CUDA(cudaMemsetAsync(gp->V, 0, (size_t)round_up(m->p, 64) * m->ldl * sizeof(double), m->stream));
   BGP_CUDA(cudaMalloc(&gp->Hrev, (size_t)m->p * m->ldh * sizeof(double)));
+  BGP_CUDA(cudaMemsetAsync(gp->Hrev, 0, (size_t)m->p * m->ldh * sizeof(double), m->stream));
   BGP_CUDA(cudaMalloc(&gp->scratch, ((size_t)4 * m->lda + 32) * sizeof(double)));
+  BGP_CUDA(cudaMemsetAsync(gp->scratch, 0, ((size_t)4 * m->lda + 32) * sizeof(double), m->stream));
   BGP_CUDA(cudaMallocHost(&gp->grad_host, 32 * sizeof(double)));
   BGP_CUDA(cudaMalloc(&m->zobs, zb));
-  BGP_CUDA(cudaMemset(m->zobs, 0, zb));
+  BGP_CUDA(cudaMemsetAsync(m->zobs, 0, zb, m->stream));
   if (make_tensormap_f64(&gp->tmA, m->A, (uint64_t)m->lda, (uint64_t)m->n, (uint64_t)m->lda, 16, LV_TM) != 0 ||
       make_tensormap_f64(&gp->tmV, gp->V, (uint64_t)m->ldl, (uint64_t)m->p, (uint64_t)m->ldl, 16, LV_TN) != 0) {
     delete gp;
@@ -623,6 +625,11 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   phase_mark(m, PH_OTHER);
   BGP_CUDA(cudaStreamSynchronize(m->stream));
   phase_harvest(m);
+  static const int grad_debug = getenv("BGP_GRAD_DEBUG") ? atoi(getenv("BGP_GRAD_DEBUG")) : 0;     // env: diagnostics (2: NaN only)
+  if (grad_debug == 1 || (grad_debug == 2 && (m->sc_host->chol_info != 0 || !(gp->grad_host[0] == gp->grad_host[0]))))
+    fprintf(stderr, "[grad] chol_info %d logdet %.17g f %.17g sumsq %.17g nonfinite %d grad0 %.17g exact %d at_mode %d\n",
+            m->sc_host->chol_info, m->sc_host->logdet, m->sc_host->f, m->sc_host->sumsq, m->sc_host->nonfinite, gp->grad_host[0],
+            (int)m->factor_is_exact, (int)m->obs_at_mode);
   if (m->sc_host->chol_info != 0) {
     // H was positive definite in the natural order; a failure of the reversed factorisation is a rounding accident
     // on a numerically singular H: NaN gradient, as TMB answers when its factorisation fails

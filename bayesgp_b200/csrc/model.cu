@@ -518,6 +518,17 @@ int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on) {
   return BGP_OK;
 }
 
+int bgp_model_ospline_bytes(const bgp_model* m, double* bytes_per_pass) {
+  if (!m || !m->osp_plan) {
+    set_error("bgp_model_ospline_bytes: the model has no O-spline moment path");
+    return BGP_ERR_ARG;
+  }
+  // per observation: u, y, previous eta in, eta out, the dense columns (+ size for the Binomial family)
+  const double per_obs = 8.0 * (4 + m->nD + (m->family == BGP_FAMILY_BINOMIAL ? 1 : 0));
+  if (bytes_per_pass) *bytes_per_pass = per_obs * (double)m->n;
+  return BGP_OK;
+}
+
 int bgp_model_set_hessian_retry(bgp_model* m, int allow) {
   if (!m) return BGP_ERR_ARG;
   m->hessian_retry = allow != 0;
@@ -603,15 +614,15 @@ int bgp_model_finalize(bgp_model* m) {
   const size_t vb = (size_t)m->lda * sizeof(double);
   auto dalloc = [&](double** ptr, size_t bytes) -> int {
     BGP_CUDA(cudaMalloc(ptr, bytes));
-    BGP_CUDA(cudaMemset(*ptr, 0, bytes));
+    BGP_CUDA(cudaMemsetAsync(*ptr, 0, bytes, m->stream));     // in stream order (the stream is non-blocking)
     return BGP_OK;
   };
   m->qfix_host.assign(qfix.begin(), qfix.begin() + m->p);
   BGP_TRY(dalloc(&m->xbuf, std::max((size_t)m->lda, (size_t)m->p * m->p) * sizeof(double)));
   BGP_TRY(dalloc(&m->mu0, vb));
   BGP_TRY(dalloc(&m->qfix, vb));
-  BGP_CUDA(cudaMemcpy(m->mu0, mu0.data(), vb, cudaMemcpyHostToDevice));
-  BGP_CUDA(cudaMemcpy(m->qfix, qfix.data(), vb, cudaMemcpyHostToDevice));
+  BGP_CUDA(cudaMemcpyAsync(m->mu0, mu0.data(), vb, cudaMemcpyHostToDevice, m->stream));
+  BGP_CUDA(cudaMemcpyAsync(m->qfix, qfix.data(), vb, cudaMemcpyHostToDevice, m->stream));
   for (double** ptr : {&m->W, &m->Wtrial, &m->Wmode, &m->g, &m->step}) BGP_TRY(dalloc(ptr, vb));
   const size_t nob = (size_t)(round_up64(n, 64) + 64) * sizeof(double);
   BGP_TRY(dalloc(&m->eta, nob));
@@ -634,8 +645,9 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_TRY(dalloc(&m->part_s, (size_t)m->lik_blocks * 4 * sizeof(double)));
   BGP_TRY(dalloc(&m->red_buf, ((size_t)m->lda + 8) * sizeof(double)));
   BGP_CUDA(cudaMalloc(&m->sc_dev, 2 * sizeof(EvalScalars)));
-  BGP_CUDA(cudaMemset(m->sc_dev, 0, 2 * sizeof(EvalScalars)));
+  BGP_CUDA(cudaMemsetAsync(m->sc_dev, 0, 2 * sizeof(EvalScalars), m->stream));
   BGP_CUDA(cudaMallocHost(&m->sc_host, 2 * sizeof(EvalScalars)));
+  BGP_CUDA(cudaStreamSynchronize(m->stream));     // the zero fills and the two copies above
   if (const char* e = getenv("BGP_NO_SPECULATION")) m->speculate = !(e[0] == '1');   // diagnostics only
   for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
   BGP_TRY(build_row_order(m));
@@ -698,6 +710,7 @@ void bgp_model_destroy(bgp_model* m) {
   for (int i = 0; i < 8; ++i)
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->sealed_pool) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }

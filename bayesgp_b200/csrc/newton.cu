@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <time.h>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -60,6 +62,19 @@ static inline double tau_of(const bgp_model* m, const double* theta) {
   return m->family == BGP_FAMILY_GAUSSIAN ? std::exp(theta[m->S - 1]) : 1.0;
 }
 
+// BGP_HOST_TRACE=1: where the host spends an evaluation (enqueue / waiting for the device / bookkeeping), printed per batch
+struct HostTrace {
+  bool on = getenv("BGP_HOST_TRACE") != nullptr;
+  double t_sync = 0, t_inner = 0, t_batch = 0;
+  int n_sync = 0, n_inner = 0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+  }
+};
+static HostTrace g_trace;
+
 static int read_scalars(bgp_model* m, EvalScalars* out) {
   BGP_CUDA(cudaMemcpyAsync(m->sc_host, m->sc_dev, sizeof(EvalScalars), cudaMemcpyDeviceToHost, m->stream));
   phase_mark(m, PH_OTHER);
@@ -67,7 +82,13 @@ static int read_scalars(bgp_model* m, EvalScalars* out) {
     m->host_hook();
     m->host_hook = nullptr;
   }
+  phase_collect(m);                         // likewise the phase timers of the previous segment
+  const double t0 = g_trace.on ? HostTrace::now() : 0.0;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
+  if (g_trace.on) {
+    g_trace.t_sync += HostTrace::now() - t0;
+    g_trace.n_sync++;
+  }
   phase_harvest(m);
   *out = *m->sc_host;
   return BGP_OK;
@@ -81,8 +102,16 @@ static int read_scalars2(bgp_model* m, EvalScalars* start, EvalScalars* out) {
     m->host_hook();
     m->host_hook = nullptr;
   }
+  phase_collect(m);                         // likewise the phase timers of the previous segment
+  const double t0 = g_trace.on ? HostTrace::now() : 0.0;
   BGP_CUDA(cudaStreamSynchronize(m->stream));
+  const double t1 = g_trace.on ? HostTrace::now() : 0.0;
   phase_harvest(m);
+  if (g_trace.on) {
+    g_trace.t_sync += t1 - t0;
+    g_trace.n_sync++;
+    g_trace.t_batch += HostTrace::now() - t1;      // harvest share (reported separately below)
+  }
   *out = m->sc_host[0];
   *start = m->sc_host[1];
   return BGP_OK;
@@ -536,7 +565,12 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
     const int j = order[oi];
     int iters = 0;
     double v = NAN;
+    const double tt0 = g_trace.on ? HostTrace::now() : 0.0;
     int st = laplace_inner(m, theta + (size_t)j * m->S, &v, &iters);
+    if (g_trace.on) {
+      g_trace.t_inner += HostTrace::now() - tt0;
+      g_trace.n_inner++;
+    }
     total += iters;
     values[j] = st == BGP_OK ? v : NAN;
     if (st == BGP_ERR_CUDA || st == BGP_ERR_NCCL) return st;
@@ -635,6 +669,11 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
     m->host_hook = nullptr;
   }
   if (m->out_stream) BGP_CUDA(cudaStreamSynchronize(m->out_stream));
+  if (g_trace.on && g_trace.n_inner > 0) {
+    fprintf(stderr, "[host] per evaluation: laplace_inner %.1f us of which waiting for the device %.1f us (%d syncs), event harvest %.1f us\n",
+            g_trace.t_inner / g_trace.n_inner, g_trace.t_sync / g_trace.n_inner, g_trace.n_sync, g_trace.t_batch / g_trace.n_inner);
+    g_trace = HostTrace();
+  }
   if (iters_total) *iters_total = total;
   return worst;
 }
@@ -785,6 +824,7 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
                           int64_t* lik_launches, int64_t* hess_launches, int64_t* chol_launches) {
   if (!m) return BGP_ERR_ARG;
   if (total_ms) *total_ms = m->t_total;
+  phase_collect(const_cast<bgp_model*>(m));     // timers are a cache of the recorded events
   if (lik_ms) *lik_ms = m->t_lik;
   if (hess_ms) *hess_ms = m->t_hess;
   if (chol_ms) *chol_ms = m->t_chol;
@@ -797,6 +837,7 @@ int bgp_model_last_timing(const bgp_model* m, double* total_ms, double* lik_ms, 
 int bgp_model_gradient_timing(const bgp_model* m, double* leverage_ms, int64_t* leverage_launches, double* leverage_flops,
                               double* dense_flops) {
   if (!m) return BGP_ERR_ARG;
+  phase_collect(const_cast<bgp_model*>(m));
   if (leverage_ms) *leverage_ms = m->t_lev;
   if (leverage_launches) *leverage_launches = m->n_lev;
   if (leverage_flops) *leverage_flops = m->lev_flops;

@@ -762,11 +762,11 @@ int osp_plan_create(bgp_model* m) {
     BGP_TRY(upload(&pl->c_side, c_side));
     auto zalloc = [&](double** ptr, size_t count) -> int {
       BGP_CUDA(cudaMalloc(ptr, std::max<size_t>(1, count) * sizeof(double)));
-      BGP_CUDA(cudaMemset(*ptr, 0, std::max<size_t>(1, count) * sizeof(double)));
+      BGP_CUDA(cudaMemsetAsync(*ptr, 0, std::max<size_t>(1, count) * sizeof(double), m->stream));
       return BGP_OK;
     };
     BGP_CUDA(cudaMalloc(&pl->done, sizeof(int)));
-    BGP_CUDA(cudaMemset(pl->done, 0, sizeof(int)));
+    BGP_CUDA(cudaMemsetAsync(pl->done, 0, sizeof(int), m->stream));
     BGP_TRY(zalloc(&pl->slots, (size_t)std::max(1, pl->np) * pl->NACC));
     BGP_TRY(zalloc(&pl->mom, (size_t)pl->NG * pl->NM));
     BGP_TRY(zalloc(&pl->glob, (size_t)(pl->NACC - pl->NM)));

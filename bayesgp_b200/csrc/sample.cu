@@ -122,8 +122,8 @@ static int sample_core(bgp_fit* f, int64_t M, const double* Z_host, uint64_t see
     BGP_CUDA(cudaMalloc(&f->Linv_dev, (size_t)p * ldl * sizeof(double)));
     BGP_CUDA(cudaMalloc(&f->LinvT_dev, (size_t)p * ldl * sizeof(double)));
     BGP_CUDA(cudaMalloc(&f->mode_dev, (size_t)ldl * sizeof(double)));
-    BGP_CUDA(cudaMemset(f->Linv_dev, 0, (size_t)p * ldl * sizeof(double)));
-    BGP_CUDA(cudaMemset(f->LinvT_dev, 0, (size_t)p * ldl * sizeof(double)));
+    BGP_CUDA(cudaMemsetAsync(f->Linv_dev, 0, (size_t)p * ldl * sizeof(double), m->stream));
+    BGP_CUDA(cudaMemsetAsync(f->LinvT_dev, 0, (size_t)p * ldl * sizeof(double), m->stream));
   }
   double *Zg = nullptr, *Zraw = nullptr, *flag_dev = nullptr;
   int32_t* perm_dev = nullptr;

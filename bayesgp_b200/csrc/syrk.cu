@@ -624,7 +624,7 @@ int syrk_plan_create(bgp_model* m) {
   BGP_TRY(upload(&pl->tile_slots_dev, tile_slots));
   m->part_H_bytes = (size_t)std::max(1, pl->nslots) * SK_TILE_ELEMS * sizeof(double);
   BGP_CUDA(cudaMalloc(&m->part_H, m->part_H_bytes));
-  BGP_CUDA(cudaMemset(m->part_H, 0, m->part_H_bytes));
+  BGP_CUDA(cudaMemsetAsync(m->part_H, 0, m->part_H_bytes, m->stream));
   BGP_CUDA(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
   m->hess_useful_flops = pl->useful_flops;
   if (getenv("BGP_SK_DEBUG")) {

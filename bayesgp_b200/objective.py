@@ -157,6 +157,12 @@ class LaplaceObjective:
         """Select the O-spline moment path (eligible models: one IWP term) or the dense DMMA path (on=False)."""
         check(self._lib.bgp_model_set_ospline(self._h, int(on)))
 
+    def ospline_bytes(self):
+        """Algorithmic bytes one likelihood pass of the moment path moves."""
+        b = C.c_double()
+        check(self._lib.bgp_model_ospline_bytes(self._h, C.byref(b)))
+        return b.value
+
     def ospline(self):
         """(eligible, on) of the O-spline moment path."""
         e, o = C.c_int(), C.c_int()

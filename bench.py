@@ -173,6 +173,21 @@ def node_grid(ff):
     return mode, sd, thetas, ff.env.last_par.copy(), T
 
 
+class L2Flush:
+    """Writes a buffer larger than the 126 MB L2 between steps (the moment path's per-step inputs, ~56 MB, would
+    otherwise stay L2-resident from one step to the next).  Outside every timed device interval: the library times a
+    step with its own event pair around the step's kernels."""
+
+    def __init__(self, device, mb=256):
+        import torch
+        self.torch = torch
+        self.buf = torch.empty(mb << 20, dtype=torch.uint8, device="cuda:%d" % device)
+
+    def __call__(self):
+        self.buf.add_(1)
+        self.torch.cuda.synchronize(self.buf.device)
+
+
 def timed_steps(step, steps, dist, sampler=None):
     """EXACTLY `steps` steps between barrier + synchronize on both sides; device ms and wall s are summed per rank
     and the maximum over ranks is returned."""
@@ -231,9 +246,12 @@ def run_b200(args):
     # from what the optimisation phase leaves behind at the grid centre and nothing else: theta_mode, the mode
     # there and its tangent d w_hat / d theta (set_start_at clears the warm-start history, then records that one
     # entry) — the state bgp_aghq_fit's own grid phase starts from on every rank.
+    flush = L2Flush(local)
+
     def step_grid(want_host=True, keep=False):
-        ff.set_start_at(np.array([mode]), w_mode, t_mode)             # H2D: 2 p + 1 doubles
+        flush()
         t0 = time.perf_counter()
+        ff.set_start_at(np.array([mode]), w_mode, t_mode)             # H2D: 2 p + 1 doubles (inside the e2e clock)
         mod = bg.marginal_laplace_tmb(ff, K_NODES, None, optresults=opt)
         ms = ff.last_timing()["total_ms"]
         iters = mod.diagnostics["grid_newton_iters"]
@@ -252,6 +270,7 @@ def run_b200(args):
 
     # the batch entry point on one rank's replica (the round-1 headline; also the single-GPU reference values)
     def step_batch():
+        flush()
         ff.set_start(w_mode)
         t0 = time.perf_counter()
         vals, modes, Hs, iters = ff.fn_batch(thetas, want_modes=True, want_hess=True)
@@ -260,6 +279,16 @@ def run_b200(args):
                 "res": {"logpost": -vals, "modes": modes, "Hs": Hs}}
 
     W = max(3, args.warmup)
+
+    def phase_figures(tm0, tm1):
+        n_h = tm1["hess_launches"] - tm0["hess_launches"]
+        n_l = tm1["lik_launches"] - tm0["lik_launches"]
+        n_c = tm1["chol_launches"] - tm0["chol_launches"]
+        return {"n_hess": n_h, "n_lik": n_l, "n_chol": n_c,
+                "hess_ms": (tm1["hess_ms"] - tm0["hess_ms"]) / max(1, n_h),
+                "lik_ms": (tm1["lik_ms"] - tm0["lik_ms"]) / max(1, n_l),
+                "chol_ms": (tm1["chol_ms"] - tm0["chol_ms"]) / max(1, n_c)}
+
     for _ in range(W):
         out_b = step_batch()
     single = out_b["res"]                   # single-GPU values of the same grid (every rank: identical replicas)
@@ -281,6 +310,23 @@ def run_b200(args):
     _, wall_s, _, _ = timed_steps(lambda: step_grid(True), args.steps, dist)
     grid_res = step_grid(True, keep=True)["res"]        # untimed: owned copies for the comparison below
     evals = K_NODES * args.steps
+    moment_path = ff.ospline()[1]
+    dense = None
+    if world == 1 and moment_path and not args.no_dense:
+        # the same step on the dense path (TMA likelihood pass + DMMA Hessian kernel): what every model with more than
+        # one smoothing term runs, and what the roofline figures of those two kernels are measured on
+        ff.set_ospline(False)
+        for _ in range(W):
+            step_grid()
+        tmd0 = ff.last_timing()
+        d_ms, _, _, _ = timed_steps(lambda: step_grid(False), args.steps, dist)
+        tmd1 = ff.last_timing()
+        _, d_wall, _, _ = timed_steps(lambda: step_grid(True), args.steps, dist)
+        dense_res = step_grid(True, keep=True)["res"]
+        dense = {"ms": d_ms, "wall": d_wall, "pf": phase_figures(tmd0, tmd1), "res": dense_res}
+        ff.set_ospline(True)
+        for _ in range(2):
+            step_grid()
     value = evals / (dev_ms * 1e-3)
     e2e = evals / wall_s
     rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, np.max(np.abs(b))))
@@ -304,6 +350,7 @@ def run_b200(args):
                          shard=(rank, world, broadcast_unique_id(nccl_unique_id, rank)))
 
         def step_obs():
+            flush()
             ffs.set_start(w_mode)
             t0 = time.perf_counter()
             vals, modes, Hs, iters = ffs.fn_batch(thetas, want_modes=True, want_hess=True)
@@ -336,11 +383,8 @@ def run_b200(args):
         if dist:
             dist.destroy_process_group()
         return
-    n_hess = tm1["hess_launches"] - tm0["hess_launches"]
-    n_lik = tm1["lik_launches"] - tm0["lik_launches"]
-    hess_ms = (tm1["hess_ms"] - tm0["hess_ms"]) / max(1, n_hess)
-    lik_ms = (tm1["lik_ms"] - tm0["lik_ms"]) / max(1, n_lik)
-    chol_ms = (tm1["chol_ms"] - tm0["chol_ms"]) / max(1, tm1["chol_launches"] - tm0["chol_launches"])
+    pf = phase_figures(tm0, tm1)
+    n_hess, hess_ms, lik_ms, chol_ms = pf["n_hess"], pf["hess_ms"], pf["lik_ms"], pf["chol_ms"]
     my_evals = max(1, cnt1["laplace_evals"] - cnt0["laplace_evals"])
     peaks, peak_src = measured_peaks()
     try:
@@ -349,13 +393,53 @@ def run_b200(args):
         fp64_peak = None
         peak_src += "; fp64 DGEMM peak unavailable (%s)" % type(e).__name__
     hf, lb = ff.hessian_flops(), ff.lik_bytes()
-    # Roofline numerators count the work on structurally non-zero {64-observation x 16-column} cells only
-    # (what the kernels execute after the zero-pattern sort); the dense-equivalent
-    # figures n p (p+1) / 8 n (lda+3) are given beside them.
-    flops = hf["structural"]
-    achieved = flops / (hess_ms * 1e-3) / 1e12
-    lik_bytes = lb["structural"]
-    lik_gbs = lik_bytes / (lik_ms * 1e-3) / 1e9
+
+    def dense_rooflines(pfd):
+        """Roofline objects of the dense path's two big kernels.  Numerators count the work on structurally non-zero
+        {64-observation x 16-column} cells only (what the kernels execute after the zero-pattern sort, DESIGN.md
+        section 5); the dense-equivalent figures n p (p+1) / 8 n (lda+3) are given beside them."""
+        flops, lik_bytes = hf["structural"], lb["structural"]
+        ach = flops / (pfd["hess_ms"] * 1e-3) / 1e12
+        gbs = lik_bytes / (pfd["lik_ms"] * 1e-3) / 1e9
+        r_h = {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": ach,
+               "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
+               "traffic": SYRK_DRAM_TRAFFIC_BYTES if n == 1_000_000 else None, "traffic_unit": "bytes",
+               "ms_per_launch": pfd["hess_ms"], "algorithmic_flops_per_launch": flops,
+               "dense_flops_per_launch": hf["dense"], "structural_fraction": hf["structural"] / hf["dense"],
+               "dense_equivalent_tflops": hf["dense"] / (pfd["hess_ms"] * 1e-3) / 1e12,
+               "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 "
+                              "figure); DMMA.8x8x4 issue-rate peak 37.0 TFLOP/s (scripts/ubench/dmma_bench.cu)"}
+        r_l = {"bound": "hbm", "kernel": "lik_kernel (eta, ll, r, w, A^T r)", "achieved": gbs,
+               "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0),
+               "ms_per_launch": pfd["lik_ms"], "algorithmic_bytes_per_launch": lik_bytes,
+               "dense_bytes_per_launch": lb["dense"],
+               "note": "ms_per_launch includes the partial-reduction and prior kernels that follow the pass",
+               "peak_source": peak_src}
+        return r_h, r_l
+
+    if moment_path:
+        # default path of this model: per evaluation two moment passes, one Hessian assembly, one Cholesky + solve —
+        # the Cholesky is the dominant kernel now
+        chol_flops = p ** 3 / 3.0 + 2.0 * p * p * (1 + ff.S)
+        ach = chol_flops / (chol_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "chol_kernel<32> (p x p Cholesky, log-det, Newton solve and tangent; one 8-CTA cluster)",
+                    "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
+                    "traffic": None, "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": chol_flops,
+                    "share_of_step": chol_ms * (pf["n_chol"] / args.steps) / (dev_ms / args.steps),
+                    "note": "latency-bound, not throughput-bound: p = %d dependent pivot steps on 8 of 148 SMs (DESIGN.md "
+                            "section 5); the two big dense-path kernels are under dense_path" % p,
+                    "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run"}
+        ob = ff.ospline_bytes()
+        gbs = ob / (lik_ms * 1e-3) / 1e9
+        roofline_lik = {"bound": "hbm", "kernel": "osp_pass_kernel + osp_reduce_kernel + osp_apply_kernel (eta, ll, r, w, "
+                                                  "knot-interval moments, A^T r, prior completion)",
+                        "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": gbs / peaks.get("hbm_gbs", 6650.0), "ms_per_launch": lik_ms,
+                        "algorithmic_bytes_per_launch": ob,
+                        "note": "ms_per_launch is the whole pass (three kernels); its inputs (%.0f MB) are L2-resident "
+                                "after the first pass of a step" % (ob / 1e6), "peak_source": peak_src}
+    else:
+        roofline, roofline_lik = dense_rooflines(pf)
     line = {
         "metric": "AGHQ-node Laplace evals/sec at n=1M,p=300",
         "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -369,7 +453,9 @@ def run_b200(args):
                    "logdet_from_last_newton_factor": "%d of %d evaluations on rank 0 (certified |d logdet| <= p max|d eta| <= "
                                                      "2e-10 |L|; bgp_model_set_factor_reuse, DESIGN.md section 5)"
                                                      % (cnt1["factor_reuses"] - cnt0["factor_reuses"], my_evals),
-                   "theta_mode": mode, "theta_sd": sd, "l2_flush": "inputs (2.4 GB design matrix) exceed the 126 MB L2",
+                   "theta_mode": mode, "theta_sd": sd, "l2_flush": "256 MB written between steps (outside the device-timed interval): the moment path's per-step "
+                                                         "inputs (56 MB) would fit the 126 MB L2; the dense path's 2.4 GB design does not",
+                   "path": "O-spline moment path (ospline.cu)" if moment_path else "dense path (lik.cu + syrk.cu)",
                    "parallelism": "node shards x%d (replicated rows), NCCL all-reduce of the 15 values" % world
                                   if world > 1 else "single GPU",
                    "model_build_s": t_build},
@@ -384,25 +470,25 @@ def run_b200(args):
         "batch_entry_point": {"value": K_NODES / (out_b["dev_ms"] * 1e-3), "e2e": K_NODES / out_b["wall_s"],
                               "unit": "evals/s", "what": "bgp_laplace_eval_batch on one replica, modes + Hessians to "
                                                          "the host (round-1 headline), last warm-up step"},
-        "roofline": {"bound": "tensor", "kernel": "syrk_kernel (H = A^T diag(w) A, FP64 DMMA)", "achieved": achieved,
-                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if fp64_peak else None,
-                     "traffic": SYRK_DRAM_TRAFFIC_BYTES if n == 1_000_000 else None, "traffic_unit": "bytes",
-                     "ms_per_launch": hess_ms, "algorithmic_flops_per_launch": flops,
-                     "dense_flops_per_launch": hf["dense"], "structural_fraction": hf["structural"] / hf["dense"],
-                     "dense_equivalent_tflops": hf["dense"] / (hess_ms * 1e-3) / 1e12,
-                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 "
-                                    "figure); DMMA.8x8x4 issue-rate peak 37.0 TFLOP/s (scripts/ubench/dmma_bench.cu)"},
-        "roofline_lik": {"bound": "hbm", "kernel": "lik_kernel (eta, ll, r, w, A^T r)", "achieved": lik_gbs,
-                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                         "frac": lik_gbs / peaks.get("hbm_gbs", 6650.0), "ms_per_launch": lik_ms,
-                         "algorithmic_bytes_per_launch": lik_bytes, "dense_bytes_per_launch": lb["dense"],
-                         "note": "ms_per_launch includes the partial-reduction and prior kernels that follow the pass",
-                         "peak_source": peak_src},
+        "roofline": roofline,
+        "roofline_lik": roofline_lik,
+        "hessian_ms_per_launch": hess_ms,
         "chol_ms_per_launch": chol_ms,
         "clocks": clocks,
         "wall_s_timed_region": region_s,
     }
     line.update(extra)
+    if dense is not None:
+        r_h, r_l = dense_rooflines(dense["pf"])
+        line["dense_path"] = {
+            "what": "the same step with bgp_model_set_ospline(m, 0): TMA-streamed likelihood pass over the dense design + "
+                    "FP64 DMMA Hessian kernel (the path of every model with more than one smoothing term; round-1/2 headline)",
+            "value": evals / (dense["ms"] * 1e-3), "e2e": evals / dense["wall"], "unit": "evals/s",
+            "ms_per_step": dense["ms"] / args.steps, "roofline": r_h, "roofline_lik": r_l,
+            "chol_ms_per_launch": dense["pf"]["chol_ms"],
+            "moment_vs_dense": {"max_rel_logpost": rel(grid_res["logpost"], dense["res"]["logpost"]),
+                                "max_rel_mode": rel(grid_res["modes"], dense["res"]["modes"]),
+                                "max_rel_hessian": rel(grid_res["Hs"], dense["res"]["Hs"])}}
     if world == 1 and not args.no_fit:
         line["fit"] = fit_leg(ff)
     if world == 1 and not args.no_grad:
@@ -633,6 +719,7 @@ def main():
     ap.add_argument("--no-predict", action="store_true", help="skip the predict GFLOP/s leg")
     ap.add_argument("--no-fit", action="store_true", help="skip the model_fit() leg")
     ap.add_argument("--no-grad", action="store_true", help="skip the ff$gr leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-path (DMMA) leg of the same step")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-nodes", type=int, default=1)
     args = ap.parse_args()

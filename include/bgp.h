@@ -159,6 +159,8 @@ int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
  * rounding; on by default for eligible models.  on = 0 selects the dense (DMMA) path, e.g. for A/B measurements. */
 int bgp_model_set_ospline(bgp_model* m, int on);
 int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on);
+/* algorithmic bytes one likelihood pass of the moment path moves (u, y, eta in / out, dense columns, size): roofline numerator */
+int bgp_model_ospline_bytes(const bgp_model* m, double* bytes_per_pass);
 /* When numDeriv's Richardson Hessian of ff$gr (d = 1e-4) is not positive definite aghq stops in chol(); so does
  * bgp_aghq_fit (BGP_ERR_NOT_PD).  allow = 1 opts into a retry with d = 1e-3 and 1e-2 (not in the reference); the
  * number of retries a fit needed is reported by bgp_fit_get_diagnostics. */
