@@ -178,6 +178,7 @@ struct bgp_model {
   std::vector<IwpTerm> iwp_terms;
   void* osp_plan = nullptr;     // opaque (ospline.cu)
   bool osp_on = false;          // the likelihood pass / Hessian go through the moment path
+  bool osp_dense_grad = false;  // ... but the Laplace gradient takes its leverages from the dense design (A/B switch)
   void* syrk_plan = nullptr;    // opaque (syrk.cu)
   void* lik_plan = nullptr;     // opaque (lik.cu)
   // {64-observation chunk} x {16-column box} occupancy (rowsort.cu): bit b of occ[c] set iff chunk c has a
@@ -279,6 +280,8 @@ int osp_plan_create(bgp_model* m);
 void osp_plan_destroy(bgp_model* m);
 int osp_launch_lik(bgp_model* m, const double* W_dev, double tau, const double* theta = nullptr);
 int osp_launch_hessian(bgp_model* m, const double* theta);
+// A^T (c3 q) for the Laplace gradient from the moments: V is the upper factor of H^-1 (grad.cu); result in red_buf[0 .. lda)
+int osp_launch_leverage(bgp_model* m, const double* V, int ldl);
 // finish.cu: reduce partials (+ allreduce when sharded), add prior terms -> f / g / gmax in sc_dev
 int launch_finish(bgp_model* m, const double* W_dev, const double* theta, double tau);
 double theta_constant(const bgp_model* m, const double* theta);

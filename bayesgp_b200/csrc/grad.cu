@@ -505,12 +505,14 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
     set_error("laplace gradient: p = %d exceeds the leverage kernel's work list (1024)", p);
     return BGP_ERR_ARG;
   }
-  // The leverages and A^T (c3 q) need the design rows: a model on the O-spline moment path (ospline.cu) takes the
-  // dense passes here (its Hessian, if one is needed, still comes from the moments of the mode's own pass).
+  // A model on the O-spline moment path (ospline.cu) stays on it: pass and Hessian at the mode from the moments, the
+  // leverages from per-interval quadratic forms (osp_launch_leverage).  bgp_model_set_ospline(m, 2) keeps the dense
+  // passes for the gradient (A/B): the design rows are resident either way.
+  const bool osp_lev = m->osp_on && !m->osp_dense_grad;
   struct DenseScope {
     bgp_model* m;
     bool was;
-    explicit DenseScope(bgp_model* mm) : m(mm), was(mm->osp_on) {
+    DenseScope(bgp_model* mm, bool act) : m(mm), was(act) {
       if (was) {
         m->osp_on = false;
         m->obs_at_mode = false;
@@ -522,7 +524,7 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
         m->obs_at_mode = false;      // the dense arrays, not the moments, hold the mode's quantities
       }
     }
-  } dense_scope(m);
+  } dense_scope(m, m->osp_on && m->osp_dense_grad);
   if (dense_scope.was && !m->factor_is_exact) {
     // Hessian at the mode from the moment path (one pass over 40-60 bytes per observation) before switching over
     m->osp_on = true;
@@ -568,7 +570,15 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
   }
   phase_mark(m, PH_OTHER);
   const double* v_dev = nullptr;
-  if (has_c3) {
+  if (has_c3 && osp_lev) {
+    phase_mark(m, PH_LEV);
+    BGP_TRY(osp_launch_leverage(m, gp->V, ldl));
+    m->n_lev++;
+    if (m->world > 1) BGP_TRY(comm_allreduce_sum(m, m->red_buf, (size_t)m->lda));
+    v_dev = m->red_buf;
+    m->obs_at_mode = false;          // the interval moments now belong to the leverage pass
+    phase_mark(m, PH_OTHER);
+  } else if (has_c3) {
     phase_mark(m, PH_LEV);
     leverage_kernel<<<(unsigned)((m->n + LV_TM - 1) / LV_TM), LV_THREADS, LV_SMEM, m->stream>>>(
         gp->tmA, gp->tmV, m->c3, (const unsigned long long*)m->occ_dev, m->nchunks, m->zobs, m->n, p, ldl);

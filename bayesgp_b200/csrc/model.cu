@@ -507,6 +507,7 @@ int bgp_model_set_ospline(bgp_model* m, int on) {
     return BGP_ERR_ARG;
   }
   m->osp_on = on != 0;
+  m->osp_dense_grad = on == 2;
   m->obs_at_mode = false;
   return BGP_OK;
 }

@@ -52,6 +52,10 @@ struct OspPlan {
   int *c_gid = nullptr, *c_gend = nullptr, *c_side = nullptr;
   // per evaluation
   int* done = nullptr;
+  // leverage path (allocated on the first gradient): V G_J per interval and its Gram matrix
+  int nside = 0, ldk = 0;
+  int *side_gbase = nullptr, *side_cbase = nullptr, *side_K = nullptr;
+  double *Yt = nullptr, *Omega = nullptr;
   double *slots = nullptr, *mom = nullptr, *glob = nullptr, *Hdb = nullptr, *G = nullptr;
 };
 
@@ -471,6 +475,173 @@ __global__ void __launch_bounds__(256) osp_hwrite_kernel(const OspHArgs a) {
   a.H[(size_t)c * a.ldh + r] = v;
 }
 
+
+// ---- leverages for the Laplace gradient -----------------------------------------------------------------------------
+// q_j = a_j^T H^-1 a_j = || V a_j ||^2 with the upper factor V of grad.cu.  A design row is a_j = G_J v_j with
+// v_j = [1, u, .., u^(P-1) | u^P | D_j] and G_J depending on the knot interval only, so q_j = v_j^T Omega_J v_j with
+// Omega_J = (V G_J)^T (V G_J), a (P + 1 + nD)-square matrix per interval:
+//   1. osp_levY: Y_J = V [tails of the columns left of J, expanded about t_J] by the recurrence
+//      Y_J = shift(Y_{J-1}, d_{J-1}) + V[:, J-1] b_{J-1}  (one thread per row of V and side, K sequential steps);
+//   2. osp_levOmega: Gram matrix of [Y_J | V[:, own] / P! | V[:, dense]] per interval;
+//   3. osp_levpass: per observation q_j, z_j = c3_j q_j (c3 = d w / d eta from the eta of the mode's own pass) and the
+//      moments sum z u^m, sum z D_c — A^T z then comes out of the same reduce / apply kernels as g_lik.
+template <int P>
+__global__ void __launch_bounds__(128) osp_levY_kernel(const double* __restrict__ V, int p, int ldl, int nD, int ldk, int nside,
+                                                       const int* __restrict__ side_gbase, const int* __restrict__ side_cbase,
+                                                       const int* __restrict__ side_K, const double* __restrict__ c_t0,
+                                                       const double* __restrict__ c_t1, double* __restrict__ Yt) {
+  const int k = blockIdx.x * 128 + threadIdx.x, sd = blockIdx.y;
+  if (k >= p || sd >= nside) return;
+  const int gbase = side_gbase[sd], cbase = side_cbase[sd], K = side_K[sd];
+  double y[P];
+#pragma unroll
+  for (int m = 0; m < P; ++m) {
+    y[m] = 0.0;
+    Yt[((size_t)gbase * P + m) * ldk + k] = 0.0;
+  }
+  const double* Vk = V + (size_t)k * ldl + nD + cbase;
+  for (int J = 1; J <= K; ++J) {
+    const int col = cbase + J - 1;
+    const double d = c_t1[col] - c_t0[col];
+    double dp[P + 1];
+    dp[0] = 1.0;
+#pragma unroll
+    for (int l = 1; l <= P; ++l) dp[l] = dp[l - 1] * d;
+    const double vk = Vk[J - 1];
+    // shift the polynomial to the next knot: y'[m] = sum_{r >= m} binom(r, m) d^(r - m) y[r]; then the column that
+    // was the interval's own one enters as a tail: + V[k][col] d^(P-m) / ((P-m)! m!)
+    double yn[P];
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      double acc = 0.0, binom = 1.0;
+#pragma unroll
+      for (int r = m; r < P; ++r) {
+        acc = fma(binom * dp[r - m], y[r], acc);
+        binom = binom * (double)(r + 1) / (double)(r + 1 - m);
+      }
+      yn[m] = fma(vk, dp[P - m] * (osp_ifact(P - m) * osp_ifact(m)), acc);
+    }
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      y[m] = yn[m];
+      Yt[((size_t)(gbase + J) * P + m) * ldk + k] = yn[m];
+    }
+  }
+}
+
+template <int P, int NDC>
+__global__ void __launch_bounds__(128) osp_levOmega_kernel(const double* __restrict__ V, int p, int ldl, int nD, int ldk,
+                                                           const int* __restrict__ g_own, const double* __restrict__ Yt,
+                                                           double* __restrict__ Omega) {
+  constexpr int NV = P + 1 + NDC, NT = NV * (NV + 1) / 2;
+  __shared__ double sm[4][NT];
+  const int gid = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int own = g_own[gid];
+  double acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+  for (int k = threadIdx.x; k < p; k += 128) {
+    double v[NV];
+#pragma unroll
+    for (int m = 0; m < P; ++m) v[m] = Yt[((size_t)gid * P + m) * ldk + k];
+    v[P] = own >= 0 ? V[(size_t)k * ldl + nD + own] * osp_ifact(P) : 0.0;
+#pragma unroll
+    for (int c = 0; c < NDC; ++c) v[P + 1 + c] = c < nD ? V[(size_t)k * ldl + c] : 0.0;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b, ++t) acc[t] = fma(v[a], v[b], acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const double s = osp_warp_sum(acc[t]);
+    if (lane == 0) sm[warp][t] = s;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NT; t += 128) {
+    const double s = (sm[0][t] + sm[1][t]) + (sm[2][t] + sm[3][t]);
+    // t -> (a, b), b <= a; both triangles
+    int a = 0;
+    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+    const int b = t - a * (a + 1) / 2;
+    Omega[(size_t)gid * NV * NV + a * NV + b] = s;
+    Omega[(size_t)gid * NV * NV + b * NV + a] = s;
+  }
+}
+
+struct OspLevArgs {
+  const double *u, *size, *D, *eta;
+  const int64_t* piece_beg;
+  const int* piece_gid;
+  const double* Omega;
+  int nD, np, family;
+  int64_t n;
+  double* slots;
+};
+
+template <int P, int NDC>
+__global__ void __launch_bounds__(128) osp_levpass_kernel(const OspLevArgs a) {
+  constexpr int NV = P + 1 + NDC, OGD = osp_offgD(P, NDC), NACC = osp_NACC(P, NDC);
+  __shared__ double sOm[4][NV * NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pc = blockIdx.x * 4 + warp; pc < a.np; pc += gridDim.x * 4) {
+    const int gid = a.piece_gid[pc];
+    const int64_t j0 = a.piece_beg[pc], j1 = a.piece_beg[pc + 1];
+    __syncwarp();
+    for (int t = lane; t < NV * NV; t += 32) sOm[warp][t] = a.Omega[(size_t)gid * NV * NV + t];
+    __syncwarp();
+    double zr[P + 1], zd[NDC];
+#pragma unroll
+    for (int m = 0; m <= P; ++m) zr[m] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NDC; ++c) zd[c] = 0.0;
+    for (int64_t j = j0 + lane; j < j1; j += 32) {
+      const double u = a.u[j], eta = a.eta[j];
+      const double sz = a.size ? a.size[j] : 1.0;
+      double v[NV];
+      v[0] = 1.0;
+#pragma unroll
+      for (int m = 1; m <= P; ++m) v[m] = v[m - 1] * u;
+#pragma unroll
+      for (int c = 0; c < NDC; ++c) v[P + 1 + c] = c < a.nD ? a.D[(size_t)c * a.n + j] : 0.0;
+      double q = 0.0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) t = fma(sOm[warp][i * NV + k], v[k], t);
+        q = fma(v[i], t, q);
+      }
+      double c3;
+      if (a.family == BGP_FAMILY_POISSON) {
+        c3 = exp(eta);
+      } else {                                   // Binomial: w (1 - 2 pi), as obs_terms
+        const double e = exp(-fabs(eta));
+        const double inv = 1.0 / (1.0 + e);
+        const double pi = eta >= 0.0 ? inv : e * inv, om = eta >= 0.0 ? e * inv : inv;
+        c3 = sz * pi * om * (om - pi);
+      }
+      const double z = c3 * q;
+#pragma unroll
+      for (int m = 0; m <= P; ++m) zr[m] = fma(z, v[m], zr[m]);
+#pragma unroll
+      for (int c = 0; c < NDC; ++c) zd[c] = fma(z, v[P + 1 + c], zd[c]);
+    }
+    double* slot = a.slots + (size_t)pc * NACC;
+#pragma unroll
+    for (int m = 0; m <= P; ++m) {
+      const double s = osp_warp_sum(zr[m]);
+      if (lane == 0) slot[m] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < NDC; ++c) {
+      const double s = osp_warp_sum(zd[c]);
+      if (lane == 0) slot[OGD + c] = s;
+    }
+  }
+}
+
 // ---- host ----------------------------------------------------------------------------------------------------------
 template <int P, int NDC>
 static void pass_launch(bgp_model* m, OspPlan* pl, const OspPassArgs& pa, const OspApplyArgs& aa, const PriorArgs& pr) {
@@ -579,12 +750,75 @@ int osp_launch_hessian(bgp_model* m, const double* theta) {
   return BGP_OK;
 }
 
+
+template <int P, int NDC>
+static void lev_launch(bgp_model* m, OspPlan* pl, const double* V, int ldl, const OspLevArgs& la, const OspApplyArgs& aa) {
+  const int p = m->p;
+  dim3 gy((p + 127) / 128, pl->nside);
+  osp_levY_kernel<P><<<gy, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->nside, pl->side_gbase, pl->side_cbase, pl->side_K,
+                                               pl->c_t0, pl->c_t1, pl->Yt);
+  osp_levOmega_kernel<P, NDC><<<pl->NG, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->g_own, pl->Yt, pl->Omega);
+  osp_levpass_kernel<P, NDC><<<std::min((pl->np + 3) / 4, pl->pass_grid), 128, 0, m->stream>>>(la);
+  osp_reduce_kernel<<<(pl->NG + 3) / 4 + (pl->NACC - pl->NM), 128, 0, m->stream>>>(pl->slots, pl->NACC, pl->NM, pl->NG, pl->gid_pbeg,
+                                                                                   pl->np, pl->mom, pl->glob);
+  PriorArgs pr;
+  memset(&pr, 0, sizeof(pr));
+  osp_apply_kernel<P, NDC><<<(pl->NC + 3) / 4 + 1, 128, 0, m->stream>>>(aa, pr);
+}
+
+// A^T (c3 * q) into red_buf[0 .. lda) from the moments (Poisson / Binomial; the eta of the last moment pass must be the
+// mode's).  V: upper factor of H^-1 = V^T V, row-major p x ldl (grad.cu).
+int osp_launch_leverage(bgp_model* m, const double* V, int ldl) {
+  OspPlan* pl = (OspPlan*)m->osp_plan;
+  if (!pl->Yt) {
+    pl->ldk = round_up(m->p, 32);
+    const int NV = pl->P + 1 + pl->NDC;
+    BGP_CUDA(cudaMalloc(&pl->Yt, (size_t)pl->NG * pl->P * pl->ldk * sizeof(double)));
+    BGP_CUDA(cudaMalloc(&pl->Omega, (size_t)pl->NG * NV * NV * sizeof(double)));
+  }
+  OspLevArgs la;
+  la.u = pl->u;
+  la.size = pl->size;
+  la.D = pl->D;
+  la.eta = pl->eta;
+  la.piece_beg = pl->piece_beg;
+  la.piece_gid = pl->piece_gid;
+  la.Omega = pl->Omega;
+  la.nD = pl->nD;
+  la.np = pl->np;
+  la.family = m->family;
+  la.n = pl->n;
+  la.slots = pl->slots;
+  OspApplyArgs aa;
+  aa.NC = pl->NC;
+  aa.nD = pl->nD;
+  aa.NM = pl->NM;
+  aa.lda = m->lda;
+  aa.c_t0 = pl->c_t0;
+  aa.c_t1 = pl->c_t1;
+  aa.g_t0 = pl->g_t0;
+  aa.c_gid = pl->c_gid;
+  aa.c_gend = pl->c_gend;
+  aa.mom = pl->mom;
+  aa.glob = pl->glob;
+  aa.red = m->red_buf;
+  aa.Hdb = pl->Hdb;
+  aa.G = pl->G;
+  aa.done = pl->done;
+  aa.fuse_prior = 0;
+  OSP_DISPATCH(lev_launch, m, pl, V, ldl, la, aa);
+  count_launch(5);
+  BGP_CUDA(cudaGetLastError());
+  return BGP_OK;
+}
+
 void osp_plan_destroy(bgp_model* m) {
   OspPlan* pl = (OspPlan*)m->osp_plan;
   if (!pl) return;
   for (void* ptr : {(void*)pl->u, (void*)pl->y, (void*)pl->size, (void*)pl->D, (void*)pl->eta, (void*)pl->piece_beg,
                     (void*)pl->piece_gid, (void*)pl->gid_pbeg, (void*)pl->g_t0, (void*)pl->g_own, (void*)pl->g_c0, (void*)pl->g_nt,
-                    (void*)pl->c_t0, (void*)pl->c_t1, (void*)pl->c_gid, (void*)pl->c_gend, (void*)pl->c_side, (void*)pl->done,
+                    (void*)pl->c_t0, (void*)pl->c_t1, (void*)pl->c_gid, (void*)pl->c_gend, (void*)pl->c_side, (void*)pl->done, (void*)pl->side_gbase, (void*)pl->side_cbase, (void*)pl->side_K, (void*)pl->Yt,
+                    (void*)pl->Omega,
                     (void*)pl->slots, (void*)pl->mom, (void*)pl->glob, (void*)pl->Hdb, (void*)pl->G})
     if (ptr) cudaFree(ptr);
   delete pl;
@@ -640,8 +874,20 @@ int osp_plan_create(bgp_model* m) {
       c_side[(size_t)cbase + i] = side;
     }
   };
-  if (nkn > 0) fill_side(it.kneg, Kn, 0, 0, 0);
-  if (nkp > 0) fill_side(it.kpos, Kp, gbase_pos, Kn, 1);
+  std::vector<int> side_gbase, side_cbase, side_K;
+  if (nkn > 0) {
+    fill_side(it.kneg, Kn, 0, 0, 0);
+    side_gbase.push_back(0);
+    side_cbase.push_back(0);
+    side_K.push_back(Kn);
+  }
+  if (nkp > 0) {
+    fill_side(it.kpos, Kp, gbase_pos, Kn, 1);
+    side_gbase.push_back(gbase_pos);
+    side_cbase.push_back(Kn);
+    side_K.push_back(Kp);
+  }
+  pl->nside = (int)side_K.size();
 
   uint32_t *gid = nullptr, *gid2 = nullptr, *idx = nullptr, *idx2 = nullptr;
   double *u0 = nullptr, *kn_dev = nullptr, *kp_dev = nullptr;
@@ -760,6 +1006,9 @@ int osp_plan_create(bgp_model* m) {
     BGP_TRY(upload(&pl->c_gid, c_gid));
     BGP_TRY(upload(&pl->c_gend, c_gend));
     BGP_TRY(upload(&pl->c_side, c_side));
+    BGP_TRY(upload(&pl->side_gbase, side_gbase));
+    BGP_TRY(upload(&pl->side_cbase, side_cbase));
+    BGP_TRY(upload(&pl->side_K, side_K));
     auto zalloc = [&](double** ptr, size_t count) -> int {
       BGP_CUDA(cudaMalloc(ptr, std::max<size_t>(1, count) * sizeof(double)));
       BGP_CUDA(cudaMemsetAsync(*ptr, 0, std::max<size_t>(1, count) * sizeof(double), m->stream));

@@ -154,7 +154,8 @@ class LaplaceObjective:
         check(self._lib.bgp_model_set_hessian_retry(self._h, int(allow)))
 
     def set_ospline(self, on=True):
-        """Select the O-spline moment path (eligible models: one IWP term) or the dense DMMA path (on=False)."""
+        """Select the O-spline moment path (eligible models: one IWP term), the dense DMMA path (on=False), or the
+        moment path with the gradient's leverages taken from the dense design (on=2; A/B)."""
         check(self._lib.bgp_model_set_ospline(self._h, int(on)))
 
     def ospline_bytes(self):

@@ -534,32 +534,42 @@ def fit_leg(ff):
 
 def gradient_leg(ff, mode, fp64_peak, reps=8):
     """ff$gr at C3: Laplace value + its theta-gradient (leverage pass q_i = a_i^T H^-1 a_i, traces, implicit term)
-    against ff$fn alone at the same thetas."""
+    against ff$fn alone at the same thetas.  On the moment path the leverages come from per-interval quadratic forms
+    (ospline.cu); the dense leverage kernel's roofline is measured with bgp_model_set_ospline(m, 2)."""
     ths = [np.array([mode + 0.01 * (i + 1)]) for i in range(reps)]
-    ff.set_start(None)
-    ff.fn(np.array([mode]))
-    t0 = time.perf_counter()
-    for th in ths:
-        ff.fn(th)
-    t_fn = (time.perf_counter() - t0) / reps
-    ff.set_start(None)
-    ff.fn(np.array([mode]))
-    g0 = ff.gradient_timing()
-    t0 = time.perf_counter()
-    for th in ths:
-        ff.gr(th)
-    t_gr = (time.perf_counter() - t0) / reps
-    g1 = ff.gradient_timing()
-    nl = max(1, g1["leverage_launches"] - g0["leverage_launches"])
-    lev_ms = (g1["leverage_ms"] - g0["leverage_ms"]) / nl
+
+    def timed(call):
+        ff.set_start(None)
+        ff.fn(np.array([mode]))
+        g0 = ff.gradient_timing()
+        t0 = time.perf_counter()
+        for th in ths:
+            call(th)
+        t = (time.perf_counter() - t0) / reps
+        g1 = ff.gradient_timing()
+        nl = max(1, g1["leverage_launches"] - g0["leverage_launches"])
+        return t, (g1["leverage_ms"] - g0["leverage_ms"]) / nl, g1
+
+    moment = ff.ospline()[1]
+    t_fn, _, _ = timed(ff.fn)
+    t_gr, lev_ms, g1 = timed(ff.gr)
+    out = {"fn_ms": t_fn * 1e3, "gr_ms": t_gr * 1e3, "gr_over_fn": t_gr / t_fn,
+           "what": "wall clock per call through the C ABI, %d thetas stepping away from the mode; gr includes fn" % reps}
+    if moment:
+        out["leverage_ms"] = lev_ms
+        out["leverage_what"] = ("moment path: V G_J per knot interval, its Gram matrix, one streaming pass for q_i and "
+                                "A^T (c3 q) (five small kernels)")
+        ff.set_ospline(2)
+        t_gr, lev_ms, g1 = timed(ff.gr)
+        ff.set_ospline(1)
+        out["gr_ms_dense_leverages"] = t_gr * 1e3
     tfl = g1["leverage_flops"] / (lev_ms * 1e-3) / 1e12 if lev_ms > 0 else None
-    return {"fn_ms": t_fn * 1e3, "gr_ms": t_gr * 1e3, "gr_over_fn": t_gr / t_fn,
-            "what": "wall clock per call through the C ABI, %d thetas stepping away from the mode; gr includes fn" % reps,
-            "leverage_kernel": {"bound": "tensor", "ms_per_launch": lev_ms, "executed_flops": g1["leverage_flops"],
-                                "dense_flops": g1["dense_flops"], "achieved_tflops": tfl,
-                                "frac_of_fp64_peak": (tfl / fp64_peak) if (tfl and fp64_peak) else None,
-                                "note": "q_i = ||U^-1 a_i||^2 with the upper factor of the reversed-order Cholesky: "
-                                        "empty {128 obs x 64 x 16} blocks skipped (round 1: 3.5 ms dense)"}}
+    out["leverage_kernel"] = {"bound": "tensor", "ms_per_launch": lev_ms, "executed_flops": g1["leverage_flops"],
+                              "dense_flops": g1["dense_flops"], "achieved_tflops": tfl,
+                              "frac_of_fp64_peak": (tfl / fp64_peak) if (tfl and fp64_peak) else None,
+                              "note": "dense-design leverages q_i = ||U^-1 a_i||^2 with the upper factor of the "
+                                      "reversed-order Cholesky: empty {128 obs x 64 x 16} blocks skipped (round 1: 3.5 ms dense)"}
+    return out
 
 
 def predict_leg(device, fp64_peak, G=100_000, M=10_000, reps=3):

@@ -156,7 +156,8 @@ int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
  * most 8 dense (boundary + fixed) columns, evaluates eta, A^T r and A^T diag(w) A from per-knot-interval moments of one
  * streaming pass over (x, y, size, dense columns) instead of the two passes over the dense design: to the right of its
  * own knot interval every O-spline column (R/01_utility.R:346-364) is a polynomial of degree order-1.  Same results to
- * rounding; on by default for eligible models.  on = 0 selects the dense (DMMA) path, e.g. for A/B measurements. */
+ * rounding; on by default for eligible models.  on = 0 selects the dense (DMMA) path, on = 2 the moment path with the
+ * Laplace gradient's leverages taken from the dense design (both for A/B measurements). */
 int bgp_model_set_ospline(bgp_model* m, int on);
 int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on);
 /* algorithmic bytes one likelihood pass of the moment path moves (u, y, eta in / out, dense columns, size): roofline numerator */

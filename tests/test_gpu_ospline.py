@@ -116,10 +116,15 @@ def test_laplace_objective(kw):
             got, _, w, Hm = ff._eval(th, want_hess=True)
             assert abs(got - want) <= 1e-8 * abs(want), (th, got, want)
             assert relerr(w, off.last_par) < 1e-6 and relerr(Hm, off.sp_hess()) < 1e-6
-            gw, gg = off.gr(th), ff.gr(th)                    # the gradient switches to the dense passes inside
+            gw, gg = off.gr(th), ff.gr(th)                    # leverages from per-interval quadratic forms
             assert np.max(np.abs(gw - gg)) <= 2e-7 * max(1.0, np.max(np.abs(gw))), (th, gw, gg)
             assert ff.ospline() == (True, True)
+            ff.set_ospline(2)                                 # moment path, leverages from the dense design rows
+            g2 = ff.gr(th)
+            assert np.max(np.abs(g2 - gg)) <= 1e-9 * max(1.0, np.max(np.abs(g2))), (th, g2, gg)
             ff.set_ospline(False)
+            g0 = ff.gr(th)
+            assert np.max(np.abs(g0 - gg)) <= 1e-9 * max(1.0, np.max(np.abs(g0))), (th, g0, gg)
             ff.set_start(None)
             gd = ff._eval(th, want_hess=True)
             assert abs(got - gd[0]) <= 1e-10 * abs(want)
