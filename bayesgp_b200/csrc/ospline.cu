@@ -843,6 +843,9 @@ int osp_plan_create(bgp_model* m) {
   if (it.order > OSP_MAXP || m->nD > OSP_MAXD || !it.x_dev) return BGP_OK;
   const int64_t n = m->n;
   if (n >= ((int64_t)1 << 31)) return BGP_OK;
+  for (const std::vector<double>* t : {&it.kneg, &it.kpos})        // the interval search needs increasing knots
+    for (size_t i = 1; i < t->size(); ++i)
+      if (!((*t)[i] > (*t)[i - 1])) return BGP_OK;
   OspPlan* pl = new OspPlan;
   m->osp_plan = pl;
   pl->P = it.order;

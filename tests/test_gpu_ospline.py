@@ -167,6 +167,42 @@ def test_model_fit_matches_dense_path_and_oracle():
     assert relerr(res[True][2], res[False][2]) < 1e-6 and relerr(res[True][3], res[False][3]) < 1e-6
 
 
+def test_skewed_intervals_and_unsorted_knots():
+    """90 % of 200k observations in one knot interval: that interval is cut into far more than 64 pieces (the
+    cooperative branch of the interval reduction); unsorted knots: not eligible, dense path, same answer as the
+    oracle either way."""
+    from bayesgp_b200.api import build_objective
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(11)
+    n = 200_000
+    x = np.where(rng.uniform(size=n) < 0.9, rng.uniform(0.500, 0.539, n), rng.uniform(0, 1, n))
+    y = rng.poisson(np.exp(0.4 + np.sin(2 * np.pi * x))).astype(np.float64)
+    knots = np.linspace(0.0, 1.0, 26)
+    mk = lambda kn: [Term("IWP", "x", x.copy(), order=3, knots=kn.copy(), initial_location=0.0)]
+    model = build_model(y, mk(knots), {}, family="Poisson")[0]
+    ff = build_objective(y, mk(knots), {}, family="Poisson")[0]
+    try:
+        assert ff.ospline() == (True, True)
+        W = 0.05 * rng.standard_normal(model.p)
+        theta = np.array([-1.5])
+        o = model.objective(W, theta, "fgH")
+        f, g, H = ff.objective(W, theta, want_grad=True, want_hess=True)
+        assert abs(f - o["f"]) <= 1e-11 * abs(o["f"])
+        assert relerr(g, o["g"]) < 1e-10 and relerr(H, o["H"]) < 1e-10
+        f2, g2, H2 = ff.objective(W, theta, want_grad=True, want_hess=True)
+        assert f == f2 and np.array_equal(g, g2) and np.array_equal(H, H2)
+    finally:
+        ff.close()
+    shuffled = knots.copy()
+    shuffled[[3, 7]] = shuffled[[7, 3]]
+    ff = build_objective(y[:5000], [Term("IWP", "x", x[:5000].copy(), order=3, knots=shuffled, initial_location=0.0)], {},
+                         family="Poisson")[0]
+    try:
+        assert ff.ospline() == (False, False)
+    finally:
+        ff.close()
+
+
 def test_eligibility():
     """Two smoothing terms, order above 4, more than 8 dense columns, caller-supplied designs: dense path only."""
     from bayesgp_b200 import BgpError, make_objective
