@@ -34,6 +34,7 @@ namespace bgp {
 
 constexpr int OSP_MAXP = 4;      // smoothness orders 1..4
 constexpr int OSP_MAXD = 8;      // dense (boundary + fixed) columns
+constexpr int OSP_STEP = OSP_MAXP * (OSP_MAXP + 1) / 2 + OSP_MAXP;   // per-column constants of the leverage recurrence
 
 struct OspPlan {
   int P = 0, nD = 0, NDC = 0, NG = 0, NC = 0, NM = 0, NACC = 0, np = 0;
@@ -55,7 +56,8 @@ struct OspPlan {
   // leverage path (allocated on the first gradient): V G_J per interval and its Gram matrix
   int nside = 0, ldk = 0;
   int *side_gbase = nullptr, *side_cbase = nullptr, *side_K = nullptr;
-  double *Yt = nullptr, *Omega = nullptr;
+  std::vector<double> c_t0_host, c_t1_host;
+  double *Yt = nullptr, *Omega = nullptr, *c_step = nullptr;
   double *slots = nullptr, *mom = nullptr, *glob = nullptr, *Hdb = nullptr, *G = nullptr;
 };
 
@@ -291,9 +293,19 @@ __global__ void __launch_bounds__(128) osp_reduce_kernel(const double* __restric
   __shared__ double sm[128];
   const int gi = blockIdx.x - nA;             // global value NM + gi
   const bool is_max = NM + gi == NACC - 1;
+  // eight independent loads in flight per thread (the pieces are ~24 deep per thread on a large model)
   double v = 0.0;
-  for (int pc = threadIdx.x; pc < np; pc += 128) {
-    const double t = slots[(size_t)pc * NACC + NM + gi];
+  const double* src = slots + NM + gi;
+  int pc = threadIdx.x;
+  for (; pc + 7 * 128 < np; pc += 8 * 128) {
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t[q] = src[(size_t)(pc + q * 128) * NACC];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v = is_max ? fmax(v, t[q]) : v + t[q];
+  }
+  for (; pc < np; pc += 128) {
+    const double t = src[(size_t)pc * NACC];
     v = is_max ? fmax(v, t) : v + t;
   }
   sm[threadIdx.x] = v;
@@ -318,7 +330,7 @@ struct OspApplyArgs {
 };
 
 // g_lik of the spline columns, the {dense x spline} block of H and the weighted suffix moments G the {spline x spline}
-// block is assembled from: one warp per column, lanes over the intervals to its right.  The last CTA moves the global
+// block is assembled from: one CTA per column, threads over the intervals to its right.  The last CTA moves the global
 // sums into the reduction buffer finish.cu reads.
 template <int P, int NDC>
 __device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
@@ -330,8 +342,11 @@ __device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
     if (threadIdx.x < 4) a.red[a.lda + threadIdx.x] = a.glob[OS + threadIdx.x];
     return;
   }
-  const int col = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (col >= a.NC) return;
+  // one CTA per column: its 128 threads stride over the intervals to the right, partial sums are combined warp by
+  // warp in a fixed order
+  __shared__ double s_part[4][NDC + 1 + NE];
+  __shared__ double s_fin[NDC + 1 + NE];
+  const int col = blockIdx.x, warp = threadIdx.x >> 5;
   const int own = a.c_gid[col], gend = a.c_gend[col];
   const double t1 = a.c_t1[col], d = t1 - a.c_t0[col];
   double acc[NDC + 1], S[NE];
@@ -339,7 +354,7 @@ __device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
   for (int e = 0; e <= NDC; ++e) acc[e] = 0.0;
 #pragma unroll
   for (int e = 0; e < NE; ++e) S[e] = 0.0;
-  for (int g = own + 1 + lane; g < gend; g += 32) {
+  for (int g = own + 1 + threadIdx.x; g < gend; g += 128) {
     const double s = a.g_t0[g] - t1;
     double al[P];
     osp_alpha<P>(d, s, al);
@@ -366,8 +381,20 @@ __device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
     }
   }
 #pragma unroll
-  for (int e = 0; e < NE; ++e) S[e] = osp_warp_sum(S[e]);
-  if (lane < P) {
+  for (int e = 0; e <= NDC; ++e) {
+    const double v = osp_warp_sum(acc[e]);
+    if (lane == 0) s_part[warp][e] = v;
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const double v = osp_warp_sum(S[e]);
+    if (lane == 0) s_part[warp][NDC + 1 + e] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NDC + 1 + NE)
+    s_fin[threadIdx.x] = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + (s_part[2][threadIdx.x] + s_part[3][threadIdx.x]);
+  __syncthreads();
+  if (threadIdx.x < P) {
     // c_k(z) = sum_{q'} beta_{q'} v^{q'},  beta_{q'} = d^{P-q'} / ((P-q')! q'!)
     double dp[P + 1];
     dp[0] = 1.0;
@@ -375,22 +402,15 @@ __device__ __forceinline__ void osp_apply_body(const OspApplyArgs& a) {
     for (int l = 1; l <= P; ++l) dp[l] = dp[l - 1] * d;
     double gq = 0.0;
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-      if (q == lane) {
-#pragma unroll
-        for (int q2 = 0; q2 < P; ++q2) gq = fma(dp[P - q2] * (osp_ifact(P - q2) * osp_ifact(q2)), S[q + q2], gq);
-      }
-    }
-    a.G[col * OSP_MAXP + lane] = gq;
+    for (int q2 = 0; q2 < P; ++q2)
+      gq = fma(dp[P - q2] * (osp_ifact(P - q2) * osp_ifact(q2)), s_fin[NDC + 1 + threadIdx.x + q2], gq);
+    a.G[col * OSP_MAXP + threadIdx.x] = gq;
   }
   const double* mo = a.mom + (size_t)own * a.NM;
-#pragma unroll
-  for (int e = 0; e <= NDC; ++e) {
-    const double v = osp_warp_sum(acc[e]);
-    if (lane == 0) {
-      if (e == 0) a.red[a.nD + col] = v + mo[P] * osp_ifact(P);
-      else if (e - 1 < a.nD) a.Hdb[(size_t)(e - 1) * a.NC + col] = v + mo[OX + (e - 1) * (P + 1) + P] * osp_ifact(P);
-    }
+  if (threadIdx.x == 32) a.red[a.nD + col] = s_fin[0] + mo[P] * osp_ifact(P);
+  if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < a.nD) {
+    const int c = threadIdx.x - 64;
+    a.Hdb[(size_t)c * a.NC + col] = s_fin[1 + c] + mo[OX + c * (P + 1) + P] * osp_ifact(P);
   }
 }
 
@@ -488,8 +508,8 @@ __global__ void __launch_bounds__(256) osp_hwrite_kernel(const OspHArgs a) {
 template <int P>
 __global__ void __launch_bounds__(128) osp_levY_kernel(const double* __restrict__ V, int p, int ldl, int nD, int ldk, int nside,
                                                        const int* __restrict__ side_gbase, const int* __restrict__ side_cbase,
-                                                       const int* __restrict__ side_K, const double* __restrict__ c_t0,
-                                                       const double* __restrict__ c_t1, double* __restrict__ Yt) {
+                                                       const int* __restrict__ side_K, const double* __restrict__ c_step,
+                                                       double* __restrict__ Yt) {
   const int k = blockIdx.x * 128 + threadIdx.x, sd = blockIdx.y;
   if (k >= p || sd >= nside) return;
   const int gbase = side_gbase[sd], cbase = side_cbase[sd], K = side_K[sd];
@@ -500,32 +520,27 @@ __global__ void __launch_bounds__(128) osp_levY_kernel(const double* __restrict_
     Yt[((size_t)gbase * P + m) * ldk + k] = 0.0;
   }
   const double* Vk = V + (size_t)k * ldl + nD + cbase;
+  double vk = K > 0 ? Vk[0] : 0.0;
   for (int J = 1; J <= K; ++J) {
-    const int col = cbase + J - 1;
-    const double d = c_t1[col] - c_t0[col];
-    double dp[P + 1];
-    dp[0] = 1.0;
-#pragma unroll
-    for (int l = 1; l <= P; ++l) dp[l] = dp[l - 1] * d;
-    const double vk = Vk[J - 1];
-    // shift the polynomial to the next knot: y'[m] = sum_{r >= m} binom(r, m) d^(r - m) y[r]; then the column that
-    // was the interval's own one enters as a tail: + V[k][col] d^(P-m) / ((P-m)! m!)
+    // per-column constants (osp_plan_create): the shift matrix binom(r, m) d^(r-m), r >= m, then the tail coefficients
+    // d^(P-m) / ((P-m)! m!) — the same for every row of V, off the dependent chain
+    const double* cs = c_step + (size_t)(cbase + J - 1) * OSP_STEP;
+    const double vnext = J < K ? Vk[J] : 0.0;          // next step's entry of V, in flight during this one
     double yn[P];
+    int t = 0;
 #pragma unroll
     for (int m = 0; m < P; ++m) {
-      double acc = 0.0, binom = 1.0;
+      double acc = vk * cs[OSP_STEP - OSP_MAXP + m];
 #pragma unroll
-      for (int r = m; r < P; ++r) {
-        acc = fma(binom * dp[r - m], y[r], acc);
-        binom = binom * (double)(r + 1) / (double)(r + 1 - m);
-      }
-      yn[m] = fma(vk, dp[P - m] * (osp_ifact(P - m) * osp_ifact(m)), acc);
+      for (int r = m; r < P; ++r, ++t) acc = fma(cs[t], y[r], acc);
+      yn[m] = acc;
     }
 #pragma unroll
     for (int m = 0; m < P; ++m) {
       y[m] = yn[m];
       Yt[((size_t)(gbase + J) * P + m) * ldk + k] = yn[m];
     }
+    vk = vnext;
   }
 }
 
@@ -643,12 +658,19 @@ __global__ void __launch_bounds__(128) osp_levpass_kernel(const OspLevArgs a) {
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+  BGP_CUDA(cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (!v.empty()) BGP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return BGP_OK;
+}
+
 template <int P, int NDC>
 static void pass_launch(bgp_model* m, OspPlan* pl, const OspPassArgs& pa, const OspApplyArgs& aa, const PriorArgs& pr) {
   osp_pass_kernel<P, NDC><<<std::min((pl->np + 3) / 4, pl->pass_grid), 128, 0, m->stream>>>(pa);
   osp_reduce_kernel<<<(pl->NG + 3) / 4 + (pl->NACC - pl->NM), 128, 0, m->stream>>>(pl->slots, pl->NACC, pl->NM, pl->NG, pl->gid_pbeg,
                                                                                    pl->np, pl->mom, pl->glob);
-  osp_apply_kernel<P, NDC><<<(pl->NC + 3) / 4 + 1, 128, 0, m->stream>>>(aa, pr);
+  osp_apply_kernel<P, NDC><<<pl->NC + 1, 128, 0, m->stream>>>(aa, pr);
 }
 template <int P, int NDC>
 static void hess_launch(bgp_model* m, OspPlan* pl, const OspHArgs& ha) {
@@ -756,14 +778,14 @@ static void lev_launch(bgp_model* m, OspPlan* pl, const double* V, int ldl, cons
   const int p = m->p;
   dim3 gy((p + 127) / 128, pl->nside);
   osp_levY_kernel<P><<<gy, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->nside, pl->side_gbase, pl->side_cbase, pl->side_K,
-                                               pl->c_t0, pl->c_t1, pl->Yt);
+                                               pl->c_step, pl->Yt);
   osp_levOmega_kernel<P, NDC><<<pl->NG, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->g_own, pl->Yt, pl->Omega);
   osp_levpass_kernel<P, NDC><<<std::min((pl->np + 3) / 4, pl->pass_grid), 128, 0, m->stream>>>(la);
   osp_reduce_kernel<<<(pl->NG + 3) / 4 + (pl->NACC - pl->NM), 128, 0, m->stream>>>(pl->slots, pl->NACC, pl->NM, pl->NG, pl->gid_pbeg,
                                                                                    pl->np, pl->mom, pl->glob);
   PriorArgs pr;
   memset(&pr, 0, sizeof(pr));
-  osp_apply_kernel<P, NDC><<<(pl->NC + 3) / 4 + 1, 128, 0, m->stream>>>(aa, pr);
+  osp_apply_kernel<P, NDC><<<pl->NC + 1, 128, 0, m->stream>>>(aa, pr);
 }
 
 // A^T (c3 * q) into red_buf[0 .. lda) from the moments (Poisson / Binomial; the eta of the last moment pass must be the
@@ -775,6 +797,24 @@ int osp_launch_leverage(bgp_model* m, const double* V, int ldl) {
     const int NV = pl->P + 1 + pl->NDC;
     BGP_CUDA(cudaMalloc(&pl->Yt, (size_t)pl->NG * pl->P * pl->ldk * sizeof(double)));
     BGP_CUDA(cudaMalloc(&pl->Omega, (size_t)pl->NG * NV * NV * sizeof(double)));
+    // per column: shift matrix entries binom(r, m) d^(r-m) for m <= r < P (row by row), then d^(P-m) / ((P-m)! m!)
+    std::vector<double> cs((size_t)pl->NC * OSP_STEP, 0.0);
+    for (int col = 0; col < pl->NC; ++col) {
+      const double d = pl->c_t1_host[(size_t)col] - pl->c_t0_host[(size_t)col];
+      double dp[OSP_MAXP + 1];
+      dp[0] = 1.0;
+      for (int l = 1; l <= pl->P; ++l) dp[l] = dp[l - 1] * d;
+      int t = 0;
+      for (int mm = 0; mm < pl->P; ++mm) {
+        double binom = 1.0;
+        for (int r = mm; r < pl->P; ++r, ++t) {
+          cs[(size_t)col * OSP_STEP + t] = binom * dp[r - mm];
+          binom = binom * (double)(r + 1) / (double)(r + 1 - mm);
+        }
+        cs[(size_t)col * OSP_STEP + OSP_STEP - OSP_MAXP + mm] = dp[pl->P - mm] * (osp_ifact(pl->P - mm) * osp_ifact(mm));
+      }
+    }
+    BGP_TRY(upload(&pl->c_step, cs));
   }
   OspLevArgs la;
   la.u = pl->u;
@@ -818,19 +858,12 @@ void osp_plan_destroy(bgp_model* m) {
   for (void* ptr : {(void*)pl->u, (void*)pl->y, (void*)pl->size, (void*)pl->D, (void*)pl->eta, (void*)pl->piece_beg,
                     (void*)pl->piece_gid, (void*)pl->gid_pbeg, (void*)pl->g_t0, (void*)pl->g_own, (void*)pl->g_c0, (void*)pl->g_nt,
                     (void*)pl->c_t0, (void*)pl->c_t1, (void*)pl->c_gid, (void*)pl->c_gend, (void*)pl->c_side, (void*)pl->done, (void*)pl->side_gbase, (void*)pl->side_cbase, (void*)pl->side_K, (void*)pl->Yt,
-                    (void*)pl->Omega,
+                    (void*)pl->Omega, (void*)pl->c_step,
                     (void*)pl->slots, (void*)pl->mom, (void*)pl->glob, (void*)pl->Hdb, (void*)pl->G})
     if (ptr) cudaFree(ptr);
   delete pl;
   m->osp_plan = nullptr;
   m->osp_on = false;
-}
-
-template <typename T>
-static int upload(T** dst, const std::vector<T>& v) {
-  BGP_CUDA(cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(T)));
-  if (!v.empty()) BGP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return BGP_OK;
 }
 
 // Called by bgp_model_finalize while the staged (column-major, caller-order) blocks are still alive.
@@ -1005,6 +1038,8 @@ int osp_plan_create(bgp_model* m) {
     BGP_TRY(upload(&pl->g_c0, g_c0));
     BGP_TRY(upload(&pl->g_nt, g_nt));
     BGP_TRY(upload(&pl->c_t0, c_t0));
+    pl->c_t0_host = c_t0;
+    pl->c_t1_host = c_t1;
     BGP_TRY(upload(&pl->c_t1, c_t1));
     BGP_TRY(upload(&pl->c_gid, c_gid));
     BGP_TRY(upload(&pl->c_gend, c_gend));
