@@ -197,6 +197,7 @@ struct bgp_model {
   double reuse_eta_tol = 1e-7, reuse_rel_tol = 1e-10;
   bool factor_is_exact = true;   // H in memory was formed at the mode itself (and L is its factor unless L_is_reversed)
   bool obs_at_mode = false;      // eta / wobs / c3 / sc_dev on the device belong to the last mode (Wmode)
+  bool L_holds_H = false;        // m->L already holds a copy of m->H (written by the moment path's Hessian kernel)
   bool L_is_reversed = false;    // the gradient left the factor of H in reversed order in L (grad.cu)
   int64_t n_evals = 0, n_newton = 0, n_reuse = 0;
   // ---- sharding ------------------------------------------------------------------------------
@@ -293,7 +294,9 @@ void syrk_plan_destroy(bgp_model* m);
 int launch_hessian(bgp_model* m, const double* theta);
 // chol.cu: L = chol(H), logdet, optionally step = -H^-1 g and max|step|
 // theta_tan / W_tan != NULL: also form the tangents d w_hat / d theta (at W_tan) into m->Tan on the cluster's idle ranks
-int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan = nullptr, const double* W_tan = nullptr);
+// write_trial (with solve): Wtrial = W + step as well (the full Newton step, no separate axpy launch)
+int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan = nullptr, const double* W_tan = nullptr,
+                      bool write_trial = false);
 constexpr int CHOL_TANGENT_MAX_S = 7;
 int launch_tangent(bgp_model* m, const double* theta);
 // basis.cu

@@ -32,6 +32,9 @@ struct CholArgs {
   double* step;      // out: -H^-1 g (p)
   EvalScalars* sc;
   int solve;
+  const double* W;   // with Wtrial: the full-step trial point W + step is written as well (lda entries, zero padded)
+  double* Wtrial;
+  int lda;
   unsigned long long* dbg;   // BGP_CHOL_DEBUG: per-phase nanoseconds of rank 0 (9 slots)
 };
 
@@ -476,8 +479,11 @@ __global__ void __cluster_dims__(CH_CS, 1, 1) __launch_bounds__(CH_THREADS, 1)
   for (int i = tid; i < p; i += CH_THREADS) {
     const double x = sv[i];
     a.step[i] = x;
+    if (a.Wtrial) a.Wtrial[i] = fma(1.0, x, a.W[i]);          // axpy_trial_kernel's t = 1 (newton.cu)
     mx = fmax(mx, isfinite(x) ? fabs(x) : INFINITY);
   }
+  if (a.Wtrial)
+    for (int i = p + tid; i < a.lda; i += CH_THREADS) a.Wtrial[i] = 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) s_red[warp] = mx;
@@ -509,10 +515,14 @@ static int launch_chol_t(bgp_model* m, const CholArgs& a, const TangentArgs& ta,
 static void fill_tangent_args(bgp_model* m, const double* theta, const double* W, TangentArgs& a);
 
 // L <- chol(H) (H is left untouched), logdet, optionally step = -H^-1 g
-int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan, const double* W_tan) {
+int launch_chol_solve(bgp_model* m, bool solve, const double* theta_tan, const double* W_tan, bool write_trial) {
   m->L_is_reversed = false;
-  BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+  if (m->L_holds_H) m->L_holds_H = false;      // the Hessian kernel of the moment path wrote L alongside H
+  else BGP_CUDA(cudaMemcpyAsync(m->L, m->H, (size_t)m->ldh * m->p * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
   CholArgs a;
+  a.W = write_trial ? m->W : nullptr;
+  a.Wtrial = write_trial ? m->Wtrial : nullptr;
+  a.lda = m->lda;
   a.L = m->L;
   a.dinv = m->Ldinv;
   a.p = m->p;

@@ -555,6 +555,7 @@ int laplace_gradient(bgp_model* m, const double* theta, double* grad) {
     reverse_sym_kernel<<<grid, 256, 0, m->stream>>>(m->H, p, m->ldh, gp->Hrev);
     count_launch();
     double* keep = m->H;
+    m->L_holds_H = false;            // the factor below is that of the reversed matrix
     m->H = gp->Hrev;
     const int st = launch_chol_solve(m, false);
     m->H = keep;

@@ -509,6 +509,7 @@ int bgp_model_set_ospline(bgp_model* m, int on) {
   m->osp_on = on != 0;
   m->osp_dense_grad = on == 2;
   m->obs_at_mode = false;
+  m->L_holds_H = false;
   return BGP_OK;
 }
 

@@ -327,12 +327,10 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     m->n_hess++;
     phase_mark(m, PH_CHOL);
     const bool tan_in_chol = m->use_predictor && m->S <= CHOL_TANGENT_MAX_S;
-    BGP_TRY(launch_chol_solve(m, true, tan_in_chol ? theta : nullptr, m->W));
+    // speculative full step: the solve writes the trial point W + step itself; it is evaluated before anything is read back
+    BGP_TRY(launch_chol_solve(m, true, tan_in_chol ? theta : nullptr, m->W, true));
     m->n_chol++;
     phase_mark(m, PH_OTHER);
-    // speculative full step: evaluate the trial point before reading anything back
-    axpy_trial_kernel<<<blocks, threads, 0, m->stream>>>(m->W, m->step, 1.0, m->p, m->lda, m->Wtrial);
-    count_launch();
     // the Cholesky scalars must be captured before the trial evaluation overwrites f / gmax:
     // they live in different fields of EvalScalars, so one read after the trial eval suffices.
     BGP_TRY(eval_fg_async(m, m->Wtrial, theta, c3w));

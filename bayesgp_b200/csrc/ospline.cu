@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(128, NDC <= 4 ? 3 : 2) osp_pass_kernel(const O
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
   double dmax = 0.0;
+#pragma unroll 2
   for (int64_t j = j0 + lane; j < j1; j += 32) {
     const double u = a.u[j];
     const double yv = a.y[j];
@@ -441,7 +442,7 @@ struct OspHArgs {
   const double *c_t0, *c_t1;
   const int *c_gid, *c_side;
   const double *mom, *glob, *Hdb, *G;
-  double* H;
+  double *H, *L;      // L != NULL: a second copy for the Cholesky kernel, which factors in place (saves its device-to-device copy)
   // Q(theta) on the diagonal (an IWP precision is diagonal): qfix on the dense columns, e^theta P_i on the spline
   // columns; NULL when the likelihood part is all-reduced over observation shards first
   const double *qfix, *Pdiag;
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(256) osp_hwrite_kernel(const OspHArgs a) {
   }
   if (r == c && a.qfix) v += r < a.nD ? a.qfix[r] : a.etheta * a.Pdiag[r - a.nD];
   a.H[(size_t)c * a.ldh + r] = v;
+  if (a.L) a.L[(size_t)c * a.ldh + r] = v;
 }
 
 
@@ -766,7 +768,9 @@ int osp_launch_hessian(bgp_model* m, const double* theta) {
   ha.Hdb = pl->Hdb;
   ha.G = pl->G;
   ha.H = m->H;
+  ha.L = theta ? m->L : nullptr;           // complete (Q included) only on a single device
   OSP_DISPATCH(hess_launch, m, pl, ha);
+  m->L_holds_H = theta != nullptr;
   count_launch();
   BGP_CUDA(cudaGetLastError());
   return BGP_OK;

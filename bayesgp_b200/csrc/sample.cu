@@ -153,6 +153,7 @@ static int sample_core(bgp_fit* f, int64_t M, const double* Z_host, uint64_t see
       // src/BayesGP.cpp:76-127 (the same z gives a different W under any other ordering), so both are rotated
       BGP_TRY(rot_H_dev(m, f->Hs_dev + (size_t)f->slot[j] * p * m->ldh, m->H, m->ldh));
       BGP_TRY(rot_vec_dev(m, f->modes_dev + (size_t)f->slot[j] * m->lda, f->mode_dev));
+      m->L_holds_H = false;
       BGP_TRY(launch_chol_solve(m, false));
       note_chol_info_kernel<<<1, 1, 0, m->stream>>>(m->sc_dev, j, flag_dev);
       count_launch();

@@ -782,6 +782,7 @@ __global__ void unpack_lower_kernel(const double* __restrict__ in, int p, int ld
 }
 
 int launch_hessian(bgp_model* m, const double* theta) {
+  m->L_holds_H = false;
   if (m->osp_on) {
     // moment path: H_lik and, on a single device, Q(theta) in one kernel
     BGP_TRY(osp_launch_hessian(m, m->world > 1 ? nullptr : theta));

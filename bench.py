@@ -510,6 +510,11 @@ def fit_leg(ff):
     (BFGS by vmmin, Richardson Hessian of ff$gr, the 15-node grid, marginals), wall clock, with the evaluation counts
     and the in-situ rate of the grid phase (to be compared with the headline)."""
     import bayesgp_b200 as bg
+    # the gradient plan (leverage buffers, tensor maps: cudaMalloc of ~20 MB, 0.05-0.1 s once per model) is created by the
+    # first ff$gr call: a one-time model cost like finalize, kept outside the clock; its wall time is reported beside the fit
+    t0 = time.perf_counter()
+    ff.gr(np.zeros(ff.S))
+    first_gr = time.perf_counter() - t0
     ff.set_start(None)
     fn0, it0 = ff.counters()["laplace_evals"], ff.counters()["newton_iters"]
     tm0 = ff.last_timing()
@@ -518,7 +523,7 @@ def fit_leg(ff):
     wall = time.perf_counter() - t0
     d, c, tm1 = mod.diagnostics, ff.counters(), ff.last_timing()
     out = {"what": "marginal_laplace_tmb(ff, k=15, theta0=0) on the resident C3 model: BFGS + Richardson + grid + marginals",
-           "wall_s": wall, "opt_s": d["opt_ms"] * 1e-3, "grid_s": d["grid_ms"] * 1e-3,
+           "wall_s": wall, "first_gradient_call_s": first_gr, "opt_s": d["opt_ms"] * 1e-3, "grid_s": d["grid_ms"] * 1e-3,
            "fn_count": mod.optresults["fn_count"], "gr_count": mod.optresults["gr_count"],
            "laplace_evals": c["laplace_evals"] - fn0, "newton_iters": c["newton_iters"] - it0,
            "kernel_launches": {k: tm1[k] - tm0[k] for k in ("lik_launches", "hess_launches", "chol_launches")},
