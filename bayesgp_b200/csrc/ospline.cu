@@ -54,7 +54,7 @@ struct OspPlan {
   // per evaluation
   int* done = nullptr;
   // leverage path (allocated on the first gradient): V G_J per interval and its Gram matrix
-  int nside = 0, ldk = 0;
+  int nside = 0, ldk = 0, maxK = 0;
   int *side_gbase = nullptr, *side_cbase = nullptr, *side_K = nullptr;
   std::vector<double> c_t0_host, c_t1_host;
   double *Yt = nullptr, *Omega = nullptr, *c_step = nullptr;
@@ -512,9 +512,13 @@ __global__ void __launch_bounds__(128) osp_levY_kernel(const double* __restrict_
                                                        const int* __restrict__ side_gbase, const int* __restrict__ side_cbase,
                                                        const int* __restrict__ side_K, const double* __restrict__ c_step,
                                                        double* __restrict__ Yt) {
+  extern __shared__ double s_cs[];                 // the side's per-column constants: K x OSP_STEP
   const int k = blockIdx.x * 128 + threadIdx.x, sd = blockIdx.y;
-  if (k >= p || sd >= nside) return;
+  if (sd >= nside) return;
   const int gbase = side_gbase[sd], cbase = side_cbase[sd], K = side_K[sd];
+  for (int t = threadIdx.x; t < K * OSP_STEP; t += 128) s_cs[t] = c_step[(size_t)cbase * OSP_STEP + t];
+  __syncthreads();
+  if (k >= p) return;
   double y[P];
 #pragma unroll
   for (int m = 0; m < P; ++m) {
@@ -522,27 +526,34 @@ __global__ void __launch_bounds__(128) osp_levY_kernel(const double* __restrict_
     Yt[((size_t)gbase * P + m) * ldk + k] = 0.0;
   }
   const double* Vk = V + (size_t)k * ldl + nD + cbase;
-  double vk = K > 0 ? Vk[0] : 0.0;
-  for (int J = 1; J <= K; ++J) {
-    // per-column constants (osp_plan_create): the shift matrix binom(r, m) d^(r-m), r >= m, then the tail coefficients
-    // d^(P-m) / ((P-m)! m!) — the same for every row of V, off the dependent chain
-    const double* cs = c_step + (size_t)(cbase + J - 1) * OSP_STEP;
-    const double vnext = J < K ? Vk[J] : 0.0;          // next step's entry of V, in flight during this one
-    double yn[P];
-    int t = 0;
+  constexpr int CH = 16;                            // this row's entries of V, sixteen loads in flight at a time
+  for (int J0 = 0; J0 < K; J0 += CH) {
+    double v[CH];
 #pragma unroll
-    for (int m = 0; m < P; ++m) {
-      double acc = vk * cs[OSP_STEP - OSP_MAXP + m];
+    for (int q = 0; q < CH; ++q) v[q] = J0 + q < K ? Vk[J0 + q] : 0.0;
 #pragma unroll
-      for (int r = m; r < P; ++r, ++t) acc = fma(cs[t], y[r], acc);
-      yn[m] = acc;
+    for (int q = 0; q < CH; ++q) {
+      const int J = J0 + q + 1;
+      if (J <= K) {
+        // shift matrix binom(r, m) d^(r-m), r >= m, then the tail coefficients d^(P-m) / ((P-m)! m!) of the column
+        // that was the previous interval's own one
+        const double* cs = s_cs + (J - 1) * OSP_STEP;
+        double yn[P];
+        int t = 0;
+#pragma unroll
+        for (int m = 0; m < P; ++m) {
+          double acc = v[q] * cs[OSP_STEP - OSP_MAXP + m];
+#pragma unroll
+          for (int r = m; r < P; ++r, ++t) acc = fma(cs[t], y[r], acc);
+          yn[m] = acc;
+        }
+#pragma unroll
+        for (int m = 0; m < P; ++m) {
+          y[m] = yn[m];
+          Yt[((size_t)(gbase + J) * P + m) * ldk + k] = yn[m];
+        }
+      }
     }
-#pragma unroll
-    for (int m = 0; m < P; ++m) {
-      y[m] = yn[m];
-      Yt[((size_t)(gbase + J) * P + m) * ldk + k] = yn[m];
-    }
-    vk = vnext;
   }
 }
 
@@ -781,7 +792,9 @@ template <int P, int NDC>
 static void lev_launch(bgp_model* m, OspPlan* pl, const double* V, int ldl, const OspLevArgs& la, const OspApplyArgs& aa) {
   const int p = m->p;
   dim3 gy((p + 127) / 128, pl->nside);
-  osp_levY_kernel<P><<<gy, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->nside, pl->side_gbase, pl->side_cbase, pl->side_K,
+  const size_t ysm = (size_t)pl->maxK * OSP_STEP * sizeof(double);
+  if (ysm > 48 * 1024) cudaFuncSetAttribute(osp_levY_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysm);
+  osp_levY_kernel<P><<<gy, 128, ysm, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->nside, pl->side_gbase, pl->side_cbase, pl->side_K,
                                                pl->c_step, pl->Yt);
   osp_levOmega_kernel<P, NDC><<<pl->NG, 128, 0, m->stream>>>(V, p, ldl, pl->nD, pl->ldk, pl->g_own, pl->Yt, pl->Omega);
   osp_levpass_kernel<P, NDC><<<std::min((pl->np + 3) / 4, pl->pass_grid), 128, 0, m->stream>>>(la);
@@ -928,6 +941,7 @@ int osp_plan_create(bgp_model* m) {
     side_K.push_back(Kp);
   }
   pl->nside = (int)side_K.size();
+  pl->maxK = std::max(Kn, Kp);
 
   uint32_t *gid = nullptr, *gid2 = nullptr, *idx = nullptr, *idx2 = nullptr;
   double *u0 = nullptr, *kn_dev = nullptr, *kp_dev = nullptr;
