@@ -86,6 +86,8 @@ SIGNATURES = {
     "bgp_model_set_ospline": (C.c_int, [C.c_void_p, C.c_int]),
     "bgp_model_get_ospline": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "bgp_model_ospline_bytes": (C.c_int, [C.c_void_p, c_double_p]),
+    "bgp_model_set_lanes": (C.c_int, [C.c_void_p, C.c_int]),
+    "bgp_model_get_lanes": (C.c_int, [C.c_void_p, c_int_p]),
     "bgp_fit_get_diagnostics": (C.c_int, [C.c_void_p, c_int_p, c_int64_p, c_double_p, c_double_p]),
     "bgp_fit_host_arrays": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]),
     "bgp_fit_node_owner": (C.c_int, [C.c_void_p, c_int32_p]),

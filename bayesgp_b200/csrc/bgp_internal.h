@@ -216,6 +216,14 @@ struct bgp_model {
   struct PoolBlock { size_t bytes; void* ptr; };
   std::vector<PoolBlock> dev_pool, pin_pool;
   std::shared_ptr<int> alive = std::make_shared<int>(1);   // fits outliving the model see 0 here
+  // ---- lanes -------------------------------------------------------------------------------------
+  // A batch of evaluations on the moment path leaves most of the device idle (its dominant kernel, the Cholesky, runs
+  // on 8 SMs): the nodes of a batch are dealt to n_lanes evaluation contexts that run concurrently, each on its own
+  // stream and host thread with its own iterate / Hessian / factor / history / moment buffers; the observations and
+  // every other read-only array are shared with the parent.  Lane 0 is the model itself.
+  int n_lanes = 1;
+  std::vector<bgp_model*> lanes;   // lanes 1 .. n_lanes - 1 (owned)
+  bool is_lane = false;
   // ---- timing ----------------------------------------------------------------------------------
   cudaEvent_t ev[8] = {nullptr};
   double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0, t_lev = 0;
@@ -312,6 +320,12 @@ int rot_vec_dev(bgp_model* m, const double* dev_int, double* dev_ext);      // p
 int rot_H_dev(bgp_model* m, const double* H_int, double* dev_ext, int lde); // p x ldh internal -> p x lde external
 int launch_sgp_block(const double* x_dev, int64_t n, double x0, double a, int k, int m, double lo, double hi, double* dstB,
                      double* dstX, cudaStream_t st);
+// model.cu: evaluation lanes (see bgp_model::n_lanes)
+int lanes_ensure(bgp_model* m, int count);
+void lanes_destroy(bgp_model* m);
+// ospline.cu: a lane's private copy of the per-evaluation buffers of the moment path
+int osp_plan_clone_for_lane(const bgp_model* parent, bgp_model* lane);
+void osp_plan_destroy_lane(bgp_model* lane);
 // model.cu: size-keyed free lists of device / pinned blocks (see bgp_model::dev_pool)
 void* pool_take(bgp_model* m, bool pinned, size_t bytes, size_t* got_bytes);
 void pool_give(bgp_model* m, bool pinned, void* ptr, size_t bytes);

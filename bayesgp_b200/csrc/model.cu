@@ -112,6 +112,117 @@ static double lchoose_sum(const double* y, const double* size, int64_t n) {
 
 }  // namespace bgp
 
+namespace bgp {
+
+static void lane_free(bgp_model* l) {
+  if (l->stream) cudaStreamSynchronize(l->stream);
+  if (l->out_stream) cudaStreamSynchronize(l->out_stream);
+  osp_plan_destroy_lane(l);
+  for (double* ptr : {l->W, l->Wtrial, l->Wmode, l->g, l->step, l->Tan, l->xbuf, l->H, l->L, l->Ldinv, l->red_buf})
+    if (ptr) cudaFree(ptr);
+  for (auto& h : l->hist) {
+    if (h.W) cudaFree(h.W);
+    if (h.T) cudaFree(h.T);
+  }
+  if (l->sc_dev) cudaFree(l->sc_dev);
+  if (l->sc_host) cudaFreeHost(l->sc_host);
+  for (int i = 0; i < 2; ++i) {
+    if (l->out_stage[i]) cudaFree(l->out_stage[i]);
+    if (l->out_ready[i]) cudaEventDestroy(l->out_ready[i]);
+    if (l->out_done[i]) cudaEventDestroy(l->out_done[i]);
+    if (l->pin_out[i]) cudaFreeHost(l->pin_out[i]);
+    if (l->pin_ev[i]) cudaEventDestroy(l->pin_ev[i]);
+  }
+  if (l->out_stream) cudaStreamDestroy(l->out_stream);
+  for (int i = 0; i < 8; ++i)
+    if (l->ev[i]) cudaEventDestroy(l->ev[i]);
+  for (cudaEvent_t e : l->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : l->sealed_pool) cudaEventDestroy(e);
+  if (l->stream) cudaStreamDestroy(l->stream);
+  delete l;
+}
+
+// Lanes 1 .. count - 1 of a finalized single-device model on the moment path: a copy of the model's description that
+// shares every read-only device array with it and owns the state one evaluation writes.
+int lanes_ensure(bgp_model* m, int count) {
+  while ((int)m->lanes.size() < count - 1) {
+    bgp_model* l = new bgp_model(*m);
+    l->is_lane = true;
+    l->n_lanes = 1;
+    l->lanes.clear();
+    // nothing below may be shared with the parent: reset, then allocate
+    l->stream = nullptr;
+    l->W = l->Wtrial = l->Wmode = l->g = l->step = l->Tan = l->xbuf = l->H = l->L = l->Ldinv = l->red_buf = nullptr;
+    for (auto& h : l->hist) {
+      h.W = h.T = nullptr;
+      h.stamp = 0;
+    }
+    l->sc_dev = nullptr;
+    l->sc_host = nullptr;
+    l->theta_dev = nullptr;
+    for (int i = 0; i < 2; ++i) {
+      l->pin_out[i] = nullptr;
+      l->pin_ev[i] = nullptr;
+      l->out_stage[i] = nullptr;
+      l->out_ready[i] = l->out_done[i] = nullptr;
+      l->out_used[i] = false;
+    }
+    l->pin_out_elems = 0;
+    l->out_stream = nullptr;
+    l->out_count = 0;
+    l->host_hook = nullptr;
+    for (int i = 0; i < 8; ++i) l->ev[i] = nullptr;
+    l->ev_pool.clear();
+    l->sealed_pool.clear();
+    l->marks.clear();
+    l->sealed_marks.clear();
+    l->grad_plan = nullptr;       // lanes never take gradients
+    l->Linv = l->zobs = nullptr;
+    l->hpack = nullptr;
+    l->dev_pool.clear();
+    l->pin_pool.clear();
+    l->alive = std::make_shared<int>(1);
+    l->osp_plan = nullptr;
+    l->t_total = l->t_lik = l->t_hess = l->t_chol = l->t_lev = 0.0;
+    l->n_lik = l->n_hess = l->n_chol = l->n_lev = 0;
+    l->n_evals = l->n_newton = l->n_reuse = 0;
+    m->lanes.push_back(l);        // owned from here on: freed with the model whatever happens below
+    BGP_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    const size_t vb = (size_t)m->lda * sizeof(double);
+    auto dalloc = [&](double** ptr, size_t bytes) -> int {
+      BGP_CUDA(cudaMalloc(ptr, bytes));
+      BGP_CUDA(cudaMemsetAsync(*ptr, 0, bytes, l->stream));
+      return BGP_OK;
+    };
+    for (double** ptr : {&l->W, &l->Wtrial, &l->Wmode, &l->g, &l->step}) BGP_TRY(dalloc(ptr, vb));
+    BGP_TRY(dalloc(&l->Tan, (size_t)std::max(1, m->S) * vb));
+    for (auto& h : l->hist) {
+      BGP_TRY(dalloc(&h.T, (size_t)std::max(1, m->S) * vb));
+      BGP_TRY(dalloc(&h.W, vb));
+    }
+    const size_t hb = (size_t)m->ldh * m->p * sizeof(double);
+    BGP_TRY(dalloc(&l->H, hb));
+    BGP_TRY(dalloc(&l->L, hb));
+    BGP_TRY(dalloc(&l->Ldinv, (size_t)m->ldh * sizeof(double)));
+    BGP_TRY(dalloc(&l->xbuf, std::max((size_t)m->lda, (size_t)m->p * m->p) * sizeof(double)));
+    BGP_TRY(dalloc(&l->red_buf, ((size_t)m->lda + 8) * sizeof(double)));
+    BGP_CUDA(cudaMalloc(&l->sc_dev, 2 * sizeof(EvalScalars)));
+    BGP_CUDA(cudaMemsetAsync(l->sc_dev, 0, 2 * sizeof(EvalScalars), l->stream));
+    BGP_CUDA(cudaMallocHost(&l->sc_host, 2 * sizeof(EvalScalars)));
+    for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&l->ev[i]));
+    BGP_TRY(osp_plan_clone_for_lane(m, l));
+    BGP_CUDA(cudaStreamSynchronize(l->stream));
+  }
+  return BGP_OK;
+}
+
+void lanes_destroy(bgp_model* m) {
+  for (bgp_model* l : m->lanes) lane_free(l);
+  m->lanes.clear();
+}
+
+}  // namespace bgp
+
 using namespace bgp;
 
 extern "C" {
@@ -520,6 +631,25 @@ int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on) {
   return BGP_OK;
 }
 
+int bgp_model_set_lanes(bgp_model* m, int lanes) {
+  if (!m || !m->finalized) {
+    set_error("bgp_model_set_lanes: model is not finalized");
+    return BGP_ERR_STATE;
+  }
+  if (lanes < 1 || lanes > 16) {
+    set_error("bgp_model_set_lanes: 1 .. 16 lanes");
+    return BGP_ERR_ARG;
+  }
+  m->n_lanes = lanes;
+  return BGP_OK;
+}
+
+int bgp_model_get_lanes(const bgp_model* m, int* lanes) {
+  if (!m || !lanes) return BGP_ERR_ARG;
+  *lanes = m->n_lanes;
+  return BGP_OK;
+}
+
 int bgp_model_ospline_bytes(const bgp_model* m, double* bytes_per_pass) {
   if (!m || !m->osp_plan) {
     set_error("bgp_model_ospline_bytes: the model has no O-spline moment path");
@@ -651,6 +781,7 @@ int bgp_model_finalize(bgp_model* m) {
   BGP_CUDA(cudaMallocHost(&m->sc_host, 2 * sizeof(EvalScalars)));
   BGP_CUDA(cudaStreamSynchronize(m->stream));     // the zero fills and the two copies above
   if (const char* e = getenv("BGP_NO_SPECULATION")) m->speculate = !(e[0] == '1');   // diagnostics only
+  if (const char* e = getenv("BGP_LANES")) m->n_lanes = std::max(1, std::min(16, atoi(e)));
   for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&m->ev[i]));
   BGP_TRY(build_row_order(m));
   BGP_TRY(syrk_plan_create(m));
@@ -673,6 +804,7 @@ void bgp_model_destroy(bgp_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  lanes_destroy(m);
   syrk_plan_destroy(m);
   lik_plan_destroy(m);
   grad_plan_destroy(m);

@@ -12,6 +12,8 @@
 
 #include <time.h>
 
+#include <thread>
+
 #include "bgp_internal.h"
 
 namespace bgp {
@@ -503,8 +505,8 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
 // the device -> pinned copy is asynchronous, the pinned -> caller copy runs while the next evaluation's kernels are
 // in flight) or by device-to-device copies (device sink: nothing crosses PCIe).  Nodes that fail get NaN and the
 // worst status is returned after all nodes were tried; values of nodes that are not mine are left untouched.
-int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char* mine, double* values,
-                  const BatchSink& sink, int* iters_total, int* first_failed) {
+static int laplace_batch_serial(bgp_model* m, int K, const double* theta, const unsigned char* mine, double* values,
+                                const BatchSink& sink, int* iters_total, int* first_failed) {
   int total = 0, worst = BGP_OK;
   if (first_failed) *first_failed = -1;
   // the deferred copies point into the caller's arrays: none may outlive this call, whichever way it returns
@@ -673,6 +675,113 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
     g_trace = HostTrace();
   }
   if (iters_total) *iters_total = total;
+  return worst;
+}
+
+// The nodes of a batch dealt to the model's evaluation lanes (bgp_model::n_lanes): contiguous runs of the caller's node
+// order (neighbours share a lane, which keeps the warm starts close — the split of a node group, one level down), one
+// host thread per lane.  Every lane starts from a copy of the model's warm-start history and evaluates its run with the
+// serial driver above; results go to disjoint slots of the same sink.  Values differ from a one-lane run only through
+// the starting points (well inside the tolerances the inner solve converges to).
+int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char* mine, double* values,
+                  const BatchSink& sink, int* iters_total, int* first_failed) {
+  int count = 0;
+  for (int j = 0; j < K; ++j) count += (!mine || mine[j]) ? 1 : 0;
+  int L = m->n_lanes;
+  if (!m->osp_on || m->world > 1 || m->is_lane) L = 1;
+  L = std::min(L, count / 2);                       // a lane's first node costs two Newton iterations: at least two nodes each
+  if (L <= 1) return laplace_batch_serial(m, K, theta, mine, values, sink, iters_total, first_failed);
+  BGP_TRY(lanes_ensure(m, L));
+  std::vector<bgp_model*> lane((size_t)L);
+  lane[0] = m;
+  for (int l = 1; l < L; ++l) lane[(size_t)l] = m->lanes[(size_t)l - 1];
+  // the model's pending work (history entries, the mode of the last evaluation) must be complete before it is copied
+  BGP_CUDA(cudaStreamSynchronize(m->stream));
+  for (int l = 1; l < L; ++l) {
+    bgp_model* ln = lane[(size_t)l];
+    ln->osp_on = true;
+    ln->osp_dense_grad = m->osp_dense_grad;
+    ln->use_predictor = m->use_predictor;
+    ln->use_hermite = m->use_hermite;
+    ln->speculate = m->speculate;
+    ln->allow_reuse = m->allow_reuse;
+    ln->reuse_eta_tol = m->reuse_eta_tol;
+    ln->reuse_rel_tol = m->reuse_rel_tol;
+    ln->grad_tol = m->grad_tol;
+    ln->step_tol = m->step_tol;
+    ln->maxit = m->maxit;
+    ln->theta_last = m->theta_last;
+    ln->tan_valid = m->tan_valid;
+    ln->hist_clock = m->hist_clock;
+    ln->factor_is_exact = false;
+    ln->obs_at_mode = false;
+    ln->L_holds_H = false;
+    const size_t vb = (size_t)m->lda * sizeof(double);
+    BGP_CUDA(cudaMemcpyAsync(ln->Wmode, m->Wmode, vb, cudaMemcpyDeviceToDevice, ln->stream));
+    BGP_CUDA(cudaMemcpyAsync(ln->Tan, m->Tan, (size_t)std::max(1, m->S) * vb, cudaMemcpyDeviceToDevice, ln->stream));
+    for (int i = 0; i < bgp_model::NHIST; ++i) {
+      ln->hist[i].theta = m->hist[i].theta;
+      ln->hist[i].stamp = m->hist[i].stamp;
+      if (!m->hist[i].stamp) continue;
+      BGP_CUDA(cudaMemcpyAsync(ln->hist[i].W, m->hist[i].W, vb, cudaMemcpyDeviceToDevice, ln->stream));
+      BGP_CUDA(cudaMemcpyAsync(ln->hist[i].T, m->hist[i].T, (size_t)std::max(1, m->S) * vb, cudaMemcpyDeviceToDevice, ln->stream));
+    }
+  }
+  for (int l = 1; l < L; ++l) BGP_CUDA(cudaStreamSynchronize(lane[(size_t)l]->stream));
+  // contiguous, count-balanced runs of the nodes that are mine
+  std::vector<std::vector<unsigned char>> mask((size_t)L, std::vector<unsigned char>((size_t)K, 0));
+  {
+    int idx = 0;
+    for (int j = 0; j < K; ++j)
+      if (!mine || mine[j]) mask[(size_t)piece_owner(idx++, count, L)][(size_t)j] = 1;
+  }
+  std::vector<int> rc((size_t)L, BGP_OK), its((size_t)L, 0), ff((size_t)L, -1);
+  std::vector<std::string> err((size_t)L);
+  auto run = [&](int l) {
+    bgp_model* ln = lane[(size_t)l];
+    if (cudaSetDevice(ln->device) != cudaSuccess) {
+      rc[(size_t)l] = BGP_ERR_CUDA;
+      err[(size_t)l] = "cudaSetDevice failed in an evaluation lane";
+      return;
+    }
+    rc[(size_t)l] = laplace_batch_serial(ln, K, theta, mask[(size_t)l].data(), values, sink, &its[(size_t)l], &ff[(size_t)l]);
+    if (rc[(size_t)l] != BGP_OK) err[(size_t)l] = g_last_error;
+    cudaStreamSynchronize(ln->stream);
+  };
+  std::vector<std::thread> th;
+  for (int l = 1; l < L; ++l) th.emplace_back(run, l);
+  run(0);
+  for (auto& t : th) t.join();
+  int total = 0, worst = BGP_OK, bad = -1;
+  for (int l = 0; l < L; ++l) {
+    total += its[(size_t)l];
+    if (rc[(size_t)l] != BGP_OK && (worst == BGP_OK || rc[(size_t)l] == BGP_ERR_CUDA)) {
+      worst = rc[(size_t)l];
+      g_last_error = err[(size_t)l];
+    }
+    if (ff[(size_t)l] >= 0 && (bad < 0 || ff[(size_t)l] < bad)) bad = ff[(size_t)l];
+    if (l > 0) {
+      // the lanes' counters and phase timers belong to the model
+      bgp_model* ln = lane[(size_t)l];
+      phase_collect(ln);
+      phase_harvest(ln);
+      phase_collect(ln);
+      m->t_lik += ln->t_lik;
+      m->t_hess += ln->t_hess;
+      m->t_chol += ln->t_chol;
+      m->n_lik += ln->n_lik;
+      m->n_hess += ln->n_hess;
+      m->n_chol += ln->n_chol;
+      m->n_evals += ln->n_evals;
+      m->n_newton += ln->n_newton;
+      m->n_reuse += ln->n_reuse;
+      ln->t_lik = ln->t_hess = ln->t_chol = 0.0;
+      ln->n_lik = ln->n_hess = ln->n_chol = 0;
+      ln->n_evals = ln->n_newton = ln->n_reuse = 0;
+    }
+  }
+  if (iters_total) *iters_total = total;
+  if (first_failed) *first_failed = bad;
   return worst;
 }
 

@@ -671,6 +671,41 @@ __global__ void __launch_bounds__(128) osp_levpass_kernel(const OspLevArgs a) {
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
+// A lane shares the observations, the piece table and the knot tables with its parent and owns what a pass writes.
+int osp_plan_clone_for_lane(const bgp_model* parent, bgp_model* lane) {
+  const OspPlan* pp = (const OspPlan*)parent->osp_plan;
+  lane->osp_plan = nullptr;
+  if (!pp) return BGP_OK;
+  OspPlan* pl = new OspPlan(*pp);
+  pl->eta = pl->slots = pl->mom = pl->glob = pl->Hdb = pl->G = pl->Yt = pl->Omega = pl->c_step = nullptr;
+  pl->done = nullptr;
+  lane->osp_plan = pl;
+  auto zalloc = [&](double** ptr, size_t count) -> int {
+    BGP_CUDA(cudaMalloc(ptr, std::max<size_t>(1, count) * sizeof(double)));
+    BGP_CUDA(cudaMemsetAsync(*ptr, 0, std::max<size_t>(1, count) * sizeof(double), lane->stream));
+    return BGP_OK;
+  };
+  BGP_TRY(zalloc(&pl->eta, (size_t)pl->n));
+  BGP_TRY(zalloc(&pl->slots, (size_t)std::max(1, pl->np) * pl->NACC));
+  BGP_TRY(zalloc(&pl->mom, (size_t)pl->NG * pl->NM));
+  BGP_TRY(zalloc(&pl->glob, (size_t)(pl->NACC - pl->NM)));
+  BGP_TRY(zalloc(&pl->Hdb, (size_t)pl->NDC * pl->NC));
+  BGP_TRY(zalloc(&pl->G, (size_t)pl->NC * OSP_MAXP));
+  BGP_CUDA(cudaMalloc(&pl->done, sizeof(int)));
+  BGP_CUDA(cudaMemsetAsync(pl->done, 0, sizeof(int), lane->stream));
+  return BGP_OK;
+}
+
+void osp_plan_destroy_lane(bgp_model* lane) {
+  OspPlan* pl = (OspPlan*)lane->osp_plan;
+  if (!pl) return;
+  for (void* ptr : {(void*)pl->eta, (void*)pl->slots, (void*)pl->mom, (void*)pl->glob, (void*)pl->Hdb, (void*)pl->G, (void*)pl->done,
+                    (void*)pl->Yt, (void*)pl->Omega, (void*)pl->c_step})
+    if (ptr) cudaFree(ptr);
+  delete pl;
+  lane->osp_plan = nullptr;
+}
+
 template <typename T>
 static int upload(T** dst, const std::vector<T>& v) {
   BGP_CUDA(cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(T)));
@@ -1086,6 +1121,7 @@ int osp_plan_create(bgp_model* m) {
     return st;
   }
   m->osp_on = true;
+  if (!getenv("BGP_LANES")) m->n_lanes = 4;     // measured on C3 (scripts/lanes_probe.sh): 1 / 2 / 3 / 4 / 6 / 8 lanes -> 2480 / 3898 / 5053 / 5533 / 5298 / 5079 evals/s
   return BGP_OK;
 }
 

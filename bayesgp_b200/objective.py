@@ -158,6 +158,15 @@ class LaplaceObjective:
         moment path with the gradient's leverages taken from the dense design (on=2; A/B)."""
         check(self._lib.bgp_model_set_ospline(self._h, int(on)))
 
+    def set_lanes(self, lanes):
+        """Concurrent evaluation contexts for batches on the moment path (bgp_model_set_lanes)."""
+        check(self._lib.bgp_model_set_lanes(self._h, int(lanes)))
+
+    def lanes(self):
+        n = C.c_int()
+        check(self._lib.bgp_model_get_lanes(self._h, C.byref(n)))
+        return n.value
+
     def ospline_bytes(self):
         """Algorithmic bytes one likelihood pass of the moment path moves."""
         b = C.c_double()

@@ -236,6 +236,8 @@ def run_b200(args):
     # bgp_aghq_fit*); at N = 1 the group is trivial and the same code path runs
     group = (rank, world, broadcast_unique_id(nccl_unique_id, rank)) if world > 1 else None
     ff = build_b200(x, y, local, x0, knots, node_group=group)
+    if args.lanes > 0:
+        ff.set_lanes(args.lanes)
     t_build = time.time() - t0
     mode, sd, thetas, w_mode, t_mode = node_grid(ff)
     p, n = ff.p, ff.n
@@ -311,6 +313,20 @@ def run_b200(args):
     grid_res = step_grid(True, keep=True)["res"]        # untimed: owned copies for the comparison below
     evals = K_NODES * args.steps
     moment_path = ff.ospline()[1]
+    lanes = ff.lanes()
+    one_lane = None
+    if moment_path and lanes > 1 and not args.no_dense:
+        # the same step with one evaluation lane: what the concurrency of the lanes buys
+        ff.set_lanes(1)
+        for _ in range(W):
+            step_grid()
+        l_ms, _, _, _ = timed_steps(lambda: step_grid(False), args.steps, dist)
+        _, l_wall, _, _ = timed_steps(lambda: step_grid(True), args.steps, dist)
+        one_lane = {"value": evals / (l_ms * 1e-3), "e2e": evals / l_wall, "unit": "evals/s",
+                    "what": "bgp_model_set_lanes(m, 1): every node of the grid on one stream, one after the other"}
+        ff.set_lanes(lanes)
+        for _ in range(2):
+            step_grid()
     dense = None
     if world == 1 and moment_path and not args.no_dense:
         # the same step on the dense path (TMA likelihood pass + DMMA Hessian kernel): what every model with more than
@@ -425,9 +441,10 @@ def run_b200(args):
         roofline = {"bound": "tensor", "kernel": "chol_kernel<32> (p x p Cholesky, log-det, Newton solve and tangent; one 8-CTA cluster)",
                     "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
                     "traffic": None, "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": chol_flops,
-                    "share_of_step": chol_ms * (pf["n_chol"] / args.steps) / (dev_ms / args.steps),
+                    "kernel_time_over_step_time": chol_ms * (pf["n_chol"] / args.steps) / (dev_ms / args.steps),
                     "note": "latency-bound, not throughput-bound: p = %d dependent pivot steps on 8 of 148 SMs (DESIGN.md "
-                            "section 5); the two big dense-path kernels are under dense_path" % p,
+                            "section 5) — which is why %d evaluation lanes run concurrently (kernel_time_over_step_time counts "
+                            "overlapping launches); the two big dense-path kernels are under dense_path" % (p, lanes),
                     "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run"}
         ob = ff.ospline_bytes()
         gbs = ob / (lik_ms * 1e-3) / 1e9
@@ -456,6 +473,7 @@ def run_b200(args):
                    "theta_mode": mode, "theta_sd": sd, "l2_flush": "256 MB written between steps (outside the device-timed interval): the moment path's per-step "
                                                          "inputs (56 MB) would fit the 126 MB L2; the dense path's 2.4 GB design does not",
                    "path": "O-spline moment path (ospline.cu)" if moment_path else "dense path (lik.cu + syrk.cu)",
+                   "lanes": lanes,
                    "parallelism": "node shards x%d (replicated rows), NCCL all-reduce of the 15 values" % world
                                   if world > 1 else "single GPU",
                    "model_build_s": t_build},
@@ -478,6 +496,8 @@ def run_b200(args):
         "wall_s_timed_region": region_s,
     }
     line.update(extra)
+    if one_lane is not None:
+        line["one_lane"] = one_lane
     if dense is not None:
         r_h, r_l = dense_rooflines(dense["pf"])
         line["dense_path"] = {
@@ -737,6 +757,7 @@ def main():
     ap.add_argument("--no-fit", action="store_true", help="skip the model_fit() leg")
     ap.add_argument("--no-grad", action="store_true", help="skip the ff$gr leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-path (DMMA) leg of the same step")
+    ap.add_argument("--lanes", type=int, default=0, help="evaluation lanes of the moment path (0: the library's default)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-nodes", type=int, default=1)
     args = ap.parse_args()

@@ -160,6 +160,14 @@ int bgp_aghq_fit(bgp_model* m, int k, const double* theta0, bgp_fit** out);
  * Laplace gradient's leverages taken from the dense design (both for A/B measurements). */
 int bgp_model_set_ospline(bgp_model* m, int on);
 int bgp_model_get_ospline(const bgp_model* m, int* eligible, int* on);
+/* Evaluation lanes.  A batch of Laplace evaluations on the moment path (bgp_laplace_eval_batch, the quadrature grids of
+ * bgp_aghq_fit*) leaves most of the device idle — its dominant kernel, the p x p Cholesky, runs on 8 SMs.  With
+ * lanes > 1 the nodes of a batch are dealt to that many evaluation contexts (own stream, host thread, iterate, Hessian,
+ * factor, warm-start history and moment buffers; observations and all read-only arrays shared) that run concurrently.
+ * Contiguous runs of the node order per lane, at least two nodes each; values differ from a one-lane run only through
+ * the starting points of the inner solves.  Dense-path and observation-sharded models always use one lane. */
+int bgp_model_set_lanes(bgp_model* m, int lanes);
+int bgp_model_get_lanes(const bgp_model* m, int* lanes);
 /* algorithmic bytes one likelihood pass of the moment path moves (u, y, eta in / out, dense columns, size): roofline numerator */
 int bgp_model_ospline_bytes(const bgp_model* m, double* bytes_per_pass);
 /* When numDeriv's Richardson Hessian of ff$gr (d = 1e-4) is not positive definite aghq stops in chol(); so does

@@ -203,6 +203,52 @@ def test_skewed_intervals_and_unsorted_knots():
         ff.close()
 
 
+def test_lanes_match_one_lane_and_oracle():
+    """Evaluation lanes (bgp_model_set_lanes): the nodes of a batch / a quadrature grid dealt to concurrent contexts.
+    Same values, modes and Hessians as the one-lane run (to the inner solve's tolerance), same fit as the oracle;
+    failing nodes keep their NaN, one lane's failure does not disturb the others."""
+    from bayesgp_b200.api import build_objective, marginal_laplace_tmb
+    from oracle.fit import build_model
+    from oracle.laplace import LaplaceObjective as OFF
+    from oracle.aghq import marginal_laplace_tmb as oracle_mlt
+    y, terms, fixed, family, size = make_case(order=3, family="Poisson", n=20000, k=40, nfixed=1, seed=8)
+    model = build_model(y, terms(), fixed, family=family, size=size)[0]
+    ff = build_objective(y, terms(), fixed, family=family, size=size)[0]
+    try:
+        thetas = np.linspace(-4.0, 1.0, 13)[:, None]
+        ff.set_lanes(1)
+        ff.set_start(None)
+        v1, m1, H1, _ = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+        for lanes in (2, 4, 6):
+            ff.set_lanes(lanes)
+            assert ff.lanes() == lanes
+            ff.set_start(None)
+            v, mm, HH, it = ff.fn_batch(thetas, want_modes=True, want_hess=True)
+            assert np.max(np.abs(v - v1) / np.abs(v1)) < 1e-10
+            assert relerr(mm, m1) < 1e-7 and relerr(HH, H1) < 1e-7
+            assert it >= len(thetas)
+        off = OFF(model)
+        for j in (0, 6, 12):
+            want = off.fn(thetas[j])
+            assert abs(v[j] - want) <= 1e-8 * abs(want)
+            assert relerr(mm[j], off.last_par) < 1e-6
+        # a node outside the posterior fails alone
+        ff.set_lanes(4)
+        bad = np.vstack([thetas, [[-80.0]]])
+        ff.set_start(None)
+        vb = ff.fn_batch(bad, want_modes=False)[0]
+        assert np.max(np.abs(vb[:13] - v1) / np.abs(v1)) < 1e-10
+        # the whole fit through the lanes
+        want = oracle_mlt(OFF(model), 7, np.zeros(1))
+        mod = marginal_laplace_tmb(ff, 7, np.zeros(1))
+        assert abs(mod.lognormconst - want.lognormconst) <= 1e-8 * abs(want.lognormconst)
+        mh = mod.modesandhessians
+        assert relerr(mh["mode"], want.modes) < 1e-6 and relerr(mh["H"], want.hessians) < 1e-6
+        mod.close()
+    finally:
+        ff.close()
+
+
 def test_eligibility():
     """Two smoothing terms, order above 4, more than 8 dense columns, caller-supplied designs: dense path only."""
     from bayesgp_b200 import BgpError, make_objective
