@@ -8,6 +8,9 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <memory>
 #include <cstdio>
@@ -77,6 +80,50 @@ struct EvalScalars {
 };
 
 struct Comm;   // NCCL communicator wrapper (comm.cpp)
+
+// A parked host thread that runs one job at a time (the lanes of a model; newton.cu posts the jobs).
+struct LaneWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, done = true, quit = false;
+  LaneWorker() {
+    th = std::thread([this] {
+      std::unique_lock<std::mutex> lk(mu);
+      for (;;) {
+        cv.wait(lk, [this] { return has_job || quit; });
+        if (quit) return;
+        std::function<void()> j = std::move(job);
+        has_job = false;
+        lk.unlock();
+        j();
+        lk.lock();
+        done = true;
+        cv.notify_all();
+      }
+    });
+  }
+  void post(std::function<void()> j) {
+    std::unique_lock<std::mutex> lk(mu);
+    job = std::move(j);
+    has_job = true;
+    done = false;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [this] { return done; });
+  }
+  ~LaneWorker() {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      quit = true;
+      cv.notify_all();
+    }
+    if (th.joinable()) th.join();
+  }
+};
 
 }  // namespace bgp
 
@@ -224,6 +271,7 @@ struct bgp_model {
   int n_lanes = 1;
   std::vector<bgp_model*> lanes;   // lanes 1 .. n_lanes - 1 (owned)
   bool is_lane = false;
+  bgp::LaneWorker* worker = nullptr;   // a lane's host thread (parked between batches)
   // ---- timing ----------------------------------------------------------------------------------
   cudaEvent_t ev[8] = {nullptr};
   double t_total = 0, t_lik = 0, t_hess = 0, t_chol = 0, t_lev = 0;

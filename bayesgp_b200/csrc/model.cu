@@ -115,6 +115,8 @@ static double lchoose_sum(const double* y, const double* size, int64_t n) {
 namespace bgp {
 
 static void lane_free(bgp_model* l) {
+  delete l->worker;             // joins the lane's host thread
+  l->worker = nullptr;
   if (l->stream) cudaStreamSynchronize(l->stream);
   if (l->out_stream) cudaStreamSynchronize(l->out_stream);
   osp_plan_destroy_lane(l);
@@ -150,6 +152,7 @@ int lanes_ensure(bgp_model* m, int count) {
     l->is_lane = true;
     l->n_lanes = 1;
     l->lanes.clear();
+    l->worker = nullptr;
     // nothing below may be shared with the parent: reset, then allocate
     l->stream = nullptr;
     l->W = l->Wtrial = l->Wmode = l->g = l->step = l->Tan = l->xbuf = l->H = l->L = l->Ldinv = l->red_buf = nullptr;
@@ -212,6 +215,7 @@ int lanes_ensure(bgp_model* m, int count) {
     for (int i = 0; i < 8; ++i) BGP_CUDA(cudaEventCreate(&l->ev[i]));
     BGP_TRY(osp_plan_clone_for_lane(m, l));
     BGP_CUDA(cudaStreamSynchronize(l->stream));
+    l->worker = new LaneWorker();
   }
   return BGP_OK;
 }

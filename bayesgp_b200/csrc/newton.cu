@@ -748,10 +748,9 @@ int laplace_batch(bgp_model* m, int K, const double* theta, const unsigned char*
     if (rc[(size_t)l] != BGP_OK) err[(size_t)l] = g_last_error;
     cudaStreamSynchronize(ln->stream);
   };
-  std::vector<std::thread> th;
-  for (int l = 1; l < L; ++l) th.emplace_back(run, l);
+  for (int l = 1; l < L; ++l) lane[(size_t)l]->worker->post([&run, l] { run(l); });
   run(0);
-  for (auto& t : th) t.join();
+  for (int l = 1; l < L; ++l) lane[(size_t)l]->worker->wait();
   int total = 0, worst = BGP_OK, bad = -1;
   for (int l = 0; l < L; ++l) {
     total += its[(size_t)l];

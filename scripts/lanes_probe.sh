@@ -1,5 +1,5 @@
 python -m pytest tests/test_gpu_ospline.py -x -q -k "lanes" 2>&1 | tail -15
-for L in 1 2 3 4 6 8; do
+for L in ${LANES_LIST:-1 2 3 4 6 8}; do
   python bench.py --steps 5 --warmup 3 --no-predict --no-cpu --no-dense --no-fit --no-grad --lanes $L > gpurun_out/osp_lanes_$L.log 2>&1
   python -c "
 import json
