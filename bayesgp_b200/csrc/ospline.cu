@@ -212,15 +212,37 @@ __global__ void __launch_bounds__(128, NDC <= 4 ? 3 : 2) osp_pass_kernel(const O
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
   double dmax = 0.0;
-#pragma unroll 2
-  for (int64_t j = j0 + lane; j < j1; j += 32) {
-    const double u = a.u[j];
-    const double yv = a.y[j];
-    const double sz = a.size ? a.size[j] : 1.0;
-    const double eta_old = a.eta[j];
+  // software pipeline: the next observation's inputs are requested before this one's arithmetic (the eta store below
+  // may alias them as far as the compiler knows, so it would not hoist the loads itself)
+  int64_t jn = j0 + lane;
+  double nu = 0.0, ny = 0.0, nsz = 1.0, neta = 0.0, nd[NDC];
+#pragma unroll
+  for (int c = 0; c < NDC; ++c) nd[c] = 0.0;
+  if (jn < j1) {
+    nu = a.u[jn];
+    ny = a.y[jn];
+    if (a.size) nsz = a.size[jn];
+    neta = a.eta[jn];
+#pragma unroll
+    for (int c = 0; c < NDC; ++c)
+      if (c < a.nD) nd[c] = a.D[(size_t)c * a.n + jn];
+  }
+  while (jn < j1) {
+    const int64_t j = jn;
+    const double u = nu, yv = ny, sz = nsz, eta_old = neta;
     double dv[NDC];
 #pragma unroll
-    for (int c = 0; c < NDC; ++c) dv[c] = c < a.nD ? a.D[(size_t)c * a.n + j] : 0.0;
+    for (int c = 0; c < NDC; ++c) dv[c] = nd[c];
+    jn += 32;
+    if (jn < j1) {
+      nu = a.u[jn];
+      ny = a.y[jn];
+      if (a.size) nsz = a.size[jn];
+      neta = a.eta[jn];
+#pragma unroll
+      for (int c = 0; c < NDC; ++c)
+        if (c < a.nD) nd[c] = a.D[(size_t)c * a.n + jn];
+    }
     double up[2 * P + 1];
     up[0] = 1.0;
 #pragma unroll
