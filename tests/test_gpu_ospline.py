@@ -249,6 +249,61 @@ def test_lanes_match_one_lane_and_oracle():
         ff.close()
 
 
+def test_tiny_and_left_of_first_knot():
+    """40 observations on 6 knots (fewer pieces than resident warps), and observations left of the first knot of an
+    all-positive knot sequence (every spline column zero there, R/01_utility.R:351)."""
+    from bayesgp_b200.api import build_objective
+    from oracle.fit import Term, build_model
+    rng = np.random.default_rng(4)
+    for n, knots, lo in ((40, np.linspace(0.0, 1.0, 7), 0.0), (3000, np.linspace(0.2, 1.0, 12), -0.3)):
+        x = rng.uniform(lo, 1.0, n)
+        y = rng.poisson(np.exp(0.2 + x)).astype(np.float64)
+        mk = lambda: [Term("IWP", "x", x.copy(), order=2, knots=knots.copy(), initial_location=0.0)]
+        model = build_model(y, mk(), {}, family="Poisson")[0]
+        ff = build_objective(y, mk(), {}, family="Poisson")[0]
+        try:
+            assert ff.ospline() == (True, True)
+            W = 0.1 * rng.standard_normal(model.p)
+            theta = np.array([-1.0])
+            o = model.objective(W, theta, "fgH")
+            f, g, H = ff.objective(W, theta, want_grad=True, want_hess=True)
+            assert abs(f - o["f"]) <= 1e-11 * abs(o["f"])
+            assert relerr(g, o["g"]) < 1e-10 and relerr(H, o["H"]) < 1e-10
+        finally:
+            ff.close()
+
+
+@pytest.mark.parametrize("family", ["Gaussian", "Binomial"])
+def test_lanes_two_dimensional_grid(family):
+    """Lanes on an S = 2 grid (Gaussian: the noise theta) and on the Binomial family: fit with 4 lanes against the fit
+    with one lane and against the oracle."""
+    from bayesgp_b200.api import build_objective, marginal_laplace_tmb
+    from oracle.fit import build_model
+    from oracle.laplace import LaplaceObjective as OFF
+    from oracle.aghq import marginal_laplace_tmb as oracle_mlt
+    y, terms, fixed, fam, size = make_case(order=2, family=family, n=6000, k=16, nfixed=1, seed=21)
+    model = build_model(y, terms(), fixed, family=fam, size=size)[0]
+    S = model.S
+    want = oracle_mlt(OFF(model), 5, np.zeros(S))
+    res = {}
+    for lanes in (1, 4):
+        ff = build_objective(y, terms(), fixed, family=fam, size=size)[0]
+        try:
+            ff.set_lanes(lanes)
+            mod = marginal_laplace_tmb(ff, 5, np.zeros(S))
+            mh = mod.modesandhessians
+            res[lanes] = (mod.lognormconst, np.array(mh["mode"]), np.array(mh["H"]),
+                          np.array(mod.normalized_posterior["nodesandweights"]["logpost"]))
+            mod.close()
+        finally:
+            ff.close()
+    assert abs(res[4][0] - want.lognormconst) <= 1e-8 * abs(want.lognormconst)
+    assert abs(res[4][0] - res[1][0]) <= 1e-10 * abs(res[1][0])
+    assert relerr(res[4][3], res[1][3]) < 1e-10
+    assert relerr(res[4][1], res[1][1]) < 1e-6 and relerr(res[4][2], res[1][2]) < 1e-6
+    assert relerr(res[4][1], want.modes) < 1e-6
+
+
 def test_eligibility():
     """Two smoothing terms, order above 4, more than 8 dense columns, caller-supplied designs: dense path only."""
     from bayesgp_b200 import BgpError, make_objective
