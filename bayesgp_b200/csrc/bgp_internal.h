@@ -247,6 +247,7 @@ struct bgp_model {
   bool L_holds_H = false;        // m->L already holds a copy of m->H (written by the moment path's Hessian kernel)
   bool L_is_reversed = false;    // the gradient left the factor of H in reversed order in L (grad.cu)
   int64_t n_evals = 0, n_newton = 0, n_reuse = 0;
+  int64_t n_refactor = 0;        // second attempts of the factorisation at the mode (newton.cu)
   // ---- sharding ------------------------------------------------------------------------------
   int rank = 0, world = 1;
   int64_t n_total = 0;

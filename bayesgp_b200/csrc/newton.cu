@@ -453,9 +453,59 @@ int laplace_inner(bgp_model* m, const double* theta, double* value, int* iters_o
     m->n_hess++;
     phase_mark(m, PH_CHOL);
     const bool tan_in_chol = m->use_predictor && m->S <= CHOL_TANGENT_MAX_S;
-    BGP_TRY(launch_chol_solve(m, false, tan_in_chol ? theta : nullptr, m->W));
+    // Rank 0 of the cluster carries a right-hand side here too (the gradient at the mode; its solution is not used).
+    // The variant without one, next to ranks that do carry tangents, reported a non-positive pivot on a positive
+    // definite matrix in ~1 of 4 runs of the whole GPU suite (Gaussian, p = 601, 16-wide panels, four tangents; never
+    // in isolation): with BGP_PIVOT_DEBUG the inputs were verified sane, a second attempt of the same variant failed
+    // the same way and the solve variant — the one every Newton iteration runs — succeeded on the re-formed matrix
+    // (DESIGN.md section 8).  The kernel-side cause was not found; the variant is no longer used with tangents.
+    BGP_TRY(launch_chol_solve(m, tan_in_chol, tan_in_chol ? theta : nullptr, m->W));
     m->n_chol++;
     BGP_TRY(read_scalars(m, &sc));
+    if (sc.chol_info != 0) {
+      // a non-positive pivot at a point reached through factorisations of (numerically) the same matrix is suspect:
+      // form H and factor once more before answering NaN; counted and reported on stderr so it cannot hide
+      const int first_pivot = sc.chol_info;
+      if (getenv("BGP_PIVOT_DEBUG")) {
+        // diagnostics: what went into the factorisation
+        std::vector<double> hd((size_t)m->p), wv((size_t)m->n), hcol((size_t)m->p), wm((size_t)m->lda);
+        cudaMemcpy2D(hd.data(), sizeof(double), m->H, (size_t)(m->ldh + 1) * sizeof(double), sizeof(double), (size_t)m->p,
+                     cudaMemcpyDeviceToHost);
+        cudaMemcpy(wv.data(), m->wobs, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hcol.data(), m->H + (size_t)(first_pivot - 1) * m->ldh, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(wm.data(), m->W, (size_t)m->lda * sizeof(double), cudaMemcpyDeviceToHost);
+        double wmin = 1e300, wmax = -1e300, dmin = 1e300, cmax = 0, wabs = 0;
+        int wbad = 0, dbad = 0, cbad = 0;
+        for (double v : wv) {
+          if (!std::isfinite(v)) ++wbad;
+          wmin = std::min(wmin, v);
+          wmax = std::max(wmax, v);
+        }
+        for (double v : hd) {
+          if (!std::isfinite(v)) ++dbad;
+          dmin = std::min(dmin, v);
+        }
+        for (double v : hcol) {
+          if (!std::isfinite(v)) ++cbad;
+          cmax = std::max(cmax, std::fabs(v));
+        }
+        for (int i = 0; i < m->p; ++i) wabs = std::max(wabs, std::fabs(wm[(size_t)i]));
+        fprintf(stderr, "[bgp] pivot debug: wobs min %.6g max %.6g nonfinite %d | diag(H) min %.6g nonfinite %d H[%d][%d] %.6g | column max %.6g nonfinite %d | max|W| %.6g | theta",
+                wmin, wmax, wbad, dmin, dbad, first_pivot - 1, first_pivot - 1, hd[(size_t)first_pivot - 1], cmax, cbad, wabs);
+        for (int k = 0; k < m->S; ++k) fprintf(stderr, " %.6g", theta[k]);
+        fprintf(stderr, "\n");
+      }
+      phase_mark(m, PH_HESS);
+      BGP_TRY(launch_hessian(m, theta));
+      m->n_hess++;
+      phase_mark(m, PH_CHOL);
+      BGP_TRY(launch_chol_solve(m, true, tan_in_chol ? theta : nullptr, m->W));      // the variant the Newton iterations run
+      m->n_chol++;
+      BGP_TRY(read_scalars(m, &sc));
+      ++m->n_refactor;
+      fprintf(stderr, "[bgp] factorisation at the mode reported pivot %d; second attempt: %s (p = %d, attempt %lld of this model)\n",
+              first_pivot, sc.chol_info == 0 ? "positive definite" : "same failure", m->p, (long long)m->n_refactor);
+    }
     if (sc.chol_info != 0) {
       set_error("Hessian not positive definite at the mode (pivot %d)", sc.chol_info);
       *value = NAN;

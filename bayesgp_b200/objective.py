@@ -230,6 +230,7 @@ class LaplaceObjective:
                                           C.byref(iters))
         self.newton_iters += iters.value
         if code in (3, 4, 5):        # NOT_PD / NONFINITE / NO_CONVERGENCE: TMB returns NaN (+ warning)
+            self.last_warning = "%d: %s" % (code, self._lib.bgp_last_error().decode("utf-8", "replace"))
             return float("nan"), (np.full(self.S, np.nan) if want_grad else None), None, None
         check(code)
         if want_mode:

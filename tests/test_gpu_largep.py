@@ -51,7 +51,7 @@ def compare_with_oracle(model, thetas):
             assert abs(got - want) <= 1e-8 * abs(want), (th, got, want)       # north_star: 1e-8 relative
             assert relerr(w, off.last_par) < 1e-6 and relerr(Hm, off.sp_hess()) < 1e-6
             gw, gg = off.gr(th), ff.gr(th)
-            assert np.max(np.abs(gw - gg)) <= 2e-7 * max(1.0, np.max(np.abs(gw))), (th, gw, gg)
+            assert np.max(np.abs(gw - gg)) <= 2e-7 * max(1.0, np.max(np.abs(gw))), (th, gw, gg, getattr(ff, "last_warning", None))
         # the batch entry point (what the quadrature grid runs through) at the same latent size
         ff.set_start(None)
         vals, modes, Hs, _ = ff.fn_batch(np.array(thetas), want_modes=True, want_hess=True)
